@@ -1,0 +1,88 @@
+"""CPU, build container only: the C restatement against the UNMODIFIED reference run
+in-process (oracle/ref_harness.py).  This is what pins the oracle; the GPU box sees
+only the golden vectors derived from the same runs."""
+import glob
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle_lib as O
+from oracle.ref_harness import REFERENCE_ROOT, load_reference
+from tests.cases import make_case
+
+pytestmark = pytest.mark.reference
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return load_reference()
+
+
+def _gif(name):
+    from PIL import Image
+    return np.asarray(Image.open(os.path.join(REFERENCE_ROOT, "data", f"{name}.gif")).convert("L"))
+
+
+def test_all_data_images_hashes_match_kat(golden):
+    """Oracle on all 50 data/*.gif == the reference's streams (by the committed hashes)."""
+    names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(REFERENCE_ROOT, "data", "*.gif")))
+    assert len(names) == 50
+    for n in names:
+        out = O.compress(_gif(n), 50)
+        assert hashlib.sha256(out).hexdigest() == golden.kat["q50"][n]["sha256"], n
+
+
+def test_kat_regenerated_from_reference(ref, golden):
+    """Do not trust the table blindly: regenerate a few entries from the reference now."""
+    for n in ("lenna", "23", "44"):
+        out = ref.compress(_gif(n), quality=50)
+        assert hashlib.sha256(out).hexdigest() == golden.kat["q50"][n]["sha256"]
+
+
+@pytest.mark.parametrize("q", [97, 90, 61, 50, 49, 33, 10, 1])
+def test_random_shapes_streams_and_coeffs(ref, q):
+    rng = np.random.default_rng(q)
+    for _ in range(4):
+        h, w = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+        kind = ["noise", "synthetic", "binary", "impulse"][int(rng.integers(0, 4))]
+        img = make_case({"kind": kind, "shape": (h, w), "seed": int(rng.integers(0, 1 << 30))})
+        try:
+            want = ref.compress(img, quality=q)
+        except KeyError:
+            with pytest.raises(O.OracleError):
+                O.compress(img, q)
+            continue
+        assert O.compress(img, q) == want, (h, w, kind, q)
+        e_ref, e_or = ref.encode(img, quality=q), O.encode(img, q)
+        assert np.array_equal(e_ref["dc"], e_or["dc"]) and np.array_equal(e_ref["ac"], e_or["ac"])
+
+
+def test_auto_table_random(ref):
+    rng = np.random.default_rng(123)
+    for q in (90, 50, 10):
+        for kind in ("noise", "synthetic", "impulse"):
+            h, w = int(rng.integers(8, 90)), int(rng.integers(8, 90))
+            img = make_case({"kind": kind, "shape": (h, w), "seed": int(rng.integers(0, 1 << 30))})
+            assert O.compress(img, q, True) == ref.compress(img, quality=q, auto_generate_huffman_table=True)
+
+
+def test_default_tables_equal_reference_literals(ref):
+    """The canonical BITS/HUFFVAL expansion equals constants.py:54-241 string by string."""
+    import tinyimgcodec_reference.constants as C
+    for cat, code in C.HUFFMAN_CATEGORY_CODEWORD[C.DC].items():
+        assert O.default_code(0, cat) == code
+    for (run, size), code in C.HUFFMAN_CATEGORY_CODEWORD[C.AC].items():
+        assert O.default_code(1, run * 16 + size) == code
+    assert len(C.HUFFMAN_CATEGORY_CODEWORD[C.AC]) == 162
+
+
+def test_roundtrip_decodes_with_reference_decoder(ref):
+    from oracle.ref_harness import reference_psnr
+    psnr = reference_psnr()
+    img = _gif("lenna")
+    out = O.compress(img, 50)
+    dec = ref.decompress(out)
+    assert dec.shape == img.shape
+    assert abs(psnr(img, dec) - 35.83) < 0.01
