@@ -1,0 +1,131 @@
+/*
+ * tinyimgcodec_cuda.h — C ABI of libtinyimgcodec_cuda.so, the B200 (sm_100a) encode path.
+ *
+ * The reference (clysto/tinyimgcodec) has no FFI/plugin layer: its boundary for the
+ * encode hot path is two Python functions,
+ *     tinyimgcodec.codec.compress(image, quality=50, auto_generate_huffman_table=False) -> bytes
+ *         (tinyimgcodec/codec.py:133-164)
+ *     tinyimgcodec.codec.encode(image, quality=50) -> dict
+ *         (tinyimgcodec/codec.py:26-43)
+ * and the CLI ./encode.py (encode.py:10-19).  This header is what a ctypes binding placed
+ * UNDER those two functions calls (INTEGRATION.md shows the stub).  Every entry point
+ * returns 0 or a negative TIC_E_* code; no C++ exception, torch type or CUDA type
+ * crosses the boundary (streams are passed as void*, i.e. a cudaStream_t value).
+ * The caller owns every buffer; the library owns only the opaque handle and the
+ * scratch memory behind it.  One handle per GPU; calls on one handle are serialised
+ * by the caller (a handle is not thread-safe), different handles run concurrently.
+ *
+ * There is no CPU fallback: every compute entry point fails with TIC_E_CUDA when no
+ * sm_100-class device is usable.
+ */
+#ifndef TINYIMGCODEC_CUDA_H
+#define TINYIMGCODEC_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TIC_OK 0
+#define TIC_E_INVALID (-1)    /* bad argument (NULL pointer, negative size, n_images < 0 ...) */
+#define TIC_E_CUDA (-2)       /* a CUDA runtime call failed; see tic_last_error() */
+#define TIC_E_QUALITY (-3)    /* quality outside 1..99: the reference raises ZeroDivisionError
+                                 for 0 (tinyimgcodec/utils.py:50) and KeyError for 100 */
+#define TIC_E_CAPACITY (-4)   /* output buffer too small; nothing past out_capacity was written */
+#define TIC_E_CATEGORY (-5)   /* a DC size >= 12 or AC size >= 11 met the fixed tables: the
+                                 reference raises KeyError (tinyimgcodec/huffman.py:62);
+                                 per-image detail is in the status array */
+#define TIC_E_UNSUPPORTED (-6)
+
+/* flags for tic_encode_batch */
+#define TIC_FLAG_AUTO_HUFFMAN 1u /* per-image tables, tinyimgcodec/codec.py:146-148 */
+
+/* per-image status bits written by the device */
+#define TIC_STATUS_CATEGORY 1 /* KeyError case above */
+#define TIC_STATUS_TABLE 2    /* auto table not serialisable (OverflowError in the reference,
+                                 tinyimgcodec/codec.py:77,83) or code longer than 32 bits */
+
+typedef struct tic_handle_s *tic_handle;
+
+/* Library version string, e.g. "tinyimgcodec_cuda 0.1 sm_100a". */
+const char *tic_version(void);
+
+/* Create / destroy the per-GPU context (scratch buffers, constant tables, one stream-ordered
+ * workspace).  Replaces nothing in the reference (which has no state); it is the price
+ * of a device. */
+int tic_create(int device, tic_handle *out);
+int tic_destroy(tic_handle h);
+
+/* Text of the last error on this handle (never NULL; valid until the next call). */
+const char *tic_last_error(tic_handle h);
+
+/* Upper bound on the bytes tic_encode_batch writes for one H x W image with the fixed
+ * tables: a 16-byte header (tinyimgcodec/codec.py:102-114), at most 1662 bits per 8x8
+ * block (DC 9+11, 63 x (16+10), EOB 4), plus 16 bytes of alignment slack.  Pure host
+ * arithmetic; usable without a GPU. */
+int64_t tic_max_out_bytes(int32_t height, int32_t width);
+
+/* Number of 8x8 blocks of the padded image (ceil(H/8)*ceil(W/8), tinyimgcodec/utils.py:56-61). */
+int64_t tic_num_blocks(int32_t height, int32_t width);
+
+/*
+ * compress() for a batch of images resident in device memory — replaces the whole body
+ * of tinyimgcodec/codec.py:133-164 (encode, run-length, header, Huffman, to_bytes) for
+ * n_images independent images in one launch sequence.
+ *
+ *   d_pixels      n_images device pointers... passed as a HOST array of device addresses;
+ *                 image i is heights[i] x widths[i] uint8, row-major, contiguous.
+ *   heights/widths HOST arrays, original (unpadded) dimensions; 0 is allowed.
+ *   quality       1..99, the same for the whole batch.
+ *   flags         TIC_FLAG_* bits.
+ *   d_out         device buffer of out_capacity bytes.  The n streams are written densely,
+ *                 each starting on a 16-byte boundary, in image order.
+ *   d_out_offsets device int64[n_images]: byte offset of stream i in d_out.
+ *   d_out_sizes   device int64[n_images]: byte length of stream i (== len(compress(...))).
+ *   d_status      device int32[n_images]: TIC_STATUS_* bits (0 = identical to reference).
+ *   stream        cudaStream_t the work is enqueued on (NULL = default stream).
+ *
+ * Asynchronous with respect to the host: results are valid after the stream is
+ * synchronised.  Errors that only the device can see (capacity, category) are reported
+ * by tic_encode_finish().
+ */
+int tic_encode_batch(tic_handle h, const void *const *d_pixels, const int32_t *heights,
+                     const int32_t *widths, int32_t n_images, int32_t quality, uint32_t flags,
+                     void *d_out, int64_t out_capacity, int64_t *d_out_offsets,
+                     int64_t *d_out_sizes, int32_t *d_status, void *stream);
+
+/* Synchronise `stream`, and report what the device saw during the last tic_encode_batch
+ * on this handle: TIC_OK, TIC_E_CAPACITY or TIC_E_CATEGORY.  *total_bytes (optional)
+ * receives the number of bytes of d_out that are in use (end of the last stream). */
+int tic_encode_finish(tic_handle h, void *stream, int64_t *total_bytes);
+
+/*
+ * encode() for one image resident in device memory — replaces tinyimgcodec/codec.py:28-36
+ * (pad, level shift, block split, FDCT, quantise, zigzag, DC difference).
+ *   d_dc  device int32[nblk]      dc[0] absolute, dc[i>0] = difference to block i-1
+ *   d_ac  device int32[nblk*63]   zigzag positions 1..63
+ * with nblk = tic_num_blocks(height, width), blocks in raster order.
+ */
+int tic_encode_coeffs(tic_handle h, const void *d_pixels, int32_t height, int32_t width,
+                      int32_t quality, int32_t *d_dc, int32_t *d_ac, void *stream);
+
+/*
+ * Host-buffer convenience around the two calls above (pinned staging, H2D, launch, D2H):
+ * what a ctypes binding of compress() for one numpy image calls.
+ *   out / out_capacity  host buffer; *out_size receives len(compress(image, quality)).
+ * Synchronous.
+ */
+int tic_compress_host(tic_handle h, const uint8_t *pixels, int32_t height, int32_t width,
+                      int32_t quality, uint32_t flags, uint8_t *out, int64_t out_capacity,
+                      int64_t *out_size, int32_t *status);
+
+/* Counters of the last tic_encode_batch on this handle (valid after tic_encode_finish):
+ *   [0] kernels launched   [1] tiles   [2] coefficients sent to the exact FP64 path
+ *   [3] coefficients the exact path changed   [4] blocks */
+int tic_last_stats(tic_handle h, int64_t stats[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TINYIMGCODEC_CUDA_H */

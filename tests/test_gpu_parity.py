@@ -1,0 +1,170 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes, via the host mirror in
+tinyimgcodec_b200/codec.py), against the committed golden vectors of the reference and against
+the CPU oracle (oracle/tic_oracle.c) on the same seeded inputs.  Bit-exact: integer coefficients
+and byte streams must be identical."""
+import hashlib
+
+import numpy as np
+import pytest
+
+from oracle import oracle_lib as O
+from tests.cases import make_case, synthetic_image
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def tic():
+    import tinyimgcodec_b200 as m
+    return m
+
+
+def _first_diff(a, b):
+    n = min(len(a), len(b))
+    for i in range(n):
+        if a[i] != b[i]:
+            return i
+    return n
+
+
+def _assert_same(got, want, what):
+    assert got == want, f"{what}: len {len(got)} vs {len(want)}, first difference at byte {_first_diff(got, want)}"
+
+
+def test_native_library_loaded(tic):
+    import tinyimgcodec_b200._lib as L
+    lib = L.load()
+    assert b"sm_100a" in lib.tic_version()
+    with open("/proc/self/maps") as f:
+        assert "libtinyimgcodec_cuda.so" in f.read()
+
+
+def test_lenna_kat(tic, golden):
+    out = tic.compress(golden.images["lenna"])
+    assert len(out) == 20765
+    assert hashlib.sha256(out).hexdigest() == "4596d8bb0d5577d2d4321e5e2ff8c086ce8fbd313b00d4879d4c65baaa8048a9"
+
+
+def test_golden_streams(tic, golden):
+    n = 0
+    for key, img, q, want in golden.stream_cases(auto=False):
+        _assert_same(tic.compress(img, q), want, key)
+        n += 1
+    assert n >= 50
+
+
+def test_golden_error_cases(tic, golden):
+    for key, img, q, exc in golden.error_cases():
+        with pytest.raises(KeyError):
+            tic.compress(img, q)
+
+
+def test_golden_coefficients(tic, golden):
+    lenna = golden.images["lenna"]
+    for q in (50, 90):
+        e = tic.encode(lenna, q)
+        assert e["dc"].dtype == np.int32 and e["ac"].dtype == np.int32
+        assert np.array_equal(e["dc"], golden.coeffs[f"lenna_q{q}_dc"])
+        assert np.array_equal(e["ac"], golden.coeffs[f"lenna_q{q}_ac"].astype(np.int32))
+        assert (e["height"], e["width"], e["quality"]) == (512, 512, q)
+
+
+def test_subset_images_batch_equals_reference_streams(tic, golden):
+    """BASELINE config 2 shape (data/*.gif as one batch), on the committed subset."""
+    names = sorted(golden.images)
+    outs = tic.compress_batch([golden.images[n] for n in names], 50)
+    for n, out in zip(names, outs):
+        kat = golden.kat["q50"][n]
+        assert (len(out), hashlib.sha256(out).hexdigest()) == (kat["size"], kat["sha256"]), n
+
+
+@pytest.mark.parametrize("q", [1, 5, 10, 20, 35, 49, 50, 51, 65, 80, 90, 95])
+def test_random_shapes_vs_oracle(tic, q):
+    rng = np.random.default_rng(1000 + q)
+    for _ in range(6):
+        h, w = int(rng.integers(1, 200)), int(rng.integers(1, 200))
+        kind = ["noise", "synthetic", "binary", "impulse", "checker", "ramp"][int(rng.integers(0, 6))]
+        img = make_case({"kind": kind, "shape": (h, w), "seed": int(rng.integers(0, 1 << 30))})
+        try:
+            want = O.compress(img, q)
+        except O.OracleError:
+            with pytest.raises(KeyError):
+                tic.compress(img, q)
+            continue
+        _assert_same(tic.compress(img, q), want, f"{kind} {h}x{w} q{q}")
+        e, eo = tic.encode(img, q), O.encode(img, q)
+        assert np.array_equal(e["dc"], eo["dc"]) and np.array_equal(e["ac"], eo["ac"])
+
+
+def test_all_qualities_vs_oracle(tic):
+    img = synthetic_image(96, 160, seed=5)
+    noise = make_case({"kind": "noise", "shape": (64, 72), "seed": 77})
+    for q in range(1, 100):
+        for im in (img, noise):
+            try:
+                want = O.compress(im, q)
+            except O.OracleError:
+                with pytest.raises(KeyError):
+                    tic.compress(im, q)
+                continue
+            _assert_same(tic.compress(im, q), want, f"q{q}")
+
+
+def test_ragged_batch_vs_oracle(tic):
+    rng = np.random.default_rng(7)
+    shapes = [(512, 512), (8, 8), (1, 1), (0, 8), (37, 51), (1024, 1024), (64, 2048), (3, 5), (1032, 520),
+              (16, 16), (129, 1025), (256, 8)]
+    imgs = []
+    for i, (h, w) in enumerate(shapes):
+        kind = ["synthetic", "noise", "impulse"][i % 3]
+        imgs.append(make_case({"kind": kind, "shape": (h, w), "seed": int(rng.integers(0, 1 << 30))}))
+    outs = tic.compress_batch(imgs, 50)
+    assert len(outs) == len(imgs)
+    for im, out in zip(imgs, outs):
+        _assert_same(out, O.compress(im, 50), f"batch {im.shape}")
+
+
+def test_1024_batch_vs_oracle(tic):
+    """BASELINE config 4 shape at a size the oracle finishes in seconds: 24 x 1024^2."""
+    imgs = [synthetic_image(1024, 1024, seed=i) for i in range(24)]
+    for q in (50, 90, 10):
+        outs = tic.compress_batch(imgs, q)
+        for i, (im, out) in enumerate(zip(imgs, outs)):
+            _assert_same(out, O.compress(im, q), f"1024^2 seed {i} q{q}")
+
+
+def test_8k_image_vs_oracle(tic):
+    """BASELINE config 3: one 7680x4320 image."""
+    img = synthetic_image(4320, 7680, seed=0)
+    _assert_same(tic.compress(img, 50), O.compress(img, 50), "8K q50")
+
+
+def test_noise_high_quality_stress_vs_oracle(tic):
+    """Uniform noise: worst case for scan/pack (6+ bits per pixel at q90) and for the tie guard."""
+    img = make_case({"kind": "noise", "shape": (1024, 2048), "seed": 3})
+    for q in (90, 50):
+        _assert_same(tic.compress(img, q), O.compress(img, q), f"noise q{q}")
+    flat = np.full((1024, 1024), 77, np.uint8)
+    _assert_same(tic.compress(flat, 50), O.compress(flat, 50), "flat")
+
+
+def test_error_behaviour_matches_reference(tic):
+    import struct
+    img = np.zeros((16, 16), np.uint8)
+    with pytest.raises(ValueError):
+        tic.compress(np.zeros((2, 3, 4), np.uint8))            # codec.py:27
+    with pytest.raises(ZeroDivisionError):
+        tic.compress(img, 0)                                   # utils.py:50
+    with pytest.raises(struct.error):
+        tic.compress(img, 50.0)                                # codec.py:103
+    with pytest.raises(KeyError):
+        tic.compress(img, 100)                                 # huffman.py:62 via utils.py:53
+    assert isinstance(tic.compress(img.astype(np.int64)), bytes)
+
+
+def test_dropin_package_names(tic):
+    import tinyimgcodec
+    from tinyimgcodec.codec import compress, encode
+    img = synthetic_image(64, 64, seed=1)
+    assert tinyimgcodec.compress(img) == compress(img) == O.compress(img, 50)
+    assert set(encode(img)) == {"height", "width", "quality", "dc", "ac"}

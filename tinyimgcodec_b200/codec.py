@@ -1,0 +1,231 @@
+"""Host-side mirror of the reference's encode entry points, on top of the C ABI.
+
+    compress(image, quality=50, auto_generate_huffman_table=False) -> bytes
+        mirrors tinyimgcodec/codec.py:133-164
+    encode(image, quality=50) -> dict
+        mirrors tinyimgcodec/codec.py:26-43
+
+Same names, argument meaning and error behaviour as the reference; the work runs in the
+sm_100a kernels behind libtinyimgcodec_cuda.so.  PyTorch is used only for device buffers
+and streams in the batch API.  There is no CPU path: without the library and a B200 the
+calls raise.
+"""
+import ctypes
+import os
+import struct
+import threading
+
+import numpy as np
+
+from . import _lib
+
+_encoders = {}
+_encoders_lock = threading.Lock()
+
+
+class TicError(RuntimeError):
+    def __init__(self, code, message):
+        super().__init__(f"libtinyimgcodec_cuda error {code}: {message}")
+        self.code = code
+
+
+def _default_device():
+    return int(os.environ.get("TIC_DEVICE", "0"))
+
+
+def _check_quality(quality):
+    """The reference packs quality with struct 'I' (codec.py:103-108) and divides by it
+    (utils.py:50): reproduce the exception types it raises."""
+    struct.pack("I", quality)  # struct.error for float / negative, like make_header
+    if quality == 0:
+        raise ZeroDivisionError("division by zero")  # utils.py:50: 5000 / quality
+    if quality == 100:
+        # utils.py:53 divides by a zero table -> int32 min -> bits_required = 32 -> KeyError
+        raise KeyError(32)
+    if quality > 100:
+        raise ValueError("quality above 100 is outside the codec's domain (negative quantisation table)")
+    return int(quality)
+
+
+def _as_u8_image(image):
+    """`height, width = image.shape` (codec.py:27) then astype(int32) (codec.py:29)."""
+    image = np.asarray(image)
+    height, width = image.shape  # ValueError for non-2-D input, like the reference
+    if image.dtype != np.uint8:
+        as_int = image.astype(np.int32)
+        if as_int.size and (as_int.min() < 0 or as_int.max() > 255):
+            raise ValueError("the B200 path encodes 8-bit grayscale: pixel values must be in 0..255")
+        image = as_int.astype(np.uint8)
+    return np.ascontiguousarray(image), int(height), int(width)
+
+
+class Encoder:
+    """One per GPU: owns the library handle (include/tinyimgcodec_cuda.h: tic_create)."""
+
+    def __init__(self, device=None):
+        self.lib = _lib.load()
+        self.device = _default_device() if device is None else int(device)
+        h = ctypes.c_void_p()
+        rc = self.lib.tic_create(self.device, ctypes.byref(h))
+        if rc != _lib.TIC_OK:
+            raise TicError(rc, f"tic_create(device={self.device}) failed: no usable sm_100 GPU "
+                               "(tinyimgcodec_b200 has no CPU fallback)")
+        self.handle = h
+        self._lock = threading.Lock()
+
+    def close(self):
+        if self.handle:
+            self.lib.tic_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _raise(self, rc):
+        msg = (self.lib.tic_last_error(self.handle) or b"").decode()
+        if rc == _lib.TIC_E_CATEGORY:
+            raise KeyError(msg)  # huffman.py:62: category not in the fixed table
+        if rc == _lib.TIC_E_UNSUPPORTED:
+            raise NotImplementedError(msg)
+        raise TicError(rc, msg)
+
+    # -- single image, host buffers ---------------------------------------------------------
+    def compress(self, image, quality=50, auto_generate_huffman_table=False):
+        img, height, width = _as_u8_image(image)
+        quality = _check_quality(quality)
+        flags = _lib.TIC_FLAG_AUTO_HUFFMAN if auto_generate_huffman_table else 0
+        cap = int(self.lib.tic_max_out_bytes(height, width))
+        out = np.empty(cap, dtype=np.uint8)
+        size = ctypes.c_int64(0)
+        status = ctypes.c_int32(0)
+        with self._lock:
+            rc = self.lib.tic_compress_host(self.handle, img.ctypes.data, height, width, quality, flags,
+                                            out.ctypes.data, cap, ctypes.byref(size), ctypes.byref(status))
+            if rc != _lib.TIC_OK:
+                self._raise(rc)
+        return out[: size.value].tobytes()
+
+    def encode(self, image, quality=50):
+        import torch
+        img, height, width = _as_u8_image(image)
+        q = _check_quality(quality)
+        nblk = int(self.lib.tic_num_blocks(height, width))
+        dev = torch.device("cuda", self.device)
+        with self._lock, torch.cuda.device(dev):
+            d_px = torch.from_numpy(img).to(dev) if img.size else torch.empty(0, dtype=torch.uint8, device=dev)
+            d_dc = torch.empty(max(nblk, 1), dtype=torch.int32, device=dev)
+            d_ac = torch.empty(max(nblk, 1) * 63, dtype=torch.int32, device=dev)
+            stream = torch.cuda.current_stream(dev)
+            rc = self.lib.tic_encode_coeffs(self.handle, d_px.data_ptr(), height, width, q, d_dc.data_ptr(),
+                                            d_ac.data_ptr(), stream.cuda_stream)
+            if rc != _lib.TIC_OK:
+                self._raise(rc)
+            stream.synchronize()
+            dc = d_dc[:nblk].cpu().numpy()
+            ac = d_ac[: nblk * 63].cpu().numpy().reshape(nblk, 63)
+        return {"height": height, "width": width, "quality": quality, "dc": dc, "ac": ac}
+
+    # -- batch, device buffers ----------------------------------------------------------------
+    def encode_batch_device(self, d_images, quality=50, out=None, stream=None):
+        """Encode a batch resident in HBM.  `d_images`: a CUDA uint8 tensor (N,H,W) or a list of
+        2-D CUDA uint8 tensors.  Returns a DeviceBatchResult; nothing is copied to the host."""
+        import torch
+        q = _check_quality(quality)
+        if isinstance(d_images, torch.Tensor):
+            if d_images.dim() != 3:
+                raise ValueError("expected an (N, H, W) uint8 tensor")
+            tensors = [d_images[i] for i in range(d_images.shape[0])]
+        else:
+            tensors = list(d_images)
+        n = len(tensors)
+        dev = torch.device("cuda", self.device)
+        for t in tensors:
+            if t.dtype != torch.uint8 or t.dim() != 2 or not t.is_contiguous() or t.device != dev:
+                raise ValueError("images must be contiguous 2-D uint8 tensors on the encoder's GPU")
+        ptrs = (ctypes.c_void_p * max(n, 1))(*[t.data_ptr() for t in tensors])
+        hs = (ctypes.c_int32 * max(n, 1))(*[t.shape[0] for t in tensors])
+        ws = (ctypes.c_int32 * max(n, 1))(*[t.shape[1] for t in tensors])
+        with torch.cuda.device(dev):
+            if out is None:
+                cap = sum(int(self.lib.tic_max_out_bytes(t.shape[0], t.shape[1])) for t in tensors) + 16
+                out = torch.empty(cap, dtype=torch.uint8, device=dev)
+            meta = torch.empty(max(n, 1) * 3, dtype=torch.int64, device=dev)
+            offs, sizes = meta[:n], meta[max(n, 1): max(n, 1) + n]
+            stat = meta[2 * max(n, 1):].view(torch.int32)[:n]
+            stream = stream or torch.cuda.current_stream(dev)
+            with self._lock:
+                rc = self.lib.tic_encode_batch(self.handle, ptrs, hs, ws, n, q, 0, out.data_ptr(), out.numel(),
+                                               offs.data_ptr(), sizes.data_ptr(), stat.data_ptr(),
+                                               stream.cuda_stream)
+                if rc != _lib.TIC_OK:
+                    self._raise(rc)
+        return DeviceBatchResult(self, out, offs, sizes, stat, stream, n)
+
+    def stats(self):
+        arr = (ctypes.c_int64 * 8)()
+        self.lib.tic_last_stats(self.handle, arr)
+        return {"launches": arr[0], "tiles": arr[1], "exact_items": arr[2], "exact_changed": arr[3],
+                "blocks": arr[4]}
+
+
+class DeviceBatchResult:
+    """Streams of one encode_batch_device call, still in HBM."""
+
+    def __init__(self, enc, out, offsets, sizes, status, stream, n):
+        self.enc, self.out, self.offsets, self.sizes, self.status = enc, out, offsets, sizes, status
+        self.stream, self.n = stream, n
+        self.total_bytes = None
+
+    def finish(self):
+        """Synchronise and raise what the reference would have raised."""
+        total = ctypes.c_int64(0)
+        with self.enc._lock:
+            rc = self.enc.lib.tic_encode_finish(self.enc.handle, self.stream.cuda_stream, ctypes.byref(total))
+            self.total_bytes = total.value
+            if rc != _lib.TIC_OK:
+                self.enc._raise(rc)
+        return self
+
+    def to_bytes(self):
+        """One D2H copy of the dense stream buffer, split into per-image bytes objects."""
+        if self.total_bytes is None:
+            self.finish()
+        host = self.out[: self.total_bytes].cpu().numpy()
+        offs = self.offsets.cpu().numpy()
+        sizes = self.sizes.cpu().numpy()
+        return [host[o: o + s].tobytes() for o, s in zip(offs, sizes)]
+
+
+def get_encoder(device=None):
+    device = _default_device() if device is None else int(device)
+    with _encoders_lock:
+        enc = _encoders.get(device)
+        if enc is None:
+            enc = _encoders[device] = Encoder(device)
+        return enc
+
+
+def compress(image, quality=50, auto_generate_huffman_table=False, device=None):
+    """Drop-in for tinyimgcodec.codec.compress (codec.py:133-164)."""
+    return get_encoder(device).compress(image, quality, auto_generate_huffman_table)
+
+
+def encode(image, quality=50, device=None):
+    """Drop-in for tinyimgcodec.codec.encode (codec.py:26-43)."""
+    return get_encoder(device).encode(image, quality)
+
+
+def compress_batch(images, quality=50, device=None):
+    """compress() for a list of 2-D uint8 arrays (or an (N,H,W) array) in one launch sequence:
+    pinned H2D, one encode, one D2H.  Returns a list of bytes objects."""
+    import torch
+    enc = get_encoder(device)
+    dev = torch.device("cuda", enc.device)
+    imgs = [_as_u8_image(im)[0] for im in images]
+    with torch.cuda.device(dev):
+        d_imgs = [torch.from_numpy(im).pin_memory().to(dev, non_blocking=True) if im.size
+                  else torch.empty(im.shape, dtype=torch.uint8, device=dev) for im in imgs]
+        return enc.encode_batch_device(d_imgs, quality).to_bytes()

@@ -1,0 +1,565 @@
+// tic_encode.cu — kernels and C ABI of libtinyimgcodec_cuda.so (see include/tinyimgcodec_cuda.h).
+//
+// Build (sm_100a only, no other architecture is supported):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -Xcompiler -fPIC -shared ...
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/tinyimgcodec_cuda.h"
+#include "tic_kernels.cuh"
+
+namespace tic {
+
+// ---------------------------------------------------------------------------------------------
+// compress(): one CTA per tile, tiles taken in stream order through a ticket so that the
+// decoupled look-back can never wait on a tile that has not started.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTile, 4)
+encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restrict__ descs, int n_images,
+                    unsigned long long* __restrict__ tile_status, unsigned long long* __restrict__ tile_tail,
+                    unsigned long long* __restrict__ counters, uint8_t* __restrict__ out, long long out_cap,
+                    long long* __restrict__ out_off, long long* __restrict__ out_end,
+                    int* __restrict__ status, int quality) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileShared& sm = *reinterpret_cast<TileShared*>(smem_raw);
+    __shared__ long long s_tile;
+    const int t = threadIdx.x;
+    const int lane = t & 31, warp = t >> 5;
+
+    if (t == 0) s_tile = (long long)atomicAdd(&counters[kCtrTicket], 1ull);
+    // default tables -> shared memory (constants.py:53-242)
+    for (int i = t; i < 256; i += kTile) {
+        sm.ac_code[i] = c_default_tables.ac_code[i];
+        sm.ac_len[i] = c_default_tables.ac_len[i];
+    }
+    if (t < 16) {
+        sm.dc_code[t] = c_default_tables.dc_code[t];
+        sm.dc_len[t] = c_default_tables.dc_len[t];
+    }
+    if (t == 0) sm.err = 0;
+    __syncthreads();
+    const long long tile = s_tile;
+    const TileInfo ti = locate_tile(descs, n_images, tile);
+
+    transform_tile(ti, qp, sm, counters);
+
+    // ---- bit lengths and the CTA scan -------------------------------------------------------
+    int err = 0;
+    int bits = (t < ti.nb) ? block_bits(sm, t, err) : 0;
+    int incl = bits;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += n;
+    }
+    if (lane == 31) sm.warp_bits[warp] = incl;
+    if (err) sm.err = 1;
+    __syncthreads();
+    int warp_base = 0, tile_bits = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) {
+        int wb = sm.warp_bits[w];
+        if (w < warp) warp_base += wb;
+        tile_bits += wb;
+    }
+    const int bitpos = warp_base + incl - bits;   // tile-relative bit offset of this block
+    const long long agg = (long long)tile_bits + (ti.first ? 128 : 0);
+
+    // publish the aggregate as early as possible: successors only need it for their offset
+    if (t == 0) {
+        st_release_u64(&tile_status[tile], kFlagAgg | (ti.closing ? kClosingBit : 0ull) | (unsigned long long)agg);
+        if (sm.err) atomicOr(&status[ti.img], TIC_STATUS_CATEGORY);
+    }
+    const int nwords = (tile_bits + 31) >> 5;
+    for (int i = t; i <= nwords; i += kTile) sm.stage[i] = 0;
+    __syncthreads();
+
+    // ---- bits into the tile-relative staging buffer ---------------------------------------------
+    if (t < ti.nb) block_emit(sm, t, bitpos);
+
+    // ---- decoupled look-back (thread 0): absolute bit position of this tile -----------------------
+    if (t == 0) {
+        long long a = 0, b = 0;   // composite of the tiles between the look-back cursor and this tile:
+        bool closed = false;      // g(P) = closed ? round_up128(P + a) + b : P + a
+        long long p_in;
+        long long j = tile - 1;
+        while (true) {
+            if (j < 0) { p_in = closed ? round_up128(a) + b : a; break; }
+            unsigned long long s;
+            do { s = ld_acquire_u64(&tile_status[j]); } while ((s & kFlagMask) == 0);
+            long long val = (long long)(s & kValueMask);
+            if ((s & kFlagMask) == kFlagPrefix) {
+                p_in = closed ? round_up128(val + a) + b : val + a;
+                break;
+            }
+            if (s & kClosingBit) {   // tile j closes an image: everything after it is 128-bit aligned
+                b = closed ? round_up128(a) + b : a;
+                a = val;
+                closed = true;
+            } else {
+                a += val;
+            }
+            j--;
+        }
+        const long long e_bits = p_in + agg;   // end of this tile's data bits
+        const long long p_out = ti.closing ? round_up128(e_bits) : e_bits;
+        st_release_u64(&tile_status[tile], kFlagPrefix | (unsigned long long)p_out);
+        const long long s_bits = p_in + (ti.first ? 128 : 0);
+        sm.s_bits = s_bits;
+        // the word shared with the previous tile of the same image
+        unsigned int tail_prev = 0;
+        if (!ti.first && (s_bits & 31)) {
+            unsigned long long tw;
+            do { tw = ld_acquire_u64(&tile_tail[tile - 1]); } while ((tw >> 63) == 0);
+            tail_prev = (unsigned int)tw;
+        }
+        sm.tail_prev = tail_prev;
+        const long long end_byte = (e_bits + 7) >> 3;
+        const bool fits = ((end_byte + 3) & ~3ll) <= out_cap;
+        if (!fits) atomicExch(&counters[kCtrOverflow], 1ull);
+        if (ti.first) {
+            out_off[ti.img] = p_in >> 3;
+            if (fits) {   // make_header, codec.py:102-114: "III" little-endian + 32 flag bits = 0
+                uint4 hdr = make_uint4((unsigned)ti.h, (unsigned)ti.w, (unsigned)quality, 0u);
+                *reinterpret_cast<uint4*>(out + (p_in >> 3)) = hdr;
+            }
+        }
+        if (ti.closing) {
+            out_end[ti.img] = end_byte;
+            atomicMax(&counters[kCtrTotalBits], (unsigned long long)(end_byte << 3));
+        }
+    }
+    __syncthreads();
+
+    // ---- copy-out: funnel shift to the global alignment, byte-swap to MSB-first byte order ------
+    const long long s_bits = sm.s_bits;
+    const long long e_bits = s_bits + tile_bits;
+    const int sh = (int)(s_bits & 31);
+    const long long g0 = s_bits >> 5;
+    // words [g0, g_end): full words, plus the final partial word when this tile closes the image
+    const long long g_end = ti.closing ? ((e_bits + 31) >> 5) : (e_bits >> 5);
+    const bool fits = (((e_bits + 7) >> 3) + 3 & ~3ll) <= out_cap;
+    const unsigned int tail_prev = sm.tail_prev;
+    uint32_t* out_words = reinterpret_cast<uint32_t*>(out);
+    for (long long g = g0 + t; g < g_end; g += kTile) {
+        int jdx = (int)(g - g0);
+        uint32_t lo = sm.stage[jdx];
+        uint32_t hi = jdx ? sm.stage[jdx - 1] : 0u;
+        uint32_t v = __funnelshift_r(lo, hi, sh);
+        if (jdx == 0) v |= tail_prev;
+        if (fits) out_words[g] = __byte_perm(v, 0, 0x0123);
+    }
+    // hand the trailing partial word to the next tile
+    if (t == 0 && !ti.closing) {
+        unsigned int tail = 0;
+        if (e_bits & 31) {
+            int jdx = (int)((e_bits >> 5) - g0);
+            uint32_t lo = sm.stage[jdx];
+            uint32_t hi = jdx ? sm.stage[jdx - 1] : 0u;
+            tail = __funnelshift_r(lo, hi, sh);
+            if (jdx == 0) tail |= tail_prev;
+        }
+        st_release_u64(&tile_tail[tile], (1ull << 63) | tail);
+    }
+}
+
+// sizes = end - offset, and the batch summary the host reads back in tic_encode_finish
+__global__ void finalize_kernel(int n_images, const long long* __restrict__ out_off,
+                                const long long* __restrict__ out_end, long long* __restrict__ out_sizes,
+                                const int* __restrict__ status, unsigned long long* __restrict__ counters) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_images) {
+        out_sizes[i] = out_end[i] - out_off[i];
+        if (status[i]) atomicOr(&counters[kCtrAnyStatus], (unsigned long long)status[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// encode(): the same transform, coefficients written out (parity checkpoint for codec.py:26-43)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTile, 4)
+coeffs_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restrict__ descs,
+              unsigned long long* __restrict__ counters, int* __restrict__ dc, int* __restrict__ ac) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileShared& sm = *reinterpret_cast<TileShared*>(smem_raw);
+    const int t = threadIdx.x;
+    const TileInfo ti = locate_tile(descs, 1, blockIdx.x);
+    transform_tile(ti, qp, sm, counters);
+    if (t < ti.nb) {
+        const size_t b = (size_t)ti.blk0 + t;
+        dc[b] = sm.dcq[t + 1] - sm.dcq[t];
+        int* row = ac + b * 63;
+        for (int k = 1; k < 64; k++) row[k - 1] = coef_get(sm, t, k);
+    }
+}
+
+}  // namespace tic
+
+// =============================================================================================
+// host side
+// =============================================================================================
+using namespace tic;
+
+struct tic_handle_s {
+    int device = 0;
+    std::string err;
+    // workspace (grown on demand)
+    ImageDesc* d_descs = nullptr;       size_t descs_cap = 0;
+    ImageDesc* h_descs = nullptr;       // pinned
+    unsigned long long* d_tile_status = nullptr; size_t tiles_cap = 0;   // status + tail, 2 * tiles_cap
+    unsigned long long* d_counters = nullptr;
+    unsigned long long* h_counters = nullptr;    // pinned
+    long long* d_out_end = nullptr;     size_t end_cap = 0;
+    // single-image host path
+    uint8_t* d_px = nullptr;            size_t px_cap = 0;
+    uint8_t* d_out = nullptr;           size_t out_cap = 0;
+    uint8_t* h_stage = nullptr;         size_t h_stage_cap = 0;          // pinned
+    long long* d_meta = nullptr;        // off, size, status for the single-image path
+    long long* h_meta = nullptr;        // pinned
+    cudaStream_t own_stream = nullptr;
+    long long last_tiles = 0, last_blocks = 0, last_launches = 0;
+    bool tables_ready = false;
+};
+
+#define TIC_CUDA(h, call)                                                                     \
+    do {                                                                                      \
+        cudaError_t e_ = (call);                                                              \
+        if (e_ != cudaSuccess) {                                                              \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                    \
+            return TIC_E_CUDA;                                                                \
+        }                                                                                     \
+    } while (0)
+
+static void build_default_tables(HuffTables& t) {
+    memset(&t, 0, sizeof t);
+    uint32_t code = 0;
+    int k = 0;
+    for (int l = 1; l <= 16; l++) {
+        for (int i = 0; i < kDcBits[l]; i++) { t.dc_code[kDcVals[k]] = code++; t.dc_len[kDcVals[k]] = (uint8_t)l; k++; }
+        code <<= 1;
+    }
+    code = 0;
+    k = 0;
+    for (int l = 1; l <= 16; l++) {
+        for (int i = 0; i < kAcBits[l]; i++) { t.ac_code[kAcVals[k]] = code++; t.ac_len[kAcVals[k]] = (uint8_t)l; k++; }
+        code <<= 1;
+    }
+}
+
+// Quality -> quantiser constants.  qt follows tinyimgcodec/utils.py:50-53 operation by operation.
+static int make_quant_params(int quality, QuantParams& qp) {
+    if (quality < 1 || quality > 99) return TIC_E_QUALITY;
+    double qt_min = 1e30;
+    for (int i = 0; i < 64; i++) {
+        double q;
+        if (quality < 50) {
+            double factor = 5000.0 / (double)quality;
+            q = ((double)kQuantBase[i] * factor) / 100.0;
+        } else {
+            long factor = 200 - 2 * (long)quality;
+            q = (double)((long)kQuantBase[i] * factor) / 100.0;
+        }
+        qp.qt[i] = q;
+        if (q < qt_min) qt_min = q;
+    }
+    // |coefficient| <= 1024 (orthonormal transform of 64 values in [-128,127]); the fixed-point
+    // value t*2^F + 2^(F-1) + guard must stay inside the 22-bit window of the magic-number trick.
+    const double t_max = 1024.0 / qt_min;
+    int F = 0;
+    while (F < 15 && (t_max + 2.0) * (double)(1 << (F + 1)) < 4194304.0 * 0.98) F++;
+    qp.fbits = F;
+    qp.fmask = (1 << F) - 1;
+    qp.magic = 12582912.0f + (F > 0 ? (float)(1 << (F - 1)) : 0.0f);
+    qp.pad = 0;
+    double aan[8];
+    aan[0] = 1.0;
+    for (int k = 1; k < 8; k++) aan[k] = cos(k * 3.14159265358979323846 / 16.0) * sqrt(2.0);
+    // kFastErr: bound on |FP32 AAN coefficient - float64 reference coefficient| in coefficient
+    // units (worst-case analysis in DESIGN.md; tests/test_gpu_parity.py measures it).  The guard
+    // band is 4x that, plus the relative error of the FP32 multiplier.
+    const double kFastErr = 6.0e-4;
+    for (int u = 0; u < 8; u++)
+        for (int v = 0; v < 8; v++) {
+            int i = u * 8 + v;
+            double m = (double)(1 << F) / (8.0 * aan[u] * aan[v] * qp.qt[i]);
+            qp.qmul[i] = (float)m;
+            double tol = kFastErr / qp.qt[i] + 2.4e-7 * (1024.0 / qp.qt[i]);
+            int g = (int)ceil(tol * (double)(1 << F) + 0.5);
+            if (F == 0) g = 0;   // every coefficient goes to the exact path
+            if (2 * g + 1 > qp.fmask) g = qp.fmask / 2;
+            qp.guard[i] = g;
+        }
+    return TIC_OK;
+}
+
+static int ensure_tables(tic_handle h) {
+    if (h->tables_ready) return TIC_OK;
+    HuffTables t;
+    build_default_tables(t);
+    TIC_CUDA(h, cudaMemcpyToSymbol(c_default_tables, &t, sizeof t));
+    TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(TileShared)));
+    TIC_CUDA(h, cudaFuncSetAttribute(coeffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(TileShared)));
+    h->tables_ready = true;
+    return TIC_OK;
+}
+
+extern "C" {
+
+const char* tic_version(void) { return "tinyimgcodec_cuda 0.1 sm_100a"; }
+
+int64_t tic_num_blocks(int32_t height, int32_t width) {
+    if (height <= 0 || width <= 0) return 0;
+    return (int64_t)((height + 7) / 8) * (int64_t)((width + 7) / 8);
+}
+
+int64_t tic_max_out_bytes(int32_t height, int32_t width) {
+    return 16 + (tic_num_blocks(height, width) * 1662 + 7) / 8 + 16;
+}
+
+int tic_create(int device, tic_handle* out) {
+    if (!out) return TIC_E_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return TIC_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return TIC_E_CUDA;
+    if (prop.major != 10) return TIC_E_CUDA;   // sm_100a binary only: no fallback, fail loudly
+    tic_handle h = new tic_handle_s();
+    h->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&h->d_counters, kCtrCount * 8) != cudaSuccess ||
+        cudaMallocHost(&h->h_counters, kCtrCount * 8) != cudaSuccess ||
+        cudaMalloc(&h->d_meta, 64) != cudaSuccess || cudaMallocHost(&h->h_meta, 64) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return TIC_E_CUDA;
+    }
+    *out = h;
+    return TIC_OK;
+}
+
+int tic_destroy(tic_handle h) {
+    if (!h) return TIC_E_INVALID;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_descs); cudaFreeHost(h->h_descs); cudaFree(h->d_tile_status); cudaFree(h->d_counters);
+    cudaFreeHost(h->h_counters); cudaFree(h->d_out_end); cudaFree(h->d_px); cudaFree(h->d_out);
+    cudaFreeHost(h->h_stage); cudaFree(h->d_meta); cudaFreeHost(h->h_meta);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+    return TIC_OK;
+}
+
+const char* tic_last_error(tic_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+static int grow_descs(tic_handle h, size_t n) {
+    if (n <= h->descs_cap) return TIC_OK;
+    size_t cap = n < 64 ? 64 : n * 2;
+    cudaFree(h->d_descs); cudaFreeHost(h->h_descs);
+    h->d_descs = nullptr; h->h_descs = nullptr; h->descs_cap = 0;
+    TIC_CUDA(h, cudaMalloc(&h->d_descs, cap * sizeof(ImageDesc)));
+    TIC_CUDA(h, cudaMallocHost(&h->h_descs, cap * sizeof(ImageDesc)));
+    h->descs_cap = cap;
+    return TIC_OK;
+}
+
+int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* heights, const int32_t* widths,
+                     int32_t n_images, int32_t quality, uint32_t flags, void* d_out, int64_t out_capacity,
+                     int64_t* d_out_offsets, int64_t* d_out_sizes, int32_t* d_status, void* stream_v) {
+    if (!h) return TIC_E_INVALID;
+    h->err.clear();
+    if (n_images < 0 || out_capacity < 0 || (n_images > 0 && (!d_pixels || !heights || !widths || !d_out ||
+                                                              !d_out_offsets || !d_out_sizes || !d_status))) {
+        h->err = "invalid argument";
+        return TIC_E_INVALID;
+    }
+    if (flags & TIC_FLAG_AUTO_HUFFMAN) {
+        h->err = "auto-generated Huffman tables are not implemented on the device yet";
+        return TIC_E_UNSUPPORTED;
+    }
+    if ((reinterpret_cast<uintptr_t>(d_out) & 15) != 0) {
+        h->err = "d_out must be 16-byte aligned";
+        return TIC_E_INVALID;
+    }
+    QuantParams qp;
+    int rc = make_quant_params(quality, qp);
+    if (rc) { h->err = "quality must be in 1..99"; return rc; }
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    TIC_CUDA(h, cudaSetDevice(h->device));
+    rc = ensure_tables(h);
+    if (rc) return rc;
+    h->last_tiles = h->last_blocks = h->last_launches = 0;
+    if (n_images == 0) {
+        TIC_CUDA(h, cudaMemsetAsync(h->d_counters, 0, kCtrCount * 8, stream));
+        return TIC_OK;
+    }
+    rc = grow_descs(h, (size_t)n_images);
+    if (rc) return rc;
+    long long ntiles = 0, nblocks = 0;
+    for (int i = 0; i < n_images; i++) {
+        if (heights[i] < 0 || widths[i] < 0) { h->err = "negative image dimension"; return TIC_E_INVALID; }
+        long long nblk = tic_num_blocks(heights[i], widths[i]);
+        if (nblk > 0x7fffffffll - kTile) { h->err = "image too large"; return TIC_E_INVALID; }
+        ImageDesc& d = h->h_descs[i];
+        d.px = (const uint8_t*)d_pixels[i];
+        d.h = heights[i];
+        d.w = widths[i];
+        d.bw = (widths[i] + 7) / 8;
+        d.nblk = (int)nblk;
+        d.tile0 = ntiles;
+        long long nt = (nblk + kTile - 1) / kTile;
+        ntiles += nt < 1 ? 1 : nt;   // an empty image still owns one tile: it writes the header
+        nblocks += nblk;
+        if (nblk > 0 && !d.px) { h->err = "null pixel pointer"; return TIC_E_INVALID; }
+    }
+    if (ntiles > 0x7fffffffll) { h->err = "batch too large for one launch"; return TIC_E_INVALID; }
+    if ((size_t)ntiles > h->tiles_cap) {
+        cudaFree(h->d_tile_status);
+        h->d_tile_status = nullptr; h->tiles_cap = 0;
+        size_t cap = (size_t)ntiles + (size_t)ntiles / 4 + 1024;
+        TIC_CUDA(h, cudaMalloc(&h->d_tile_status, cap * 16));
+        h->tiles_cap = cap;
+    }
+    if ((size_t)n_images > h->end_cap) {
+        cudaFree(h->d_out_end);
+        h->d_out_end = nullptr; h->end_cap = 0;
+        TIC_CUDA(h, cudaMalloc(&h->d_out_end, (size_t)n_images * 2 * 8));
+        h->end_cap = (size_t)n_images * 2;
+    }
+    unsigned long long* d_status_words = h->d_tile_status;
+    unsigned long long* d_tail_words = h->d_tile_status + h->tiles_cap;
+    TIC_CUDA(h, cudaMemcpyAsync(h->d_descs, h->h_descs, (size_t)n_images * sizeof(ImageDesc),
+                                cudaMemcpyHostToDevice, stream));
+    TIC_CUDA(h, cudaMemsetAsync(d_status_words, 0, (size_t)ntiles * 8, stream));
+    TIC_CUDA(h, cudaMemsetAsync(d_tail_words, 0, (size_t)ntiles * 8, stream));
+    TIC_CUDA(h, cudaMemsetAsync(h->d_counters, 0, kCtrCount * 8, stream));
+    TIC_CUDA(h, cudaMemsetAsync(d_status, 0, (size_t)n_images * 4, stream));
+    encode_tiles_kernel<<<(unsigned)ntiles, kTile, sizeof(TileShared), stream>>>(
+        qp, h->d_descs, n_images, d_status_words, d_tail_words, h->d_counters, (uint8_t*)d_out,
+        (long long)out_capacity, (long long*)d_out_offsets, h->d_out_end, d_status, quality);
+    TIC_CUDA(h, cudaGetLastError());
+    finalize_kernel<<<(n_images + 255) / 256, 256, 0, stream>>>(n_images, (const long long*)d_out_offsets,
+                                                               h->d_out_end, (long long*)d_out_sizes, d_status,
+                                                               h->d_counters);
+    TIC_CUDA(h, cudaGetLastError());
+    h->last_tiles = ntiles;
+    h->last_blocks = nblocks;
+    h->last_launches = 2;
+    return TIC_OK;
+}
+
+int tic_encode_finish(tic_handle h, void* stream_v, int64_t* total_bytes) {
+    if (!h) return TIC_E_INVALID;
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    TIC_CUDA(h, cudaSetDevice(h->device));
+    TIC_CUDA(h, cudaMemcpyAsync(h->h_counters, h->d_counters, kCtrCount * 8, cudaMemcpyDeviceToHost, stream));
+    TIC_CUDA(h, cudaStreamSynchronize(stream));
+    if (total_bytes) *total_bytes = (int64_t)(h->h_counters[kCtrTotalBits] >> 3);
+    if (h->h_counters[kCtrOverflow]) { h->err = "output buffer too small"; return TIC_E_CAPACITY; }
+    if (h->h_counters[kCtrAnyStatus] & TIC_STATUS_CATEGORY) {
+        h->err = "coefficient category outside the fixed Huffman tables (reference: KeyError)";
+        return TIC_E_CATEGORY;
+    }
+    return TIC_OK;
+}
+
+int tic_last_stats(tic_handle h, int64_t stats[8]) {
+    if (!h || !stats) return TIC_E_INVALID;
+    memset(stats, 0, 8 * sizeof(int64_t));
+    stats[0] = h->last_launches;
+    stats[1] = h->last_tiles;
+    stats[2] = (int64_t)h->h_counters[kCtrExactItems];
+    stats[3] = (int64_t)h->h_counters[kCtrExactChanged];
+    stats[4] = h->last_blocks;
+    return TIC_OK;
+}
+
+int tic_encode_coeffs(tic_handle h, const void* d_pixels, int32_t height, int32_t width, int32_t quality,
+                      int32_t* d_dc, int32_t* d_ac, void* stream_v) {
+    if (!h) return TIC_E_INVALID;
+    h->err.clear();
+    if (height < 0 || width < 0) { h->err = "negative image dimension"; return TIC_E_INVALID; }
+    QuantParams qp;
+    int rc = make_quant_params(quality, qp);
+    if (rc) { h->err = "quality must be in 1..99"; return rc; }
+    long long nblk = tic_num_blocks(height, width);
+    if (nblk == 0) return TIC_OK;
+    if (!d_pixels || !d_dc || !d_ac) { h->err = "invalid argument"; return TIC_E_INVALID; }
+    if (nblk > 0x7fffffffll - kTile) { h->err = "image too large"; return TIC_E_INVALID; }
+    cudaStream_t stream = (cudaStream_t)stream_v;
+    TIC_CUDA(h, cudaSetDevice(h->device));
+    rc = ensure_tables(h);
+    if (rc) return rc;
+    rc = grow_descs(h, 1);
+    if (rc) return rc;
+    ImageDesc& d = h->h_descs[0];
+    d.px = (const uint8_t*)d_pixels;
+    d.h = height; d.w = width; d.bw = (width + 7) / 8; d.nblk = (int)nblk; d.tile0 = 0;
+    TIC_CUDA(h, cudaMemcpyAsync(h->d_descs, h->h_descs, sizeof(ImageDesc), cudaMemcpyHostToDevice, stream));
+    TIC_CUDA(h, cudaMemsetAsync(h->d_counters, 0, kCtrCount * 8, stream));
+    long long ntiles = (nblk + kTile - 1) / kTile;
+    coeffs_kernel<<<(unsigned)ntiles, kTile, sizeof(TileShared), stream>>>(qp, h->d_descs, h->d_counters, d_dc, d_ac);
+    TIC_CUDA(h, cudaGetLastError());
+    h->last_launches = 1;
+    h->last_tiles = ntiles;
+    h->last_blocks = nblk;
+    return TIC_OK;
+}
+
+int tic_compress_host(tic_handle h, const uint8_t* pixels, int32_t height, int32_t width, int32_t quality,
+                      uint32_t flags, uint8_t* out, int64_t out_capacity, int64_t* out_size, int32_t* status) {
+    if (!h) return TIC_E_INVALID;
+    h->err.clear();
+    if (height < 0 || width < 0 || !out || !out_size || out_capacity < 16) { h->err = "invalid argument"; return TIC_E_INVALID; }
+    TIC_CUDA(h, cudaSetDevice(h->device));
+    const size_t npx = (size_t)height * (size_t)width;
+    if (npx && !pixels) { h->err = "null pixels"; return TIC_E_INVALID; }
+    const size_t need_out = (size_t)tic_max_out_bytes(height, width);
+    if (npx > h->px_cap) {
+        cudaFree(h->d_px); h->d_px = nullptr; h->px_cap = 0;
+        TIC_CUDA(h, cudaMalloc(&h->d_px, npx + 16));
+        h->px_cap = npx;
+    }
+    if (need_out > h->out_cap) {
+        cudaFree(h->d_out); h->d_out = nullptr; h->out_cap = 0;
+        TIC_CUDA(h, cudaMalloc(&h->d_out, need_out));
+        h->out_cap = need_out;
+    }
+    const size_t need_stage = npx > need_out ? npx : need_out;
+    if (need_stage > h->h_stage_cap) {
+        cudaFreeHost(h->h_stage); h->h_stage = nullptr; h->h_stage_cap = 0;
+        TIC_CUDA(h, cudaMallocHost(&h->h_stage, need_stage));
+        h->h_stage_cap = need_stage;
+    }
+    cudaStream_t s = h->own_stream;
+    if (npx) {
+        memcpy(h->h_stage, pixels, npx);
+        TIC_CUDA(h, cudaMemcpyAsync(h->d_px, h->h_stage, npx, cudaMemcpyHostToDevice, s));
+    }
+    const void* ptrs[1] = {h->d_px};
+    int32_t hs[1] = {height}, ws[1] = {width};
+    long long* d_off = h->d_meta;
+    long long* d_size = h->d_meta + 1;
+    int32_t* d_stat = (int32_t*)(h->d_meta + 2);
+    int rc = tic_encode_batch(h, ptrs, hs, ws, 1, quality, flags, h->d_out, (int64_t)h->out_cap, (int64_t*)d_off,
+                              (int64_t*)d_size, d_stat, s);
+    if (rc) return rc;
+    TIC_CUDA(h, cudaMemcpyAsync(h->h_meta, h->d_meta, 24, cudaMemcpyDeviceToHost, s));
+    int64_t total = 0;
+    rc = tic_encode_finish(h, s, &total);
+    if (status) *status = *(int32_t*)(h->h_meta + 2);
+    if (rc) return rc;
+    const int64_t size = h->h_meta[1];
+    *out_size = size;
+    if (size > out_capacity) { h->err = "host output buffer too small"; return TIC_E_CAPACITY; }
+    TIC_CUDA(h, cudaMemcpyAsync(h->h_stage, h->d_out + h->h_meta[0], (size_t)size, cudaMemcpyDeviceToHost, s));
+    TIC_CUDA(h, cudaStreamSynchronize(s));
+    memcpy(out, h->h_stage, (size_t)size);
+    return TIC_OK;
+}
+
+}  // extern "C"
