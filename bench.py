@@ -1,0 +1,428 @@
+#!/usr/bin/env python3
+"""bench.py — encoded Mpixel/s of the tinyimgcodec encode path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--images M]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[3]): 4096 synthetic 1024x1024 grayscale images, quality 50,
+sharded by image across the N GPUs (no collective on the data path; strong scaling: the batch
+is fixed, each rank encodes 4096/N images).  A step is one encode of the whole batch.
+
+  value        whole-job Mpixel/s with pixels already resident in HBM and the streams left in
+               HBM (CUDA events, max over ranks)
+  e2e          the same through the public host API: pinned host pixels -> H2D -> encode -> D2H
+  roofline     algorithmic bytes (pixels in + stream bytes out) / average device duration of one
+               encode, against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline the reference's own C encoder (oracle/_ref/encode, built from /root/reference/c)
+               one process per host core, plus the C port of the Python path (oracle/), both on a
+               bounded sample; rank 0, N=1 only
+
+`--impl reference` times only the CPU reference arm (rank 0), printing the same JSON shape.
+Only the cpu_baseline / reference legs and the post-run parity spot check touch oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "encoded Mpixel/s"
+UNIT = "Mpixel/s"
+IMG_H = IMG_W = 1024
+QUALITY = 50
+TOTAL_IMAGES = 4096
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic data: the BASELINE.md §4 generator (coarse random grid, integer bilinear x32, +-10 noise),
+# evaluated on the GPU with torch's generator (seed = global image index // chunk) so that 4 GiB of
+# distinct pixels never cross PCIe.  Integer-only, deterministic for a given torch build.
+# ---------------------------------------------------------------------------------------------------
+def synth_images_device(first, count, device, h=IMG_H, w=IMG_W, chunk=128):
+    import torch
+    out = torch.empty((count, h, w), dtype=torch.uint8, device=device)
+    ys = torch.arange(h, device=device)
+    xs = torch.arange(w, device=device)
+    gy, fy = ys // 32, (ys % 32).view(1, h, 1).to(torch.int32)
+    gx, fx = xs // 32, (xs % 32).view(1, 1, w).to(torch.int32)
+    for lo in range(0, count, chunk):
+        n = min(chunk, count - lo)
+        gen = torch.Generator(device=device)
+        gen.manual_seed(1_000_003 * (first + lo) + 17)
+        g = torch.randint(0, 256, (n, h // 32 + 2, w // 32 + 2), generator=gen, device=device, dtype=torch.int32)
+        a = g[:, gy][:, :, gx]
+        b = g[:, gy][:, :, gx + 1]
+        c = g[:, gy + 1][:, :, gx]
+        d = g[:, gy + 1][:, :, gx + 1]
+        base = ((a * (32 - fx) + b * fx) * (32 - fy) + (c * (32 - fx) + d * fx) * fy) // 1024
+        del a, b, c, d
+        noise = torch.randint(-10, 11, (n, h, w), generator=gen, device=device, dtype=torch.int32)
+        out[lo:lo + n] = (base + noise).clamp_(0, 255).to(torch.uint8)
+        del base, noise
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks during the timed region (NVML, sampled from a thread)
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, index, period=0.01):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._halt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._halt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=2)
+        med = float(np.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arms (test infrastructure: oracle/_ref = the reference's C encoder, oracle/ = C port)
+# ---------------------------------------------------------------------------------------------------
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def _numpy_sample_images(count):
+    from tests.cases import synthetic_image
+    return [synthetic_image(IMG_H, IMG_W, seed=i) for i in range(count)]
+
+
+def time_reference_c_encoder(cores, images_per_core, distinct=4):
+    """The reference's own C encoder (c/encode.c), one process per core, raw rows on stdin,
+    `med` quality, exactly how tests/cbenchmark.py:24-26 drives it — but with the input in a file
+    so that the pipe is not the test.  Emits the flag-bit-30 stream variant (integer AAN DCT)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "encode")
+    if not os.path.isfile(exe):
+        return None
+    imgs = _numpy_sample_images(distinct)
+    with tempfile.TemporaryDirectory() as td:
+        path = os.path.join(td, "in.raw")
+        with open(path, "wb") as f:
+            for i in range(images_per_core):
+                f.write(imgs[i % distinct].tobytes())
+        # one tall image: encode.c reads 8-row stripes until EOF (c/encode.c:47-60)
+        cmd = [exe, str(IMG_W), str(IMG_H * images_per_core), "med"]
+        subprocess.run(cmd, stdin=open(path, "rb"), stdout=subprocess.DEVNULL, check=True)   # warm the page cache
+        t0 = time.perf_counter()
+        procs = [subprocess.Popen(cmd, stdin=open(path, "rb"), stdout=subprocess.DEVNULL) for _ in range(cores)]
+        for p in procs:
+            p.wait()
+        dt = time.perf_counter() - t0
+    return cores * images_per_core * IMG_H * IMG_W / dt / 1e6, dt
+
+
+def time_oracle_port(cores, images_per_core, distinct=4):
+    """The C restatement of the Python path (oracle/tic_oracle.c), one thread per core."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle_lib as O
+    imgs = _numpy_sample_images(distinct)
+    O.compress(imgs[0], QUALITY)
+
+    def work(_):
+        for i in range(images_per_core):
+            O.compress(imgs[i % distinct], QUALITY)   # ctypes releases the GIL
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(cores) as ex:
+        list(ex.map(work, range(cores)))
+    dt = time.perf_counter() - t0
+    return cores * images_per_core * IMG_H * IMG_W / dt / 1e6, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = host_cores()
+    per_core = 48
+    kind = "reference"
+    vals = []
+    if args.warmup > 0:
+        time_reference_c_encoder(cores, 8)   # one short untimed pass (page cache, CPU clocks)
+    steps = max(1, min(args.steps, 5))
+    for _ in range(steps):
+        r = time_reference_c_encoder(cores, per_core)
+        if r is None:
+            kind = "port"
+            r = time_oracle_port(cores, per_core)
+        vals.append(r)
+    total_px = steps * cores * per_core * IMG_H * IMG_W
+    total_t = sum(dt for _, dt in vals)
+    value = total_px / total_t / 1e6
+    sample = (f"{cores} procs x {per_core} synthetic 1024x1024 images per step "
+              + ("(reference C encoder c/encode.c, quality 'med', flag-bit-30 stream variant)" if kind == "reference"
+                 else "(C port of the Python path, q50)"))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_t / steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": {"workload": "4096 synthetic 1024x1024 grayscale images, q50 (bounded sample per step)",
+                   "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload_key):
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        return t.get(workload_key)
+    except Exception:
+        return None
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    import tinyimgcodec_b200 as tic
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    total = args.images
+    lo, hi = rank * total // n_gpus, (rank + 1) * total // n_gpus
+    n_local = hi - lo
+
+    enc = tic.get_encoder(local_rank)
+    d_images = synth_images_device(lo, n_local, dev)
+    torch.cuda.synchronize()
+    out_cap = int(n_local * IMG_H * IMG_W * 0.5) + (1 << 20)
+    d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def step():
+        return enc.encode_batch_device(d_images, QUALITY, out=d_out, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        res = step()
+    res.finish()
+    stream_bytes_local = int(res.sizes.sum().item())
+    stats = enc.stats()
+
+    sampler = ClockSampler(local_rank)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler.start()
+    t_begin.record(stream)
+    for i in range(args.steps):
+        ev[i][0].record(stream)
+        res = step()
+        ev[i][1].record(stream)
+    t_end.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    res.finish()
+    elapsed_ms = t_begin.elapsed_time(t_end)
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    if world > 1:
+        tt = torch.tensor([elapsed_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(tt.item())
+        sb = torch.tensor([stream_bytes_local], device=dev, dtype=torch.int64)
+        dist.all_reduce(sb)
+        stream_bytes_total = int(sb.item())
+    else:
+        stream_bytes_total = stream_bytes_local
+    ms_per_step = elapsed_ms / args.steps
+    total_px = total * IMG_H * IMG_W
+    value = total_px / (ms_per_step * 1e-3) / 1e6
+
+    # roofline of the dominant kernel (encode_tiles_kernel; one launch per step per rank)
+    peak, peak_src = measured_peak()
+    alg_bytes = n_local * IMG_H * IMG_W + stream_bytes_local
+    avg_launch_ms = float(np.mean(step_ms))
+    achieved = alg_bytes / (avg_launch_ms * 1e-3) / 1e9
+    wl_key = f"{n_local}x{IMG_H}x{IMG_W}_q{QUALITY}"
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic(wl_key), "peak_source": peak_src, "kernel": "encode_tiles_kernel",
+                "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": avg_launch_ms,
+                "launch_ms_min": float(np.min(step_ms)),
+                "note": "launch_ms = CUDA events around one tic_encode_batch on its stream "
+                        "(4 small memsets + encode_tiles_kernel + finalize_kernel)"}
+
+    # end to end through the public host API: pinned host pixels in, streams back on the host
+    e2e = None
+    try:
+        if args.no_e2e:
+            raise RuntimeError("skipped (--no-e2e)")
+        h_images = torch.empty((n_local, IMG_H, IMG_W), dtype=torch.uint8).pin_memory()
+        h_images.copy_(d_images)
+        torch.cuda.synchronize()
+        enc.compress_batch_pinned(h_images, QUALITY)   # warm-up (allocates the pipeline buffers)
+        e2e_steps = max(1, min(args.steps, 3))
+        barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(e2e_steps):
+            h_out, index = enc.compress_batch_pinned(h_images, QUALITY)
+            d2h = sum(s for _, s in index)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        e2e = {"value": total_px * e2e_steps / dt / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": n_local * IMG_H * IMG_W * n_gpus, "d2h_bytes_per_step": d2h * n_gpus,
+               "steps": e2e_steps, "api": "Encoder.compress_batch_pinned (chunked H2D / encode / D2H pipeline)",
+               "timing": "host wall clock around the API calls, max over ranks"}
+        del h_images
+    except Exception as ex:  # keep the device-timed line even if the host leg cannot run
+        e2e = {"value": None, "unit": UNIT, "error": f"{type(ex).__name__}: {ex}"}
+
+    line = None
+    if rank == 0:
+        # parity spot check of the benchmarked data against the oracle (outside every timed region)
+        parity = {"checked": 0, "identical": 0}
+        try:
+            from oracle import oracle_lib as O
+            streams = res.to_bytes()
+            for i in sorted({0, 1, n_local // 2, n_local - 1}):
+                px = d_images[i].cpu().numpy()
+                parity["checked"] += 1
+                parity["identical"] += int(streams[i] == O.compress(px, QUALITY))
+        except Exception as ex:
+            parity["error"] = f"{type(ex).__name__}: {ex}"
+        cpu_baseline = None
+        extra = {}
+        if n_gpus == 1 and not args.no_cpu:
+            cores = host_cores()
+            r = time_reference_c_encoder(cores, 64)
+            if r is not None:
+                cpu_baseline = {"value": r[0], "unit": UNIT, "cores": cores, "kind": "reference",
+                                "sample": f"{cores} procs x 64 synthetic 1024x1024 images, reference C encoder "
+                                          f"(c/encode.c, 'med', flag-bit-30 variant), {r[1]:.1f} s"}
+            p = time_oracle_port(cores, 32)
+            extra["cpu_baseline_port"] = {"value": p[0], "unit": UNIT, "cores": cores, "kind": "port",
+                                          "sample": f"{cores} threads x 32 synthetic 1024x1024 images, C port of the "
+                                                    f"Python path (oracle/tic_oracle.c, q50, byte-identical streams), {p[1]:.1f} s"}
+            if cpu_baseline is None:
+                cpu_baseline = extra.pop("cpu_baseline_port")
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32 fdct + f64 exact ties, int32 entropy",
+            "data": "synthetic",
+            "config": {"workload": f"{total} synthetic {IMG_H}x{IMG_W} grayscale images, quality {QUALITY}, "
+                                   f"default Huffman tables, sharded by image over {n_gpus} GPU(s)",
+                       "images_per_gpu": n_local, "l2": "inputs larger than L2 (per-GPU pixel bytes >> 126 MB)",
+                       "generator": "BASELINE.md §4 synthetic generator evaluated on-device (torch RNG)",
+                       "stream_bytes": stream_bytes_total, "bits_per_pixel": 8.0 * stream_bytes_total / total_px,
+                       "exact_path": {k: stats[k] for k in ("exact_items", "exact_changed", "blocks", "tiles")}},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps * n_gpus, "roofline": roofline,
+            "cpu_baseline": cpu_baseline, "parity": parity,
+        }
+        line.update(extra)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--images", type=int, default=TOTAL_IMAGES, help="total images in the batch (default 4096)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host end-to-end leg (profiling runs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.gpus > 1 and world == 1:
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
+               "--images", str(args.images)] + (["--no-cpu"] if args.no_cpu else []) + (["--no-e2e"] if args.no_e2e else [])
+        return subprocess.call(cmd)
+    return run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

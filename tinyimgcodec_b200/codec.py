@@ -164,6 +164,74 @@ class Encoder:
                     self._raise(rc)
         return DeviceBatchResult(self, out, offs, sizes, stat, stream, n)
 
+    # -- batch, host buffers, pipelined -----------------------------------------------------------
+    def compress_batch_pinned(self, h_images, quality=50, chunk=256, out_bytes_per_pixel=0.75):
+        """End-to-end encode of an (N,H,W) uint8 tensor in PINNED host memory: chunked H2D on a copy
+        stream overlapped with the encode of the previous chunk, streams copied back to pinned host
+        memory.  Returns (host_buffer, [(offset, size)] per image) with offsets into host_buffer."""
+        import torch
+        n, hgt, wid = h_images.shape
+        dev = torch.device("cuda", self.device)
+        chunk = max(1, min(chunk, n))
+        cap = int(chunk * hgt * wid * out_bytes_per_pixel) + 4096
+        cap = (cap + 15) & ~15
+        with torch.cuda.device(dev):
+            if getattr(self, "_pipe_key", None) != (chunk, hgt, wid, cap):
+                self._pipe = {
+                    "d_in": [torch.empty((chunk, hgt, wid), dtype=torch.uint8, device=dev) for _ in range(2)],
+                    "d_out": [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(2)],
+                    "s_in": torch.cuda.Stream(dev), "s_comp": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
+                }
+                self._pipe_key = (chunk, hgt, wid, cap)
+            P = self._pipe
+            h_out = getattr(self, "_h_out", None)
+            need = int(n * hgt * wid * out_bytes_per_pixel) + 4096 * ((n + chunk - 1) // chunk)
+            if h_out is None or h_out.numel() < need:
+                h_out = self._h_out = torch.empty(need, dtype=torch.uint8).pin_memory()
+            nchunks = (n + chunk - 1) // chunk
+            h_meta = getattr(self, "_h_meta", None)
+            if h_meta is None or h_meta.shape[0] < nchunks or h_meta.shape[2] < chunk:
+                h_meta = self._h_meta = torch.empty((nchunks, 2, chunk), dtype=torch.int64).pin_memory()
+            ev_in = [torch.cuda.Event() for _ in range(nchunks)]
+            ev_comp = [torch.cuda.Event() for _ in range(nchunks)]
+            ev_out = [torch.cuda.Event() for _ in range(nchunks)]
+            results, index, h_pos = [], [], 0
+
+            def issue_h2d(c):
+                lo, hi = c * chunk, min(n, (c + 1) * chunk)
+                with torch.cuda.stream(P["s_in"]):
+                    if c >= 2:
+                        P["s_in"].wait_event(ev_comp[c - 2])   # input buffer free again
+                    P["d_in"][c & 1][: hi - lo].copy_(h_images[lo:hi], non_blocking=True)
+                    ev_in[c].record(P["s_in"])
+
+            issue_h2d(0)
+            for c in range(nchunks):
+                lo, hi = c * chunk, min(n, (c + 1) * chunk)
+                if c + 1 < nchunks:
+                    issue_h2d(c + 1)
+                P["s_comp"].wait_event(ev_in[c])
+                if c >= 2:
+                    P["s_comp"].wait_event(ev_out[c - 2])      # output buffer drained
+                res = self.encode_batch_device(P["d_in"][c & 1][: hi - lo], quality, out=P["d_out"][c & 1],
+                                               stream=P["s_comp"])
+                with torch.cuda.stream(P["s_comp"]):
+                    h_meta[c, 0, : hi - lo].copy_(res.offsets, non_blocking=True)
+                    h_meta[c, 1, : hi - lo].copy_(res.sizes, non_blocking=True)
+                ev_comp[c].record(P["s_comp"])
+                res.finish()                                     # waits for chunk c only; chunk c+1's H2D is in flight
+                with torch.cuda.stream(P["s_out"]):
+                    P["s_out"].wait_event(ev_comp[c])
+                    h_out[h_pos: h_pos + res.total_bytes].copy_(P["d_out"][c & 1][: res.total_bytes], non_blocking=True)
+                    ev_out[c].record(P["s_out"])
+                results.append((h_pos, h_meta[c, :, : hi - lo]))
+                h_pos += (res.total_bytes + 15) & ~15
+            P["s_out"].synchronize()
+            for base, meta in results:
+                offs, sizes = meta[0].numpy(), meta[1].numpy()
+                index.extend((int(base + o), int(s)) for o, s in zip(offs, sizes))
+        return h_out, index
+
     def stats(self):
         arr = (ctypes.c_int64 * 8)()
         self.lib.tic_last_stats(self.handle, arr)

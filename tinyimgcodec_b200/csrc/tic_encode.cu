@@ -71,7 +71,7 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
 
     // publish the aggregate as early as possible: successors only need it for their offset
     if (t == 0) {
-        st_release_u64(&tile_status[tile], kFlagAgg | (ti.closing ? kClosingBit : 0ull) | (unsigned long long)agg);
+        st_relaxed_u64(&tile_status[tile], kFlagAgg | (ti.closing ? kClosingBit : 0ull) | (unsigned long long)agg);
         if (sm.err) atomicOr(&status[ti.img], TIC_STATUS_CATEGORY);
     }
     const int nwords = (tile_bits + 31) >> 5;
@@ -81,56 +81,70 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
     // ---- bits into the tile-relative staging buffer ---------------------------------------------
     if (t < ti.nb) block_emit(sm, t, bitpos);
 
-    // ---- decoupled look-back (thread 0): absolute bit position of this tile -----------------------
-    if (t == 0) {
-        long long a = 0, b = 0;   // composite of the tiles between the look-back cursor and this tile:
-        bool closed = false;      // g(P) = closed ? round_up128(P + a) + b : P + a
-        long long p_in;
-        long long j = tile - 1;
+    // ---- decoupled look-back (warp 0, 32 predecessors per round): absolute bit position ----------
+    if (warp == 0) {
+        // composite of the tiles between the look-back cursor and this tile:
+        //   g(P) = closed ? round_up128(P + a) + b : P + a
+        long long a = 0, b = 0;
+        bool closed = false;
+        long long p_in = 0;
+        long long j = tile - 1;   // nearest predecessor not folded in yet
         while (true) {
-            if (j < 0) { p_in = closed ? round_up128(a) + b : a; break; }
-            unsigned long long s;
-            do { s = ld_acquire_u64(&tile_status[j]); } while ((s & kFlagMask) == 0);
-            long long val = (long long)(s & kValueMask);
-            if ((s & kFlagMask) == kFlagPrefix) {
-                p_in = closed ? round_up128(val + a) + b : val + a;
+            const long long idx = j - lane;
+            unsigned long long s = kFlagPrefix;   // before the first tile: prefix 0
+            if (idx >= 0) s = ld_relaxed_u64(&tile_status[idx]);
+            while (__any_sync(0xffffffffu, (s & kFlagMask) == 0)) {
+                if ((s & kFlagMask) == 0) s = ld_relaxed_u64(&tile_status[idx]);
+            }
+            const unsigned prefix_mask = __ballot_sync(0xffffffffu, (s & kFlagMask) == kFlagPrefix);
+            const int p = prefix_mask ? (__ffs(prefix_mask) - 1) : 32;   // lanes < p hold aggregates
+            const unsigned below = p >= 32 ? 0xffffffffu : ((1u << p) - 1u);
+            const unsigned closing_mask = __ballot_sync(0xffffffffu, (s & kClosingBit) != 0) & below;
+            const long long val = (long long)(s & kValueMask);
+            if (closing_mask == 0) {
+                long long v = (lane < p) ? val : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                a += v;
+            } else {
+                for (int l = 0; l < p; l++) {   // nearest first: prepend tile j-l to the composite
+                    long long v = __shfl_sync(0xffffffffu, val, l);
+                    if ((closing_mask >> l) & 1) {   // it closes an image: what follows is 128-bit aligned
+                        b = closed ? round_up128(a) + b : a;
+                        a = v;
+                        closed = true;
+                    } else {
+                        a += v;
+                    }
+                }
+            }
+            if (p < 32) {
+                long long base = __shfl_sync(0xffffffffu, val, p);
+                p_in = closed ? round_up128(base + a) + b : base + a;
                 break;
             }
-            if (s & kClosingBit) {   // tile j closes an image: everything after it is 128-bit aligned
-                b = closed ? round_up128(a) + b : a;
-                a = val;
-                closed = true;
-            } else {
-                a += val;
+            j -= 32;
+        }
+        if (lane == 0) {
+            const long long e_bits = p_in + agg;   // end of this tile's data bits
+            const long long p_out = ti.closing ? round_up128(e_bits) : e_bits;
+            st_relaxed_u64(&tile_status[tile], kFlagPrefix | (unsigned long long)p_out);
+            const long long s_bits = p_in + (ti.first ? 128 : 0);
+            sm.s_bits = s_bits;
+            const long long end_byte = (e_bits + 7) >> 3;
+            const bool fits = ((end_byte + 3) & ~3ll) <= out_cap;
+            if (!fits) atomicExch(&counters[kCtrOverflow], 1ull);
+            if (ti.first) {
+                out_off[ti.img] = p_in >> 3;
+                if (fits) {   // make_header, codec.py:102-114: "III" little-endian + 32 flag bits = 0
+                    uint4 hdr = make_uint4((unsigned)ti.h, (unsigned)ti.w, (unsigned)quality, 0u);
+                    *reinterpret_cast<uint4*>(out + (p_in >> 3)) = hdr;
+                }
             }
-            j--;
-        }
-        const long long e_bits = p_in + agg;   // end of this tile's data bits
-        const long long p_out = ti.closing ? round_up128(e_bits) : e_bits;
-        st_release_u64(&tile_status[tile], kFlagPrefix | (unsigned long long)p_out);
-        const long long s_bits = p_in + (ti.first ? 128 : 0);
-        sm.s_bits = s_bits;
-        // the word shared with the previous tile of the same image
-        unsigned int tail_prev = 0;
-        if (!ti.first && (s_bits & 31)) {
-            unsigned long long tw;
-            do { tw = ld_acquire_u64(&tile_tail[tile - 1]); } while ((tw >> 63) == 0);
-            tail_prev = (unsigned int)tw;
-        }
-        sm.tail_prev = tail_prev;
-        const long long end_byte = (e_bits + 7) >> 3;
-        const bool fits = ((end_byte + 3) & ~3ll) <= out_cap;
-        if (!fits) atomicExch(&counters[kCtrOverflow], 1ull);
-        if (ti.first) {
-            out_off[ti.img] = p_in >> 3;
-            if (fits) {   // make_header, codec.py:102-114: "III" little-endian + 32 flag bits = 0
-                uint4 hdr = make_uint4((unsigned)ti.h, (unsigned)ti.w, (unsigned)quality, 0u);
-                *reinterpret_cast<uint4*>(out + (p_in >> 3)) = hdr;
+            if (ti.closing) {
+                out_end[ti.img] = end_byte;
+                atomicMax(&counters[kCtrTotalBits], (unsigned long long)(end_byte << 3));
             }
-        }
-        if (ti.closing) {
-            out_end[ti.img] = end_byte;
-            atomicMax(&counters[kCtrTotalBits], (unsigned long long)(end_byte << 3));
         }
     }
     __syncthreads();
@@ -142,28 +156,33 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
     const long long g0 = s_bits >> 5;
     // words [g0, g_end): full words, plus the final partial word when this tile closes the image
     const long long g_end = ti.closing ? ((e_bits + 31) >> 5) : (e_bits >> 5);
-    const bool fits = (((e_bits + 7) >> 3) + 3 & ~3ll) <= out_cap;
-    const unsigned int tail_prev = sm.tail_prev;
+    const bool fits = ((((e_bits + 7) >> 3) + 3) & ~3ll) <= out_cap;
     uint32_t* out_words = reinterpret_cast<uint32_t*>(out);
-    for (long long g = g0 + t; g < g_end; g += kTile) {
-        int jdx = (int)(g - g0);
-        uint32_t lo = sm.stage[jdx];
-        uint32_t hi = jdx ? sm.stage[jdx - 1] : 0u;
-        uint32_t v = __funnelshift_r(lo, hi, sh);
-        if (jdx == 0) v |= tail_prev;
-        if (fits) out_words[g] = __byte_perm(v, 0, 0x0123);
-    }
-    // hand the trailing partial word to the next tile
-    if (t == 0 && !ti.closing) {
+    const bool need_prev = !ti.first && sh != 0;   // word g0 starts with the previous tile's last bits
+    if (t == 0) {
+        // Hand the trailing partial word to the next tile FIRST (it only depends on the previous
+        // tile's tail when this whole tile sits inside one word), then wait for our own head.
         unsigned int tail = 0;
-        if (e_bits & 31) {
-            int jdx = (int)((e_bits >> 5) - g0);
-            uint32_t lo = sm.stage[jdx];
-            uint32_t hi = jdx ? sm.stage[jdx - 1] : 0u;
-            tail = __funnelshift_r(lo, hi, sh);
-            if (jdx == 0) tail |= tail_prev;
+        const int jt = (int)((e_bits >> 5) - g0);
+        if (e_bits & 31) tail = __funnelshift_r(sm.stage[jt], jt ? sm.stage[jt - 1] : 0u, sh);
+        const bool chained = need_prev && jt == 0;
+        if (!ti.closing && !chained) st_relaxed_u64(&tile_tail[tile], (1ull << 63) | tail);
+        unsigned int tail_prev = 0;
+        if (need_prev) {
+            unsigned long long tw;
+            do { tw = ld_relaxed_u64(&tile_tail[tile - 1]); } while ((tw >> 63) == 0);
+            tail_prev = (unsigned int)tw;
         }
-        st_release_u64(&tile_tail[tile], (1ull << 63) | tail);
+        if (!ti.closing && chained) st_relaxed_u64(&tile_tail[tile], (1ull << 63) | tail | tail_prev);
+        if (g0 < g_end && fits) {
+            uint32_t v = __funnelshift_r(sm.stage[0], 0u, sh) | tail_prev;
+            out_words[g0] = __byte_perm(v, 0, 0x0123);
+        }
+    }
+    for (long long g = g0 + 1 + t; g < g_end; g += kTile) {
+        int jdx = (int)(g - g0);
+        uint32_t v = __funnelshift_r(sm.stage[jdx], sm.stage[jdx - 1], sh);
+        if (fits) out_words[g] = __byte_perm(v, 0, 0x0123);
     }
 }
 

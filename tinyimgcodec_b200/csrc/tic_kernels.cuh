@@ -82,13 +82,16 @@ __device__ __forceinline__ int bitlen(int v) {               // bits_required, u
     return 32 - __clz(v < 0 ? -v : v);
 }
 
-__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+// Look-back words are self-contained 64-bit messages (flag + value in one word), so relaxed
+// gpu-scope accesses are enough: nothing else has to become visible with them.  (acquire loads
+// compile to LDG + CCTL.IVALL, an L1 invalidate per poll.)
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
     unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 __device__ __forceinline__ long long round_up128(long long v) { return (v + 127) & ~127ll; }
