@@ -20,36 +20,38 @@ namespace tic {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTile, 4)
 encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restrict__ descs, int n_images,
-                    unsigned long long* __restrict__ tile_status, unsigned long long* __restrict__ tile_tail,
-                    unsigned long long* __restrict__ counters, uint8_t* __restrict__ out, long long out_cap,
-                    long long* __restrict__ out_off, long long* __restrict__ out_end,
-                    int* __restrict__ status, int quality) {
+                    long long ntiles, unsigned long long* __restrict__ tile_status,
+                    unsigned long long* __restrict__ tile_tail, unsigned long long* __restrict__ counters,
+                    uint8_t* __restrict__ out, long long out_cap, long long* __restrict__ out_off,
+                    long long* __restrict__ out_end, int* __restrict__ status, int quality) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileShared& sm = *reinterpret_cast<TileShared*>(smem_raw);
     __shared__ long long s_tile;
     const int t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
+    const int bias = qp.qbias;
 
-    if (t == 0) s_tile = (long long)atomicAdd(&counters[kCtrTicket], 1ull);
-    // default tables -> shared memory (constants.py:53-242)
-    for (int i = t; i < 256; i += kTile) {
-        sm.ac_code[i] = c_default_tables.ac_code[i];
-        sm.ac_len[i] = c_default_tables.ac_len[i];
+    // default tables -> shared memory, once per (persistent) CTA (constants.py:53-242)
+    for (int i = t; i < 256; i += kTile)
+        sm.ac_tab[i] = make_uint2(c_default_tables.ac[i].code, c_default_tables.ac[i].len);
+    if (t < 16) sm.dc_tab[t] = make_uint2(c_default_tables.dc[t].code, c_default_tables.dc[t].len);
+
+  for (;;) {   // persistent: tiles are claimed in stream order through the ticket
+    __syncthreads();   // previous tile fully copied out; tables visible
+    if (t == 0) {
+        s_tile = (long long)atomicAdd(&counters[kCtrTicket], 1ull);
+        sm.err = 0;
     }
-    if (t < 16) {
-        sm.dc_code[t] = c_default_tables.dc_code[t];
-        sm.dc_len[t] = c_default_tables.dc_len[t];
-    }
-    if (t == 0) sm.err = 0;
     __syncthreads();
     const long long tile = s_tile;
+    if (tile >= ntiles) break;
     const TileInfo ti = locate_tile(descs, n_images, tile);
 
     transform_tile(ti, qp, sm, counters);
 
     // ---- bit lengths and the CTA scan -------------------------------------------------------
     int err = 0;
-    int bits = (t < ti.nb) ? block_bits(sm, t, err) : 0;
+    int bits = (t < ti.nb) ? block_bits(sm, t, bias, err) : 0;
     int incl = bits;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -79,7 +81,7 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
     __syncthreads();
 
     // ---- bits into the tile-relative staging buffer ---------------------------------------------
-    if (t < ti.nb) block_emit(sm, t, bitpos);
+    if (t < ti.nb) block_emit(sm, t, bias, bitpos);
 
     // ---- decoupled look-back (warp 0, 32 predecessors per round): absolute bit position ----------
     if (warp == 0) {
@@ -184,6 +186,7 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
         uint32_t v = __funnelshift_r(sm.stage[jdx], sm.stage[jdx - 1], sh);
         if (fits) out_words[g] = __byte_perm(v, 0, 0x0123);
     }
+  }   // persistent loop
 }
 
 // sizes = end - offset, and the batch summary the host reads back in tic_encode_finish
@@ -212,7 +215,7 @@ coeffs_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restric
         const size_t b = (size_t)ti.blk0 + t;
         dc[b] = sm.dcq[t + 1] - sm.dcq[t];
         int* row = ac + b * 63;
-        for (int k = 1; k < 64; k++) row[k - 1] = coef_get(sm, t, k);
+        for (int k = 1; k < 64; k++) row[k - 1] = coef_get(sm, t, k, qp.qbias);
     }
 }
 
@@ -242,6 +245,7 @@ struct tic_handle_s {
     cudaStream_t own_stream = nullptr;
     long long last_tiles = 0, last_blocks = 0, last_launches = 0;
     bool tables_ready = false;
+    int sm_count = 148, ctas_per_sm = 4;
 };
 
 #define TIC_CUDA(h, call)                                                                     \
@@ -258,13 +262,13 @@ static void build_default_tables(HuffTables& t) {
     uint32_t code = 0;
     int k = 0;
     for (int l = 1; l <= 16; l++) {
-        for (int i = 0; i < kDcBits[l]; i++) { t.dc_code[kDcVals[k]] = code++; t.dc_len[kDcVals[k]] = (uint8_t)l; k++; }
+        for (int i = 0; i < kDcBits[l]; i++) { t.dc[kDcVals[k]].code = code++; t.dc[kDcVals[k]].len = (uint32_t)l; k++; }
         code <<= 1;
     }
     code = 0;
     k = 0;
     for (int l = 1; l <= 16; l++) {
-        for (int i = 0; i < kAcBits[l]; i++) { t.ac_code[kAcVals[k]] = code++; t.ac_len[kAcVals[k]] = (uint8_t)l; k++; }
+        for (int i = 0; i < kAcBits[l]; i++) { t.ac[kAcVals[k]].code = code++; t.ac[kAcVals[k]].len = (uint32_t)l; k++; }
         code <<= 1;
     }
 }
@@ -285,21 +289,24 @@ static int make_quant_params(int quality, QuantParams& qp) {
         qp.qt[i] = q;
         if (q < qt_min) qt_min = q;
     }
-    // |coefficient| <= 1024 (orthonormal transform of 64 values in [-128,127]); the fixed-point
-    // value t*2^F + 2^(F-1) + guard must stay inside the 22-bit window of the magic-number trick.
+    // |coefficient| <= 1024 (orthonormal transform of 64 values in [-128,127]).  The fixed-point
+    // value round(t*2^F) + 2^(F-1) + 2^(k-1) must stay inside the +-2^22 window of the
+    // magic-number rounding; F is chosen with a factor 2 to spare.
     const double t_max = 1024.0 / qt_min;
     int F = 0;
     while (F < 15 && (t_max + 2.0) * (double)(1 << (F + 1)) < 4194304.0 * 0.98) F++;
     qp.fbits = F;
-    qp.fmask = (1 << F) - 1;
-    qp.magic = 12582912.0f + (F > 0 ? (float)(1 << (F - 1)) : 0.0f);
-    qp.pad = 0;
+    qp.qbias = 0x4B400000 >> F;
+    qp.pad[0] = qp.pad[1] = 0;
+    const int fmask = (1 << F) - 1;
     double aan[8];
     aan[0] = 1.0;
     for (int k = 1; k < 8; k++) aan[k] = cos(k * 3.14159265358979323846 / 16.0) * sqrt(2.0);
     // kFastErr: bound on |FP32 AAN coefficient - float64 reference coefficient| in coefficient
-    // units (worst-case analysis in DESIGN.md; tests/test_gpu_parity.py measures it).  The guard
-    // band is 4x that, plus the relative error of the FP32 multiplier.
+    // units ("tie guard").  A coefficient can only be rounded differently from the
+    // reference if a .5 tie lies within tol = kFastErr/qt (+ the FP32 multiplier's relative error)
+    // of the fast value; the window [-2^(k-1), 2^(k-1)) in 2^-F units around every tie covers
+    // tol*2^F + 1 (the +1: round-to-integer of the FFMA and the one-sided window).
     const double kFastErr = 6.0e-4;
     for (int u = 0; u < 8; u++)
         for (int v = 0; v < 8; v++) {
@@ -307,10 +314,12 @@ static int make_quant_params(int quality, QuantParams& qp) {
             double m = (double)(1 << F) / (8.0 * aan[u] * aan[v] * qp.qt[i]);
             qp.qmul[i] = (float)m;
             double tol = kFastErr / qp.qt[i] + 2.4e-7 * (1024.0 / qp.qt[i]);
-            int g = (int)ceil(tol * (double)(1 << F) + 0.5);
-            if (F == 0) g = 0;   // every coefficient goes to the exact path
-            if (2 * g + 1 > qp.fmask) g = qp.fmask / 2;
-            qp.guard[i] = g;
+            int g = (int)ceil(tol * (double)(1 << F) + 1.0);
+            int k = 1;
+            while ((1 << (k - 1)) < g + 1 && k <= F) k++;
+            if (k > F) k = F;   // whole range: every coefficient goes to the exact path
+            qp.gmask[i] = F == 0 ? 0 : (fmask & ~((1 << k) - 1));
+            qp.magic[i] = 12582912.0f + (F > 0 ? (float)(1 << (F - 1)) : 0.0f) + (F > 0 ? (float)(1 << (k - 1)) : 0.0f);
         }
     return TIC_OK;
 }
@@ -324,6 +333,12 @@ static int ensure_tables(tic_handle h) {
                                      (int)sizeof(TileShared)));
     TIC_CUDA(h, cudaFuncSetAttribute(coeffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(TileShared)));
+    int per_sm = 0;
+    TIC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_tiles_kernel, kTile, sizeof(TileShared)));
+    cudaDeviceProp prop;
+    TIC_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
+    h->sm_count = prop.multiProcessorCount;
+    h->ctas_per_sm = per_sm > 0 ? per_sm : 1;
     h->tables_ready = true;
     return TIC_OK;
 }
@@ -457,8 +472,10 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     TIC_CUDA(h, cudaMemsetAsync(d_tail_words, 0, (size_t)ntiles * 8, stream));
     TIC_CUDA(h, cudaMemsetAsync(h->d_counters, 0, kCtrCount * 8, stream));
     TIC_CUDA(h, cudaMemsetAsync(d_status, 0, (size_t)n_images * 4, stream));
-    encode_tiles_kernel<<<(unsigned)ntiles, kTile, sizeof(TileShared), stream>>>(
-        qp, h->d_descs, n_images, d_status_words, d_tail_words, h->d_counters, (uint8_t*)d_out,
+    long long grid = (long long)h->sm_count * h->ctas_per_sm;
+    if (grid > ntiles) grid = ntiles;
+    encode_tiles_kernel<<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
+        qp, h->d_descs, n_images, ntiles, d_status_words, d_tail_words, h->d_counters, (uint8_t*)d_out,
         (long long)out_capacity, (long long*)d_out_offsets, h->d_out_end, d_status, quality);
     TIC_CUDA(h, cudaGetLastError());
     finalize_kernel<<<(n_images + 255) / 256, 256, 0, stream>>>(n_images, (const long long*)d_out_offsets,

@@ -44,12 +44,12 @@ constexpr unsigned long long kValueMask = (1ull << 61) - 1;
 // operand of the FFMA / compare that uses it.
 struct QuantParams {
     float qmul[64];   // [u*8+v]  2^F / (8 * aan[u] * aan[v] * qt[u][v])
+    float magic[64];  // [u*8+v]  1.5*2^23 + 2^(F-1) + 2^(k-1): rounding offset + tie-window offset
+    int gmask[64];    // [u*8+v]  (2^F - 1) & ~(2^k - 1): inside the tie window iff (bits & gmask) == 0
     double qt[64];    // [u*8+v]  the reference's float64 divisor (utils.py:50-53)
-    int guard[64];    // [u*8+v]  half-width of the tie guard band in 2^-F units
-    float magic;      // 1.5*2^23 + 2^(F-1)
-    int fbits;        // F
-    int fmask;        // 2^F - 1
-    int pad;
+    int fbits;        // F: fixed-point fraction bits of the fast quantiser
+    int qbias;        // 0x4B400000 >> F: what (bits >> F) reads for a zero coefficient
+    int pad[2];
 };
 
 struct ImageDesc {
@@ -191,10 +191,8 @@ struct TileShared {
     int dcq[kTile + 1];              // quantised DC: [0] = block before the tile, [t+1] = thread t
     uint32_t work[kWorkCap];         // exact-path worklist: thread << 6 | zigzag index; bit 31: halo DC
     double colres[kExactPerRound][8];
-    uint32_t ac_code[256];
-    uint32_t dc_code[16];
-    uint8_t ac_len[256];
-    uint8_t dc_len[16];
+    uint2 ac_tab[256];               // {code, length} per (run << 4 | size); length 0 = not in table
+    uint2 dc_tab[16];                // {code, length} per size category
     int work_count;
     int pending;                     // flagged coefficients that did not fit the worklist this round
     int warp_bits[kWarps];
@@ -254,39 +252,34 @@ __device__ __forceinline__ void quantise_pairs(const float (&d)[64], const Quant
     if constexpr (I < 32) {
         constexpr int k0 = 2 * I, k1 = 2 * I + 1;
         constexpr int r0 = ZZ<k0>::r, r1 = ZZ<k1>::r;
-        const int magic_bits = 0x4B400000;
-        int x0 = __float_as_int(fmaf(d[r0], qp.qmul[r0], qp.magic)) - magic_bits;
-        int x1 = __float_as_int(fmaf(d[r1], qp.qmul[r1], qp.magic)) - magic_bits;
-        int q0 = x0 >> qp.fbits, q1 = x1 >> qp.fbits;
-        bool f0 = (unsigned)((x0 + qp.guard[r0]) & qp.fmask) <= (unsigned)(2 * qp.guard[r0]);
-        bool f1 = (unsigned)((x1 + qp.guard[r1]) & qp.fmask) <= (unsigned)(2 * qp.guard[r1]);
+        // bits = 0x4B400000 + round(t * 2^F) + 2^(F-1) + 2^(k-1)   (one FFMA, magic-number rounding)
+        const int b0 = __float_as_int(fmaf(d[r0], qp.qmul[r0], qp.magic[r0]));
+        const int b1 = __float_as_int(fmaf(d[r1], qp.qmul[r1], qp.magic[r1]));
+        const int s0 = b0 >> qp.fbits, s1 = b1 >> qp.fbits;   // qbias + floor(t + 0.5) outside the window
+        const bool f0 = (b0 & qp.gmask[r0]) == 0;             // within the tie window: exact path decides
+        const bool f1 = (b1 & qp.gmask[r1]) == 0;
         if constexpr (k0 < 32) {
-            if (q0 != 0 && k0 != 0) nz_lo |= 1u << k0;
-            if (q1 != 0) nz_lo |= 1u << k1;
+            if (k0 != 0 && s0 != qp.qbias) nz_lo |= 1u << k0;
+            if (s1 != qp.qbias) nz_lo |= 1u << k1;
             if (f0) fl_lo |= 1u << k0;
             if (f1) fl_lo |= 1u << k1;
         } else {
-            if (q0 != 0) nz_hi |= 1u << (k0 - 32);
-            if (q1 != 0) nz_hi |= 1u << (k1 - 32);
+            if (s0 != qp.qbias) nz_hi |= 1u << (k0 - 32);
+            if (s1 != qp.qbias) nz_hi |= 1u << (k1 - 32);
             if (f0) fl_hi |= 1u << (k0 - 32);
             if (f1) fl_hi |= 1u << (k1 - 32);
         }
-        if constexpr (I == 0) sm.dcq[t + 1] = q0;
-        sm.coef[I][t] = ((uint32_t)q0 & 0xffffu) | ((uint32_t)q1 << 16);
+        if constexpr (I == 0) sm.dcq[t + 1] = s0 - qp.qbias;
+        sm.coef[I][t] = __byte_perm((uint32_t)s0, (uint32_t)s1, 0x5410);   // biased int16 pair
         quantise_pairs<I + 1>(d, qp, sm, t, nz_lo, nz_hi, fl_lo, fl_hi);
     }
 }
 
-__device__ __forceinline__ int coef_get(const TileShared& sm, int t, int k) {
+// Coefficients sit in shared memory as 16-bit values biased by (qbias & 0xffff).
+__device__ __forceinline__ int coef_get(const TileShared& sm, int t, int k, int bias) {
     uint32_t w = sm.coef[k >> 1][t];
-    return (k & 1) ? ((int)w >> 16) : (int)(short)(w & 0xffffu);
+    return (int)(short)(((k & 1) ? (w >> 16) : w) - (uint32_t)bias);
 }
-__device__ __forceinline__ void coef_set(TileShared& sm, int t, int k, int v) {
-    uint32_t w = sm.coef[k >> 1][t];
-    w = (k & 1) ? ((w & 0x0000ffffu) | ((uint32_t)v << 16)) : ((w & 0xffff0000u) | ((uint32_t)v & 0xffffu));
-    sm.coef[k >> 1][t] = w;
-}
-
 __device__ __forceinline__ void transform_block(const TileInfo& ti, const QuantParams& qp, TileShared& sm,
                                                 int t, uint32_t& fl_lo, uint32_t& fl_hi) {
     const int b = ti.blk0 + t;
@@ -303,8 +296,8 @@ __device__ __forceinline__ void transform_block(const TileInfo& ti, const QuantP
         for (int i = 0; i < 8; i++) {
 #pragma unroll
             for (int j = 0; j < 4; j++) {
-                d[i * 8 + j] = (float)((rows[i].x >> (8 * j)) & 255u) - 128.0f;
-                d[i * 8 + 4 + j] = (float)((rows[i].y >> (8 * j)) & 255u) - 128.0f;
+                d[i * 8 + j] = (float)((rows[i].x >> (8 * j)) & 255u);
+                d[i * 8 + 4 + j] = (float)((rows[i].y >> (8 * j)) & 255u);
             }
         }
     } else {
@@ -315,7 +308,7 @@ __device__ __forceinline__ void transform_block(const TileInfo& ti, const QuantP
         for (int i = 0; i < 8; i++) {
             const uint8_t* row = ti.px + (size_t)reflect_idx(y0 + i, ti.h) * ti.w;
 #pragma unroll
-            for (int j = 0; j < 8; j++) d[i * 8 + j] = (float)__ldg(row + cx[j]) - 128.0f;
+            for (int j = 0; j < 8; j++) d[i * 8 + j] = (float)__ldg(row + cx[j]);
         }
     }
 #pragma unroll
@@ -325,6 +318,7 @@ __device__ __forceinline__ void transform_block(const TileInfo& ti, const QuantP
     for (int r = 0; r < 8; r++)
         aan8(d[r * 8], d[r * 8 + 1], d[r * 8 + 2], d[r * 8 + 3], d[r * 8 + 4], d[r * 8 + 5], d[r * 8 + 6],
              d[r * 8 + 7]);
+    d[0] -= 8192.0f;   // level shift (codec.py:29) only moves the DC term: 64 * 128, exact in FP32
     uint32_t nz_lo = 0, nz_hi = 0;
     quantise_pairs<0>(d, qp, sm, t, nz_lo, nz_hi, fl_lo, fl_hi);
     sm.nz_lo[t] = nz_lo;
@@ -367,15 +361,15 @@ __device__ __forceinline__ void exact_round(const TileInfo& ti, const QuantParam
             if (halo) {
                 sm.dcq[0] = q;
             } else {
-                int old = coef_get(sm, owner, k);
+                int old = coef_get(sm, owner, k, qp.qbias);
                 if (old != q) {
                     // two flagged coefficients of one block may share a packed word: serialise
                     // through a 32-bit CAS on that word
                     uint32_t* wp = &sm.coef[k >> 1][owner];
                     uint32_t seen = *wp, want;
                     do {
-                        want = (k & 1) ? ((seen & 0x0000ffffu) | ((uint32_t)q << 16))
-                                       : ((seen & 0xffff0000u) | ((uint32_t)q & 0xffffu));
+                        const uint32_t qb = (uint32_t)(q + qp.qbias) & 0xffffu;
+                        want = (k & 1) ? ((seen & 0x0000ffffu) | (qb << 16)) : ((seen & 0xffff0000u) | qb);
                         uint32_t prev = atomicCAS(wp, seen, want);
                         if (prev == seen) break;
                         seen = prev;
@@ -436,25 +430,25 @@ __device__ __forceinline__ void transform_tile(const TileInfo& ti, const QuantPa
 // ---------------------------------------------------------------------------------------------
 // phase 3: symbols.  Bit length of one block, then its bits.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int block_bits(const TileShared& sm, int t, int& err) {
+__device__ __forceinline__ int block_bits(const TileShared& sm, int t, int bias, int& err) {
     int diff = sm.dcq[t + 1] - sm.dcq[t];                      // codec.py:34-35
     int s = bitlen(diff);
-    if (s > 15 || sm.dc_len[s] == 0) { err = 1; s = 0; }       // KeyError, huffman.py:62
-    int bits = sm.dc_len[s] + s;
+    if (s > 15 || sm.dc_tab[s].y == 0) { err = 1; s = 0; }     // KeyError, huffman.py:62
+    int bits = (int)sm.dc_tab[s].y + s;
     uint32_t lo = sm.nz_lo[t], hi = sm.nz_hi[t];
     int prev = 0;
-    const int zrl = sm.ac_len[0xF0];
+    const int zrl = (int)sm.ac_tab[0xF0].y;
     while (lo | hi) {
         int k;
         if (lo) { k = __ffs(lo) - 1; lo &= lo - 1; } else { k = 31 + __ffs(hi); hi &= hi - 1; }
         int run = k - prev - 1;
         prev = k;
-        int sz = bitlen(coef_get(sm, t, k));
+        int sz = bitlen(coef_get(sm, t, k, bias));
         int sym = ((run & 15) << 4) | sz;
-        if (sz > 15 || sm.ac_len[sym & 255] == 0) { err = 1; sz = 1; sym = ((run & 15) << 4) | 1; }
-        bits += (run >> 4) * zrl + sm.ac_len[sym] + sz;        // huffman.py:25-29
+        if (sz > 15 || sm.ac_tab[sym & 255].y == 0) { err = 1; sz = 1; sym = ((run & 15) << 4) | 1; }
+        bits += (run >> 4) * zrl + (int)sm.ac_tab[sym].y + sz; // huffman.py:25-29
     }
-    return bits + sm.ac_len[0];                                // EOB always, huffman.py:33
+    return bits + (int)sm.ac_tab[0].y;                         // EOB always, huffman.py:33
 }
 
 struct BitSink {
@@ -484,7 +478,7 @@ __device__ __forceinline__ uint32_t value_bits(int v, int sz) {   // huffman.py:
     return (uint32_t)(v + (v >> 31)) & ((1u << sz) - 1u);
 }
 
-__device__ __forceinline__ void block_emit(TileShared& sm, int t, int bitpos) {
+__device__ __forceinline__ void block_emit(TileShared& sm, int t, int bias, int bitpos) {
     BitSink s;
     s.stage = sm.stage;
     s.acc = 0;
@@ -493,25 +487,36 @@ __device__ __forceinline__ void block_emit(TileShared& sm, int t, int bitpos) {
     s.first = true;
     int diff = sm.dcq[t + 1] - sm.dcq[t];
     int sz = bitlen(diff);
-    if (sz > 15 || sm.dc_len[sz] == 0) sz = 0;
-    s.put(sm.dc_code[sz], sm.dc_len[sz]);
-    if (sz) s.put(value_bits(diff, sz), sz);
+    if (sz > 15 || sm.dc_tab[sz].y == 0) sz = 0;
+    uint2 e = sm.dc_tab[sz];
+    if ((int)e.y + sz <= 32) {
+        s.put((e.x << sz) | value_bits(diff, sz), (int)e.y + sz);
+    } else {
+        s.put(e.x, (int)e.y);
+        s.put(value_bits(diff, sz), sz);
+    }
     uint32_t lo = sm.nz_lo[t], hi = sm.nz_hi[t];
     int prev = 0;
+    const uint2 zrl = sm.ac_tab[0xF0];
     while (lo | hi) {
         int k;
         if (lo) { k = __ffs(lo) - 1; lo &= lo - 1; } else { k = 31 + __ffs(hi); hi &= hi - 1; }
         int run = k - prev - 1;
         prev = k;
-        int v = coef_get(sm, t, k);
+        int v = coef_get(sm, t, k, bias);
         sz = bitlen(v);
         int sym = ((run & 15) << 4) | sz;
-        if (sz > 15 || sm.ac_len[sym & 255] == 0) { sz = 1; sym = ((run & 15) << 4) | 1; v = 1; }
-        for (int z = run >> 4; z > 0; z--) s.put(sm.ac_code[0xF0], sm.ac_len[0xF0]);
-        s.put(sm.ac_code[sym], sm.ac_len[sym]);
-        s.put(value_bits(v, sz), sz);
+        if (sz > 15 || sm.ac_tab[sym & 255].y == 0) { sz = 1; sym = ((run & 15) << 4) | 1; v = 1; }
+        for (int z = run >> 4; z > 0; z--) s.put(zrl.x, (int)zrl.y);
+        e = sm.ac_tab[sym];
+        if ((int)e.y + sz <= 32) {
+            s.put((e.x << sz) | value_bits(v, sz), (int)e.y + sz);   // code + value bits in one go
+        } else {
+            s.put(e.x, (int)e.y);
+            s.put(value_bits(v, sz), sz);
+        }
     }
-    s.put(sm.ac_code[0], sm.ac_len[0]);
+    s.put(sm.ac_tab[0].x, (int)sm.ac_tab[0].y);
     s.flush();
 }
 
