@@ -20,13 +20,12 @@ namespace tic {
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kTile, 4)
 encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restrict__ descs, int n_images,
-                    long long ntiles, unsigned long long* __restrict__ tile_status,
+                    int uniform_tpi, long long ntiles, unsigned long long* __restrict__ tile_status,
                     unsigned long long* __restrict__ tile_tail, unsigned long long* __restrict__ counters,
                     uint8_t* __restrict__ out, long long out_cap, long long* __restrict__ out_off,
                     long long* __restrict__ out_end, int* __restrict__ status, int quality) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileShared& sm = *reinterpret_cast<TileShared*>(smem_raw);
-    __shared__ long long s_tile;
     const int t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
     const int bias = qp.qbias;
@@ -38,14 +37,20 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
 
   for (;;) {   // persistent: tiles are claimed in stream order through the ticket
     __syncthreads();   // previous tile fully copied out; tables visible
-    if (t == 0) {
-        s_tile = (long long)atomicAdd(&counters[kCtrTicket], 1ull);
-        sm.err = 0;
+    if (warp == 0) {   // claim the next tile and find its image
+        long long tk = 0;
+        if (lane == 0) tk = (long long)atomicAdd(&counters[kCtrTicket], 1ull);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        if (tk < ntiles) {
+            const TileInfo f = locate_tile(descs, n_images, tk, uniform_tpi);
+            if (lane == 0) sm.ti = f;
+        }
+        if (lane == 0) { sm.tile = tk; sm.err = 0; }
     }
     __syncthreads();
-    const long long tile = s_tile;
+    const long long tile = sm.tile;
     if (tile >= ntiles) break;
-    const TileInfo ti = locate_tile(descs, n_images, tile);
+    const TileInfo ti = sm.ti;
 
     transform_tile(ti, qp, sm, counters);
 
@@ -209,7 +214,12 @@ coeffs_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restric
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileShared& sm = *reinterpret_cast<TileShared*>(smem_raw);
     const int t = threadIdx.x;
-    const TileInfo ti = locate_tile(descs, 1, blockIdx.x);
+    if (t < 32) {
+        const TileInfo f = locate_tile(descs, 1, blockIdx.x, 0);
+        if (t == 0) sm.ti = f;
+    }
+    __syncthreads();
+    const TileInfo ti = sm.ti;
     transform_tile(ti, qp, sm, counters);
     if (t < ti.nb) {
         const size_t b = (size_t)ti.blk0 + t;
@@ -434,6 +444,7 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     rc = grow_descs(h, (size_t)n_images);
     if (rc) return rc;
     long long ntiles = 0, nblocks = 0;
+    int uniform_tpi = 0;
     for (int i = 0; i < n_images; i++) {
         if (heights[i] < 0 || widths[i] < 0) { h->err = "negative image dimension"; return TIC_E_INVALID; }
         long long nblk = tic_num_blocks(heights[i], widths[i]);
@@ -446,10 +457,13 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
         d.nblk = (int)nblk;
         d.tile0 = ntiles;
         long long nt = (nblk + kTile - 1) / kTile;
-        ntiles += nt < 1 ? 1 : nt;   // an empty image still owns one tile: it writes the header
+        if (nt < 1) nt = 1;          // an empty image still owns one tile: it writes the header
+        if (i == 0) uniform_tpi = (int)nt; else if (nt != uniform_tpi) uniform_tpi = -1;
+        ntiles += nt;
         nblocks += nblk;
         if (nblk > 0 && !d.px) { h->err = "null pixel pointer"; return TIC_E_INVALID; }
     }
+    if (uniform_tpi < 0) uniform_tpi = 0;
     if (ntiles > 0x7fffffffll) { h->err = "batch too large for one launch"; return TIC_E_INVALID; }
     if ((size_t)ntiles > h->tiles_cap) {
         cudaFree(h->d_tile_status);
@@ -475,7 +489,7 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     long long grid = (long long)h->sm_count * h->ctas_per_sm;
     if (grid > ntiles) grid = ntiles;
     encode_tiles_kernel<<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
-        qp, h->d_descs, n_images, ntiles, d_status_words, d_tail_words, h->d_counters, (uint8_t*)d_out,
+        qp, h->d_descs, n_images, uniform_tpi, ntiles, d_status_words, d_tail_words, h->d_counters, (uint8_t*)d_out,
         (long long)out_capacity, (long long*)d_out_offsets, h->d_out_end, d_status, quality);
     TIC_CUDA(h, cudaGetLastError());
     finalize_kernel<<<(n_images + 255) / 256, 256, 0, stream>>>(n_images, (const long long*)d_out_offsets,

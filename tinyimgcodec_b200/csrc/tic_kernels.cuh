@@ -181,6 +181,16 @@ __device__ __noinline__ double dct8_exact(const double x0, const double x1, cons
     return sel < 4 ? __dmul_rn(0.5, __dadd_rn(t1, t2)) : __dmul_rn(0.5, __dsub_rn(t1, t2));
 }
 
+struct TileInfo {
+    const uint8_t* px;
+    int h, w, bw;
+    int img;          // image index
+    int blk0;         // first block of the tile within the image
+    int nb;           // blocks in this tile (0..kTile)
+    bool first;       // first tile of its image (writes the header)
+    bool closing;     // last tile of its image (pads to a byte, closes the stream)
+};
+
 // ---------------------------------------------------------------------------------------------
 // shared memory of one tile
 // ---------------------------------------------------------------------------------------------
@@ -199,32 +209,39 @@ struct TileShared {
     int err;
     long long s_bits;                // absolute bit position where this tile's block data starts
     unsigned int tail_prev;
+    TileInfo ti;                     // the tile being encoded (written by warp 0)
+    long long tile;                  // its index, or >= ntiles when the work is exhausted
     uint32_t stage[kStageWords];     // tile-relative MSB-first bit buffer
 };
 
-struct TileInfo {
-    const uint8_t* px;
-    int h, w, bw;
-    int img;          // image index
-    int blk0;         // first block of the tile within the image
-    int nb;           // blocks in this tile (0..kTile)
-    bool first;       // first tile of its image (writes the header)
-    bool closing;     // last tile of its image (pads to a byte, closes the stream)
-};
 
+// Warp-cooperative (all 32 lanes of one warp call): 32-ary search for the last image whose first
+// tile is <= tile.  uniform_tpi > 0: every image has that many tiles (the common batch), no search.
 __device__ __forceinline__ TileInfo locate_tile(const ImageDesc* __restrict__ descs, int n_images,
-                                                long long tile) {
-    int lo = 0, hi = n_images - 1;   // last image whose tile0 <= tile
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        if (descs[mid].tile0 <= tile) lo = mid; else hi = mid - 1;
+                                                long long tile, int uniform_tpi) {
+    const int lane = threadIdx.x & 31;
+    int lo = 0;
+    if (uniform_tpi > 0) {
+        lo = (int)(tile / uniform_tpi);
+    } else {
+        int hi = n_images;   // answer in [lo, hi)
+        while (hi - lo > 1) {
+            const int span = hi - lo;
+            const int step = (span + 31) >> 5;
+            const int probe = lo + (lane + 1) * step;   // candidates lo+step, lo+2*step, ...
+            const bool le = probe < hi && __ldg(&descs[probe].tile0) <= tile;
+            const int cnt = __popc(__ballot_sync(0xffffffffu, le));   // monotone: first cnt probes are <= tile
+            const int new_lo = lo + cnt * step;
+            hi = new_lo + step < hi ? new_lo + step : hi;
+            lo = new_lo;
+        }
     }
-    ImageDesc d = descs[lo];
+    const ImageDesc d = descs[lo];
     TileInfo ti;
     ti.px = d.px; ti.h = d.h; ti.w = d.w; ti.bw = d.bw; ti.img = lo;
-    long long lt = tile - d.tile0;
+    const long long lt = tile - d.tile0;
     ti.blk0 = (int)(lt * kTile);
-    int rem = d.nblk - ti.blk0;
+    const int rem = d.nblk - ti.blk0;
     ti.nb = rem < 0 ? 0 : (rem > kTile ? kTile : rem);
     ti.first = (lt == 0);
     ti.closing = (ti.blk0 + kTile >= d.nblk);
