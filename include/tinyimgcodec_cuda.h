@@ -36,7 +36,10 @@ extern "C" {
 #define TIC_E_CATEGORY (-5)   /* a DC size >= 12 or AC size >= 11 met the fixed tables: the
                                  reference raises KeyError (tinyimgcodec/huffman.py:62);
                                  per-image detail is in the status array */
-#define TIC_E_UNSUPPORTED (-6)
+#define TIC_E_UNSUPPORTED (-6) /* auto-table code longer than 32 bits (device limit; the reference
+                                 allows up to 255) */
+#define TIC_E_TABLE (-7)      /* auto table not serialisable: the reference raises OverflowError from
+                                 int2ba (tinyimgcodec/codec.py:76-77,81-83) */
 
 /* flags for tic_encode_batch */
 #define TIC_FLAG_AUTO_HUFFMAN 1u /* per-image tables, tinyimgcodec/codec.py:146-148 */
@@ -44,7 +47,8 @@ extern "C" {
 /* per-image status bits written by the device */
 #define TIC_STATUS_CATEGORY 1 /* KeyError case above */
 #define TIC_STATUS_TABLE 2    /* auto table not serialisable (OverflowError in the reference,
-                                 tinyimgcodec/codec.py:77,83) or code longer than 32 bits */
+                                 tinyimgcodec/codec.py:76-77,81-83) */
+#define TIC_STATUS_LONGCODE 4 /* auto-table code longer than 32 bits: not supported on the device */
 
 typedef struct tic_handle_s *tic_handle;
 
@@ -62,8 +66,10 @@ const char *tic_last_error(tic_handle h);
 
 /* Upper bound on the bytes tic_encode_batch writes for one H x W image with the fixed
  * tables: a 16-byte header (tinyimgcodec/codec.py:102-114), at most 1662 bits per 8x8
- * block (DC 9+11, 63 x (16+10), EOB 4), plus 16 bytes of alignment slack.  Pure host
- * arithmetic; usable without a GPU. */
+ * block (DC 9+11, 63 x (16+10), EOB 4), plus 16 bytes of alignment slack.  With
+ * TIC_FLAG_AUTO_HUFFMAN add 1664 bytes for the serialised tables (a stream larger than that is
+ * reported as TIC_E_CAPACITY, never written out of bounds).  Pure host arithmetic; usable
+ * without a GPU. */
 int64_t tic_max_out_bytes(int32_t height, int32_t width);
 
 /* Number of 8x8 blocks of the padded image (ceil(H/8)*ceil(W/8), tinyimgcodec/utils.py:56-61). */

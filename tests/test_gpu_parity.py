@@ -168,3 +168,43 @@ def test_dropin_package_names(tic):
     img = synthetic_image(64, 64, seed=1)
     assert tinyimgcodec.compress(img) == compress(img) == O.compress(img, 50)
     assert set(encode(img)) == {"height", "width", "quality", "dc", "ac"}
+
+
+def test_golden_auto_table_streams(tic, golden):
+    """auto_generate_huffman_table=True (codec.py:146-148): tables built on the device must reproduce
+    the reference's heapq tree and its serialised header bit for bit."""
+    n = 0
+    for key, img, q, want in golden.stream_cases(auto=True):
+        _assert_same(tic.compress(img, q, True), want, key)
+        n += 1
+    assert n >= 6
+    for q, kat in golden.kat["lenna_auto"].items():
+        out = tic.compress(golden.images["lenna"], int(q), auto_generate_huffman_table=True)
+        assert (len(out), hashlib.sha256(out).hexdigest()) == (kat["size"], kat["sha256"])
+
+
+def test_auto_table_random_vs_oracle(tic):
+    rng = np.random.default_rng(4242)
+    for q in (95, 90, 50, 10, 2):
+        for kind in ("noise", "synthetic", "impulse", "flat", "binary"):
+            h, w = int(rng.integers(1, 150)), int(rng.integers(1, 150))
+            spec = {"kind": kind, "shape": (h, w), "seed": int(rng.integers(0, 1 << 30)), "value": 128}
+            img = make_case(spec)
+            try:
+                want = O.compress(img, q, True)
+            except O.OracleError as e:
+                assert e.status == 2
+                with pytest.raises(OverflowError):
+                    tic.compress(img, q, True)
+                continue
+            _assert_same(tic.compress(img, q, True), want, f"auto {kind} {h}x{w} q{q}")
+
+
+def test_auto_table_batch_vs_oracle(tic):
+    imgs = [synthetic_image(1024, 1024, seed=3), make_case({"kind": "noise", "shape": (200, 312), "seed": 5}),
+            np.full((64, 64), 128, np.uint8), synthetic_image(8, 8, seed=1), synthetic_image(520, 1032, seed=9)]
+    outs = tic.compress_batch(imgs, 50, auto_generate_huffman_table=True)
+    for im, out in zip(imgs, outs):
+        _assert_same(out, O.compress(im, 50, True), f"auto batch {im.shape}")
+    with pytest.raises(IndexError):
+        tic.compress(np.zeros((0, 8), np.uint8), 50, True)

@@ -16,9 +16,12 @@ TIC_E_QUALITY = -3
 TIC_E_CAPACITY = -4
 TIC_E_CATEGORY = -5
 TIC_E_UNSUPPORTED = -6
+TIC_E_TABLE = -7
 TIC_FLAG_AUTO_HUFFMAN = 1
 TIC_STATUS_CATEGORY = 1
 TIC_STATUS_TABLE = 2
+TIC_STATUS_LONGCODE = 4
+AUTO_HEADER_SLACK = 1664
 
 # every symbol include/tinyimgcodec_cuda.h declares
 EXPORTS = ["tic_version", "tic_create", "tic_destroy", "tic_last_error", "tic_max_out_bytes",

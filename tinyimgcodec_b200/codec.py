@@ -90,6 +90,8 @@ class Encoder:
             raise KeyError(msg)  # huffman.py:62: category not in the fixed table
         if rc == _lib.TIC_E_UNSUPPORTED:
             raise NotImplementedError(msg)
+        if rc == _lib.TIC_E_TABLE:
+            raise OverflowError(msg)  # int2ba in write_huffman_table, codec.py:76-77,81-83
         raise TicError(rc, msg)
 
     # -- single image, host buffers ---------------------------------------------------------
@@ -97,7 +99,10 @@ class Encoder:
         img, height, width = _as_u8_image(image)
         quality = _check_quality(quality)
         flags = _lib.TIC_FLAG_AUTO_HUFFMAN if auto_generate_huffman_table else 0
-        cap = int(self.lib.tic_max_out_bytes(height, width))
+        if flags and img.size == 0:
+            # calc_huffman_table indexes an empty symbol array (huffman.py:102-103)
+            raise IndexError("index 1 is out of bounds for axis 1 with size 0")
+        cap = int(self.lib.tic_max_out_bytes(height, width)) + (_lib.AUTO_HEADER_SLACK if flags else 0)
         out = np.empty(cap, dtype=np.uint8)
         size = ctypes.c_int64(0)
         status = ctypes.c_int32(0)
@@ -129,7 +134,7 @@ class Encoder:
         return {"height": height, "width": width, "quality": quality, "dc": dc, "ac": ac}
 
     # -- batch, device buffers ----------------------------------------------------------------
-    def encode_batch_device(self, d_images, quality=50, out=None, stream=None):
+    def encode_batch_device(self, d_images, quality=50, out=None, stream=None, auto_generate_huffman_table=False):
         """Encode a batch resident in HBM.  `d_images`: a CUDA uint8 tensor (N,H,W) or a list of
         2-D CUDA uint8 tensors.  Returns a DeviceBatchResult; nothing is copied to the host."""
         import torch
@@ -150,14 +155,16 @@ class Encoder:
         ws = (ctypes.c_int32 * max(n, 1))(*[t.shape[1] for t in tensors])
         with torch.cuda.device(dev):
             if out is None:
-                cap = sum(int(self.lib.tic_max_out_bytes(t.shape[0], t.shape[1])) for t in tensors) + 16
+                slack = _lib.AUTO_HEADER_SLACK if auto_generate_huffman_table else 0
+                cap = sum(int(self.lib.tic_max_out_bytes(t.shape[0], t.shape[1])) + slack for t in tensors) + 16
                 out = torch.empty(cap, dtype=torch.uint8, device=dev)
             meta = torch.empty(max(n, 1) * 3, dtype=torch.int64, device=dev)
             offs, sizes = meta[:n], meta[max(n, 1): max(n, 1) + n]
             stat = meta[2 * max(n, 1):].view(torch.int32)[:n]
             stream = stream or torch.cuda.current_stream(dev)
             with self._lock:
-                rc = self.lib.tic_encode_batch(self.handle, ptrs, hs, ws, n, q, 0, out.data_ptr(), out.numel(),
+                flags = _lib.TIC_FLAG_AUTO_HUFFMAN if auto_generate_huffman_table else 0
+                rc = self.lib.tic_encode_batch(self.handle, ptrs, hs, ws, n, q, flags, out.data_ptr(), out.numel(),
                                                offs.data_ptr(), sizes.data_ptr(), stat.data_ptr(),
                                                stream.cuda_stream)
                 if rc != _lib.TIC_OK:
@@ -286,7 +293,7 @@ def encode(image, quality=50, device=None):
     return get_encoder(device).encode(image, quality)
 
 
-def compress_batch(images, quality=50, device=None):
+def compress_batch(images, quality=50, device=None, auto_generate_huffman_table=False):
     """compress() for a list of 2-D uint8 arrays (or an (N,H,W) array) in one launch sequence:
     pinned H2D, one encode, one D2H.  Returns a list of bytes objects."""
     import torch
@@ -296,4 +303,7 @@ def compress_batch(images, quality=50, device=None):
     with torch.cuda.device(dev):
         d_imgs = [torch.from_numpy(im).pin_memory().to(dev, non_blocking=True) if im.size
                   else torch.empty(im.shape, dtype=torch.uint8, device=dev) for im in imgs]
-        return enc.encode_batch_device(d_imgs, quality).to_bytes()
+        if auto_generate_huffman_table and any(im.size == 0 for im in imgs):
+            raise IndexError("index 1 is out of bounds for axis 1 with size 0")   # huffman.py:102-103
+        return enc.encode_batch_device(d_imgs, quality,
+                                       auto_generate_huffman_table=auto_generate_huffman_table).to_bytes()

@@ -23,7 +23,8 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
                     int uniform_tpi, long long ntiles, unsigned long long* __restrict__ tile_status,
                     unsigned long long* __restrict__ tile_tail, unsigned long long* __restrict__ counters,
                     uint8_t* __restrict__ out, long long out_cap, long long* __restrict__ out_off,
-                    long long* __restrict__ out_end, int* __restrict__ status, int quality) {
+                    long long* __restrict__ out_end, int* __restrict__ status, int quality,
+                    const AutoTables* __restrict__ auto_tabs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileShared& sm = *reinterpret_cast<TileShared*>(smem_raw);
     const int t = threadIdx.x;
@@ -35,6 +36,7 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
         sm.ac_tab[i] = make_uint2(c_default_tables.ac[i].code, c_default_tables.ac[i].len);
     if (t < 16) sm.dc_tab[t] = make_uint2(c_default_tables.dc[t].code, c_default_tables.dc[t].len);
 
+    int tab_img = -1;   // auto mode: image whose tables are in shared memory
   for (;;) {   // persistent: tiles are claimed in stream order through the ticket
     __syncthreads();   // previous tile fully copied out; tables visible
     if (warp == 0) {   // claim the next tile and find its image
@@ -51,6 +53,12 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
     const long long tile = sm.tile;
     if (tile >= ntiles) break;
     const TileInfo ti = sm.ti;
+    if (auto_tabs != nullptr && tab_img != ti.img) {   // per-image tables (codec.py:146-148); uniform branch
+        const HuffTables& g = auto_tabs[ti.img].tab;
+        for (int i = t; i < 256; i += kTile) sm.ac_tab[i] = make_uint2(g.ac[i].code, g.ac[i].len);
+        if (t < 16) sm.dc_tab[t] = make_uint2(g.dc[t].code, g.dc[t].len);
+        tab_img = ti.img;   // visible to everyone after the barriers inside transform_tile
+    }
 
     transform_tile(ti, qp, sm, counters);
 
@@ -73,20 +81,38 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
         if (w < warp) warp_base += wb;
         tile_bits += wb;
     }
-    const int bitpos = warp_base + incl - bits;   // tile-relative bit offset of this block
-    const long long agg = (long long)tile_bits + (ti.first ? 128 : 0);
+    // the first tile of an image carries the header in front of its blocks: 128 bits with the fixed
+    // tables (codec.py:102-114), 128 + the serialised tables in auto mode (codec.py:110-112)
+    const int hdr_bits = !ti.first ? 0 : (auto_tabs ? (int)auto_tabs[ti.img].hdr_bits : 128);
+    const int bitpos = hdr_bits + warp_base + incl - bits;   // tile-relative bit offset of this block
+    tile_bits += hdr_bits;
+    const long long agg = (long long)tile_bits;
+    const bool stage_ok = tile_bits <= (kStageWords - 2) * 32;   // only long auto-table codes can overflow
 
     // publish the aggregate as early as possible: successors only need it for their offset
     if (t == 0) {
         st_relaxed_u64(&tile_status[tile], kFlagAgg | (ti.closing ? kClosingBit : 0ull) | (unsigned long long)agg);
         if (sm.err) atomicOr(&status[ti.img], TIC_STATUS_CATEGORY);
+        if (!stage_ok) atomicOr(&status[ti.img], TIC_STATUS_LONGCODE);
     }
-    const int nwords = (tile_bits + 31) >> 5;
-    for (int i = t; i <= nwords; i += kTile) sm.stage[i] = 0;
+    const int nwords = stage_ok ? ((tile_bits + 31) >> 5) : 0;
+    const int hdr_words = (hdr_bits + 31) >> 5;
+    for (int i = t; i <= nwords; i += kTile) {
+        uint32_t w = 0;
+        if (i < hdr_words) {
+            if (auto_tabs) {
+                w = auto_tabs[ti.img].hdr_words[i];
+            } else {   // struct.pack("III") is little-endian, the stream is MSB-first; flag word 0
+                const uint32_t v = i == 0 ? (uint32_t)ti.h : (i == 1 ? (uint32_t)ti.w : (i == 2 ? (uint32_t)quality : 0u));
+                w = __byte_perm(v, 0, 0x0123);
+            }
+        }
+        sm.stage[i] = w;
+    }
     __syncthreads();
 
     // ---- bits into the tile-relative staging buffer ---------------------------------------------
-    if (t < ti.nb) block_emit(sm, t, bias, bitpos);
+    if (t < ti.nb && stage_ok) block_emit(sm, t, bias, bitpos);
 
     // ---- decoupled look-back (warp 0, 32 predecessors per round): absolute bit position ----------
     if (warp == 0) {
@@ -136,18 +162,12 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
             const long long e_bits = p_in + agg;   // end of this tile's data bits
             const long long p_out = ti.closing ? round_up128(e_bits) : e_bits;
             st_relaxed_u64(&tile_status[tile], kFlagPrefix | (unsigned long long)p_out);
-            const long long s_bits = p_in + (ti.first ? 128 : 0);
+            const long long s_bits = p_in;   // the header (first tile) sits in the staging buffer too
             sm.s_bits = s_bits;
             const long long end_byte = (e_bits + 7) >> 3;
             const bool fits = ((end_byte + 3) & ~3ll) <= out_cap;
             if (!fits) atomicExch(&counters[kCtrOverflow], 1ull);
-            if (ti.first) {
-                out_off[ti.img] = p_in >> 3;
-                if (fits) {   // make_header, codec.py:102-114: "III" little-endian + 32 flag bits = 0
-                    uint4 hdr = make_uint4((unsigned)ti.h, (unsigned)ti.w, (unsigned)quality, 0u);
-                    *reinterpret_cast<uint4*>(out + (p_in >> 3)) = hdr;
-                }
-            }
+            if (ti.first) out_off[ti.img] = p_in >> 3;
             if (ti.closing) {
                 out_end[ti.img] = end_byte;
                 atomicMax(&counters[kCtrTotalBits], (unsigned long long)(end_byte << 3));
@@ -163,7 +183,7 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
     const long long g0 = s_bits >> 5;
     // words [g0, g_end): full words, plus the final partial word when this tile closes the image
     const long long g_end = ti.closing ? ((e_bits + 31) >> 5) : (e_bits >> 5);
-    const bool fits = ((((e_bits + 7) >> 3) + 3) & ~3ll) <= out_cap;
+    const bool fits = stage_ok && ((((e_bits + 7) >> 3) + 3) & ~3ll) <= out_cap;
     uint32_t* out_words = reinterpret_cast<uint32_t*>(out);
     const bool need_prev = !ti.first && sh != 0;   // word g0 starts with the previous tile's last bits
     if (t == 0) {
@@ -192,6 +212,188 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
         if (fits) out_words[g] = __byte_perm(v, 0, 0x0123);
     }
   }   // persistent loop
+}
+
+// ---------------------------------------------------------------------------------------------
+// auto_generate_huffman_table=True (codec.py:146-148): symbol statistics, then the tables
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTile, 4)
+symbol_stats_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restrict__ descs, int n_images,
+                    int uniform_tpi, long long ntiles, unsigned long long* __restrict__ counters,
+                    uint32_t* __restrict__ g_hist, unsigned long long* __restrict__ g_first,
+                    int* __restrict__ status) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    TileShared& sm = *reinterpret_cast<TileShared*>(smem_raw);
+    const int t = threadIdx.x;
+    uint32_t* hist = sm.stage;                                                       // 272 counters
+    unsigned long long* first = reinterpret_cast<unsigned long long*>(sm.stage + 512); // 272 keys
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        __syncthreads();
+        if (t < 32) {
+            const TileInfo f = locate_tile(descs, n_images, tile, uniform_tpi);
+            if (t == 0) { sm.ti = f; sm.err = 0; }
+        }
+        for (int i = t; i < 272; i += kTile) { hist[i] = 0; first[i] = ~0ull; }
+        __syncthreads();
+        const TileInfo ti = sm.ti;
+        transform_tile(ti, qp, sm, counters);
+        int err = 0;
+        if (t < ti.nb) block_stats(sm, t, qp.qbias, (unsigned long long)(ti.blk0 + t), hist, first, err);
+        if (err) sm.err = 1;
+        __syncthreads();
+        for (int i = t; i < 272; i += kTile) {
+            uint32_t c = hist[i] + (i == 0 ? (uint32_t)ti.nb : 0u);   // one EOB per block (huffman.py:33)
+            if (c) {
+                atomicAdd(&g_hist[(size_t)ti.img * 272 + i], c);
+                atomicMin(&g_first[(size_t)ti.img * 272 + i], first[i]);
+            }
+        }
+        if (t == 0 && sm.err) atomicOr(&status[ti.img], TIC_STATUS_TABLE);
+    }
+}
+
+// One thread per image: HuffmanTree (huffman.py:112-194) on CPython's heapq, which
+// queue.PriorityQueue uses — leaves pushed in first-occurrence order, nodes compared by frequency
+// only, DFS with left = "0" — then write_huffman_table (codec.py:73-84) into the header words.
+struct TreeScratch {
+    unsigned long long freq[544];
+    short left[544], right[544], sym[544];
+    short heap[272];
+    short stack_node[272];
+    unsigned int stack_code[272];
+    unsigned char stack_len[272];
+};
+
+__device__ void heap_siftdown(TreeScratch& s, int startpos, int pos) {   // heapq._siftdown
+    short newitem = s.heap[pos];
+    while (pos > startpos) {
+        int parentpos = (pos - 1) >> 1;
+        short parent = s.heap[parentpos];
+        if (s.freq[newitem] < s.freq[parent]) { s.heap[pos] = parent; pos = parentpos; continue; }
+        break;
+    }
+    s.heap[pos] = newitem;
+}
+__device__ void heap_siftup(TreeScratch& s, int hlen, int pos) {   // heapq._siftup
+    int startpos = pos;
+    short newitem = s.heap[pos];
+    int childpos = 2 * pos + 1;
+    while (childpos < hlen) {
+        int rightpos = childpos + 1;
+        if (rightpos < hlen && !(s.freq[s.heap[childpos]] < s.freq[s.heap[rightpos]])) childpos = rightpos;
+        s.heap[pos] = s.heap[childpos];
+        pos = childpos;
+        childpos = 2 * pos + 1;
+    }
+    s.heap[pos] = newitem;
+    heap_siftdown(s, startpos, pos);
+}
+
+struct HdrWriter {
+    uint32_t* words;
+    int nbits;
+    __device__ void put(uint32_t v, int n) {   // n <= 32, MSB-first
+        for (int i = n - 1; i >= 0; i--) {
+            if (nbits < kMaxHdrWords * 32 && ((v >> i) & 1)) words[nbits >> 5] |= 0x80000000u >> (nbits & 31);
+            nbits++;
+        }
+    }
+};
+
+// Builds one alphabet: symbols base..base+count-1 of hist/first.  Returns status bits.
+__device__ int build_alphabet(TreeScratch& s, const uint32_t* hist, const unsigned long long* first, int base,
+                              int count, bool is_dc, HuffEntry* table, HdrWriter& hw) {
+    // present symbols in first-occurrence order (dict insertion order, huffman.py:187-194)
+    short order[256];
+    int n = 0;
+    for (int i = 0; i < count; i++) {
+        if (hist[base + i] == 0) continue;
+        int j = n++;
+        while (j > 0 && first[base + order[j - 1]] > first[base + i]) { order[j] = order[j - 1]; j--; }
+        order[j] = (short)i;
+    }
+    int status = 0;
+    hw.put((uint32_t)n, 16);                                     // codec.py:74,79
+    if (n == 0) return status;
+    int nnodes = 0, hlen = 0;
+    for (int i = 0; i < n; i++) {                                // huffman.py:156-157
+        s.freq[nnodes] = hist[base + order[i]];
+        s.sym[nnodes] = order[i];
+        s.left[nnodes] = s.right[nnodes] = -1;
+        s.heap[hlen++] = (short)nnodes++;
+        heap_siftdown(s, 0, hlen - 1);
+    }
+    while (hlen >= 2) {                                          // huffman.py:159-163
+        short uv[2];
+        for (int r = 0; r < 2; r++) {                            // heapq.heappop
+            short last = s.heap[--hlen];
+            if (hlen) { uv[r] = s.heap[0]; s.heap[0] = last; heap_siftup(s, hlen, 0); } else uv[r] = last;
+        }
+        s.freq[nnodes] = s.freq[uv[0]] + s.freq[uv[1]];
+        s.sym[nnodes] = -1;
+        s.left[nnodes] = uv[0];
+        s.right[nnodes] = uv[1];
+        s.heap[hlen++] = (short)nnodes++;
+        heap_siftdown(s, 0, hlen - 1);
+    }
+    // DFS, left = "0" first (huffman.py:175-185); table order = DFS order
+    int sp = 0;
+    s.stack_node[0] = s.heap[0]; s.stack_code[0] = 0; s.stack_len[0] = 0; sp = 1;
+    while (sp) {
+        sp--;
+        const int node = s.stack_node[sp];
+        const unsigned int code = s.stack_code[sp];
+        const int len = s.stack_len[sp];
+        if (s.sym[node] >= 0) {
+            const int sym = s.sym[node];
+            if (len > 32) status |= TIC_STATUS_LONGCODE;         // device limit: codes up to 32 bits
+            table[sym].code = code;
+            table[sym].len = kHuffPresent | (uint32_t)(len > 32 ? 32 : len);
+            if (is_dc) {                                         // codec.py:75-78
+                if (len >= 16) status |= TIC_STATUS_TABLE;       // int2ba(len, 4) raises OverflowError
+                hw.put((uint32_t)sym, 4);
+                hw.put((uint32_t)len & 15u, 4);
+            } else {                                             // codec.py:80-84
+                hw.put((uint32_t)sym >> 4, 4);
+                hw.put((uint32_t)sym & 15u, 4);
+                hw.put((uint32_t)len & 255u, 8);
+            }
+            hw.put(code, len > 32 ? 32 : len);
+            continue;
+        }
+        // push right first so that the left subtree is visited first
+        s.stack_node[sp] = s.right[node]; s.stack_code[sp] = (code << 1) | 1u; s.stack_len[sp] = (unsigned char)(len + 1); sp++;
+        s.stack_node[sp] = s.left[node];  s.stack_code[sp] = (code << 1);      s.stack_len[sp] = (unsigned char)(len + 1); sp++;
+    }
+    return status;
+}
+
+__global__ void build_tables_kernel(const ImageDesc* __restrict__ descs, int n_images, int quality,
+                                    const uint32_t* __restrict__ g_hist,
+                                    const unsigned long long* __restrict__ g_first,
+                                    AutoTables* __restrict__ tabs, TreeScratch* __restrict__ scratch,
+                                    int* __restrict__ status) {
+    const int img = blockIdx.x * blockDim.x + threadIdx.x;
+    if (img >= n_images) return;
+    AutoTables& at = tabs[img];
+    TreeScratch& s = scratch[img];
+    for (int i = 0; i < 256; i++) at.tab.ac[i].code = at.tab.ac[i].len = 0;
+    for (int i = 0; i < 16; i++) at.tab.dc[i].code = at.tab.dc[i].len = 0;
+    for (int i = 0; i < kMaxHdrWords; i++) at.hdr_words[i] = 0;
+    HdrWriter hw{at.hdr_words, 0};
+    const ImageDesc d = descs[img];
+    hw.put(__byte_perm((uint32_t)d.h, 0, 0x0123), 32);           // struct.pack("III"), codec.py:103-109
+    hw.put(__byte_perm((uint32_t)d.w, 0, 0x0123), 32);
+    hw.put(__byte_perm((uint32_t)quality, 0, 0x0123), 32);
+    hw.put(0x80000000u, 32);                                     // codec.py:111
+    const uint32_t* hist = g_hist + (size_t)img * 272;
+    const unsigned long long* first = g_first + (size_t)img * 272;
+    int st = build_alphabet(s, hist, first, 256, 16, true, at.tab.dc, hw);    // table[DC] first, codec.py:74-78
+    st |= build_alphabet(s, hist, first, 0, 256, false, at.tab.ac, hw);        // then table[AC], codec.py:79-84
+    if (hw.nbits > kMaxHdrWords * 32) st |= TIC_STATUS_LONGCODE;
+    at.hdr_bits = (uint32_t)hw.nbits;
+    at.status = (uint32_t)st;
+    if (st) atomicOr(&status[img], st);
 }
 
 // sizes = end - offset, and the batch summary the host reads back in tic_encode_finish
@@ -246,6 +448,9 @@ struct tic_handle_s {
     unsigned long long* d_counters = nullptr;
     unsigned long long* h_counters = nullptr;    // pinned
     long long* d_out_end = nullptr;     size_t end_cap = 0;
+    // auto-table mode: per-image statistics, tables, tree scratch
+    uint32_t* d_hist = nullptr; unsigned long long* d_first = nullptr; AutoTables* d_tabs = nullptr;
+    TreeScratch* d_tree = nullptr;      size_t auto_cap = 0;
     // single-image host path
     uint8_t* d_px = nullptr;            size_t px_cap = 0;
     uint8_t* d_out = nullptr;           size_t out_cap = 0;
@@ -272,13 +477,13 @@ static void build_default_tables(HuffTables& t) {
     uint32_t code = 0;
     int k = 0;
     for (int l = 1; l <= 16; l++) {
-        for (int i = 0; i < kDcBits[l]; i++) { t.dc[kDcVals[k]].code = code++; t.dc[kDcVals[k]].len = (uint32_t)l; k++; }
+        for (int i = 0; i < kDcBits[l]; i++) { t.dc[kDcVals[k]].code = code++; t.dc[kDcVals[k]].len = kHuffPresent | (uint32_t)l; k++; }
         code <<= 1;
     }
     code = 0;
     k = 0;
     for (int l = 1; l <= 16; l++) {
-        for (int i = 0; i < kAcBits[l]; i++) { t.ac[kAcVals[k]].code = code++; t.ac[kAcVals[k]].len = (uint32_t)l; k++; }
+        for (int i = 0; i < kAcBits[l]; i++) { t.ac[kAcVals[k]].code = code++; t.ac[kAcVals[k]].len = kHuffPresent | (uint32_t)l; k++; }
         code <<= 1;
     }
 }
@@ -343,6 +548,8 @@ static int ensure_tables(tic_handle h) {
                                      (int)sizeof(TileShared)));
     TIC_CUDA(h, cudaFuncSetAttribute(coeffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(TileShared)));
+    TIC_CUDA(h, cudaFuncSetAttribute(symbol_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(TileShared)));
     int per_sm = 0;
     TIC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_tiles_kernel, kTile, sizeof(TileShared)));
     cudaDeviceProp prop;
@@ -391,6 +598,7 @@ int tic_destroy(tic_handle h) {
     if (!h) return TIC_E_INVALID;
     cudaSetDevice(h->device);
     cudaFree(h->d_descs); cudaFreeHost(h->h_descs); cudaFree(h->d_tile_status); cudaFree(h->d_counters);
+    cudaFree(h->d_hist); cudaFree(h->d_first); cudaFree(h->d_tabs); cudaFree(h->d_tree);
     cudaFreeHost(h->h_counters); cudaFree(h->d_out_end); cudaFree(h->d_px); cudaFree(h->d_out);
     cudaFreeHost(h->h_stage); cudaFree(h->d_meta); cudaFreeHost(h->h_meta);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -421,10 +629,7 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
         h->err = "invalid argument";
         return TIC_E_INVALID;
     }
-    if (flags & TIC_FLAG_AUTO_HUFFMAN) {
-        h->err = "auto-generated Huffman tables are not implemented on the device yet";
-        return TIC_E_UNSUPPORTED;
-    }
+    const bool auto_mode = (flags & TIC_FLAG_AUTO_HUFFMAN) != 0;
     if ((reinterpret_cast<uintptr_t>(d_out) & 15) != 0) {
         h->err = "d_out must be 16-byte aligned";
         return TIC_E_INVALID;
@@ -488,9 +693,33 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     TIC_CUDA(h, cudaMemsetAsync(d_status, 0, (size_t)n_images * 4, stream));
     long long grid = (long long)h->sm_count * h->ctas_per_sm;
     if (grid > ntiles) grid = ntiles;
+    const AutoTables* d_tabs = nullptr;
+    h->last_launches = 2;
+    if (auto_mode) {   // calc_huffman_table (huffman.py:101-109) + write_huffman_table (codec.py:73-84)
+        if ((size_t)n_images > h->auto_cap) {
+            cudaFree(h->d_hist); cudaFree(h->d_first); cudaFree(h->d_tabs); cudaFree(h->d_tree);
+            h->d_hist = nullptr; h->d_first = nullptr; h->d_tabs = nullptr; h->d_tree = nullptr; h->auto_cap = 0;
+            size_t cap = (size_t)n_images + (size_t)n_images / 4 + 8;
+            TIC_CUDA(h, cudaMalloc(&h->d_hist, cap * 272 * sizeof(uint32_t)));
+            TIC_CUDA(h, cudaMalloc(&h->d_first, cap * 272 * sizeof(unsigned long long)));
+            TIC_CUDA(h, cudaMalloc(&h->d_tabs, cap * sizeof(AutoTables)));
+            TIC_CUDA(h, cudaMalloc(&h->d_tree, cap * sizeof(TreeScratch)));
+            h->auto_cap = cap;
+        }
+        TIC_CUDA(h, cudaMemsetAsync(h->d_hist, 0, (size_t)n_images * 272 * sizeof(uint32_t), stream));
+        TIC_CUDA(h, cudaMemsetAsync(h->d_first, 0xff, (size_t)n_images * 272 * sizeof(unsigned long long), stream));
+        symbol_stats_kernel<<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
+            qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_counters, h->d_hist, h->d_first, d_status);
+        TIC_CUDA(h, cudaGetLastError());
+        build_tables_kernel<<<(n_images + 31) / 32, 32, 0, stream>>>(h->d_descs, n_images, quality, h->d_hist,
+                                                                    h->d_first, h->d_tabs, h->d_tree, d_status);
+        TIC_CUDA(h, cudaGetLastError());
+        d_tabs = h->d_tabs;
+        h->last_launches = 4;
+    }
     encode_tiles_kernel<<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
         qp, h->d_descs, n_images, uniform_tpi, ntiles, d_status_words, d_tail_words, h->d_counters, (uint8_t*)d_out,
-        (long long)out_capacity, (long long*)d_out_offsets, h->d_out_end, d_status, quality);
+        (long long)out_capacity, (long long*)d_out_offsets, h->d_out_end, d_status, quality, d_tabs);
     TIC_CUDA(h, cudaGetLastError());
     finalize_kernel<<<(n_images + 255) / 256, 256, 0, stream>>>(n_images, (const long long*)d_out_offsets,
                                                                h->d_out_end, (long long*)d_out_sizes, d_status,
@@ -498,7 +727,6 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     TIC_CUDA(h, cudaGetLastError());
     h->last_tiles = ntiles;
     h->last_blocks = nblocks;
-    h->last_launches = 2;
     return TIC_OK;
 }
 
@@ -510,6 +738,14 @@ int tic_encode_finish(tic_handle h, void* stream_v, int64_t* total_bytes) {
     TIC_CUDA(h, cudaStreamSynchronize(stream));
     if (total_bytes) *total_bytes = (int64_t)(h->h_counters[kCtrTotalBits] >> 3);
     if (h->h_counters[kCtrOverflow]) { h->err = "output buffer too small"; return TIC_E_CAPACITY; }
+    if (h->h_counters[kCtrAnyStatus] & TIC_STATUS_TABLE) {
+        h->err = "auto-generated Huffman table cannot be serialised (reference: OverflowError)";
+        return TIC_E_TABLE;
+    }
+    if (h->h_counters[kCtrAnyStatus] & TIC_STATUS_LONGCODE) {
+        h->err = "auto-generated Huffman code longer than 32 bits is not supported on the device";
+        return TIC_E_UNSUPPORTED;
+    }
     if (h->h_counters[kCtrAnyStatus] & TIC_STATUS_CATEGORY) {
         h->err = "coefficient category outside the fixed Huffman tables (reference: KeyError)";
         return TIC_E_CATEGORY;
@@ -568,7 +804,7 @@ int tic_compress_host(tic_handle h, const uint8_t* pixels, int32_t height, int32
     TIC_CUDA(h, cudaSetDevice(h->device));
     const size_t npx = (size_t)height * (size_t)width;
     if (npx && !pixels) { h->err = "null pixels"; return TIC_E_INVALID; }
-    const size_t need_out = (size_t)tic_max_out_bytes(height, width);
+    const size_t need_out = (size_t)tic_max_out_bytes(height, width) + ((flags & TIC_FLAG_AUTO_HUFFMAN) ? 1664 : 0);
     if (npx > h->px_cap) {
         cudaFree(h->d_px); h->d_px = nullptr; h->px_cap = 0;
         TIC_CUDA(h, cudaMalloc(&h->d_px, npx + 16));

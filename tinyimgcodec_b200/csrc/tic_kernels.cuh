@@ -29,7 +29,7 @@ namespace tic {
 
 constexpr int kTile = 128;                                  // blocks (= threads) per tile
 constexpr int kWarps = kTile / 32;
-constexpr int kStageWords = (kTile * 1662 + 31) / 32 + 4;   // worst case bits of a tile
+constexpr int kStageWords = (kTile * 1662 + 31) / 32 + kMaxHdrWords + 4;   // worst case bits of a tile + header
 constexpr int kWorkCap = 512;                               // exact-path worklist entries
 constexpr int kExactPerRound = kTile / 8;                   // 8 lanes per worklist entry
 
@@ -451,10 +451,10 @@ __device__ __forceinline__ int block_bits(const TileShared& sm, int t, int bias,
     int diff = sm.dcq[t + 1] - sm.dcq[t];                      // codec.py:34-35
     int s = bitlen(diff);
     if (s > 15 || sm.dc_tab[s].y == 0) { err = 1; s = 0; }     // KeyError, huffman.py:62
-    int bits = (int)sm.dc_tab[s].y + s;
+    int bits = (int)(sm.dc_tab[s].y & kHuffLenMask) + s;
     uint32_t lo = sm.nz_lo[t], hi = sm.nz_hi[t];
     int prev = 0;
-    const int zrl = (int)sm.ac_tab[0xF0].y;
+    const int zrl = (int)(sm.ac_tab[0xF0].y & kHuffLenMask);
     while (lo | hi) {
         int k;
         if (lo) { k = __ffs(lo) - 1; lo &= lo - 1; } else { k = 31 + __ffs(hi); hi &= hi - 1; }
@@ -463,9 +463,42 @@ __device__ __forceinline__ int block_bits(const TileShared& sm, int t, int bias,
         int sz = bitlen(coef_get(sm, t, k, bias));
         int sym = ((run & 15) << 4) | sz;
         if (sz > 15 || sm.ac_tab[sym & 255].y == 0) { err = 1; sz = 1; sym = ((run & 15) << 4) | 1; }
-        bits += (run >> 4) * zrl + (int)sm.ac_tab[sym].y + sz; // huffman.py:25-29
+        bits += (run >> 4) * zrl + (int)(sm.ac_tab[sym].y & kHuffLenMask) + sz; // huffman.py:25-29
     }
-    return bits + (int)sm.ac_tab[0].y;                         // EOB always, huffman.py:33
+    return bits + (int)(sm.ac_tab[0].y & kHuffLenMask);        // EOB always, huffman.py:33
+}
+
+// Symbol statistics of one block for the per-image tables (huffman.py:101-109, 187-194): counts
+// and, for the dict-insertion order the reference's tree depends on, the first occurrence of every
+// symbol as key = block index * 256 + ordinal of the symbol inside the block's list.
+// hist/first: 272 entries, [0,256) AC (run*16+size), [256,272) DC size.
+__device__ __forceinline__ void block_stats(const TileShared& sm, int t, int bias, unsigned long long blk,
+                                            uint32_t* hist, unsigned long long* first, int& err) {
+    int diff = sm.dcq[t + 1] - sm.dcq[t];
+    int s = bitlen(diff);
+    if (s > 15) { err = 1; s = 15; }   // int2ba(category, 4) overflows in the reference (codec.py:76)
+    atomicAdd(&hist[256 + s], 1u);
+    atomicMin(&first[256 + s], blk << 8);
+    uint32_t lo = sm.nz_lo[t], hi = sm.nz_hi[t];
+    int prev = 0, ord = 0;
+    while (lo | hi) {
+        int k;
+        if (lo) { k = __ffs(lo) - 1; lo &= lo - 1; } else { k = 31 + __ffs(hi); hi &= hi - 1; }
+        int run = k - prev - 1;
+        prev = k;
+        int sz = bitlen(coef_get(sm, t, k, bias));
+        if (sz > 15) { err = 1; sz = 15; }
+        if (run >> 4) {
+            atomicAdd(&hist[0xF0], (uint32_t)(run >> 4));
+            atomicMin(&first[0xF0], (blk << 8) | (unsigned)ord);
+            ord += run >> 4;
+        }
+        int sym = ((run & 15) << 4) | sz;
+        atomicAdd(&hist[sym], 1u);
+        atomicMin(&first[sym], (blk << 8) | (unsigned)ord);
+        ord++;
+    }
+    atomicMin(&first[0], (blk << 8) | (unsigned)ord);   // EOB; its count is the number of blocks
 }
 
 struct BitSink {
@@ -506,6 +539,7 @@ __device__ __forceinline__ void block_emit(TileShared& sm, int t, int bias, int 
     int sz = bitlen(diff);
     if (sz > 15 || sm.dc_tab[sz].y == 0) sz = 0;
     uint2 e = sm.dc_tab[sz];
+    e.y &= kHuffLenMask;
     if ((int)e.y + sz <= 32) {
         s.put((e.x << sz) | value_bits(diff, sz), (int)e.y + sz);
     } else {
@@ -514,7 +548,8 @@ __device__ __forceinline__ void block_emit(TileShared& sm, int t, int bias, int 
     }
     uint32_t lo = sm.nz_lo[t], hi = sm.nz_hi[t];
     int prev = 0;
-    const uint2 zrl = sm.ac_tab[0xF0];
+    uint2 zrl = sm.ac_tab[0xF0];
+    zrl.y &= kHuffLenMask;
     while (lo | hi) {
         int k;
         if (lo) { k = __ffs(lo) - 1; lo &= lo - 1; } else { k = 31 + __ffs(hi); hi &= hi - 1; }
@@ -526,6 +561,7 @@ __device__ __forceinline__ void block_emit(TileShared& sm, int t, int bias, int 
         if (sz > 15 || sm.ac_tab[sym & 255].y == 0) { sz = 1; sym = ((run & 15) << 4) | 1; v = 1; }
         for (int z = run >> 4; z > 0; z--) s.put(zrl.x, (int)zrl.y);
         e = sm.ac_tab[sym];
+        e.y &= kHuffLenMask;
         if ((int)e.y + sz <= 32) {
             s.put((e.x << sz) | value_bits(v, sz), (int)e.y + sz);   // code + value bits in one go
         } else {
@@ -533,7 +569,7 @@ __device__ __forceinline__ void block_emit(TileShared& sm, int t, int bias, int 
             s.put(value_bits(v, sz), sz);
         }
     }
-    s.put(sm.ac_tab[0].x, (int)sm.ac_tab[0].y);
+    s.put(sm.ac_tab[0].x, (int)(sm.ac_tab[0].y & kHuffLenMask));
     s.flush();
 }
 

@@ -38,8 +38,11 @@ static const uint8_t kAcVals[162] = {
     0xd4, 0xd5, 0xd6, 0xd7, 0xd8, 0xd9, 0xda, 0xe1, 0xe2, 0xe3, 0xe4, 0xe5, 0xe6, 0xe7, 0xe8,
     0xe9, 0xea, 0xf1, 0xf2, 0xf3, 0xf4, 0xf5, 0xf6, 0xf7, 0xf8, 0xf9, 0xfa};
 
-// Huffman table as the device sees it: {code (right-aligned), length} per symbol.
-// DC: symbol = size category (0..15).  AC: symbol = run*16 + size.  length 0 = not in table.
+// Huffman table as the device sees it: {code (right-aligned), kHuffPresent | length} per symbol.
+// DC: symbol = size category (0..15).  AC: symbol = run*16 + size.  len == 0: not in the table
+// (a present symbol can have a zero-length code: a one-symbol alphabet, huffman.py:175-180).
+constexpr uint32_t kHuffPresent = 0x100;
+constexpr uint32_t kHuffLenMask = 0xff;
 struct HuffEntry {
     uint32_t code;
     uint32_t len;
@@ -47,6 +50,16 @@ struct HuffEntry {
 struct HuffTables {
     HuffEntry ac[256];
     HuffEntry dc[16];
+};
+
+// Per-image tables of the auto_generate_huffman_table mode (codec.py:146-148), built on the device:
+// the (code,len) entries plus the serialised header (codec.py:102-112, 73-84) as MSB-first words.
+constexpr int kMaxHdrWords = 416;   // 160 + 16*(8+32) + 16 + 256*(16+32) bits
+struct AutoTables {
+    HuffTables tab;
+    uint32_t hdr_bits;
+    uint32_t status;
+    uint32_t hdr_words[kMaxHdrWords];
 };
 
 }  // namespace tic
