@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtinyimgcodec_cuda.so")
+LIB_PATH = os.environ.get("TIC_LIB_PATH") or os.path.join(_HERE, "libtinyimgcodec_cuda.so")   # override: kernel experiments
 
 TIC_OK = 0
 TIC_E_INVALID = -1

@@ -18,7 +18,7 @@ namespace tic {
 // compress(): one CTA per tile, tiles taken in stream order through a ticket so that the
 // decoupled look-back can never wait on a tile that has not started.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTile, 4)
+__global__ void __launch_bounds__(kTile, 8)
 encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restrict__ descs, int n_images,
                     int uniform_tpi, long long ntiles, unsigned long long* __restrict__ tile_status,
                     unsigned long long* __restrict__ tile_tail, unsigned long long* __restrict__ counters,
@@ -87,112 +87,138 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
     const int bitpos = hdr_bits + warp_base + incl - bits;   // tile-relative bit offset of this block
     tile_bits += hdr_bits;
     const long long agg = (long long)tile_bits;
-    const bool stage_ok = tile_bits <= (kStageWords - 2) * 32;   // only long auto-table codes can overflow
 
     // publish the aggregate as early as possible: successors only need it for their offset
     if (t == 0) {
         st_relaxed_u64(&tile_status[tile], kFlagAgg | (ti.closing ? kClosingBit : 0ull) | (unsigned long long)agg);
         if (sm.err) atomicOr(&status[ti.img], TIC_STATUS_CATEGORY);
-        if (!stage_ok) atomicOr(&status[ti.img], TIC_STATUS_LONGCODE);
     }
-    const int nwords = stage_ok ? ((tile_bits + 31) >> 5) : 0;
+    const int nwords = (tile_bits + 31) >> 5;       // tile-relative words holding data
     const int hdr_words = (hdr_bits + 31) >> 5;
-    for (int i = t; i <= nwords; i += kTile) {
-        uint32_t w = 0;
-        if (i < hdr_words) {
-            if (auto_tabs) {
-                w = auto_tabs[ti.img].hdr_words[i];
-            } else {   // struct.pack("III") is little-endian, the stream is MSB-first; flag word 0
-                const uint32_t v = i == 0 ? (uint32_t)ti.h : (i == 1 ? (uint32_t)ti.w : (i == 2 ? (uint32_t)quality : 0u));
-                w = __byte_perm(v, 0, 0x0123);
-            }
-        }
-        sm.stage[i] = w;
-    }
-    __syncthreads();
+    const int rounds = nwords > kWinWords ? (nwords + kWinWords - 1) / kWinWords : 1;
+    uint32_t* out_words = reinterpret_cast<uint32_t*>(out);
+    long long s_bits = 0, e_bits = 0, g0 = 0, g_end = 0;
+    int sh = 0;
+    bool fits = true;
+    unsigned int v_first = 0, tail = 0;             // thread 0: word g0 without its head; trailing partial word
 
-    // ---- bits into the tile-relative staging buffer ---------------------------------------------
-    if (t < ti.nb && stage_ok) block_emit(sm, t, bias, bitpos);
-
-    // ---- decoupled look-back (warp 0, 32 predecessors per round): absolute bit position ----------
-    if (warp == 0) {
-        // composite of the tiles between the look-back cursor and this tile:
-        //   g(P) = closed ? round_up128(P + a) + b : P + a
-        long long a = 0, b = 0;
-        bool closed = false;
-        long long p_in = 0;
-        long long j = tile - 1;   // nearest predecessor not folded in yet
-        while (true) {
-            const long long idx = j - lane;
-            unsigned long long s = kFlagPrefix;   // before the first tile: prefix 0
-            if (idx >= 0) s = ld_relaxed_u64(&tile_status[idx]);
-            while (__any_sync(0xffffffffu, (s & kFlagMask) == 0)) {
-                if ((s & kFlagMask) == 0) s = ld_relaxed_u64(&tile_status[idx]);
-            }
-            const unsigned prefix_mask = __ballot_sync(0xffffffffu, (s & kFlagMask) == kFlagPrefix);
-            const int p = prefix_mask ? (__ffs(prefix_mask) - 1) : 32;   // lanes < p hold aggregates
-            const unsigned below = p >= 32 ? 0xffffffffu : ((1u << p) - 1u);
-            const unsigned closing_mask = __ballot_sync(0xffffffffu, (s & kClosingBit) != 0) & below;
-            const long long val = (long long)(s & kValueMask);
-            if (closing_mask == 0) {
-                long long v = (lane < p) ? val : 0;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                a += v;
-            } else {
-                for (int l = 0; l < p; l++) {   // nearest first: prepend tile j-l to the composite
-                    long long v = __shfl_sync(0xffffffffu, val, l);
-                    if ((closing_mask >> l) & 1) {   // it closes an image: what follows is 128-bit aligned
-                        b = closed ? round_up128(a) + b : a;
-                        a = v;
-                        closed = true;
-                    } else {
-                        a += v;
-                    }
+    for (int r = 0; r < rounds; r++) {
+        const int wbase = r * kWinWords;
+        const int nw = nwords - wbase < kWinWords ? nwords - wbase : kWinWords;   // data words in this window
+        for (int i = t; i <= nw; i += kTile) {       // clear the window (+1 word read by the funnel shift)
+            uint32_t w = 0;
+            if (wbase + i < hdr_words) {
+                if (auto_tabs) {
+                    w = auto_tabs[ti.img].hdr_words[wbase + i];
+                } else {   // struct.pack("III") is little-endian, the stream is MSB-first; flag word 0
+                    const uint32_t v = i == 0 ? (uint32_t)ti.h : (i == 1 ? (uint32_t)ti.w : (i == 2 ? (uint32_t)quality : 0u));
+                    w = __byte_perm(v, 0, 0x0123);
                 }
             }
-            if (p < 32) {
-                long long base = __shfl_sync(0xffffffffu, val, p);
-                p_in = closed ? round_up128(base + a) + b : base + a;
-                break;
-            }
-            j -= 32;
+            sm.stage[i] = w;
         }
-        if (lane == 0) {
-            const long long e_bits = p_in + agg;   // end of this tile's data bits
-            const long long p_out = ti.closing ? round_up128(e_bits) : e_bits;
-            st_relaxed_u64(&tile_status[tile], kFlagPrefix | (unsigned long long)p_out);
-            const long long s_bits = p_in;   // the header (first tile) sits in the staging buffer too
-            sm.s_bits = s_bits;
-            const long long end_byte = (e_bits + 7) >> 3;
-            const bool fits = ((end_byte + 3) & ~3ll) <= out_cap;
-            if (!fits) atomicExch(&counters[kCtrOverflow], 1ull);
-            if (ti.first) out_off[ti.img] = p_in >> 3;
-            if (ti.closing) {
-                out_end[ti.img] = end_byte;
-                atomicMax(&counters[kCtrTotalBits], (unsigned long long)(end_byte << 3));
+        __syncthreads();
+
+        // ---- bits into the window of the tile-relative staging buffer ----------------------------
+        if (t < ti.nb && bitpos + bits > wbase * 32 && bitpos < (wbase + kWinWords) * 32)
+            block_emit(sm, t, bias, bitpos, wbase);
+
+        // ---- decoupled look-back (warp 0, 32 predecessors per round): absolute bit position -------
+        if (r == 0 && warp == 0) {
+            // composite of the tiles between the look-back cursor and this tile:
+            //   g(P) = closed ? round_up128(P + a) + b : P + a
+            long long a = 0, b = 0;
+            bool closed = false;
+            long long p_in = 0;
+            long long j = tile - 1;   // nearest predecessor not folded in yet
+            while (true) {
+                const long long idx = j - lane;
+                unsigned long long sw = kFlagPrefix;   // before the first tile: prefix 0
+                if (idx >= 0) sw = ld_relaxed_u64(&tile_status[idx]);
+                while (__any_sync(0xffffffffu, (sw & kFlagMask) == 0)) {
+                    if ((sw & kFlagMask) == 0) sw = ld_relaxed_u64(&tile_status[idx]);
+                }
+                const unsigned prefix_mask = __ballot_sync(0xffffffffu, (sw & kFlagMask) == kFlagPrefix);
+                const int p = prefix_mask ? (__ffs(prefix_mask) - 1) : 32;   // lanes < p hold aggregates
+                const unsigned below = p >= 32 ? 0xffffffffu : ((1u << p) - 1u);
+                const unsigned closing_mask = __ballot_sync(0xffffffffu, (sw & kClosingBit) != 0) & below;
+                const long long val = (long long)(sw & kValueMask);
+                if (closing_mask == 0) {
+                    long long v = (lane < p) ? val : 0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    a += v;
+                } else {
+                    for (int l = 0; l < p; l++) {   // nearest first: prepend tile j-l to the composite
+                        long long v = __shfl_sync(0xffffffffu, val, l);
+                        if ((closing_mask >> l) & 1) {   // it closes an image: what follows is 128-bit aligned
+                            b = closed ? round_up128(a) + b : a;
+                            a = v;
+                            closed = true;
+                        } else {
+                            a += v;
+                        }
+                    }
+                }
+                if (p < 32) {
+                    long long base = __shfl_sync(0xffffffffu, val, p);
+                    p_in = closed ? round_up128(base + a) + b : base + a;
+                    break;
+                }
+                j -= 32;
             }
+            if (lane == 0) {
+                const long long eb = p_in + agg;   // end of this tile's data bits
+                const long long p_out = ti.closing ? round_up128(eb) : eb;
+                st_relaxed_u64(&tile_status[tile], kFlagPrefix | (unsigned long long)p_out);
+                sm.s_bits = p_in;   // the header (first tile) sits in the staging buffer too
+                const long long end_byte = (eb + 7) >> 3;
+                if (((end_byte + 3) & ~3ll) > out_cap) atomicExch(&counters[kCtrOverflow], 1ull);
+                if (ti.first) out_off[ti.img] = p_in >> 3;
+                if (ti.closing) {
+                    out_end[ti.img] = end_byte;
+                    atomicMax(&counters[kCtrTotalBits], (unsigned long long)(end_byte << 3));
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- copy-out: funnel shift to the global alignment, byte-swap to MSB-first byte order ----
+        if (r == 0) {
+            s_bits = sm.s_bits;
+            e_bits = s_bits + tile_bits;
+            sh = (int)(s_bits & 31);
+            g0 = s_bits >> 5;
+            // words [g0, g_end): full words, plus the final partial word when this tile closes the image
+            g_end = ti.closing ? ((e_bits + 31) >> 5) : (e_bits >> 5);
+            fits = ((((e_bits + 7) >> 3) + 3) & ~3ll) <= out_cap;
+        }
+        const int nout = (int)(g_end - g0);                      // output words of this tile
+        const int j_hi = wbase + kWinWords < nout ? wbase + kWinWords : nout;
+        const unsigned int carry = r ? sm.carry : 0u;            // tile-relative word wbase-1
+        for (int jdx = wbase + t; jdx < j_hi; jdx += kTile) {
+            const int i = jdx - wbase;
+            const uint32_t prev = i ? sm.stage[i - 1] : carry;
+            const uint32_t v = __funnelshift_r(sm.stage[i], prev, sh);
+            if (jdx == 0) v_first = v;                            // word g0: written last, with its head
+            else if (fits) out_words[g0 + jdx] = __byte_perm(v, 0, 0x0123);
+        }
+        if (t == 0 && r == rounds - 1 && (e_bits & 31)) {         // trailing partial word for the next tile
+            const int i = (int)((e_bits >> 5) - g0) - wbase;
+            const uint32_t prev = i ? sm.stage[i - 1] : carry;
+            tail = __funnelshift_r(sm.stage[i], prev, sh);
+        }
+        if (r + 1 < rounds) {                                     // multi-round tiles only
+            __syncthreads();
+            if (t == 0) sm.carry = sm.stage[kWinWords - 1];
+            __syncthreads();
         }
     }
-    __syncthreads();
-
-    // ---- copy-out: funnel shift to the global alignment, byte-swap to MSB-first byte order ------
-    const long long s_bits = sm.s_bits;
-    const long long e_bits = s_bits + tile_bits;
-    const int sh = (int)(s_bits & 31);
-    const long long g0 = s_bits >> 5;
-    // words [g0, g_end): full words, plus the final partial word when this tile closes the image
-    const long long g_end = ti.closing ? ((e_bits + 31) >> 5) : (e_bits >> 5);
-    const bool fits = stage_ok && ((((e_bits + 7) >> 3) + 3) & ~3ll) <= out_cap;
-    uint32_t* out_words = reinterpret_cast<uint32_t*>(out);
-    const bool need_prev = !ti.first && sh != 0;   // word g0 starts with the previous tile's last bits
     if (t == 0) {
         // Hand the trailing partial word to the next tile FIRST (it only depends on the previous
         // tile's tail when this whole tile sits inside one word), then wait for our own head.
-        unsigned int tail = 0;
-        const int jt = (int)((e_bits >> 5) - g0);
-        if (e_bits & 31) tail = __funnelshift_r(sm.stage[jt], jt ? sm.stage[jt - 1] : 0u, sh);
-        const bool chained = need_prev && jt == 0;
+        const bool need_prev = !ti.first && sh != 0;   // word g0 starts with the previous tile's last bits
+        const bool chained = need_prev && (e_bits >> 5) == g0;
         if (!ti.closing && !chained) st_relaxed_u64(&tile_tail[tile], (1ull << 63) | tail);
         unsigned int tail_prev = 0;
         if (need_prev) {
@@ -201,15 +227,7 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
             tail_prev = (unsigned int)tw;
         }
         if (!ti.closing && chained) st_relaxed_u64(&tile_tail[tile], (1ull << 63) | tail | tail_prev);
-        if (g0 < g_end && fits) {
-            uint32_t v = __funnelshift_r(sm.stage[0], 0u, sh) | tail_prev;
-            out_words[g0] = __byte_perm(v, 0, 0x0123);
-        }
-    }
-    for (long long g = g0 + 1 + t; g < g_end; g += kTile) {
-        int jdx = (int)(g - g0);
-        uint32_t v = __funnelshift_r(sm.stage[jdx], sm.stage[jdx - 1], sh);
-        if (fits) out_words[g] = __byte_perm(v, 0, 0x0123);
+        if (g0 < g_end && fits) out_words[g0] = __byte_perm(v_first | tail_prev, 0, 0x0123);
     }
   }   // persistent loop
 }
@@ -217,7 +235,7 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
 // ---------------------------------------------------------------------------------------------
 // auto_generate_huffman_table=True (codec.py:146-148): symbol statistics, then the tables
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTile, 4)
+__global__ void __launch_bounds__(kTile, 8)
 symbol_stats_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restrict__ descs, int n_images,
                     int uniform_tpi, long long ntiles, unsigned long long* __restrict__ counters,
                     uint32_t* __restrict__ g_hist, unsigned long long* __restrict__ g_first,

@@ -29,8 +29,12 @@ namespace tic {
 
 constexpr int kTile = 128;                                  // blocks (= threads) per tile
 constexpr int kWarps = kTile / 32;
-constexpr int kStageWords = (kTile * 1662 + 31) / 32 + kMaxHdrWords + 4;   // worst case bits of a tile + header
-constexpr int kWorkCap = 512;                               // exact-path worklist entries
+// The bits of a tile are packed through a WINDOW of kWinWords 32-bit words of shared memory: a tile
+// whose stream is longer (worst case 128 x 1662 bits + a table header) is emitted in several
+// rounds.  Typical tiles (<= 320 bits per block on average) need one.
+constexpr int kWinWords = 1280;
+constexpr int kStageWords = kWinWords + 2;
+constexpr int kWorkCap = 64;                                // exact-path worklist entries per round
 constexpr int kExactPerRound = kTile / 8;                   // 8 lanes per worklist entry
 
 // look-back status word: [63:62] flag, [61] closing, [60:0] value
@@ -211,7 +215,8 @@ struct TileShared {
     unsigned int tail_prev;
     TileInfo ti;                     // the tile being encoded (written by warp 0)
     long long tile;                  // its index, or >= ntiles when the work is exhausted
-    uint32_t stage[kStageWords];     // tile-relative MSB-first bit buffer
+    unsigned int carry;              // last word of the previous window (multi-round tiles)
+    alignas(16) uint32_t stage[kStageWords];   // window of the tile-relative MSB-first bit buffer
 };
 
 
@@ -502,10 +507,10 @@ __device__ __forceinline__ void block_stats(const TileShared& sm, int t, int bia
 }
 
 struct BitSink {
-    uint32_t* stage;
+    uint32_t* stage;          // window of the tile's bit buffer
     unsigned long long acc;   // left-aligned pending bits
     int nb;                   // number of pending bits (< 32 between calls)
-    int word;
+    int word;                 // window-relative index of the word being filled (may be outside)
     bool first;
     __device__ __forceinline__ void put(uint32_t code, int len) {   // 0 <= len <= 32
         if (len == 0) return;
@@ -513,14 +518,17 @@ struct BitSink {
         nb += len;
         if (nb >= 32) {
             uint32_t w = (uint32_t)(acc >> 32);
-            if (first) { atomicOr(&stage[word], w); first = false; } else stage[word] = w;
+            if ((unsigned)word < (unsigned)kWinWords) {   // words outside the window belong to another round
+                if (first) atomicOr(&stage[word], w); else stage[word] = w;
+            }
+            first = false;
             word++;
             acc <<= 32;
             nb -= 32;
         }
     }
     __device__ __forceinline__ void flush() {
-        if (nb > 0) atomicOr(&stage[word], (uint32_t)(acc >> 32));
+        if (nb > 0 && (unsigned)word < (unsigned)kWinWords) atomicOr(&stage[word], (uint32_t)(acc >> 32));
     }
 };
 
@@ -528,12 +536,12 @@ __device__ __forceinline__ uint32_t value_bits(int v, int sz) {   // huffman.py:
     return (uint32_t)(v + (v >> 31)) & ((1u << sz) - 1u);
 }
 
-__device__ __forceinline__ void block_emit(TileShared& sm, int t, int bias, int bitpos) {
+__device__ __forceinline__ void block_emit(TileShared& sm, int t, int bias, int bitpos, int wbase) {
     BitSink s;
     s.stage = sm.stage;
     s.acc = 0;
     s.nb = bitpos & 31;
-    s.word = bitpos >> 5;
+    s.word = (bitpos >> 5) - wbase;
     s.first = true;
     int diff = sm.dcq[t + 1] - sm.dcq[t];
     int sz = bitlen(diff);
