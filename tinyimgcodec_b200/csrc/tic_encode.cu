@@ -14,228 +14,329 @@
 
 namespace tic {
 
+// Huffman tables -> shared memory in the form the walk wants (see TileShared::ac_tab).
+template <bool kAuto>
+__device__ __forceinline__ void load_tables(TileShared& sm, const HuffTables& g) {
+    for (int i = threadIdx.x; i < 256; i += kTile) {
+        const uint32_t len = g.ac[i].len, code = g.ac[i].code;
+        if constexpr (kAuto) sm.ac_tab[i] = make_uint2(code, len);
+        else sm.ac_tab[i] = len ? make_uint2(code << (i & 15), len + (uint32_t)(i & 15)) : make_uint2(0u, 0u);
+    }
+    if (threadIdx.x < 16) {
+        const int i = threadIdx.x;
+        const uint32_t len = g.dc[i].len, code = g.dc[i].code;
+        if constexpr (kAuto) sm.dc_tab[i] = make_uint2(code, len);
+        else sm.dc_tab[i] = len ? make_uint2(code << i, len + (uint32_t)i) : make_uint2(0u, 0u);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
-// compress(): one CTA per tile, tiles taken in stream order through a ticket so that the
-// decoupled look-back can never wait on a tile that has not started.
+// compress(), stage 1: every tile -> its bits in the arena + a TileRec.  Persistent CTAs, tiles
+// dealt round-robin; no tile waits for another.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTile, 8)
+template <bool kAuto>
+__global__ void __launch_bounds__(kTile, kCtasPerSm)
 encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restrict__ descs, int n_images,
-                    int uniform_tpi, long long ntiles, unsigned long long* __restrict__ tile_status,
-                    unsigned long long* __restrict__ tile_tail, unsigned long long* __restrict__ counters,
-                    uint8_t* __restrict__ out, long long out_cap, long long* __restrict__ out_off,
-                    long long* __restrict__ out_end, int* __restrict__ status, int quality,
-                    const AutoTables* __restrict__ auto_tabs) {
+                    int uniform_tpi, long long ntiles, TileRec* __restrict__ recs, uint4* __restrict__ arena,
+                    unsigned long long arena_cap16, unsigned long long* __restrict__ counters,
+                    int* __restrict__ status, int quality, const AutoTables* __restrict__ auto_tabs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileShared& sm = *reinterpret_cast<TileShared*>(smem_raw);
     const int t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
-    const int bias = qp.qbias;
 
-    // default tables -> shared memory, once per (persistent) CTA (constants.py:53-242)
-    for (int i = t; i < 256; i += kTile)
-        sm.ac_tab[i] = make_uint2(c_default_tables.ac[i].code, c_default_tables.ac[i].len);
-    if (t < 16) sm.dc_tab[t] = make_uint2(c_default_tables.dc[t].code, c_default_tables.dc[t].len);
+    if constexpr (!kAuto) load_tables<false>(sm, c_default_tables);   // constants.py:53-242
+    for (int i = t; i < kWinWords; i += kTile) sm.stage[i] = 0;
+    __syncthreads();
 
+    ExactStats st{0u, 0u};
     int tab_img = -1;   // auto mode: image whose tables are in shared memory
-  for (;;) {   // persistent: tiles are claimed in stream order through the ticket
-    __syncthreads();   // previous tile fully copied out; tables visible
-    if (warp == 0) {   // claim the next tile and find its image
-        long long tk = 0;
-        if (lane == 0) tk = (long long)atomicAdd(&counters[kCtrTicket], 1ull);
-        tk = __shfl_sync(0xffffffffu, tk, 0);
-        if (tk < ntiles) {
-            const TileInfo f = locate_tile(descs, n_images, tk, uniform_tpi);
-            if (lane == 0) sm.ti = f;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const TileInfo ti = locate_tile(descs, n_images, tile, uniform_tpi);
+        if constexpr (kAuto) {
+            if (tab_img != ti.img) {   // per-image tables (codec.py:146-148); CTA-uniform branch
+                __syncthreads();       // everyone is done with the previous image's tables
+                load_tables<true>(sm, auto_tabs[ti.img].tab);
+                tab_img = ti.img;
+                __syncthreads();
+            }
         }
-        if (lane == 0) { sm.tile = tk; sm.err = 0; }
-    }
-    __syncthreads();
-    const long long tile = sm.tile;
-    if (tile >= ntiles) break;
-    const TileInfo ti = sm.ti;
-    if (auto_tabs != nullptr && tab_img != ti.img) {   // per-image tables (codec.py:146-148); uniform branch
-        const HuffTables& g = auto_tabs[ti.img].tab;
-        for (int i = t; i < 256; i += kTile) sm.ac_tab[i] = make_uint2(g.ac[i].code, g.ac[i].len);
-        if (t < 16) sm.dc_tab[t] = make_uint2(g.dc[t].code, g.dc[t].len);
-        tab_img = ti.img;   // visible to everyone after the barriers inside transform_tile
-    }
 
-    transform_tile(ti, qp, sm, counters);
-
-    // ---- bit lengths and the CTA scan -------------------------------------------------------
-    int err = 0;
-    int bits = (t < ti.nb) ? block_bits(sm, t, bias, err) : 0;
-    int incl = bits;
+        // ---- per warp: coefficients, then the bits of every block into its private words ---------
+        transform_warp(ti, qp, sm, st);
+        int err = 0, bits = 0, nwords = 0, diff = 0;
+        if (t < ti.nb) {
+            diff = sm.dcq[t] - dc_before(sm, t);                      // codec.py:34-35
+            BitSink<false> s;
+            s.col = &sm.priv[0][t];
+            bits = walk_block<kAuto, false>(sm, t, diff, s, err);
+            nwords = s.cnt;
+        }
+        int incl = bits;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        int n = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += n;
-    }
-    if (lane == 31) sm.warp_bits[warp] = incl;
-    if (err) sm.err = 1;
-    __syncthreads();
-    int warp_base = 0, tile_bits = 0;
+        for (int o = 1; o < 32; o <<= 1) {
+            int n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += n;
+        }
+        const bool warp_err = __any_sync(0xffffffffu, err != 0);
+        if (lane == 31) { sm.warp_bits[warp] = incl; sm.warp_err[warp] = warp_err ? 1 : 0; }
+        __syncthreads();   // B1: warp totals visible; the staging window is zero (previous copy-out done)
+
+        int warp_base = 0, tile_bits = 0, tile_err = 0;
 #pragma unroll
-    for (int w = 0; w < kWarps; w++) {
-        int wb = sm.warp_bits[w];
-        if (w < warp) warp_base += wb;
-        tile_bits += wb;
-    }
-    // the first tile of an image carries the header in front of its blocks: 128 bits with the fixed
-    // tables (codec.py:102-114), 128 + the serialised tables in auto mode (codec.py:110-112)
-    const int hdr_bits = !ti.first ? 0 : (auto_tabs ? (int)auto_tabs[ti.img].hdr_bits : 128);
-    const int bitpos = hdr_bits + warp_base + incl - bits;   // tile-relative bit offset of this block
-    tile_bits += hdr_bits;
-    const long long agg = (long long)tile_bits;
+        for (int w = 0; w < kWarps; w++) {
+            const int wb = sm.warp_bits[w];
+            if (w < warp) warp_base += wb;
+            tile_bits += wb;
+            tile_err |= sm.warp_err[w];
+        }
+        // the first tile of an image carries the header in front of its blocks: 128 bits with the fixed
+        // tables (codec.py:102-114), 128 + the serialised tables in auto mode (codec.py:110-112)
+        const int hdr_bits = !ti.first ? 0 : (kAuto ? (int)auto_tabs[ti.img].hdr_bits : 128);
+        const int bitpos = hdr_bits + warp_base + incl - bits;   // tile-relative bit offset of this block
+        tile_bits += hdr_bits;
+        const int nw_tile = (tile_bits + 31) >> 5;               // tile-relative words holding data
+        const int n16_tile = (nw_tile + 3) >> 2;
+        if (t == 0) {   // reserve the tile's slot in the arena; the latency hides behind the placement
+            const unsigned long long off = atomicAdd(&counters[kCtrArena], (unsigned long long)n16_tile);
+            const bool ok = off + (unsigned long long)n16_tile <= arena_cap16;
+            if (!ok) atomicExch(&counters[kCtrOverflow], 1ull);
+            sm.arena_off = ok ? (unsigned int)off : 0xffffffffu;
+            TileRec r;
+            r.bits = (uint32_t)tile_bits | (ti.first ? kRecFirst : 0u) | (ti.closing ? kRecClosing : 0u);
+            r.off16 = ok ? (unsigned int)off : 0u;
+            r.img = ti.img;
+            r.pad = ok ? 0u : 1u;
+            *reinterpret_cast<uint4*>(&recs[tile]) = *reinterpret_cast<uint4*>(&r);
+            if (tile_err) atomicOr(&status[ti.img], TIC_STATUS_CATEGORY);
+        }
 
-    // publish the aggregate as early as possible: successors only need it for their offset
-    if (t == 0) {
-        st_relaxed_u64(&tile_status[tile], kFlagAgg | (ti.closing ? kClosingBit : 0ull) | (unsigned long long)agg);
-        if (sm.err) atomicOr(&status[ti.img], TIC_STATUS_CATEGORY);
-    }
-    const int nwords = (tile_bits + 31) >> 5;       // tile-relative words holding data
-    const int hdr_words = (hdr_bits + 31) >> 5;
-    const int rounds = nwords > kWinWords ? (nwords + kWinWords - 1) / kWinWords : 1;
-    uint32_t* out_words = reinterpret_cast<uint32_t*>(out);
-    long long s_bits = 0, e_bits = 0, g0 = 0, g_end = 0;
-    int sh = 0;
-    bool fits = true;
-    unsigned int v_first = 0, tail = 0;             // thread 0: word g0 without its head; trailing partial word
-
-    for (int r = 0; r < rounds; r++) {
-        const int wbase = r * kWinWords;
-        const int nw = nwords - wbase < kWinWords ? nwords - wbase : kWinWords;   // data words in this window
-        for (int i = t; i <= nw; i += kTile) {       // clear the window (+1 word read by the funnel shift)
-            uint32_t w = 0;
-            if (wbase + i < hdr_words) {
-                if (auto_tabs) {
-                    w = auto_tabs[ti.img].hdr_words[wbase + i];
-                } else {   // struct.pack("III") is little-endian, the stream is MSB-first; flag word 0
-                    const uint32_t v = i == 0 ? (uint32_t)ti.h : (i == 1 ? (uint32_t)ti.w : (i == 2 ? (uint32_t)quality : 0u));
-                    w = __byte_perm(v, 0, 0x0123);
+        const int hdr_words = (hdr_bits + 31) >> 5;
+        const int rounds = nw_tile > kWinWords ? (nw_tile + kWinWords - 1) / kWinWords : 1;
+        for (int r = 0; r < rounds; r++) {
+            const int wbase = r * kWinWords;
+            // ---- header words (they OR into the zeroed window like everything else) --------------
+            if (ti.first) {
+                for (int i = wbase + t; i < hdr_words && i < wbase + kWinWords; i += kTile) {
+                    uint32_t w;
+                    if constexpr (kAuto) {
+                        w = auto_tabs[ti.img].hdr_words[i];
+                    } else {   // struct.pack("III") is little-endian, the stream is MSB-first; flag word 0
+                        const uint32_t v = i == 0 ? (uint32_t)ti.h : (i == 1 ? (uint32_t)ti.w : (i == 2 ? (uint32_t)quality : 0u));
+                        w = __byte_perm(v, 0, 0x0123);
+                    }
+                    if (w) atomicOr(&sm.stage[i - wbase], w);
                 }
             }
-            sm.stage[i] = w;
-        }
-        __syncthreads();
-
-        // ---- bits into the window of the tile-relative staging buffer ----------------------------
-        if (t < ti.nb && bitpos + bits > wbase * 32 && bitpos < (wbase + kWinWords) * 32)
-            block_emit(sm, t, bias, bitpos, wbase);
-
-        // ---- decoupled look-back (warp 0, 32 predecessors per round): absolute bit position -------
-        if (r == 0 && warp == 0) {
-            // composite of the tiles between the look-back cursor and this tile:
-            //   g(P) = closed ? round_up128(P + a) + b : P + a
-            long long a = 0, b = 0;
-            bool closed = false;
-            long long p_in = 0;
-            long long j = tile - 1;   // nearest predecessor not folded in yet
-            while (true) {
-                const long long idx = j - lane;
-                unsigned long long sw = kFlagPrefix;   // before the first tile: prefix 0
-                if (idx >= 0) sw = ld_relaxed_u64(&tile_status[idx]);
-                while (__any_sync(0xffffffffu, (sw & kFlagMask) == 0)) {
-                    if ((sw & kFlagMask) == 0) sw = ld_relaxed_u64(&tile_status[idx]);
-                }
-                const unsigned prefix_mask = __ballot_sync(0xffffffffu, (sw & kFlagMask) == kFlagPrefix);
-                const int p = prefix_mask ? (__ffs(prefix_mask) - 1) : 32;   // lanes < p hold aggregates
-                const unsigned below = p >= 32 ? 0xffffffffu : ((1u << p) - 1u);
-                const unsigned closing_mask = __ballot_sync(0xffffffffu, (sw & kClosingBit) != 0) & below;
-                const long long val = (long long)(sw & kValueMask);
-                if (closing_mask == 0) {
-                    long long v = (lane < p) ? val : 0;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                    a += v;
-                } else {
-                    for (int l = 0; l < p; l++) {   // nearest first: prepend tile j-l to the composite
-                        long long v = __shfl_sync(0xffffffffu, val, l);
-                        if ((closing_mask >> l) & 1) {   // it closes an image: what follows is 128-bit aligned
-                            b = closed ? round_up128(a) + b : a;
-                            a = v;
-                            closed = true;
-                        } else {
-                            a += v;
+            // ---- private words -> window, shifted to the block's bit offset ------------------------
+            if (t < ti.nb && bitpos + bits > wbase * 32 && bitpos < (wbase + kWinWords) * 32) {
+                const int sh = bitpos & 31;
+                const int w0 = (bitpos >> 5) - wbase;
+                if (nwords <= kPrivWords) {
+                    const int nout = (sh + bits + 31) >> 5;
+                    uint32_t prev = 0;
+                    for (int j = 0; j < nout; j++) {
+                        const uint32_t x = j < nwords ? sm.priv[j][t] : 0u;
+                        const uint32_t v = __funnelshift_r(x, prev, sh);   // (prev << (32 - sh)) | (x >> sh)
+                        prev = x;
+                        const int W = w0 + j;
+                        if ((unsigned)W < (unsigned)kWinWords) {
+                            // a word entirely inside this block needs no atomic
+                            if (j > 0 && (j + 1) * 32 - sh <= bits) sm.stage[W] = v; else atomicOr(&sm.stage[W], v);
                         }
                     }
-                }
-                if (p < 32) {
-                    long long base = __shfl_sync(0xffffffffu, val, p);
-                    p_in = closed ? round_up128(base + a) + b : base + a;
-                    break;
-                }
-                j -= 32;
-            }
-            if (lane == 0) {
-                const long long eb = p_in + agg;   // end of this tile's data bits
-                const long long p_out = ti.closing ? round_up128(eb) : eb;
-                st_relaxed_u64(&tile_status[tile], kFlagPrefix | (unsigned long long)p_out);
-                sm.s_bits = p_in;   // the header (first tile) sits in the staging buffer too
-                const long long end_byte = (eb + 7) >> 3;
-                if (((end_byte + 3) & ~3ll) > out_cap) atomicExch(&counters[kCtrOverflow], 1ull);
-                if (ti.first) out_off[ti.img] = p_in >> 3;
-                if (ti.closing) {
-                    out_end[ti.img] = end_byte;
-                    atomicMax(&counters[kCtrTotalBits], (unsigned long long)(end_byte << 3));
+                } else {   // long block: walk again, straight into the window
+                    BitSink<true> s;
+                    s.stage = sm.stage; s.w0 = w0; s.sh = sh;
+                    int e2 = 0;
+                    walk_block<kAuto, true>(sm, t, diff, s, e2);
                 }
             }
-        }
-        __syncthreads();
+            __syncthreads();   // B2: window complete, arena offset visible
 
-        // ---- copy-out: funnel shift to the global alignment, byte-swap to MSB-first byte order ----
-        if (r == 0) {
-            s_bits = sm.s_bits;
-            e_bits = s_bits + tile_bits;
-            sh = (int)(s_bits & 31);
-            g0 = s_bits >> 5;
-            // words [g0, g_end): full words, plus the final partial word when this tile closes the image
-            g_end = ti.closing ? ((e_bits + 31) >> 5) : (e_bits >> 5);
-            fits = ((((e_bits + 7) >> 3) + 3) & ~3ll) <= out_cap;
-        }
-        const int nout = (int)(g_end - g0);                      // output words of this tile
-        const int j_hi = wbase + kWinWords < nout ? wbase + kWinWords : nout;
-        const unsigned int carry = r ? sm.carry : 0u;            // tile-relative word wbase-1
-        for (int jdx = wbase + t; jdx < j_hi; jdx += kTile) {
-            const int i = jdx - wbase;
-            const uint32_t prev = i ? sm.stage[i - 1] : carry;
-            const uint32_t v = __funnelshift_r(sm.stage[i], prev, sh);
-            if (jdx == 0) v_first = v;                            // word g0: written last, with its head
-            else if (fits) out_words[g0 + jdx] = __byte_perm(v, 0, 0x0123);
-        }
-        if (t == 0 && r == rounds - 1 && (e_bits & 31)) {         // trailing partial word for the next tile
-            const int i = (int)((e_bits >> 5) - g0) - wbase;
-            const uint32_t prev = i ? sm.stage[i - 1] : carry;
-            tail = __funnelshift_r(sm.stage[i], prev, sh);
-        }
-        if (r + 1 < rounds) {                                     // multi-round tiles only
-            __syncthreads();
-            if (t == 0) sm.carry = sm.stage[kWinWords - 1];
-            __syncthreads();
+            // ---- window -> arena (16-byte stores), and the window is zero again -----------------
+            const unsigned int aoff = sm.arena_off;
+            const int i_end = (n16_tile - wbase / 4) < kWinWords / 4 ? (n16_tile - wbase / 4) : kWinWords / 4;
+            uint4* st4 = reinterpret_cast<uint4*>(sm.stage);
+            for (int i = t; i < i_end; i += kTile) {
+                const uint4 v = st4[i];
+                st4[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (aoff != 0xffffffffu) arena[(size_t)aoff + (size_t)(wbase / 4) + i] = v;
+            }
+            if (r + 1 < rounds) __syncthreads();
         }
     }
-    if (t == 0) {
-        // Hand the trailing partial word to the next tile FIRST (it only depends on the previous
-        // tile's tail when this whole tile sits inside one word), then wait for our own head.
-        const bool need_prev = !ti.first && sh != 0;   // word g0 starts with the previous tile's last bits
-        const bool chained = need_prev && (e_bits >> 5) == g0;
-        if (!ti.closing && !chained) st_relaxed_u64(&tile_tail[tile], (1ull << 63) | tail);
-        unsigned int tail_prev = 0;
-        if (need_prev) {
-            unsigned long long tw;
-            do { tw = ld_relaxed_u64(&tile_tail[tile - 1]); } while ((tw >> 63) == 0);
-            tail_prev = (unsigned int)tw;
-        }
-        if (!ti.closing && chained) st_relaxed_u64(&tile_tail[tile], (1ull << 63) | tail | tail_prev);
-        if (g0 < g_end && fits) out_words[g0] = __byte_perm(v_first | tail_prev, 0, 0x0123);
+    // exact-path statistics: one atomic per warp at the very end
+    unsigned int items = st.items, changed = st.changed;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        items += __shfl_xor_sync(0xffffffffu, items, o);
+        changed += __shfl_xor_sync(0xffffffffu, changed, o);
     }
-  }   // persistent loop
+    if (lane == 0) {
+        if (items) atomicAdd(&counters[kCtrExactItems], (unsigned long long)items);
+        if (changed) atomicAdd(&counters[kCtrExactChanged], (unsigned long long)changed);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// compress(), stage 2: absolute bit position of every tile.  Chunks of kScanChunk tiles:
+//   scan_chunks_kernel   what each chunk does to the position (a Span)
+//   scan_spine_kernel    one CTA: position at the start of every chunk
+//   scan_apply_kernel    position of every tile; stream offset / end of every image
+// ---------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256, kScanItems = 8, kScanChunk = kScanThreads * kScanItems;
+
+// Exclusive scan of one Span per thread over the CTA (in thread order); `total` = all of them.
+template <int kThreads>
+__device__ __forceinline__ Span cta_exclusive_span(const Span& mine, Span* warp_tot /* smem [kThreads/32] */, Span& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Span incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const Span n = span_shfl_up(incl, o);
+        if (lane >= o) incl = span_then(n, incl);
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    Span before{0, 0, 0};
+    total = Span{0, 0, 0};
+    for (int w = 0; w < kThreads / 32; w++) {
+        if (w == warp) before = total;
+        total = span_then(total, warp_tot[w]);
+    }
+    Span up = span_shfl_up(incl, 1);
+    if (lane == 0) up = Span{0, 0, 0};
+    __syncthreads();   // warp_tot may be reused by the caller
+    return span_then(before, up);
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_chunks_kernel(const TileRec* __restrict__ recs, long long ntiles, Span* __restrict__ chunk_span) {
+    __shared__ Span warp_tot[kScanThreads / 32];
+    const long long base = (long long)blockIdx.x * kScanChunk + (long long)threadIdx.x * kScanItems;
+    Span mine{0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++)
+        if (base + i < ntiles) mine = span_then(mine, span_of(recs[base + i].bits));
+    Span total;
+    cta_exclusive_span<kScanThreads>(mine, warp_tot, total);
+    if (threadIdx.x == 0) chunk_span[blockIdx.x] = total;
+}
+
+constexpr int kSpineThreads = 1024;
+__global__ void __launch_bounds__(kSpineThreads)
+scan_spine_kernel(const Span* __restrict__ chunk_span, long long nchunks, long long* __restrict__ chunk_pos) {
+    __shared__ Span warp_tot[kSpineThreads / 32];
+    const long long per = (nchunks + kSpineThreads - 1) / kSpineThreads;
+    const long long lo = (long long)threadIdx.x * per;
+    const long long hi = lo + per < nchunks ? lo + per : nchunks;
+    Span mine{0, 0, 0};
+    for (long long c = lo; c < hi; c++) mine = span_then(mine, chunk_span[c]);
+    Span total;
+    const Span before = cta_exclusive_span<kSpineThreads>(mine, warp_tot, total);
+    long long p = span_apply(0, before);
+    for (long long c = lo; c < hi; c++) {
+        chunk_pos[c] = p;
+        p = span_apply(p, chunk_span[c]);
+    }
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+scan_apply_kernel(const TileRec* __restrict__ recs, long long ntiles, const long long* __restrict__ chunk_pos,
+                  long long* __restrict__ tile_pos, long long out_cap, long long* __restrict__ out_off,
+                  long long* __restrict__ out_end, unsigned long long* __restrict__ counters) {
+    __shared__ Span warp_tot[kScanThreads / 32];
+    const long long base = (long long)blockIdx.x * kScanChunk + (long long)threadIdx.x * kScanItems;
+    uint32_t rb[kScanItems];
+    int img[kScanItems];
+    Span mine{0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        rb[i] = 0; img[i] = 0;
+        if (base + i < ntiles) {
+            const TileRec r = recs[base + i];
+            rb[i] = r.bits; img[i] = r.img;
+            mine = span_then(mine, span_of(r.bits));
+        }
+    }
+    Span total;
+    const Span before = cta_exclusive_span<kScanThreads>(mine, warp_tot, total);
+    long long p = span_apply(chunk_pos[blockIdx.x], before);
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        if (base + i >= ntiles) break;
+        tile_pos[base + i] = p;
+        const long long eb = p + (long long)(rb[i] & kRecBitsMask);   // end of this tile's data bits
+        if (rb[i] & kRecFirst) out_off[img[i]] = p >> 3;
+        if (rb[i] & kRecClosing) {
+            const long long end_byte = (eb + 7) >> 3;
+            out_end[img[i]] = end_byte;
+            if (((end_byte + 3) & ~3ll) > out_cap) atomicExch(&counters[kCtrOverflow], 1ull);
+            atomicMax(&counters[kCtrTotalBits], (unsigned long long)(end_byte << 3));
+        }
+        p = span_apply(p, span_of(rb[i]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// compress(), stage 3: arena -> dense output.  One warp per tile; every 32-bit output word is written
+// by exactly one lane: the tile that holds the word's LAST bit owns it (a closing tile also owns the
+// final partial word) and gathers the leading bits from the tiles before it.  Funnel shift to the
+// final bit position, byte swap to the stream's MSB-first byte order (bitbuffer.py:36-40).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tile_bits_at(const uint32_t* __restrict__ src, int nw, long long rb) {
+    // 32 bits of the tile starting at its bit rb >= 0, left-aligned; words past the tile read as 0
+    const int i = (int)(rb >> 5), s = (int)(rb & 31);
+    const uint32_t hi = i < nw ? __ldg(src + i) : 0u;
+    const uint32_t lo = (s && i + 1 < nw) ? __ldg(src + i + 1) : 0u;
+    return __funnelshift_l(lo, hi, s);
+}
+
+constexpr int kCompactThreads = 256;
+__global__ void __launch_bounds__(kCompactThreads)
+compact_kernel(const TileRec* __restrict__ recs, const long long* __restrict__ tile_pos, long long ntiles,
+               const uint32_t* __restrict__ arena_words, uint32_t* __restrict__ out_words, long long out_cap) {
+    const int lane = threadIdx.x & 31;
+    const long long nwarps = ((long long)gridDim.x * kCompactThreads) >> 5;
+    for (long long tile = ((long long)blockIdx.x * kCompactThreads + threadIdx.x) >> 5; tile < ntiles; tile += nwarps) {
+        const TileRec r = recs[tile];
+        if (r.pad) continue;   // the arena was exhausted: TIC_E_CAPACITY is already flagged
+        const long long bits = (long long)(r.bits & kRecBitsMask);
+        const long long P = tile_pos[tile], E = P + bits;
+        if (((((E + 7) >> 3) + 3) & ~3ll) > out_cap) continue;   // nothing past out_capacity is written
+        const uint32_t* src = arena_words + (size_t)r.off16 * 4;
+        const int nw = (int)((bits + 31) >> 5);
+        const long long w_lo = P >> 5;
+        const long long w_hi = (r.bits & kRecClosing) ? ((E + 31) >> 5) : (E >> 5);
+        for (long long W = w_lo + lane; W < w_hi; W += 32) {
+            const long long rb = W * 32 - P;   // tile-relative bit of the word's first bit
+            uint32_t val;
+            if (rb >= 0) {
+                val = tile_bits_at(src, nw, rb);
+            } else {   // the word starts in earlier tiles (never in another image: streams start 128-bit aligned)
+                int need = (int)(-rb);   // 1..31 leading bits
+                val = (nw > 0 ? __ldg(src) : 0u) >> need;
+                for (long long pt = tile - 1; need > 0 && pt >= 0; pt--) {
+                    const TileRec pr = recs[pt];
+                    const long long pb = (long long)(pr.bits & kRecBitsMask);
+                    if (pb == 0) continue;
+                    const int take = pb < need ? (int)pb : need;
+                    const uint32_t* psrc = arena_words + (size_t)pr.off16 * 4;
+                    const uint32_t v = tile_bits_at(psrc, (int)((pb + 31) >> 5), pb - take) >> (32 - take);
+                    val |= v << (32 - need);
+                    need -= take;
+                }
+            }
+            out_words[W] = __byte_perm(val, 0, 0x0123);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
 // auto_generate_huffman_table=True (codec.py:146-148): symbol statistics, then the tables
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTile, 8)
+__global__ void __launch_bounds__(kTile, kCtasPerSm)
 symbol_stats_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restrict__ descs, int n_images,
                     int uniform_tpi, long long ntiles, unsigned long long* __restrict__ counters,
                     uint32_t* __restrict__ g_hist, unsigned long long* __restrict__ g_first,
@@ -245,19 +346,17 @@ symbol_stats_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
     const int t = threadIdx.x;
     uint32_t* hist = sm.stage;                                                       // 272 counters
     unsigned long long* first = reinterpret_cast<unsigned long long*>(sm.stage + 512); // 272 keys
+    ExactStats st{0u, 0u};
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         __syncthreads();
-        if (t < 32) {
-            const TileInfo f = locate_tile(descs, n_images, tile, uniform_tpi);
-            if (t == 0) { sm.ti = f; sm.err = 0; }
-        }
+        const TileInfo ti = locate_tile(descs, n_images, tile, uniform_tpi);
         for (int i = t; i < 272; i += kTile) { hist[i] = 0; first[i] = ~0ull; }
+        if (t == 0) sm.warp_err[0] = 0;
         __syncthreads();
-        const TileInfo ti = sm.ti;
-        transform_tile(ti, qp, sm, counters);
+        transform_warp(ti, qp, sm, st);
         int err = 0;
-        if (t < ti.nb) block_stats(sm, t, qp.qbias, (unsigned long long)(ti.blk0 + t), hist, first, err);
-        if (err) sm.err = 1;
+        if (t < ti.nb) block_stats(sm, t, (unsigned long long)(ti.blk0 + t), hist, first, err);
+        if (err) sm.warp_err[0] = 1;
         __syncthreads();
         for (int i = t; i < 272; i += kTile) {
             uint32_t c = hist[i] + (i == 0 ? (uint32_t)ti.nb : 0u);   // one EOB per block (huffman.py:33)
@@ -266,8 +365,9 @@ symbol_stats_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
                 atomicMin(&g_first[(size_t)ti.img * 272 + i], first[i]);
             }
         }
-        if (t == 0 && sm.err) atomicOr(&status[ti.img], TIC_STATUS_TABLE);
+        if (t == 0 && sm.warp_err[0]) atomicOr(&status[ti.img], TIC_STATUS_TABLE);
     }
+    (void)counters;
 }
 
 // One thread per image: HuffmanTree (huffman.py:112-194) on CPython's heapq, which
@@ -428,25 +528,27 @@ __global__ void finalize_kernel(int n_images, const long long* __restrict__ out_
 // ---------------------------------------------------------------------------------------------
 // encode(): the same transform, coefficients written out (parity checkpoint for codec.py:26-43)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTile, 4)
+__global__ void __launch_bounds__(kTile, kCtasPerSm)
 coeffs_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restrict__ descs,
               unsigned long long* __restrict__ counters, int* __restrict__ dc, int* __restrict__ ac) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileShared& sm = *reinterpret_cast<TileShared*>(smem_raw);
     const int t = threadIdx.x;
-    if (t < 32) {
-        const TileInfo f = locate_tile(descs, 1, blockIdx.x, 0);
-        if (t == 0) sm.ti = f;
-    }
-    __syncthreads();
-    const TileInfo ti = sm.ti;
-    transform_tile(ti, qp, sm, counters);
+    const TileInfo ti = locate_tile(descs, 1, blockIdx.x, 0);
+    ExactStats st{0u, 0u};
+    transform_warp(ti, qp, sm, st);
     if (t < ti.nb) {
         const size_t b = (size_t)ti.blk0 + t;
-        dc[b] = sm.dcq[t + 1] - sm.dcq[t];
+        dc[b] = sm.dcq[t] - dc_before(sm, t);
         int* row = ac + b * 63;
-        for (int k = 1; k < 64; k++) row[k - 1] = coef_get(sm, t, k, qp.qbias);
+        const uint32_t lo = sm.nz_lo[t], hi = sm.nz_hi[t];
+        for (int k = 1; k < 64; k++) {   // a coefficient without its mask bit was never stored: it is 0
+            const bool nz = ((k < 32 ? lo : hi) >> (31 - (k & 31))) & 1u;
+            row[k - 1] = nz ? coef_get(sm, t, k) : 0;
+        }
     }
+    if (st.items) atomicAdd(&counters[kCtrExactItems], (unsigned long long)st.items);
+    if (st.changed) atomicAdd(&counters[kCtrExactChanged], (unsigned long long)st.changed);
 }
 
 }  // namespace tic
@@ -462,7 +564,9 @@ struct tic_handle_s {
     // workspace (grown on demand)
     ImageDesc* d_descs = nullptr;       size_t descs_cap = 0;
     ImageDesc* h_descs = nullptr;       // pinned
-    unsigned long long* d_tile_status = nullptr; size_t tiles_cap = 0;   // status + tail, 2 * tiles_cap
+    TileRec* d_recs = nullptr; long long* d_tile_pos = nullptr; size_t tiles_cap = 0;
+    Span* d_chunk_span = nullptr; long long* d_chunk_pos = nullptr; size_t chunks_cap = 0;
+    uint4* d_arena = nullptr;           size_t arena_cap16 = 0;          // 16-byte units
     unsigned long long* d_counters = nullptr;
     unsigned long long* h_counters = nullptr;    // pinned
     long long* d_out_end = nullptr;     size_t end_cap = 0;
@@ -478,7 +582,7 @@ struct tic_handle_s {
     cudaStream_t own_stream = nullptr;
     long long last_tiles = 0, last_blocks = 0, last_launches = 0;
     bool tables_ready = false;
-    int sm_count = 148, ctas_per_sm = 4;
+    int sm_count = 148, ctas_per_sm = kCtasPerSm;
 };
 
 #define TIC_CUDA(h, call)                                                                     \
@@ -509,7 +613,6 @@ static void build_default_tables(HuffTables& t) {
 // Quality -> quantiser constants.  qt follows tinyimgcodec/utils.py:50-53 operation by operation.
 static int make_quant_params(int quality, QuantParams& qp) {
     if (quality < 1 || quality > 99) return TIC_E_QUALITY;
-    double qt_min = 1e30;
     for (int i = 0; i < 64; i++) {
         double q;
         if (quality < 50) {
@@ -520,39 +623,27 @@ static int make_quant_params(int quality, QuantParams& qp) {
             q = (double)((long)kQuantBase[i] * factor) / 100.0;
         }
         qp.qt[i] = q;
-        if (q < qt_min) qt_min = q;
     }
-    // |coefficient| <= 1024 (orthonormal transform of 64 values in [-128,127]).  The fixed-point
-    // value round(t*2^F) + 2^(F-1) + 2^(k-1) must stay inside the +-2^22 window of the
-    // magic-number rounding; F is chosen with a factor 2 to spare.
-    const double t_max = 1024.0 / qt_min;
-    int F = 0;
-    while (F < 15 && (t_max + 2.0) * (double)(1 << (F + 1)) < 4194304.0 * 0.98) F++;
-    qp.fbits = F;
-    qp.qbias = 0x4B400000 >> F;
-    qp.pad[0] = qp.pad[1] = 0;
-    const int fmask = (1 << F) - 1;
     double aan[8];
     aan[0] = 1.0;
     for (int k = 1; k < 8; k++) aan[k] = cos(k * 3.14159265358979323846 / 16.0) * sqrt(2.0);
     // kFastErr: bound on |FP32 AAN coefficient - float64 reference coefficient| in coefficient
     // units ("tie guard").  A coefficient can only be rounded differently from the
-    // reference if a .5 tie lies within tol = kFastErr/qt (+ the FP32 multiplier's relative error)
-    // of the fast value; the window [-2^(k-1), 2^(k-1)) in 2^-F units around every tie covers
-    // tol*2^F + 1 (the +1: round-to-integer of the FFMA and the one-sided window).
+    // reference if a .5 tie lies within w = kFastErr/qt (+ the FP32 multiplier's relative error at
+    // the largest possible |t| = 1024/qt, + the rounding of the residual itself) of the fast value t;
+    // every such coefficient has |t - round(t)| > 0.5 - w and is recomputed exactly.
     const double kFastErr = 6.0e-4;
     for (int u = 0; u < 8; u++)
         for (int v = 0; v < 8; v++) {
             int i = u * 8 + v;
-            double m = (double)(1 << F) / (8.0 * aan[u] * aan[v] * qp.qt[i]);
+            double m = 1.0 / (8.0 * aan[u] * aan[v] * qp.qt[i]);
+            double w = kFastErr / qp.qt[i] + 2.4e-7 * (1024.0 / qp.qt[i]) + 1.0e-6;
+            double hthr = 0.5 - w;
+            if (hthr < 0.0) hthr = 0.0;   // every coefficient goes to the exact path
             qp.qmul[i] = (float)m;
-            double tol = kFastErr / qp.qt[i] + 2.4e-7 * (1024.0 / qp.qt[i]);
-            int g = (int)ceil(tol * (double)(1 << F) + 1.0);
-            int k = 1;
-            while ((1 << (k - 1)) < g + 1 && k <= F) k++;
-            if (k > F) k = F;   // whole range: every coefficient goes to the exact path
-            qp.gmask[i] = F == 0 ? 0 : (fmask & ~((1 << k) - 1));
-            qp.magic[i] = 12582912.0f + (F > 0 ? (float)(1 << (F - 1)) : 0.0f) + (F > 0 ? (float)(1 << (k - 1)) : 0.0f);
+            qp.hthr[i] = (float)(hthr * (1.0 - 1.0e-6));
+            // |d * zmul| < 1  =>  |t| < hthr: rounds to zero, and the residual test cannot fire
+            qp.zmul[i] = hthr > 0.0 ? (float)(m / hthr * (1.0 + 1.0e-6)) : 3.0e38f;
         }
     return TIC_OK;
 }
@@ -562,14 +653,16 @@ static int ensure_tables(tic_handle h) {
     HuffTables t;
     build_default_tables(t);
     TIC_CUDA(h, cudaMemcpyToSymbol(c_default_tables, &t, sizeof t));
-    TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(TileShared)));
+    TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(TileShared)));
     TIC_CUDA(h, cudaFuncSetAttribute(coeffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(TileShared)));
     TIC_CUDA(h, cudaFuncSetAttribute(symbol_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(TileShared)));
     int per_sm = 0;
-    TIC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_tiles_kernel, kTile, sizeof(TileShared)));
+    TIC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_tiles_kernel<false>, kTile, sizeof(TileShared)));
     cudaDeviceProp prop;
     TIC_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
     h->sm_count = prop.multiProcessorCount;
@@ -615,7 +708,8 @@ int tic_create(int device, tic_handle* out) {
 int tic_destroy(tic_handle h) {
     if (!h) return TIC_E_INVALID;
     cudaSetDevice(h->device);
-    cudaFree(h->d_descs); cudaFreeHost(h->h_descs); cudaFree(h->d_tile_status); cudaFree(h->d_counters);
+    cudaFree(h->d_descs); cudaFreeHost(h->h_descs); cudaFree(h->d_recs); cudaFree(h->d_tile_pos); cudaFree(h->d_chunk_span); cudaFree(h->d_chunk_pos);
+    cudaFree(h->d_arena); cudaFree(h->d_counters);
     cudaFree(h->d_hist); cudaFree(h->d_first); cudaFree(h->d_tabs); cudaFree(h->d_tree);
     cudaFreeHost(h->h_counters); cudaFree(h->d_out_end); cudaFree(h->d_px); cudaFree(h->d_out);
     cudaFreeHost(h->h_stage); cudaFree(h->d_meta); cudaFreeHost(h->h_meta);
@@ -666,7 +760,7 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     }
     rc = grow_descs(h, (size_t)n_images);
     if (rc) return rc;
-    long long ntiles = 0, nblocks = 0;
+    long long ntiles = 0, nblocks = 0, worst = 16;
     int uniform_tpi = 0;
     for (int i = 0; i < n_images; i++) {
         if (heights[i] < 0 || widths[i] < 0) { h->err = "negative image dimension"; return TIC_E_INVALID; }
@@ -684,16 +778,39 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
         if (i == 0) uniform_tpi = (int)nt; else if (nt != uniform_tpi) uniform_tpi = -1;
         ntiles += nt;
         nblocks += nblk;
+        worst += tic_max_out_bytes(heights[i], widths[i]) + (auto_mode ? 1664 : 0);
         if (nblk > 0 && !d.px) { h->err = "null pixel pointer"; return TIC_E_INVALID; }
     }
     if (uniform_tpi < 0) uniform_tpi = 0;
     if (ntiles > 0x7fffffffll) { h->err = "batch too large for one launch"; return TIC_E_INVALID; }
+    const long long nchunks = (ntiles + kScanChunk - 1) / kScanChunk;
     if ((size_t)ntiles > h->tiles_cap) {
-        cudaFree(h->d_tile_status);
-        h->d_tile_status = nullptr; h->tiles_cap = 0;
+        cudaFree(h->d_recs); cudaFree(h->d_tile_pos);
+        h->d_recs = nullptr; h->d_tile_pos = nullptr; h->tiles_cap = 0;
         size_t cap = (size_t)ntiles + (size_t)ntiles / 4 + 1024;
-        TIC_CUDA(h, cudaMalloc(&h->d_tile_status, cap * 16));
+        TIC_CUDA(h, cudaMalloc(&h->d_recs, cap * sizeof(TileRec)));
+        TIC_CUDA(h, cudaMalloc(&h->d_tile_pos, cap * sizeof(long long)));
         h->tiles_cap = cap;
+    }
+    if ((size_t)nchunks > h->chunks_cap) {
+        cudaFree(h->d_chunk_span); cudaFree(h->d_chunk_pos);
+        h->d_chunk_span = nullptr; h->d_chunk_pos = nullptr; h->chunks_cap = 0;
+        size_t cap = (size_t)nchunks * 2 + 64;
+        TIC_CUDA(h, cudaMalloc(&h->d_chunk_span, cap * sizeof(Span)));
+        TIC_CUDA(h, cudaMalloc(&h->d_chunk_pos, cap * sizeof(long long)));
+        h->chunks_cap = cap;
+    }
+    // The arena holds every tile's bits at a 16-byte granule before they move to their final place:
+    // never more than the streams themselves (<= out_capacity, or the caller gets TIC_E_CAPACITY
+    // anyway) plus one granule of slack per tile.
+    unsigned long long arena_need = (unsigned long long)(worst < out_capacity ? worst : out_capacity);
+    arena_need = (arena_need + 15) / 16 + (unsigned long long)ntiles + 4096;
+    if (arena_need > 0xfffffff0ull) arena_need = 0xfffffff0ull;   // 32-bit granule offsets: 64 GiB
+    if (arena_need > h->arena_cap16) {
+        cudaFree(h->d_arena);
+        h->d_arena = nullptr; h->arena_cap16 = 0;
+        TIC_CUDA(h, cudaMalloc(&h->d_arena, (size_t)arena_need * 16));
+        h->arena_cap16 = (size_t)arena_need;
     }
     if ((size_t)n_images > h->end_cap) {
         cudaFree(h->d_out_end);
@@ -701,18 +818,14 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
         TIC_CUDA(h, cudaMalloc(&h->d_out_end, (size_t)n_images * 2 * 8));
         h->end_cap = (size_t)n_images * 2;
     }
-    unsigned long long* d_status_words = h->d_tile_status;
-    unsigned long long* d_tail_words = h->d_tile_status + h->tiles_cap;
     TIC_CUDA(h, cudaMemcpyAsync(h->d_descs, h->h_descs, (size_t)n_images * sizeof(ImageDesc),
                                 cudaMemcpyHostToDevice, stream));
-    TIC_CUDA(h, cudaMemsetAsync(d_status_words, 0, (size_t)ntiles * 8, stream));
-    TIC_CUDA(h, cudaMemsetAsync(d_tail_words, 0, (size_t)ntiles * 8, stream));
     TIC_CUDA(h, cudaMemsetAsync(h->d_counters, 0, kCtrCount * 8, stream));
     TIC_CUDA(h, cudaMemsetAsync(d_status, 0, (size_t)n_images * 4, stream));
     long long grid = (long long)h->sm_count * h->ctas_per_sm;
     if (grid > ntiles) grid = ntiles;
     const AutoTables* d_tabs = nullptr;
-    h->last_launches = 2;
+    h->last_launches = 6;
     if (auto_mode) {   // calc_huffman_table (huffman.py:101-109) + write_huffman_table (codec.py:73-84)
         if ((size_t)n_images > h->auto_cap) {
             cudaFree(h->d_hist); cudaFree(h->d_first); cudaFree(h->d_tabs); cudaFree(h->d_tree);
@@ -733,11 +846,30 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
                                                                     h->d_first, h->d_tabs, h->d_tree, d_status);
         TIC_CUDA(h, cudaGetLastError());
         d_tabs = h->d_tabs;
-        h->last_launches = 4;
+        h->last_launches = 8;
+        encode_tiles_kernel<true><<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
+            qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_recs, h->d_arena, (unsigned long long)h->arena_cap16,
+            h->d_counters, d_status, quality, d_tabs);
+    } else {
+        encode_tiles_kernel<false><<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
+            qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_recs, h->d_arena, (unsigned long long)h->arena_cap16,
+            h->d_counters, d_status, quality, d_tabs);
     }
-    encode_tiles_kernel<<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
-        qp, h->d_descs, n_images, uniform_tpi, ntiles, d_status_words, d_tail_words, h->d_counters, (uint8_t*)d_out,
-        (long long)out_capacity, (long long*)d_out_offsets, h->d_out_end, d_status, quality, d_tabs);
+    TIC_CUDA(h, cudaGetLastError());
+    scan_chunks_kernel<<<(unsigned)nchunks, kScanThreads, 0, stream>>>(h->d_recs, ntiles, h->d_chunk_span);
+    TIC_CUDA(h, cudaGetLastError());
+    scan_spine_kernel<<<1, kSpineThreads, 0, stream>>>(h->d_chunk_span, nchunks, h->d_chunk_pos);
+    TIC_CUDA(h, cudaGetLastError());
+    scan_apply_kernel<<<(unsigned)nchunks, kScanThreads, 0, stream>>>(h->d_recs, ntiles, h->d_chunk_pos, h->d_tile_pos,
+                                                                      (long long)out_capacity, (long long*)d_out_offsets,
+                                                                      h->d_out_end, h->d_counters);
+    TIC_CUDA(h, cudaGetLastError());
+    long long cgrid = (ntiles * 32 + kCompactThreads - 1) / kCompactThreads;
+    const long long cmax = (long long)h->sm_count * 8 * 4;
+    if (cgrid > cmax) cgrid = cmax;
+    compact_kernel<<<(unsigned)cgrid, kCompactThreads, 0, stream>>>(h->d_recs, h->d_tile_pos, ntiles,
+                                                                    (const uint32_t*)h->d_arena, (uint32_t*)d_out,
+                                                                    (long long)out_capacity);
     TIC_CUDA(h, cudaGetLastError());
     finalize_kernel<<<(n_images + 255) / 256, 256, 0, stream>>>(n_images, (const long long*)d_out_offsets,
                                                                h->d_out_end, (long long*)d_out_sizes, d_status,

@@ -1,24 +1,28 @@
 // tic_kernels.cuh — sm_100a device code of the tinyimgcodec encode path.
 //
-// One CTA encodes one TILE: kTile consecutive 8x8 blocks of one image in the stream's
-// block-raster order (tinyimgcodec/codec.py:34-36), one thread per block.  Everything the
-// reference does between `image` and `bytes` happens inside that CTA:
+// A TILE is kTile consecutive 8x8 blocks of one image in the stream's block-raster order
+// (tinyimgcodec/codec.py:34-36), one thread per block.  The encode kernel turns a tile into its
+// piece of the bit stream without talking to any other tile:
 //
 //   load      8 x LDG.64 per thread; a warp reads 256 contiguous bytes per pixel row
 //   transform level shift + 8x8 FDCT in registers, FP32 (AAN butterflies), scaled into the
 //             quantiser: the fast path for utils.py:32-37,48-53
-//   quantise  one FFMA per coefficient into 2^-F fixed point; a coefficient whose fraction
-//             is within a guard band of a .5 rounding tie is sent to the EXACT path
-//   exact     the reference's float64 FDCT (SciPy/ducc0 op order),
-//             8 lanes per flagged coefficient: reproduces the reference's rounding of ties
-//   symbols   zigzag (constants.py:23-34), DC difference (codec.py:34-35), run lengths
-//             (huffman.py:12-33), Huffman code + value bits (huffman.py:41-63)
-//   scan      bit lengths -> CTA scan -> decoupled look-back across tiles and images
-//   pack      MSB-first bit packing (bitbuffer.py:17-40) into shared memory, then a
-//             funnel-shifted, byte-swapped copy to the global stream; the word shared
-//             with the previous tile arrives through a 64-bit mailbox
+//   quantise  groups of 8 zigzag coefficients; a group the whole warp quantises to zero is skipped
+//             after one multiply + max per coefficient; otherwise round-to-nearest by magic number,
+//             and a coefficient whose fraction is within a guard band of a .5 tie goes to the EXACT path
+//   exact     the reference's float64 FDCT (SciPy/ducc0 op order), 8 lanes per
+//             flagged coefficient, per warp: reproduces the reference's rounding of ties.  The DC of
+//             the block in front of each warp's 32 blocks is one more exact item (codec.py:34-35).
+//   symbols   one walk over the non-zero mask per block: zigzag (constants.py:23-34), DC difference,
+//             run lengths (huffman.py:12-33), Huffman code + value bits (huffman.py:41-63) packed
+//             MSB-first (bitbuffer.py:17-40) into a few private 32-bit words
+//   scan      bit lengths -> warp shuffle scan -> CTA scan: tile-relative bit offset of every block
+//   place     private words funnel-shifted into the tile's staging window in shared memory
+//   copy      staging window -> the tile's slot in the ARENA (bump-allocated, 16-byte granules)
 //
-// Quantised coefficients never touch HBM: algorithmic traffic is pixels in + stream out.
+// Three small kernels then scan the tile bit counts (scan_*), and compact_kernel moves every tile
+// from the arena to its final bit position in the dense output (funnel shift + byte swap).
+// Quantised coefficients never touch HBM.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -29,31 +33,19 @@ namespace tic {
 
 constexpr int kTile = 128;                                  // blocks (= threads) per tile
 constexpr int kWarps = kTile / 32;
-// The bits of a tile are packed through a WINDOW of kWinWords 32-bit words of shared memory: a tile
-// whose stream is longer (worst case 128 x 1662 bits + a table header) is emitted in several
-// rounds.  Typical tiles (<= 320 bits per block on average) need one.
+constexpr int kCtasPerSm = 6;
+constexpr int kPrivWords = 16;                              // private words per block on the fast path (512 bits)
+// The bits of a tile are assembled in a WINDOW of kWinWords 32-bit words of shared memory: a tile
+// whose stream is longer (worst case 128 x 1662 bits + a table header) is emitted in several rounds.
 constexpr int kWinWords = 1280;
-constexpr int kStageWords = kWinWords + 2;
-constexpr int kWorkCap = 64;                                // exact-path worklist entries per round
-constexpr int kExactPerRound = kTile / 8;                   // 8 lanes per worklist entry
+constexpr int kWarpWork = 32;                               // exact-path worklist entries per warp and round
 
-// look-back status word: [63:62] flag, [61] closing, [60:0] value
-constexpr unsigned long long kFlagAgg = 1ull << 62;
-constexpr unsigned long long kFlagPrefix = 2ull << 62;
-constexpr unsigned long long kFlagMask = 3ull << 62;
-constexpr unsigned long long kClosingBit = 1ull << 61;
-constexpr unsigned long long kValueMask = (1ull << 61) - 1;
-
-// Quality-dependent constants, passed BY VALUE so that every entry is a constant-bank
-// operand of the FFMA / compare that uses it.
+// Quality-dependent constants, passed BY VALUE so that every entry is a constant-bank operand.
 struct QuantParams {
-    float qmul[64];   // [u*8+v]  2^F / (8 * aan[u] * aan[v] * qt[u][v])
-    float magic[64];  // [u*8+v]  1.5*2^23 + 2^(F-1) + 2^(k-1): rounding offset + tie-window offset
-    int gmask[64];    // [u*8+v]  (2^F - 1) & ~(2^k - 1): inside the tie window iff (bits & gmask) == 0
+    float qmul[64];   // [u*8+v]  1 / (8 * aan[u] * aan[v] * qt[u][v]):   t = d * qmul is coefficient / qt
+    float zmul[64];   // [u*8+v]  qmul / hthr: |d * zmul| < 1  =>  rounds to 0 and is nowhere near a tie
+    float hthr[64];   // [u*8+v]  0.5 - w: |t - round(t)| > hthr  =>  within the guard band of a .5 tie
     double qt[64];    // [u*8+v]  the reference's float64 divisor (utils.py:50-53)
-    int fbits;        // F: fixed-point fraction bits of the fast quantiser
-    int qbias;        // 0x4B400000 >> F: what (bits >> F) reads for a zero coefficient
-    int pad[2];
 };
 
 struct ImageDesc {
@@ -64,8 +56,17 @@ struct ImageDesc {
     long long tile0;   // index of this image's first tile in the batch
 };
 
+// What the encode kernel leaves behind per tile.
+struct TileRec {
+    uint32_t bits;     // [29:0] bits of the tile (header included for a first tile), [30] first, [31] closing
+    uint32_t off16;    // arena offset of the tile's words, in 16-byte units
+    int32_t img;
+    uint32_t pad;
+};
+constexpr uint32_t kRecFirst = 1u << 30, kRecClosing = 1u << 31, kRecBitsMask = (1u << 30) - 1u;
+
 // counters[] layout in the workspace
-enum { kCtrTicket = 0, kCtrOverflow = 1, kCtrExactItems = 2, kCtrExactChanged = 3, kCtrTotalBits = 4,
+enum { kCtrArena = 0, kCtrOverflow = 1, kCtrExactItems = 2, kCtrExactChanged = 3, kCtrTotalBits = 4,
        kCtrAnyStatus = 5, kCtrCount = 8 };
 
 __device__ __constant__ uint8_t c_zigzag[64] = {TIC_ZIGZAG_LIST};
@@ -84,18 +85,6 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {   // numpy "reflect",
 
 __device__ __forceinline__ int bitlen(int v) {               // bits_required, utils.py:9-10
     return 32 - __clz(v < 0 ? -v : v);
-}
-
-// Look-back words are self-contained 64-bit messages (flag + value in one word), so relaxed
-// gpu-scope accesses are enough: nothing else has to become visible with them.  (acquire loads
-// compile to LDG + CCTL.IVALL, an L1 invalidate per poll.)
-__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 __device__ __forceinline__ long long round_up128(long long v) { return (v + 127) & ~127ll; }
@@ -160,11 +149,10 @@ __device__ __noinline__ double dct8_exact(const double x0, const double x1, cons
         s = __dmul_rn(0.25, __dsub_rn(a, e1));
         return __dmul_rn(s, TW3);
     }
-    double a = __dadd_rn(h0, h3), b = __dsub_rn(h0, h3);
-    double e1 = __dmul_rn(2.0, h1), e2 = __dmul_rn(2.0, h2);
+    double b = __dsub_rn(h0, h3);
+    double e2 = __dmul_rn(2.0, h2);
     double a2 = __dadd_rn(h4, h7), b2 = __dsub_rn(h4, h7);
     double e5 = __dmul_rn(2.0, h5), e6 = __dmul_rn(2.0, h6);
-    (void)a; (void)e1;
     double sk, skc, twk, twkc;  // pair (k, kc=8-k): t1 = tw[k-1]*s_kc + tw[kc-1]*s_k
     int k = sel < 4 ? sel : 8 - sel;
     if (k == 1) {
@@ -191,37 +179,35 @@ struct TileInfo {
     int img;          // image index
     int blk0;         // first block of the tile within the image
     int nb;           // blocks in this tile (0..kTile)
-    bool first;       // first tile of its image (writes the header)
-    bool closing;     // last tile of its image (pads to a byte, closes the stream)
+    bool first;       // first tile of its image (carries the header)
+    bool closing;     // last tile of its image (the stream is padded to a byte after it)
 };
 
 // ---------------------------------------------------------------------------------------------
-// shared memory of one tile
+// shared memory of one CTA
 // ---------------------------------------------------------------------------------------------
 struct TileShared {
     uint32_t coef[32][kTile];        // zigzag pairs (2i, 2i+1) packed lo/hi int16, one column per thread
-    uint32_t nz_lo[kTile];           // bit k set: zigzag coefficient k != 0 (k = 1..31; bit 0 unused)
-    uint32_t nz_hi[kTile];           // k = 32..63
-    int dcq[kTile + 1];              // quantised DC: [0] = block before the tile, [t+1] = thread t
-    uint32_t work[kWorkCap];         // exact-path worklist: thread << 6 | zigzag index; bit 31: halo DC
-    double colres[kExactPerRound][8];
-    uint2 ac_tab[256];               // {code, length} per (run << 4 | size); length 0 = not in table
-    uint2 dc_tab[16];                // {code, length} per size category
-    int work_count;
-    int pending;                     // flagged coefficients that did not fit the worklist this round
+    uint32_t priv[kPrivWords][kTile];// the block's bits, MSB-first from block bit 0, one column per thread
+    uint32_t nz_lo[kTile];           // bit 31-k set: zigzag coefficient k != 0 (k = 1..31; k = 0 unused)
+    uint32_t nz_hi[kTile];           // bit 63-k set, k = 32..63
+    int dcq[kTile];                  // quantised DC of thread t's block
+    int dc_halo[kWarps];             // quantised DC of the block in front of the warp's first block
+    uint32_t work[kWarps][kWarpWork];// exact-path worklist: lane << 6 | zigzag index; bit 31: halo DC
+    double colres[kWarps][4][8];
+    int work_count[kWarps];
+    int pending[kWarps];             // flagged coefficients that did not fit the worklist this round
+    uint2 ac_tab[256];               // per (run << 4 | size): fixed tables {code << size, P | len + size},
+    uint2 dc_tab[16];                //   auto tables {code, P | len};  P = kHuffPresent, 0 = not in table
     int warp_bits[kWarps];
-    int err;
-    long long s_bits;                // absolute bit position where this tile's block data starts
-    unsigned int tail_prev;
-    TileInfo ti;                     // the tile being encoded (written by warp 0)
-    long long tile;                  // its index, or >= ntiles when the work is exhausted
-    unsigned int carry;              // last word of the previous window (multi-round tiles)
-    alignas(16) uint32_t stage[kStageWords];   // window of the tile-relative MSB-first bit buffer
+    int warp_err[kWarps];
+    unsigned int arena_off;          // 16-byte units; 0xffffffff: arena exhausted
+    alignas(16) uint32_t stage[kWinWords];   // window of the tile-relative MSB-first bit buffer (kept zeroed)
 };
 
-
-// Warp-cooperative (all 32 lanes of one warp call): 32-ary search for the last image whose first
-// tile is <= tile.  uniform_tpi > 0: every image has that many tiles (the common batch), no search.
+// Warp-cooperative (all 32 lanes of one warp call): the image a tile belongs to and its place in it.
+// uniform_tpi > 0: every image has that many tiles (the common batch), no search; otherwise a 32-ary
+// search for the last image whose first tile is <= tile.
 __device__ __forceinline__ TileInfo locate_tile(const ImageDesc* __restrict__ descs, int n_images,
                                                 long long tile, int uniform_tpi) {
     const int lane = threadIdx.x & 31;
@@ -259,7 +245,7 @@ __device__ __forceinline__ double load_px_exact(const TileInfo& ti, int y, int x
 }
 
 // ---------------------------------------------------------------------------------------------
-// phase 1: pixels -> quantised zigzag coefficients in shared memory (fast path) + worklist
+// phase 1: pixels -> quantised zigzag coefficients in shared memory (fast path) + flags
 // ---------------------------------------------------------------------------------------------
 template <int K>
 struct ZZ {  // compile-time zigzag -> raster
@@ -267,49 +253,71 @@ struct ZZ {  // compile-time zigzag -> raster
     static constexpr int r = tab[K];
 };
 
-template <int I>
-__device__ __forceinline__ void quantise_pairs(const float (&d)[64], const QuantParams& qp, TileShared& sm,
-                                               int t, uint32_t& nz_lo, uint32_t& nz_hi, uint32_t& fl_lo,
-                                               uint32_t& fl_hi) {
-    if constexpr (I < 32) {
-        constexpr int k0 = 2 * I, k1 = 2 * I + 1;
-        constexpr int r0 = ZZ<k0>::r, r1 = ZZ<k1>::r;
-        // bits = 0x4B400000 + round(t * 2^F) + 2^(F-1) + 2^(k-1)   (one FFMA, magic-number rounding)
-        const int b0 = __float_as_int(fmaf(d[r0], qp.qmul[r0], qp.magic[r0]));
-        const int b1 = __float_as_int(fmaf(d[r1], qp.qmul[r1], qp.magic[r1]));
-        const int s0 = b0 >> qp.fbits, s1 = b1 >> qp.fbits;   // qbias + floor(t + 0.5) outside the window
-        const bool f0 = (b0 & qp.gmask[r0]) == 0;             // within the tie window: exact path decides
-        const bool f1 = (b1 & qp.gmask[r1]) == 0;
-        if constexpr (k0 < 32) {
-            if (k0 != 0 && s0 != qp.qbias) nz_lo |= 1u << k0;
-            if (s1 != qp.qbias) nz_lo |= 1u << k1;
-            if (f0) fl_lo |= 1u << k0;
-            if (f1) fl_lo |= 1u << k1;
-        } else {
-            if (s0 != qp.qbias) nz_hi |= 1u << (k0 - 32);
-            if (s1 != qp.qbias) nz_hi |= 1u << (k1 - 32);
-            if (f0) fl_hi |= 1u << (k0 - 32);
-            if (f1) fl_hi |= 1u << (k1 - 32);
-        }
-        if constexpr (I == 0) sm.dcq[t + 1] = s0 - qp.qbias;
-        sm.coef[I][t] = __byte_perm((uint32_t)s0, (uint32_t)s1, 0x5410);   // biased int16 pair
-        quantise_pairs<I + 1>(d, qp, sm, t, nz_lo, nz_hi, fl_lo, fl_hi);
+// Group G = zigzag coefficients 8G .. 8G+7 of every block of the warp.  All 32 lanes call.
+template <int G, int J>
+__device__ __forceinline__ float group_peak(const float (&d)[64], const QuantParams& qp) {
+    if constexpr (J == 8) {
+        return 0.0f;
+    } else {
+        constexpr int r = ZZ<8 * G + J>::r;
+        return fmaxf(fabsf(d[r] * qp.zmul[r]), group_peak<G, J + 1>(d, qp));
     }
 }
 
-// Coefficients sit in shared memory as 16-bit values biased by (qbias & 0xffff).
-__device__ __forceinline__ int coef_get(const TileShared& sm, int t, int k, int bias) {
-    uint32_t w = sm.coef[k >> 1][t];
-    return (int)(short)(((k & 1) ? (w >> 16) : w) - (uint32_t)bias);
+template <int G, int P>
+__device__ __forceinline__ void quantise_pairs(const float (&d)[64], const QuantParams& qp, TileShared& sm,
+                                               int t, uint32_t& nz, uint32_t& fl, int& dc) {
+    if constexpr (P < 4) {
+        constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23: (x + kMagic) - kMagic = round-to-nearest-even(x)
+        constexpr int k0 = 8 * G + 2 * P, k1 = k0 + 1;
+        constexpr int r0 = ZZ<k0>::r, r1 = ZZ<k1>::r;
+        const float b0 = fmaf(d[r0], qp.qmul[r0], kMagic), b1 = fmaf(d[r1], qp.qmul[r1], kMagic);
+        const float q0 = b0 - kMagic, q1 = b1 - kMagic;
+        const float e0 = fmaf(d[r0], qp.qmul[r0], -q0), e1 = fmaf(d[r1], qp.qmul[r1], -q1);   // t - round(t)
+        if (k0 != 0 && q0 != 0.0f) nz |= 0x80000000u >> (k0 & 31);
+        if (q1 != 0.0f) nz |= 0x80000000u >> (k1 & 31);
+        if (fabsf(e0) > qp.hthr[r0]) fl |= 0x80000000u >> (k0 & 31);   // the exact path decides
+        if (fabsf(e1) > qp.hthr[r1]) fl |= 0x80000000u >> (k1 & 31);
+        if constexpr (k0 == 0) dc = __float_as_int(b0) - 0x4B400000;
+        // the low 16 bits of the magic sums are the two's-complement quantised values
+        sm.coef[k0 >> 1][t] = __byte_perm(__float_as_uint(b0), __float_as_uint(b1), 0x5410);
+        quantise_pairs<G, P + 1>(d, qp, sm, t, nz, fl, dc);
+    }
 }
+
+template <int G>
+__device__ __forceinline__ void quantise_groups(const float (&d)[64], const QuantParams& qp, TileShared& sm,
+                                                int t, uint32_t& nz_lo, uint32_t& nz_hi, uint32_t& fl_lo,
+                                                uint32_t& fl_hi, int& dc) {
+    if constexpr (G < 8) {
+        bool live = true;
+        if constexpr (G > 0) live = __any_sync(0xffffffffu, group_peak<G, 0>(d, qp) >= 1.0f);
+        if (live) {   // warp-uniform
+            if constexpr (G < 4) quantise_pairs<G, 0>(d, qp, sm, t, nz_lo, fl_lo, dc);
+            else quantise_pairs<G, 0>(d, qp, sm, t, nz_hi, fl_hi, dc);
+        }
+        quantise_groups<G + 1>(d, qp, sm, t, nz_lo, nz_hi, fl_lo, fl_hi, dc);
+    }
+}
+
+// Coefficients sit in shared memory as two's-complement 16-bit values.
+__device__ __forceinline__ int coef_get(const TileShared& sm, int t, int k) {
+    const uint32_t w = sm.coef[k >> 1][t];
+    return (int)(short)((k & 1) ? (w >> 16) : w);
+}
+
+// One block, all 32 lanes of the warp call (the group test votes); `active` = the block exists.
 __device__ __forceinline__ void transform_block(const TileInfo& ti, const QuantParams& qp, TileShared& sm,
-                                                int t, uint32_t& fl_lo, uint32_t& fl_hi) {
+                                                int t, bool active, uint32_t& fl_lo, uint32_t& fl_hi) {
     const int b = ti.blk0 + t;
     const int br = b / ti.bw, bc = b - br * ti.bw;
     const int y0 = br * 8, x0 = bc * 8;
     float d[64];
     const bool fast = ((ti.w & 7) == 0) && ((reinterpret_cast<uintptr_t>(ti.px) & 7) == 0) && (y0 + 8 <= ti.h);
-    if (fast) {
+    if (!active) {
+#pragma unroll
+        for (int i = 0; i < 64; i++) d[i] = 128.0f;
+    } else if (fast) {
         const uint8_t* p = ti.px + (size_t)y0 * ti.w + x0;
         uint2 rows[8];
 #pragma unroll
@@ -342,30 +350,38 @@ __device__ __forceinline__ void transform_block(const TileInfo& ti, const QuantP
              d[r * 8 + 7]);
     d[0] -= 8192.0f;   // level shift (codec.py:29) only moves the DC term: 64 * 128, exact in FP32
     uint32_t nz_lo = 0, nz_hi = 0;
-    quantise_pairs<0>(d, qp, sm, t, nz_lo, nz_hi, fl_lo, fl_hi);
+    int dc = 0;
+    quantise_groups<0>(d, qp, sm, t, nz_lo, nz_hi, fl_lo, fl_hi, dc);
     sm.nz_lo[t] = nz_lo;
     sm.nz_hi[t] = nz_hi;
+    sm.dcq[t] = dc;
+    if (!active) fl_lo = fl_hi = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
-// phase 2: exact recomputation of every flagged coefficient (and of the DC of the block that
-// precedes the tile, which the DC difference of codec.py:34-35 needs).  8 lanes per entry:
-// lane c transforms column c of the block (axis -2 first, utils.py:33-34), lane 0 the row.
+// phase 2: exact recomputation of every flagged coefficient of the warp's 32 blocks (and of the DC
+// of the block in front of them, which the DC difference of codec.py:34-35 needs).  8 lanes per
+// entry: lane c transforms column c of the block (axis -2 first, utils.py:33-34), lane 0 the row.
 // ---------------------------------------------------------------------------------------------
+struct ExactStats {
+    unsigned int items, changed;
+};
+
 __device__ __forceinline__ void exact_round(const TileInfo& ti, const QuantParams& qp, TileShared& sm,
-                                            int count, unsigned long long* counters) {
-    const int tid = threadIdx.x;
-    const int grp = tid >> 3, c = tid & 7;
-    for (int base = 0; base < count; base += kExactPerRound) {
+                                            int warp, int count, ExactStats& st) {
+    const int lane = threadIdx.x & 31;
+    const int grp = lane >> 3, c = lane & 7;
+    const int wt0 = warp * 32;   // first thread of the warp
+    for (int base = 0; base < count; base += 4) {
         const int idx = base + grp;
         const bool act = idx < count;   // uniform per 8-lane group
-        uint32_t item = act ? sm.work[idx] : 0;
+        const uint32_t item = act ? sm.work[warp][idx] : 0;
         const bool halo = (item >> 31) != 0;
-        const int owner = (int)((item >> 6) & 0xffff);
+        const int owner = wt0 + (int)((item >> 6) & 31);
         const int k = (int)(item & 63);
         const int r = c_zigzag[k];
         const int u = r >> 3, v = r & 7;
-        const int b = halo ? ti.blk0 - 1 : ti.blk0 + owner;
+        const int b = halo ? ti.blk0 + wt0 - 1 : ti.blk0 + owner;
         if (act) {
             const int br = b / ti.bw, bc = b - br * ti.bw;
             const int y0 = br * 8, x = bc * 8 + c;
@@ -373,37 +389,37 @@ __device__ __forceinline__ void exact_round(const TileInfo& ti, const QuantParam
             double x2 = load_px_exact(ti, y0 + 2, x), x3 = load_px_exact(ti, y0 + 3, x);
             double x4 = load_px_exact(ti, y0 + 4, x), x5 = load_px_exact(ti, y0 + 5, x);
             double x6 = load_px_exact(ti, y0 + 6, x), x7 = load_px_exact(ti, y0 + 7, x);
-            sm.colres[grp][c] = dct8_exact(x0, x1, x2, x3, x4, x5, x6, x7, u);
+            sm.colres[warp][grp][c] = dct8_exact(x0, x1, x2, x3, x4, x5, x6, x7, u);
         }
         __syncwarp();
         if (act && c == 0) {
-            const double* cr = sm.colres[grp];
+            const double* cr = sm.colres[warp][grp];
             double y = dct8_exact(cr[0], cr[1], cr[2], cr[3], cr[4], cr[5], cr[6], cr[7], v);
             int q = __double2int_rn(__ddiv_rn(y, qp.qt[r]));   // np.round(coeffs / qt), utils.py:53
             if (halo) {
-                sm.dcq[0] = q;
+                sm.dc_halo[warp] = q;
             } else {
-                int old = coef_get(sm, owner, k, qp.qbias);
+                int old = k == 0 ? sm.dcq[owner] : coef_get(sm, owner, k);
                 if (old != q) {
                     // two flagged coefficients of one block may share a packed word: serialise
                     // through a 32-bit CAS on that word
                     uint32_t* wp = &sm.coef[k >> 1][owner];
                     uint32_t seen = *wp, want;
                     do {
-                        const uint32_t qb = (uint32_t)(q + qp.qbias) & 0xffffu;
+                        const uint32_t qb = (uint32_t)q & 0xffffu;
                         want = (k & 1) ? ((seen & 0x0000ffffu) | (qb << 16)) : ((seen & 0xffff0000u) | qb);
                         uint32_t prev = atomicCAS(wp, seen, want);
                         if (prev == seen) break;
                         seen = prev;
                     } while (true);
                     if (k == 0) {
-                        sm.dcq[owner + 1] = q;
-                    } else if (k < 32) {
-                        if (q) atomicOr(&sm.nz_lo[owner], 1u << k); else atomicAnd(&sm.nz_lo[owner], ~(1u << k));
+                        sm.dcq[owner] = q;
                     } else {
-                        if (q) atomicOr(&sm.nz_hi[owner], 1u << (k - 32)); else atomicAnd(&sm.nz_hi[owner], ~(1u << (k - 32)));
+                        uint32_t* m = k < 32 ? &sm.nz_lo[owner] : &sm.nz_hi[owner];
+                        const uint32_t bit = 0x80000000u >> (k & 31);
+                        if (q) atomicOr(m, bit); else atomicAnd(m, ~bit);
                     }
-                    atomicAdd(&counters[kCtrExactChanged], 1ull);
+                    st.changed++;
                 }
             }
         }
@@ -411,75 +427,147 @@ __device__ __forceinline__ void exact_round(const TileInfo& ti, const QuantParam
     }
 }
 
-// Runs phases 1 and 2 for the tile.  On return (after a __syncthreads) sm.coef / nz / dcq hold
-// the reference's quantised coefficients for every block of the tile.
-__device__ __forceinline__ void transform_tile(const TileInfo& ti, const QuantParams& qp, TileShared& sm,
-                                               unsigned long long* counters) {
-    const int t = threadIdx.x;
-    if (t == 0) {
-        sm.work_count = 0;
-        sm.pending = 0;
-        sm.dcq[0] = 0;
-        if (ti.blk0 > 0 && ti.nb > 0) {   // halo: DC of the previous block of the same image
-            sm.work[0] = 0x80000000u;
-            sm.work_count = 1;
+// Phases 1 and 2 for the 32 blocks of one warp; only warp-level synchronisation.  On return
+// sm.coef / nz / dcq / dc_halo hold the reference's quantised coefficients for those blocks.
+__device__ __forceinline__ void transform_warp(const TileInfo& ti, const QuantParams& qp, TileShared& sm,
+                                               ExactStats& st) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (lane == 0) {
+        sm.pending[warp] = 0;
+        sm.dc_halo[warp] = 0;
+        int n = 0;
+        if (ti.blk0 + warp * 32 > 0 && warp * 32 < ti.nb) {   // halo: DC of the block in front of the warp
+            sm.work[warp][0] = 0x80000000u;
+            n = 1;
         }
+        sm.work_count[warp] = n;
     }
-    __syncthreads();
+    __syncwarp();
     uint32_t fl_lo = 0, fl_hi = 0;
-    if (t < ti.nb) transform_block(ti, qp, sm, t, fl_lo, fl_hi);
-    // push flagged coefficients; loop in rounds if the worklist overflows (very high quality only)
+    transform_block(ti, qp, sm, t, t < ti.nb, fl_lo, fl_hi);
+    // push flagged coefficients; loop in rounds if the worklist overflows (high quality only)
     while (true) {
         while (fl_lo | fl_hi) {
-            int k = fl_lo ? (__ffs(fl_lo) - 1) : (31 + __ffs(fl_hi));
-            int slot = atomicAdd(&sm.work_count, 1);
-            if (slot >= kWorkCap) { atomicAdd(&sm.pending, 1); break; }
-            sm.work[slot] = ((uint32_t)t << 6) | (uint32_t)k;
-            if (k < 32) fl_lo &= fl_lo - 1; else fl_hi &= fl_hi - 1;
+            const int k = fl_lo ? __clz(fl_lo) : 32 + __clz(fl_hi);
+            const int slot = atomicAdd(&sm.work_count[warp], 1);
+            if (slot >= kWarpWork) { atomicAdd(&sm.pending[warp], 1); break; }
+            sm.work[warp][slot] = ((uint32_t)lane << 6) | (uint32_t)k;
+            if (k < 32) fl_lo ^= 0x80000000u >> k; else fl_hi ^= 0x80000000u >> (k - 32);
         }
-        __syncthreads();
-        int count = sm.work_count < kWorkCap ? sm.work_count : kWorkCap;
-        int pending = sm.pending;
-        if (t == 0 && count) atomicAdd(&counters[kCtrExactItems], (unsigned long long)count);
-        exact_round(ti, qp, sm, count, counters);
-        __syncthreads();
+        __syncwarp();
+        const int raw = sm.work_count[warp];
+        const int count = raw < kWarpWork ? raw : kWarpWork;
+        const int pending = sm.pending[warp];
+        __syncwarp();
+        if (count) {   // warp-uniform
+            if (lane == 0) st.items += (unsigned)count;
+            exact_round(ti, qp, sm, warp, count, st);
+        }
         if (pending == 0) break;
-        if (t == 0) { sm.work_count = 0; sm.pending = 0; }
-        __syncthreads();
+        if (lane == 0) { sm.work_count[warp] = 0; sm.pending[warp] = 0; }
+        __syncwarp();
     }
+    __syncwarp();
+}
+
+// DC of the block before thread t's block, after transform_warp (codec.py:34-35: plain difference
+// over the whole image, no reset per block row; 0 in front of the first block).
+__device__ __forceinline__ int dc_before(const TileShared& sm, int t) {
+    return (t & 31) ? sm.dcq[t - 1] : sm.dc_halo[t >> 5];
 }
 
 // ---------------------------------------------------------------------------------------------
-// phase 3: symbols.  Bit length of one block, then its bits.
+// phase 3: symbols -> bits.  One walk per block; the words go to the thread's private column
+// (fast path) or, for the rare block longer than kPrivWords words, straight into the staging window.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int block_bits(const TileShared& sm, int t, int bias, int& err) {
-    int diff = sm.dcq[t + 1] - sm.dcq[t];                      // codec.py:34-35
-    int s = bitlen(diff);
-    if (s > 15 || sm.dc_tab[s].y == 0) { err = 1; s = 0; }     // KeyError, huffman.py:62
-    int bits = (int)(sm.dc_tab[s].y & kHuffLenMask) + s;
+template <bool kToStage>
+struct BitSink {
+    uint32_t cur = 0;   // word being filled, MSB-first
+    int nb = 0;         // bits in cur (< 32 between calls)
+    int cnt = 0;        // completed words
+    // kToStage == false
+    uint32_t* col = nullptr;      // &sm.priv[0][t]
+    // kToStage == true: the block starts at window-relative bit (w0 * 32 + sh); w0 may be outside the window
+    uint32_t* stage = nullptr;
+    int w0 = 0, sh = 0;
+
+    __device__ __forceinline__ void word(uint32_t w) {
+        if constexpr (!kToStage) {
+            if (cnt < kPrivWords) col[cnt * kTile] = w;
+        } else {
+            const int W = w0 + cnt;
+            if ((unsigned)W < (unsigned)kWinWords) atomicOr(&stage[W], w >> sh);
+            if (sh && (unsigned)(W + 1) < (unsigned)kWinWords) atomicOr(&stage[W + 1], w << (32 - sh));
+        }
+        cnt++;
+    }
+    __device__ __forceinline__ void put(uint32_t bits, int n) {   // 0 <= n <= 32, bits < 2^n
+        const uint32_t x = bits << ((32 - n) & 31);               // left-aligned (n == 0: bits == 0)
+        cur |= x >> nb;
+        const uint32_t nxt = __funnelshift_r(0u, x, nb);          // what did not fit (0 when nb == 0)
+        nb += n;
+        if (nb >= 32) {
+            word(cur);
+            cur = nxt;
+            nb -= 32;
+        }
+    }
+    // returns the block's bit count; cnt then counts the words it occupies
+    __device__ __forceinline__ int finish() {
+        const int bits = cnt * 32 + nb;
+        if (nb > 0) word(cur);
+        return bits;
+    }
+};
+
+__device__ __forceinline__ uint32_t value_bits(int v, int sz) {   // huffman.py:59-63
+    return (uint32_t)(v + (v >> 31)) & ((1u << sz) - 1u);
+}
+
+template <bool kAuto, bool kToStage>
+__device__ __forceinline__ void put_symbol(BitSink<kToStage>& s, uint2 e, int v, int sz) {
+    const int len = (int)(e.y & kHuffLenMask);
+    if constexpr (kAuto) {   // code up to 32 bits + value up to 15
+        s.put(e.x, len);
+        s.put(value_bits(v, sz), sz);
+    } else {                 // e.x = code << size, len = code length + size <= 26
+        s.put(e.x | value_bits(v, sz), len);
+    }
+}
+
+// Emits the bits of thread t's block (DC difference `diff`, AC from sm.coef / nz masks).
+template <bool kAuto, bool kToStage>
+__device__ __forceinline__ int walk_block(const TileShared& sm, int t, int diff, BitSink<kToStage>& s, int& err) {
+    int sz = bitlen(diff);
+    if (sz > 15 || sm.dc_tab[sz].y == 0) { err = 1; sz = 0; }    // KeyError, huffman.py:62
+    put_symbol<kAuto, kToStage>(s, sm.dc_tab[sz], diff, sz);
     uint32_t lo = sm.nz_lo[t], hi = sm.nz_hi[t];
     int prev = 0;
-    const int zrl = (int)(sm.ac_tab[0xF0].y & kHuffLenMask);
+    const uint2 zrl = sm.ac_tab[0xF0];
     while (lo | hi) {
         int k;
-        if (lo) { k = __ffs(lo) - 1; lo &= lo - 1; } else { k = 31 + __ffs(hi); hi &= hi - 1; }
+        if (lo) { k = __clz(lo); lo ^= 0x80000000u >> k; } else { k = __clz(hi); hi ^= 0x80000000u >> k; k += 32; }
         int run = k - prev - 1;
         prev = k;
-        int sz = bitlen(coef_get(sm, t, k, bias));
-        int sym = ((run & 15) << 4) | sz;
-        if (sz > 15 || sm.ac_tab[sym & 255].y == 0) { err = 1; sz = 1; sym = ((run & 15) << 4) | 1; }
-        bits += (run >> 4) * zrl + (int)(sm.ac_tab[sym].y & kHuffLenMask) + sz; // huffman.py:25-29
+        int v = coef_get(sm, t, k);
+        sz = bitlen(v);
+        for (; run >= 16; run -= 16) s.put(zrl.x, (int)(zrl.y & kHuffLenMask));   // huffman.py:25-29
+        int sym = (run << 4) | sz;
+        if (sz > 15 || sm.ac_tab[sym & 255].y == 0) { err = 1; sz = 1; sym = (run << 4) | 1; v = 1; }
+        put_symbol<kAuto, kToStage>(s, sm.ac_tab[sym], v, sz);
     }
-    return bits + (int)(sm.ac_tab[0].y & kHuffLenMask);        // EOB always, huffman.py:33
+    const uint2 eob = sm.ac_tab[0];
+    s.put(eob.x, (int)(eob.y & kHuffLenMask));                   // EOB always, huffman.py:33
+    return s.finish();
 }
 
 // Symbol statistics of one block for the per-image tables (huffman.py:101-109, 187-194): counts
 // and, for the dict-insertion order the reference's tree depends on, the first occurrence of every
 // symbol as key = block index * 256 + ordinal of the symbol inside the block's list.
 // hist/first: 272 entries, [0,256) AC (run*16+size), [256,272) DC size.
-__device__ __forceinline__ void block_stats(const TileShared& sm, int t, int bias, unsigned long long blk,
+__device__ __forceinline__ void block_stats(const TileShared& sm, int t, unsigned long long blk,
                                             uint32_t* hist, unsigned long long* first, int& err) {
-    int diff = sm.dcq[t + 1] - sm.dcq[t];
+    int diff = sm.dcq[t] - dc_before(sm, t);
     int s = bitlen(diff);
     if (s > 15) { err = 1; s = 15; }   // int2ba(category, 4) overflows in the reference (codec.py:76)
     atomicAdd(&hist[256 + s], 1u);
@@ -488,10 +576,10 @@ __device__ __forceinline__ void block_stats(const TileShared& sm, int t, int bia
     int prev = 0, ord = 0;
     while (lo | hi) {
         int k;
-        if (lo) { k = __ffs(lo) - 1; lo &= lo - 1; } else { k = 31 + __ffs(hi); hi &= hi - 1; }
+        if (lo) { k = __clz(lo); lo ^= 0x80000000u >> k; } else { k = __clz(hi); hi ^= 0x80000000u >> k; k += 32; }
         int run = k - prev - 1;
         prev = k;
-        int sz = bitlen(coef_get(sm, t, k, bias));
+        int sz = bitlen(coef_get(sm, t, k));
         if (sz > 15) { err = 1; sz = 15; }
         if (run >> 4) {
             atomicAdd(&hist[0xF0], (uint32_t)(run >> 4));
@@ -506,79 +594,39 @@ __device__ __forceinline__ void block_stats(const TileShared& sm, int t, int bia
     atomicMin(&first[0], (blk << 8) | (unsigned)ord);   // EOB; its count is the number of blocks
 }
 
-struct BitSink {
-    uint32_t* stage;          // window of the tile's bit buffer
-    unsigned long long acc;   // left-aligned pending bits
-    int nb;                   // number of pending bits (< 32 between calls)
-    int word;                 // window-relative index of the word being filled (may be outside)
-    bool first;
-    __device__ __forceinline__ void put(uint32_t code, int len) {   // 0 <= len <= 32
-        if (len == 0) return;
-        acc |= (unsigned long long)code << (64 - nb - len);
-        nb += len;
-        if (nb >= 32) {
-            uint32_t w = (uint32_t)(acc >> 32);
-            if ((unsigned)word < (unsigned)kWinWords) {   // words outside the window belong to another round
-                if (first) atomicOr(&stage[word], w); else stage[word] = w;
-            }
-            first = false;
-            word++;
-            acc <<= 32;
-            nb -= 32;
-        }
-    }
-    __device__ __forceinline__ void flush() {
-        if (nb > 0 && (unsigned)word < (unsigned)kWinWords) atomicOr(&stage[word], (uint32_t)(acc >> 32));
-    }
+// ---------------------------------------------------------------------------------------------
+// the scan over tiles.  A tile moves the write position by its bit count; a tile that closes an image
+// then rounds the position up to 128 bits (streams start 16-byte aligned).  Any run of tiles acts as
+//     g(P) = closed ? round_up128(P + a) + b : P + a
+// and these compose associatively.
+// ---------------------------------------------------------------------------------------------
+struct Span {
+    long long a, b;
+    int closed;
 };
-
-__device__ __forceinline__ uint32_t value_bits(int v, int sz) {   // huffman.py:59-63
-    return (uint32_t)(v + (v >> 31)) & ((1u << sz) - 1u);
+__device__ __forceinline__ Span span_of(uint32_t rec_bits) {
+    Span s;
+    s.a = (long long)(rec_bits & kRecBitsMask);
+    s.b = 0;
+    s.closed = (rec_bits & kRecClosing) ? 1 : 0;
+    return s;
 }
-
-__device__ __forceinline__ void block_emit(TileShared& sm, int t, int bias, int bitpos, int wbase) {
-    BitSink s;
-    s.stage = sm.stage;
-    s.acc = 0;
-    s.nb = bitpos & 31;
-    s.word = (bitpos >> 5) - wbase;
-    s.first = true;
-    int diff = sm.dcq[t + 1] - sm.dcq[t];
-    int sz = bitlen(diff);
-    if (sz > 15 || sm.dc_tab[sz].y == 0) sz = 0;
-    uint2 e = sm.dc_tab[sz];
-    e.y &= kHuffLenMask;
-    if ((int)e.y + sz <= 32) {
-        s.put((e.x << sz) | value_bits(diff, sz), (int)e.y + sz);
-    } else {
-        s.put(e.x, (int)e.y);
-        s.put(value_bits(diff, sz), sz);
-    }
-    uint32_t lo = sm.nz_lo[t], hi = sm.nz_hi[t];
-    int prev = 0;
-    uint2 zrl = sm.ac_tab[0xF0];
-    zrl.y &= kHuffLenMask;
-    while (lo | hi) {
-        int k;
-        if (lo) { k = __ffs(lo) - 1; lo &= lo - 1; } else { k = 31 + __ffs(hi); hi &= hi - 1; }
-        int run = k - prev - 1;
-        prev = k;
-        int v = coef_get(sm, t, k, bias);
-        sz = bitlen(v);
-        int sym = ((run & 15) << 4) | sz;
-        if (sz > 15 || sm.ac_tab[sym & 255].y == 0) { sz = 1; sym = ((run & 15) << 4) | 1; v = 1; }
-        for (int z = run >> 4; z > 0; z--) s.put(zrl.x, (int)zrl.y);
-        e = sm.ac_tab[sym];
-        e.y &= kHuffLenMask;
-        if ((int)e.y + sz <= 32) {
-            s.put((e.x << sz) | value_bits(v, sz), (int)e.y + sz);   // code + value bits in one go
-        } else {
-            s.put(e.x, (int)e.y);
-            s.put(value_bits(v, sz), sz);
-        }
-    }
-    s.put(sm.ac_tab[0].x, (int)(sm.ac_tab[0].y & kHuffLenMask));
-    s.flush();
+__device__ __forceinline__ Span span_then(const Span& x, const Span& y) {   // x first, then y
+    Span r;
+    if (!x.closed) { r.a = x.a + y.a; r.b = y.b; r.closed = y.closed; }
+    else if (!y.closed) { r.a = x.a; r.b = x.b + y.a; r.closed = 1; }
+    else { r.a = x.a; r.b = round_up128(x.b + y.a) + y.b; r.closed = 1; }
+    return r;
+}
+__device__ __forceinline__ long long span_apply(long long p, const Span& s) {
+    return s.closed ? round_up128(p + s.a) + s.b : p + s.a;
+}
+__device__ __forceinline__ Span span_shfl_up(const Span& s, int o) {
+    Span r;
+    r.a = __shfl_up_sync(0xffffffffu, s.a, o);
+    r.b = __shfl_up_sync(0xffffffffu, s.b, o);
+    r.closed = __shfl_up_sync(0xffffffffu, s.closed, o);
+    return r;
 }
 
 }  // namespace tic

@@ -3,8 +3,8 @@
 set -u
 TAG=${1:-}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python bench.py --no-cpu --no-e2e --steps 10 --warmup 3 > gpurun_out/quick.json 2> gpurun_out/quick.err || tail -5 gpurun_out/quick.err
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
+timeout 600 python bench.py --no-cpu --no-e2e --steps 10 --warmup 3 > gpurun_out/quick.json 2> gpurun_out/quick.err || tail -5 gpurun_out/quick.err
 python - <<'PY'
 import json
 d=json.load(open("gpurun_out/quick.json"))
@@ -12,8 +12,10 @@ print("BENCH value=%.0f Mpx/s ms=%.3f frac=%.4f parity=%s clocks=%s exact=%s" % 
 PY
 if [ -n "$TAG" ]; then
   PROF="python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e"
-  $PROF > gpurun_out/plain_${TAG}.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:encode_tiles_kernel -s 3 -c 1 \
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv \
+      --log-file gpurun_out/launches_${TAG}.csv $PROF > gpurun_out/ncu_launch_${TAG}.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:encode_tiles_kernel -s 3 -c 1 \
       -o gpurun_out/prof_${TAG} -f $PROF > gpurun_out/ncu_full_${TAG}.log 2>&1
   echo "full capture rc=$?"
+  cp tinyimgcodec_b200/libtinyimgcodec_cuda.so gpurun_out/lib_${TAG}.so
 fi
