@@ -20,13 +20,13 @@ __device__ __forceinline__ void load_tables(TileShared& sm, const HuffTables& g)
     for (int i = threadIdx.x; i < 256; i += kTile) {
         const uint32_t len = g.ac[i].len, code = g.ac[i].code;
         if constexpr (kAuto) sm.ac_tab[i] = make_uint2(code, len);
-        else sm.ac_tab[i] = len ? make_uint2(code << (i & 15), len + (uint32_t)(i & 15)) : make_uint2(0u, 0u);
+        else sm.ac_tab[i] = len ? make_uint2(code << (i & 15), (len & kHuffLenMask) + (uint32_t)(i & 15)) : make_uint2(0u, 0u);
     }
     if (threadIdx.x < 16) {
         const int i = threadIdx.x;
         const uint32_t len = g.dc[i].len, code = g.dc[i].code;
         if constexpr (kAuto) sm.dc_tab[i] = make_uint2(code, len);
-        else sm.dc_tab[i] = len ? make_uint2(code << i, len + (uint32_t)i) : make_uint2(0u, 0u);
+        else sm.dc_tab[i] = len ? make_uint2(code << i, (len & kHuffLenMask) + (uint32_t)i) : make_uint2(0u, 0u);
     }
 }
 
@@ -44,6 +44,8 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
     TileShared& sm = *reinterpret_cast<TileShared*>(smem_raw);
     const int t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
+    uint32_t sbase = smem_u32(smem_raw);   // kept in a register: the walk addresses shared memory directly
+    asm volatile("mov.u32 %0, %0;" : "+r"(sbase));
 
     if constexpr (!kAuto) load_tables<false>(sm, c_default_tables);   // constants.py:53-242
     for (int i = t; i < kWinWords; i += kTile) sm.stage[i] = 0;
@@ -51,8 +53,21 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
 
     ExactStats st{0u, 0u};
     int tab_img = -1;   // auto mode: image whose tables are in shared memory
+    // uniform batch: (image, tile within image) advance by a fixed step, no division in the loop
+    int u_img = 0, u_lt = 0, u_dq = 0, u_dr = 0;
+    if (uniform_tpi > 0) {
+        u_img = (int)blockIdx.x / uniform_tpi; u_lt = (int)blockIdx.x - u_img * uniform_tpi;
+        u_dq = (int)gridDim.x / uniform_tpi;   u_dr = (int)gridDim.x - u_dq * uniform_tpi;
+    }
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const TileInfo ti = locate_tile(descs, n_images, tile, uniform_tpi);
+        TileInfo ti;
+        if (uniform_tpi > 0) {
+            ti = tile_info(descs[u_img], u_img, u_lt);
+            u_img += u_dq; u_lt += u_dr;
+            if (u_lt >= uniform_tpi) { u_lt -= uniform_tpi; u_img++; }
+        } else {
+            ti = locate_tile(descs, n_images, tile, 0);
+        }
         if constexpr (kAuto) {
             if (tab_img != ti.img) {   // per-image tables (codec.py:146-148); CTA-uniform branch
                 __syncthreads();       // everyone is done with the previous image's tables
@@ -68,9 +83,10 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
         if (t < ti.nb) {
             diff = sm.dcq[t] - dc_before(sm, t);                      // codec.py:34-35
             BitSink<false> s;
-            s.col = &sm.priv[0][t];
-            bits = walk_block<kAuto, false>(sm, t, diff, s, err);
-            nwords = s.cnt;
+            s.ptr = sbase + (uint32_t)offsetof(TileShared, priv) + (uint32_t)t * 4u;
+            s.ptr_end = s.ptr + (uint32_t)kPrivWords * kTile * 4u;
+            bits = walk_block<kAuto, false>(sm, sbase, t, diff, s, err);
+            nwords = (bits + 31) >> 5;
         }
         int incl = bits;
 #pragma unroll
@@ -149,7 +165,7 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
                     BitSink<true> s;
                     s.stage = sm.stage; s.w0 = w0; s.sh = sh;
                     int e2 = 0;
-                    walk_block<kAuto, true>(sm, t, diff, s, e2);
+                    walk_block<kAuto, true>(sm, sbase, t, diff, s, e2);
                 }
             }
             __syncthreads();   // B2: window complete, arena offset visible
@@ -633,18 +649,19 @@ static int make_quant_params(int quality, QuantParams& qp) {
     // the largest possible |t| = 1024/qt, + the rounding of the residual itself) of the fast value t;
     // every such coefficient has |t - round(t)| > 0.5 - w and is recomputed exactly.
     const double kFastErr = 6.0e-4;
-    for (int u = 0; u < 8; u++)
-        for (int v = 0; v < 8; v++) {
-            int i = u * 8 + v;
-            double m = 1.0 / (8.0 * aan[u] * aan[v] * qp.qt[i]);
-            double w = kFastErr / qp.qt[i] + 2.4e-7 * (1024.0 / qp.qt[i]) + 1.0e-6;
-            double hthr = 0.5 - w;
-            if (hthr < 0.0) hthr = 0.0;   // every coefficient goes to the exact path
-            qp.qmul[i] = (float)m;
-            qp.hthr[i] = (float)(hthr * (1.0 - 1.0e-6));
-            // |d * zmul| < 1  =>  |t| < hthr: rounds to zero, and the residual test cannot fire
-            qp.zmul[i] = hthr > 0.0 ? (float)(m / hthr * (1.0 + 1.0e-6)) : 3.0e38f;
-        }
+    static const int zigzag[64] = {TIC_ZIGZAG_LIST};
+    for (int k = 0; k < 64; k++) {
+        const int i = zigzag[k], u = i >> 3, v = i & 7;
+        double m = 1.0 / (8.0 * aan[u] * aan[v] * qp.qt[i]);
+        double w = kFastErr / qp.qt[i] + 2.4e-7 * (1024.0 / qp.qt[i]) + 1.0e-6;
+        double hthr = 0.5 - w;
+        if (hthr < 0.0) hthr = 0.0;   // every coefficient goes to the exact path
+        qp.qmul[k] = (float)m;
+        qp.hthr[k] = (float)(hthr * (1.0 - 1.0e-6));
+        // |d * zmul| < 1  =>  |t| < hthr: rounds to zero, and the residual test cannot fire
+        qp.zmul[k] = hthr > 0.0 ? (float)(m / hthr * (1.0 + 1.0e-6)) : 3.0e38f;
+    }
+    qp.dcinv = 1.0 / (8.0 * qp.qt[0]);
     return TIC_OK;
 }
 

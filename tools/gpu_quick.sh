@@ -12,7 +12,7 @@ print("BENCH value=%.0f Mpx/s ms=%.3f frac=%.4f parity=%s clocks=%s exact=%s" % 
 PY
 if [ -n "$TAG" ]; then
   PROF="python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e"
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 40 --csv \
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"compact_kernel|encode_tiles_kernel|finalize_kernel|scan_|symbol_stats|build_tables" -c 40 --csv \
       --log-file gpurun_out/launches_${TAG}.csv $PROF > gpurun_out/ncu_launch_${TAG}.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:encode_tiles_kernel -s 3 -c 1 \
       -o gpurun_out/prof_${TAG} -f $PROF > gpurun_out/ncu_full_${TAG}.log 2>&1
