@@ -15,6 +15,8 @@ Outputs:
                                   q50, Lenna at q in {90,80,50,20,10,5}, auto-table
                                   Lenna at q in {90,50,10}  
   tests/golden/images.npz         pixels of a 6-image subset of data/*.gif (inputs)
+  tests/golden/gifs_all.npz       pixels of all 50 data/*.gif (BASELINE config 2 inputs; `--images-only`
+                                  regenerates just this file)
   tests/golden/streams.npz        full reference streams: subset x qualities, odd
                                   shapes / adversarial images from seeded generators,
                                   auto-table streams
@@ -44,7 +46,17 @@ def load_gif(name):
     return np.asarray(Image.open(os.path.join(REFERENCE_ROOT, "data", f"{name}.gif")).convert("L"))
 
 
+def dump_all_gifs():
+    """BASELINE config 2 needs the pixels of all 50 data/*.gif on the GPU box (the reference tree does not
+    travel): the decoded grayscale pixels — data, not code — go into tests/golden/gifs_all.npz."""
+    names = [str(i) for i in range(1, 50)] + ["lenna"]
+    np.savez_compressed(os.path.join(GOLD, "gifs_all.npz"), **{n: load_gif(n) for n in names})
+
+
 def main():
+    if "--images-only" in sys.argv:
+        dump_all_gifs()
+        return
     ref = load_reference()
     os.makedirs(GOLD, exist_ok=True)
     kat = {"q50": {}, "lenna_sweep": {}, "lenna_auto": {}}
@@ -70,6 +82,7 @@ def main():
 
     images = {n: load_gif(n) for n in SUBSET}
     np.savez_compressed(os.path.join(GOLD, "images.npz"), **images)
+    dump_all_gifs()
 
     streams = {}
     for n in SUBSET:

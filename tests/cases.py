@@ -24,6 +24,20 @@ def synthetic_image(h, w, seed=0):
     return np.clip(base + noise, 0, 255).astype(np.uint8)
 
 
+def big_synthetic(h, w, seed=0, cell=4096):
+    """A large natural-like image in seconds: one `cell` x `cell` synthetic_image tiled over h x w, with a
+    different brightness offset per tile so that no two tile rows give the same stream."""
+    base = synthetic_image(cell, cell, seed)
+    ny, nx = (h + cell - 1) // cell, (w + cell - 1) // cell
+    img = np.tile(base, (ny, nx))[:h, :w]
+    for ty in range(ny):
+        for tx in range(nx):
+            off = (37 * ty + 11 * tx + seed) % 23 - 11
+            blk = img[ty * cell:(ty + 1) * cell, tx * cell:(tx + 1) * cell]
+            np.clip(blk.astype(np.int16) + off, 0, 255, out=blk, casting="unsafe")
+    return img
+
+
 def make_case(spec):
     kind = spec["kind"]
     h, w = spec["shape"]

@@ -19,6 +19,10 @@ class Golden:
         self.streams = {k: v.tobytes() for k, v in np.load(os.path.join(GOLD, "streams.npz")).items()}
         self.coeffs = dict(np.load(os.path.join(GOLD, "coeffs.npz")))
 
+    def all_gifs(self):
+        """name -> pixels for all 50 data/*.gif (BASELINE config 2); loaded on demand (8 MB)."""
+        return dict(np.load(os.path.join(GOLD, "gifs_all.npz")))
+
     def stream_cases(self, auto=False):
         """Yield (key, image, quality, expected bytes) for default- or auto-table streams."""
         for key, data in sorted(self.streams.items()):

@@ -78,6 +78,18 @@ def test_subset_images_batch_equals_reference_streams(tic, golden):
         assert (len(out), hashlib.sha256(out).hexdigest()) == (kat["size"], kat["sha256"]), n
 
 
+def test_all_50_gifs_one_batch_equals_reference(tic, golden):
+    """BASELINE config 2 in full: all 50 data/*.gif as ONE batch, every stream checked against the
+    reference's own bytes (size + sha256 recorded by oracle/gen_golden.py from the unmodified reference)."""
+    gifs = golden.all_gifs()
+    names = sorted(gifs)
+    assert len(names) == 50
+    outs = tic.compress_batch([gifs[n] for n in names], 50)
+    for n, out in zip(names, outs):
+        kat = golden.kat["q50"][n]
+        assert (len(out), hashlib.sha256(out).hexdigest()) == (kat["size"], kat["sha256"]), n
+
+
 @pytest.mark.parametrize("q", [1, 5, 10, 20, 35, 49, 50, 51, 65, 80, 90, 95])
 def test_random_shapes_vs_oracle(tic, q):
     rng = np.random.default_rng(1000 + q)
@@ -137,6 +149,47 @@ def test_8k_image_vs_oracle(tic):
     """BASELINE config 3: one 7680x4320 image."""
     img = synthetic_image(4320, 7680, seed=0)
     _assert_same(tic.compress(img, 50), O.compress(img, 50), "8K q50")
+
+
+def _device_stream(tic, d_img, q):
+    """One image resident in HBM through the batch C ABI; returns the stream bytes."""
+    import torch
+    res = tic.get_encoder(0).encode_batch_device([d_img], q).finish()
+    off, size = int(res.offsets[0]), int(res.sizes[0])
+    got = res.out[off: off + size].cpu().numpy().tobytes()
+    del res
+    torch.cuda.empty_cache()
+    return got
+
+
+def test_32k_image_quality_sweep(tic):
+    """BASELINE config 5: one 32768 x 32768 image (16.8 M blocks, 131,072 tiles in ONE stream — the
+    scan / compaction stress) at the reference's benchmarked qualities (tests/benchmark.py:13).
+    The extremes and q50 are compared byte for byte with the C oracle (about 20 s of host time each); the other
+    qualities through a size-independent property: blocks are coded in raster order with a running DC
+    predictor and no resets, so the stream of the top 1024 rows alone is, header aside, a bit-prefix of
+    the full image's stream."""
+    import torch
+    from tests.cases import big_synthetic
+    img = big_synthetic(32768, 32768, seed=5)
+    d_img = torch.from_numpy(img).cuda()
+    for q in (90, 50, 5):
+        _assert_same(_device_stream(tic, d_img, q), O.compress(img, q), f"32768^2 q{q}")
+    top = np.ascontiguousarray(img[:1024])
+    for q in (80, 20, 10):
+        full, part = _device_stream(tic, d_img, q), O.compress(top, q)
+        assert full[:4] == (32768).to_bytes(4, "little") and full[4:16] == part[4:16]
+        assert full[16: len(part) - 1] == part[16:-1], f"prefix property q{q}"   # last byte: padding bits
+        assert len(full) > 30 * len(part)
+
+
+def test_stream_longer_than_2_pow_32_bits_vs_oracle(tic):
+    """Uniform noise at 32768^2, quality 90: more than 2^32 bits in one stream (64-bit bit positions)."""
+    import torch
+    img = np.random.default_rng(99).integers(0, 256, (32768, 32768), dtype=np.uint8)
+    got = _device_stream(tic, torch.from_numpy(img).cuda(), 90)
+    assert len(got) * 8 > (1 << 32)
+    _assert_same(got, O.compress(img, 90), "noise 32768^2 q90")
 
 
 def test_noise_high_quality_stress_vs_oracle(tic):

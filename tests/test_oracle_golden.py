@@ -52,6 +52,16 @@ def test_kat_subset_hashes(golden):
         "4596d8bb0d5577d2d4321e5e2ff8c086ce8fbd313b00d4879d4c65baaa8048a9"
 
 
+def test_kat_all_50_gifs(golden):
+    """The oracle on all 50 data/*.gif against the reference's recorded size + sha256 (config 2 inputs)."""
+    gifs = golden.all_gifs()
+    assert len(gifs) == 50
+    for name, img in gifs.items():
+        out = O.compress(img, 50)
+        kat = golden.kat["q50"][name]
+        assert (len(out), hashlib.sha256(out).hexdigest()) == (kat["size"], kat["sha256"]), name
+
+
 def test_coefficients(golden):
     from tests.cases import ODD_CASES, make_case
     lenna = golden.images["lenna"]
