@@ -128,7 +128,10 @@ int tic_compress_host(tic_handle h, const uint8_t *pixels, int32_t height, int32
 
 /* Counters of the last tic_encode_batch on this handle (valid after tic_encode_finish):
  *   [0] kernels launched   [1] tiles   [2] coefficients sent to the exact FP64 path
- *   [3] coefficients the exact path changed   [4] blocks */
+ *   [3] coefficients the exact path changed   [4] blocks
+ *   [5] device time of encode_tiles_kernel, ns   [6] device time of compact_kernel, ns, both summed
+ *       over the [7] batches enqueued since the previous tic_encode_finish (CUDA events recorded
+ *       on the batches' stream around those two launches; the newest 64 batches at most) */
 int tic_last_stats(tic_handle h, int64_t stats[8]);
 
 #ifdef __cplusplus

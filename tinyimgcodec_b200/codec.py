@@ -139,25 +139,37 @@ class Encoder:
         2-D CUDA uint8 tensors.  Returns a DeviceBatchResult; nothing is copied to the host."""
         import torch
         q = _check_quality(quality)
+        dev = torch.device("cuda", self.device)
         if isinstance(d_images, torch.Tensor):
+            # (N, H, W) tensor: the pointer / size arrays are built with numpy, no per-image Python work
             if d_images.dim() != 3:
                 raise ValueError("expected an (N, H, W) uint8 tensor")
-            tensors = [d_images[i] for i in range(d_images.shape[0])]
+            if d_images.dtype != torch.uint8 or not d_images.is_contiguous() or d_images.device != dev:
+                raise ValueError("images must be a contiguous uint8 tensor on the encoder's GPU")
+            n, hgt, wid = (int(v) for v in d_images.shape)
+            keep = d_images
+            ptrs_np = np.uint64(d_images.data_ptr()) + np.arange(n, dtype=np.uint64) * np.uint64(hgt * wid)
+            hs_np = np.full(max(n, 1), hgt, dtype=np.int32)
+            ws_np = np.full(max(n, 1), wid, dtype=np.int32)
+            worst = n * int(self.lib.tic_max_out_bytes(hgt, wid))
         else:
             tensors = list(d_images)
-        n = len(tensors)
-        dev = torch.device("cuda", self.device)
-        for t in tensors:
-            if t.dtype != torch.uint8 or t.dim() != 2 or not t.is_contiguous() or t.device != dev:
-                raise ValueError("images must be contiguous 2-D uint8 tensors on the encoder's GPU")
-        ptrs = (ctypes.c_void_p * max(n, 1))(*[t.data_ptr() for t in tensors])
-        hs = (ctypes.c_int32 * max(n, 1))(*[t.shape[0] for t in tensors])
-        ws = (ctypes.c_int32 * max(n, 1))(*[t.shape[1] for t in tensors])
+            n = len(tensors)
+            for t in tensors:
+                if t.dtype != torch.uint8 or t.dim() != 2 or not t.is_contiguous() or t.device != dev:
+                    raise ValueError("images must be contiguous 2-D uint8 tensors on the encoder's GPU")
+            keep = tensors
+            ptrs_np = np.array([t.data_ptr() for t in tensors], dtype=np.uint64).reshape(-1)
+            hs_np = np.array([t.shape[0] for t in tensors] or [0], dtype=np.int32)
+            ws_np = np.array([t.shape[1] for t in tensors] or [0], dtype=np.int32)
+            worst = sum(int(self.lib.tic_max_out_bytes(t.shape[0], t.shape[1])) for t in tensors)
+        if ptrs_np.size == 0:
+            ptrs_np = np.zeros(1, dtype=np.uint64)
+        ptrs, hs, ws = ptrs_np.ctypes.data, hs_np.ctypes.data, ws_np.ctypes.data
         with torch.cuda.device(dev):
             if out is None:
                 slack = _lib.AUTO_HEADER_SLACK if auto_generate_huffman_table else 0
-                cap = sum(int(self.lib.tic_max_out_bytes(t.shape[0], t.shape[1])) + slack for t in tensors) + 16
-                out = torch.empty(cap, dtype=torch.uint8, device=dev)
+                out = torch.empty(worst + n * slack + 16, dtype=torch.uint8, device=dev)
             meta = torch.empty(max(n, 1) * 3, dtype=torch.int64, device=dev)
             offs, sizes = meta[:n], meta[max(n, 1): max(n, 1) + n]
             stat = meta[2 * max(n, 1):].view(torch.int32)[:n]
@@ -169,7 +181,7 @@ class Encoder:
                                                stream.cuda_stream)
                 if rc != _lib.TIC_OK:
                     self._raise(rc)
-        return DeviceBatchResult(self, out, offs, sizes, stat, stream, n)
+        return DeviceBatchResult(self, out, offs, sizes, stat, stream, n, keep)
 
     # -- batch, host buffers, pipelined -----------------------------------------------------------
     def compress_batch_pinned(self, h_images, quality=50, chunk=256, out_bytes_per_pixel=0.75):
@@ -243,15 +255,17 @@ class Encoder:
         arr = (ctypes.c_int64 * 8)()
         self.lib.tic_last_stats(self.handle, arr)
         return {"launches": arr[0], "tiles": arr[1], "exact_items": arr[2], "exact_changed": arr[3],
-                "blocks": arr[4]}
+                "blocks": arr[4], "encode_kernel_ms_sum": arr[5] * 1e-6, "compact_kernel_ms_sum": arr[6] * 1e-6,
+                "timed_batches": arr[7]}
 
 
 class DeviceBatchResult:
     """Streams of one encode_batch_device call, still in HBM."""
 
-    def __init__(self, enc, out, offsets, sizes, status, stream, n):
+    def __init__(self, enc, out, offsets, sizes, status, stream, n, inputs=None):
         self.enc, self.out, self.offsets, self.sizes, self.status = enc, out, offsets, sizes, status
         self.stream, self.n = stream, n
+        self.inputs = inputs   # keeps the pixel tensors alive until the result is dropped
         self.total_bytes = None
 
     def finish(self):

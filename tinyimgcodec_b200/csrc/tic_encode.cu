@@ -596,6 +596,12 @@ struct tic_handle_s {
     long long* d_meta = nullptr;        // off, size, status for the single-image path
     long long* h_meta = nullptr;        // pinned
     cudaStream_t own_stream = nullptr;
+    // device timing of the two big kernels: a ring of event quadruples, one per batch since the last finish
+    static constexpr int kEvRing = 64;
+    cudaEvent_t ev[kEvRing][4] = {};
+    long long ev_batches = 0;            // batches enqueued since the last tic_encode_finish
+    double sum_encode_ms = 0.0, sum_compact_ms = 0.0;
+    long long timed_batches = 0;
     long long last_tiles = 0, last_blocks = 0, last_launches = 0;
     bool tables_ready = false;
     int sm_count = 148, ctas_per_sm = kCtasPerSm;
@@ -718,6 +724,9 @@ int tic_create(int device, tic_handle* out) {
         delete h;
         return TIC_E_CUDA;
     }
+    for (int i = 0; i < tic_handle_s::kEvRing; i++)
+        for (int j = 0; j < 4; j++)
+            if (cudaEventCreate(&h->ev[i][j]) != cudaSuccess) { tic_destroy(h); return TIC_E_CUDA; }
     *out = h;
     return TIC_OK;
 }
@@ -731,6 +740,8 @@ int tic_destroy(tic_handle h) {
     cudaFreeHost(h->h_counters); cudaFree(h->d_out_end); cudaFree(h->d_px); cudaFree(h->d_out);
     cudaFreeHost(h->h_stage); cudaFree(h->d_meta); cudaFreeHost(h->h_meta);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    for (int i = 0; i < tic_handle_s::kEvRing; i++)
+        for (int j = 0; j < 4; j++) if (h->ev[i][j]) cudaEventDestroy(h->ev[i][j]);
     delete h;
     return TIC_OK;
 }
@@ -771,6 +782,7 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     rc = ensure_tables(h);
     if (rc) return rc;
     h->last_tiles = h->last_blocks = h->last_launches = 0;
+    cudaEvent_t* evq = h->ev[h->ev_batches % tic_handle_s::kEvRing];
     if (n_images == 0) {
         TIC_CUDA(h, cudaMemsetAsync(h->d_counters, 0, kCtrCount * 8, stream));
         return TIC_OK;
@@ -864,15 +876,18 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
         TIC_CUDA(h, cudaGetLastError());
         d_tabs = h->d_tabs;
         h->last_launches = 8;
+        TIC_CUDA(h, cudaEventRecord(evq[0], stream));
         encode_tiles_kernel<true><<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
             qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_recs, h->d_arena, (unsigned long long)h->arena_cap16,
             h->d_counters, d_status, quality, d_tabs);
     } else {
+        TIC_CUDA(h, cudaEventRecord(evq[0], stream));
         encode_tiles_kernel<false><<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
             qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_recs, h->d_arena, (unsigned long long)h->arena_cap16,
             h->d_counters, d_status, quality, d_tabs);
     }
     TIC_CUDA(h, cudaGetLastError());
+    TIC_CUDA(h, cudaEventRecord(evq[1], stream));
     scan_chunks_kernel<<<(unsigned)nchunks, kScanThreads, 0, stream>>>(h->d_recs, ntiles, h->d_chunk_span);
     TIC_CUDA(h, cudaGetLastError());
     scan_spine_kernel<<<1, kSpineThreads, 0, stream>>>(h->d_chunk_span, nchunks, h->d_chunk_pos);
@@ -884,10 +899,13 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     long long cgrid = (ntiles * 32 + kCompactThreads - 1) / kCompactThreads;
     const long long cmax = (long long)h->sm_count * 8 * 4;
     if (cgrid > cmax) cgrid = cmax;
+    TIC_CUDA(h, cudaEventRecord(evq[2], stream));
     compact_kernel<<<(unsigned)cgrid, kCompactThreads, 0, stream>>>(h->d_recs, h->d_tile_pos, ntiles,
                                                                     (const uint32_t*)h->d_arena, (uint32_t*)d_out,
                                                                     (long long)out_capacity);
     TIC_CUDA(h, cudaGetLastError());
+    TIC_CUDA(h, cudaEventRecord(evq[3], stream));
+    h->ev_batches++;
     finalize_kernel<<<(n_images + 255) / 256, 256, 0, stream>>>(n_images, (const long long*)d_out_offsets,
                                                                h->d_out_end, (long long*)d_out_sizes, d_status,
                                                                h->d_counters);
@@ -903,6 +921,18 @@ int tic_encode_finish(tic_handle h, void* stream_v, int64_t* total_bytes) {
     TIC_CUDA(h, cudaSetDevice(h->device));
     TIC_CUDA(h, cudaMemcpyAsync(h->h_counters, h->d_counters, kCtrCount * 8, cudaMemcpyDeviceToHost, stream));
     TIC_CUDA(h, cudaStreamSynchronize(stream));
+    // device time of the two big kernels, summed over the batches enqueued since the last finish
+    // (CUDA events recorded on the batches' stream; at most the newest kEvRing batches)
+    h->sum_encode_ms = h->sum_compact_ms = 0.0;
+    h->timed_batches = h->ev_batches < tic_handle_s::kEvRing ? h->ev_batches : tic_handle_s::kEvRing;
+    for (long long b = h->ev_batches - h->timed_batches; b < h->ev_batches; b++) {
+        cudaEvent_t* q = h->ev[b % tic_handle_s::kEvRing];
+        float a = 0.f, c = 0.f;
+        if (cudaEventElapsedTime(&a, q[0], q[1]) == cudaSuccess) h->sum_encode_ms += a;
+        if (cudaEventElapsedTime(&c, q[2], q[3]) == cudaSuccess) h->sum_compact_ms += c;
+    }
+    h->ev_batches = 0;
+    (void)cudaGetLastError();
     if (total_bytes) *total_bytes = (int64_t)(h->h_counters[kCtrTotalBits] >> 3);
     if (h->h_counters[kCtrOverflow]) { h->err = "output buffer too small"; return TIC_E_CAPACITY; }
     if (h->h_counters[kCtrAnyStatus] & TIC_STATUS_TABLE) {
@@ -928,6 +958,9 @@ int tic_last_stats(tic_handle h, int64_t stats[8]) {
     stats[2] = (int64_t)h->h_counters[kCtrExactItems];
     stats[3] = (int64_t)h->h_counters[kCtrExactChanged];
     stats[4] = h->last_blocks;
+    stats[5] = (int64_t)(h->sum_encode_ms * 1.0e6);
+    stats[6] = (int64_t)(h->sum_compact_ms * 1.0e6);
+    stats[7] = h->timed_batches;
     return TIC_OK;
 }
 

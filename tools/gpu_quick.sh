@@ -8,7 +8,7 @@ timeout 600 python bench.py --no-cpu --no-e2e --steps 10 --warmup 3 > gpurun_out
 python - <<'PY'
 import json
 d=json.load(open("gpurun_out/quick.json"))
-print("BENCH value=%.0f Mpx/s ms=%.3f frac=%.4f parity=%s clocks=%s exact=%s" % (d["value"], d["ms_per_step"], d["roofline"]["frac"], d["parity"], d["clocks"], d["config"]["exact_path"]))
+print("BENCH value=%.0f Mpx/s step_ms=%.3f kernel_ms=%.3f compact_ms=%.3f frac=%.4f parity=%s clocks=%s exact=%s" % (d["value"], d["ms_per_step"], d["roofline"]["launch_ms"], d["roofline"]["other_kernels_ms"]["compact_kernel"], d["roofline"]["frac"], d["parity"], d["clocks"], d["config"]["exact_path"]))
 PY
 if [ -n "$TAG" ]; then
   PROF="python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e"
