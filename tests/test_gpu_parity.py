@@ -201,6 +201,41 @@ def test_noise_high_quality_stress_vs_oracle(tic):
     _assert_same(tic.compress(flat, 50), O.compress(flat, 50), "flat")
 
 
+def test_device_tensor_batch_and_stats(tic):
+    """(N, H, W) tensor resident in HBM -> streams in HBM (the bench's call), plus the counters of
+    tic_last_stats."""
+    import torch
+    imgs = np.stack([synthetic_image(256, 384, seed=s) for s in range(9)])
+    enc = tic.get_encoder(0)
+    res = enc.encode_batch_device(torch.from_numpy(imgs).cuda(), 50).finish()
+    for im, out in zip(imgs, res.to_bytes()):
+        _assert_same(out, O.compress(im, 50), "tensor batch")
+    offs = res.offsets.cpu().numpy()
+    assert np.all(offs % 16 == 0) and np.all(np.diff(offs) > 0)          # dense, 16-byte aligned, in order
+    st = enc.stats()
+    assert st["launches"] == 6 and st["blocks"] == 9 * 32 * 48 and st["tiles"] == 9 * 12
+    assert st["timed_batches"] == 1 and st["encode_kernel_ms_sum"] > 0 and st["compact_kernel_ms_sum"] > 0
+
+
+def test_output_capacity_is_respected(tic):
+    """TIC_E_CAPACITY: a too-small d_out is reported, and nothing past out_capacity is written."""
+    import torch
+    img = make_case({"kind": "noise", "shape": (512, 512), "seed": 21})
+    need = len(O.compress(img, 90))
+    enc = tic.get_encoder(0)
+    d_img = torch.from_numpy(img).cuda()
+    for cap in (need // 3, need - 5, 64):
+        cap16 = cap & ~15
+        buf = torch.full((cap16 + 4096,), 0xA5, dtype=torch.uint8, device="cuda")
+        with pytest.raises(tic.TicError) as ei:
+            enc.encode_batch_device([d_img], 90, out=buf[:cap16]).finish()
+        assert ei.value.code == -4
+        assert bool((buf[cap16:] == 0xA5).all()), f"write past capacity {cap16}"
+    buf = torch.full((((need + 3) & ~3) + 4096,), 0xA5, dtype=torch.uint8, device="cuda")
+    res = enc.encode_batch_device([d_img], 90, out=buf[: (need + 3) & ~3]).finish()       # exactly enough
+    assert res.to_bytes()[0] == O.compress(img, 90) and bool((buf[(need + 3) & ~3:] == 0xA5).all())
+
+
 def test_error_behaviour_matches_reference(tic):
     import struct
     img = np.zeros((16, 16), np.uint8)
