@@ -128,9 +128,7 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
         }
 
         const int hdr_words = (hdr_bits + 31) >> 5;
-        const int rounds = nw_tile > kWinWords ? (nw_tile + kWinWords - 1) / kWinWords : 1;
-        for (int r = 0; r < rounds; r++) {
-            const int wbase = r * kWinWords;
+        for (int wbase = 0;;) {   // one round per window; a second one only for tiles longer than the window
             // ---- header words (they OR into the zeroed window like everything else) --------------
             if (ti.first) {
                 for (int i = wbase + t; i < hdr_words && i < wbase + kWinWords; i += kTile) {
@@ -179,7 +177,9 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
                 st4[i] = make_uint4(0u, 0u, 0u, 0u);
                 if (aoff != 0xffffffffu) arena[(size_t)aoff + (size_t)(wbase / 4) + i] = v;
             }
-            if (r + 1 < rounds) __syncthreads();
+            wbase += kWinWords;
+            if (wbase >= nw_tile) break;
+            __syncthreads();
         }
     }
     // exact-path statistics: one atomic per warp at the very end
@@ -616,6 +616,13 @@ struct tic_handle_s {
         }                                                                                     \
     } while (0)
 
+static int bw_shift_of(int bw) {   // log2 for a power of two, else -1
+    if (bw <= 0 || (bw & (bw - 1))) return -1;
+    int s = 0;
+    while ((1 << s) < bw) s++;
+    return s;
+}
+
 static void build_default_tables(HuffTables& t) {
     memset(&t, 0, sizeof t);
     uint32_t code = 0;
@@ -800,6 +807,8 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
         d.h = heights[i];
         d.w = widths[i];
         d.bw = (widths[i] + 7) / 8;
+        d.bw_shift = bw_shift_of(d.bw);
+        d.pad = 0;
         d.nblk = (int)nblk;
         d.tile0 = ntiles;
         long long nt = (nblk + kTile - 1) / kTile;
@@ -985,6 +994,7 @@ int tic_encode_coeffs(tic_handle h, const void* d_pixels, int32_t height, int32_
     ImageDesc& d = h->h_descs[0];
     d.px = (const uint8_t*)d_pixels;
     d.h = height; d.w = width; d.bw = (width + 7) / 8; d.nblk = (int)nblk; d.tile0 = 0;
+    d.bw_shift = bw_shift_of(d.bw); d.pad = 0;
     TIC_CUDA(h, cudaMemcpyAsync(h->d_descs, h->h_descs, sizeof(ImageDesc), cudaMemcpyHostToDevice, stream));
     TIC_CUDA(h, cudaMemsetAsync(h->d_counters, 0, kCtrCount * 8, stream));
     long long ntiles = (nblk + kTile - 1) / kTile;

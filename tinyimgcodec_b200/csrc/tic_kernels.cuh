@@ -70,6 +70,8 @@ struct ImageDesc {
     int bw;            // blocks per row = ceil(w/8)
     int nblk;          // ceil(h/8)*ceil(w/8)
     long long tile0;   // index of this image's first tile in the batch
+    int bw_shift;      // log2(bw) when bw is a power of two (block row = block >> bw_shift), else -1
+    int pad;
 };
 
 // What the encode kernel leaves behind per tile.
@@ -250,7 +252,7 @@ __device__ __noinline__ double dct8_exact(const double x0, const double x1, cons
 
 struct TileInfo {
     const uint8_t* px;
-    int h, w, bw;
+    int h, w, bw, bw_shift;
     int img;          // image index
     int blk0;         // first block of the tile within the image
     int nb;           // blocks in this tile (0..kTile)
@@ -284,7 +286,7 @@ struct TileShared {
 // Tile number lt of image `img`.
 __device__ __forceinline__ TileInfo tile_info(const ImageDesc& d, int img, long long lt) {
     TileInfo ti;
-    ti.px = d.px; ti.h = d.h; ti.w = d.w; ti.bw = d.bw; ti.img = img;
+    ti.px = d.px; ti.h = d.h; ti.w = d.w; ti.bw = d.bw; ti.bw_shift = d.bw_shift; ti.img = img;
     ti.blk0 = (int)lt * kTile;
     const int rem = d.nblk - ti.blk0;
     ti.nb = rem < 0 ? 0 : (rem > kTile ? kTile : rem);
@@ -390,15 +392,17 @@ __device__ __forceinline__ int coef_get(const TileShared& sm, int t, int k) {
     return (int)(short)((k & 1) ? (w >> 16) : w);
 }
 
-// One block, all 32 lanes of the warp call (the group test votes); `active` = the block exists.
+// One block, all 32 lanes of a warp that owns at least one block call (the group test votes); `active` =
+// this lane's block exists.
 __device__ __forceinline__ void transform_block(const TileInfo& ti, const QuantParams& qp, TileShared& sm,
                                                 int t, bool active, uint32_t& fl_lo, uint32_t& fl_hi) {
-    const int b = ti.blk0 + t;
+    // a lane without a block of its own (last tile of an image) transforms a copy of the tile's last block:
+    // its results land in its own shared-memory column and are never read
+    const int b = ti.blk0 + (active ? t : ti.nb - 1);
     int br, bc;
-    if (ti.bw >= kTile) {   // the tile spans at most two block rows: one division per tile, not per block
-        br = ti.blk0 / ti.bw;
-        bc = ti.blk0 - br * ti.bw + t;
-        if (bc >= ti.bw) { bc -= ti.bw; br++; }
+    if (ti.bw_shift >= 0) {   // blocks per row is a power of two (uniform branch)
+        br = b >> ti.bw_shift;
+        bc = b & (ti.bw - 1);
     } else {
         br = b / ti.bw;
         bc = b - br * ti.bw;
@@ -406,10 +410,7 @@ __device__ __forceinline__ void transform_block(const TileInfo& ti, const QuantP
     const int y0 = br * 8, x0 = bc * 8;
     float d[64];
     const bool fast = ((ti.w & 7) == 0) && ((reinterpret_cast<uintptr_t>(ti.px) & 7) == 0) && (y0 + 8 <= ti.h);
-    if (!active) {
-#pragma unroll
-        for (int i = 0; i < 64; i++) d[i] = 128.0f;
-    } else if (fast) {
+    if (fast) {
         const uint8_t* p = ti.px + (size_t)y0 * ti.w + x0;
         uint2 rows[8];
 #pragma unroll
@@ -535,7 +536,7 @@ __device__ __forceinline__ void transform_warp(const TileInfo& ti, const QuantPa
     }
     __syncwarp();
     uint32_t fl_lo = 0, fl_hi = 0;
-    transform_block(ti, qp, sm, t, t < ti.nb, fl_lo, fl_hi);
+    if (warp * 32 < ti.nb) transform_block(ti, qp, sm, t, t < ti.nb, fl_lo, fl_hi);   // warp-uniform
     // halo: quantised DC of the block in front of the warp's first block.  The DC coefficient is
     // (sum of pixels - 8192) / 8 exactly, so unless its quotient by qt lands within 1e-9 of a .5 tie
     // (where the reference's float64 rounding errors decide) one pixel sum settles it; otherwise, and
