@@ -168,29 +168,50 @@ __device__ __forceinline__ void aan8x2(f32x2& d0, f32x2& d1, f32x2& d2, f32x2& d
     d7 = sub2(z11, z4);
 }
 
+// Column pass for a pair of adjacent columns with a SCALAR final stage: the 16 results are written as single
+// floats, so that they can be re-paired by rows for the second pass without a single register move.
+__device__ __forceinline__ void aan8x2_split(f32x2 d0, f32x2 d1, f32x2 d2, f32x2 d3, f32x2 d4, f32x2 d5, f32x2 d6,
+                                             f32x2 d7, float (&lo)[8], float (&hi)[8]) {
+    const f32x2 c707 = pk2(0.707106781f, 0.707106781f), c382 = pk2(0.382683433f, 0.382683433f);
+    const f32x2 c541 = pk2(0.541196100f, 0.541196100f), c1306 = pk2(1.306562965f, 1.306562965f);
+    f32x2 t0 = add2(d0, d7), t7 = sub2(d0, d7), t1 = add2(d1, d6), t6 = sub2(d1, d6);
+    f32x2 t2 = add2(d2, d5), t5 = sub2(d2, d5), t3 = add2(d3, d4), t4 = sub2(d3, d4);
+    f32x2 t10 = add2(t0, t3), t13 = sub2(t0, t3), t11 = add2(t1, t2), t12 = sub2(t1, t2);
+    f32x2 z1 = mul2(add2(t12, t13), c707);
+    f32x2 u10 = add2(t4, t5), u11 = add2(t5, t6), u12 = add2(t6, t7);
+    f32x2 z5 = mul2(sub2(u10, u12), c382);
+    f32x2 z2 = fma2(c541, u10, z5);
+    f32x2 z4 = fma2(c1306, u12, z5);
+    f32x2 z3 = mul2(u11, c707);
+    f32x2 z11 = add2(t7, z3), z13 = sub2(t7, z3);
+    float a0, a1, b0, b1;
+    upk2(t10, a0, a1); upk2(t11, b0, b1); lo[0] = a0 + b0; hi[0] = a1 + b1; lo[4] = a0 - b0; hi[4] = a1 - b1;
+    upk2(t13, a0, a1); upk2(z1, b0, b1);  lo[2] = a0 + b0; hi[2] = a1 + b1; lo[6] = a0 - b0; hi[6] = a1 - b1;
+    upk2(z13, a0, a1); upk2(z2, b0, b1);  lo[5] = a0 + b0; hi[5] = a1 + b1; lo[3] = a0 - b0; hi[3] = a1 - b1;
+    upk2(z11, a0, a1); upk2(z4, b0, b1);  lo[1] = a0 + b0; hi[1] = a1 + b1; lo[7] = a0 - b0; hi[7] = a1 - b1;
+}
+
 // 2-D transform of d[y*8+x] in place: columns two at a time, then rows two at a time.
 __device__ __forceinline__ void fdct8x8(float (&d)[64]) {
-    f32x2 p[8][4];   // p[y][j] = (d[y][2j], d[y][2j+1])
+    float z[8][8];   // after the column pass
 #pragma unroll
-    for (int y = 0; y < 8; y++)
+    for (int j = 0; j < 4; j++) {
+        float lo[8], hi[8];
+        aan8x2_split(pk2(d[0 * 8 + 2 * j], d[0 * 8 + 2 * j + 1]), pk2(d[1 * 8 + 2 * j], d[1 * 8 + 2 * j + 1]),
+                     pk2(d[2 * 8 + 2 * j], d[2 * 8 + 2 * j + 1]), pk2(d[3 * 8 + 2 * j], d[3 * 8 + 2 * j + 1]),
+                     pk2(d[4 * 8 + 2 * j], d[4 * 8 + 2 * j + 1]), pk2(d[5 * 8 + 2 * j], d[5 * 8 + 2 * j + 1]),
+                     pk2(d[6 * 8 + 2 * j], d[6 * 8 + 2 * j + 1]), pk2(d[7 * 8 + 2 * j], d[7 * 8 + 2 * j + 1]), lo, hi);
 #pragma unroll
-        for (int j = 0; j < 4; j++) p[y][j] = pk2(d[y * 8 + 2 * j], d[y * 8 + 2 * j + 1]);
+        for (int u = 0; u < 8; u++) { z[u][2 * j] = lo[u]; z[u][2 * j + 1] = hi[u]; }
+    }
 #pragma unroll
-    for (int j = 0; j < 4; j++) aan8x2(p[0][j], p[1][j], p[2][j], p[3][j], p[4][j], p[5][j], p[6][j], p[7][j]);
-#pragma unroll
-    for (int u = 0; u < 8; u += 2) {   // rows u and u+1: re-pair (row u, row u+1) per column
+    for (int u = 0; u < 8; u += 2) {   // rows u and u+1
         f32x2 q[8];
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            float a, b, c, e;
-            upk2(p[u][j], a, b);
-            upk2(p[u + 1][j], c, e);
-            q[2 * j] = pk2(a, c);
-            q[2 * j + 1] = pk2(b, e);
-        }
+        for (int c = 0; c < 8; c++) q[c] = pk2(z[u][c], z[u + 1][c]);
         aan8x2(q[0], q[1], q[2], q[3], q[4], q[5], q[6], q[7]);
 #pragma unroll
-        for (int v = 0; v < 8; v++) upk2(q[v], d[u * 8 + v], d[(u + 1) * 8 + v]);
+        for (int c = 0; c < 8; c++) upk2(q[c], d[u * 8 + c], d[(u + 1) * 8 + c]);
     }
 }
 
