@@ -365,10 +365,9 @@ def run_gpu_arm(args):
     except Exception as ex:  # keep the device-timed line even if the host leg cannot run
         e2e = {"value": None, "unit": UNIT, "error": f"{type(ex).__name__}: {ex}"}
 
-    line = None
+    # parity spot check of the benchmarked data against the oracle (outside every timed region)
+    parity = {"checked": 0, "identical": 0}
     if rank == 0:
-        # parity spot check of the benchmarked data against the oracle (outside every timed region)
-        parity = {"checked": 0, "identical": 0}
         try:
             from oracle import oracle_lib as O
             streams = res.to_bytes()
@@ -376,8 +375,51 @@ def run_gpu_arm(args):
                 px = d_images[i].cpu().numpy()
                 parity["checked"] += 1
                 parity["identical"] += int(streams[i] == O.compress(px, QUALITY))
+            del streams
         except Exception as ex:
             parity["error"] = f"{type(ex).__name__}: {ex}"
+
+    # the same batch as the C-variant stream (TIC_FLAG_C_VARIANT, quality 'med'): the format the reference's C
+    # encoder — the CPU arm of this bench — emits, so that arm and this figure code the same thing
+    c_variant = None
+    try:
+        cv_steps = max(1, min(args.steps, 10))
+        for _ in range(2):
+            cres = enc.encode_batch_device(d_images, "med", out=d_out, stream=stream, c_variant=True)
+        cres.finish()
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(cv_steps):
+            cres = enc.encode_batch_device(d_images, "med", out=d_out, stream=stream, c_variant=True)
+        c1.record(stream)
+        barrier()
+        cres.finish()
+        cms = c0.elapsed_time(c1) / cv_steps
+        if world > 1:
+            tt = torch.tensor([cms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            cms = float(tt.item())
+        cst = enc.stats()
+        c_variant = {"value": total_px / (cms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": cms, "steps": cv_steps,
+                     "encode_kernel_ms": cst["encode_kernel_ms_sum"] / max(1, int(cst["timed_batches"])),
+                     "stream_bytes_rank0": int(cres.sizes.sum().item()),
+                     "what": "integer-FDCT stream of c/encode.c, quality 'med', device-resident, CUDA events"}
+        if rank == 0:
+            from oracle import oracle_lib as O
+            if O.ref_c_available():   # the reference binary itself, 2 images (outside every timed region)
+                outs = cres.to_bytes()
+                ok = 0
+                for i in (0, n_local - 1):
+                    want = O.ref_c_compress(d_images[i].cpu().numpy(), "med")
+                    ok += int(outs[i][:-1] == want[: len(outs[i]) - 1])
+                c_variant["parity_vs_reference_binary"] = {"checked": 2, "identical_up_to_flush_byte": ok}
+        del cres
+    except Exception as ex:
+        c_variant = {"value": None, "error": f"{type(ex).__name__}: {ex}"}
+
+    line = None
+    if rank == 0:
         cpu_baseline = None
         extra = {}
         if n_gpus == 1 and not args.no_cpu:
@@ -405,7 +447,7 @@ def run_gpu_arm(args):
                        "stream_bytes": stream_bytes_total, "bits_per_pixel": 8.0 * stream_bytes_total / total_px,
                        "exact_path": {k: stats[k] for k in ("exact_items", "exact_changed", "blocks", "tiles")}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(stats["launches"]) * args.steps * n_gpus, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "parity": parity,
+            "cpu_baseline": cpu_baseline, "parity": parity, "c_variant": c_variant,
         }
         line.update(extra)
         print(json.dumps(line), flush=True)

@@ -43,6 +43,15 @@ extern "C" {
 
 /* flags for tic_encode_batch */
 #define TIC_FLAG_AUTO_HUFFMAN 1u /* per-image tables, tinyimgcodec/codec.py:146-148 */
+#define TIC_FLAG_C_VARIANT 2u    /* the stream of the reference's embedded C encoder (c/encode.c, c/img.c:
+                                    header flag bit 30, integer AAN FDCT, scaled integer quantiser, one flush
+                                    byte).  `quality` is then IMG_Q_BEST..IMG_Q_LOW = 0..3 (c/img.h:22); width
+                                    and height must be multiples of 8 (c/encode.c:38-41).  Byte-identical to
+                                    the reference binary for every block of the image; the extra block row that
+                                    binary appends (c/encode.c:47: one more loop pass at EOF over a stack buffer
+                                    the C library has overwritten — its bits differ from run to run of the
+                                    reference itself) is not produced.  Not combinable with
+                                    TIC_FLAG_AUTO_HUFFMAN. */
 
 /* per-image status bits written by the device */
 #define TIC_STATUS_CATEGORY 1 /* KeyError case above */

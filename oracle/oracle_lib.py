@@ -115,3 +115,27 @@ def default_code(is_ac, sym):
     if rc:
         return None
     return format(code.value, f"0{ln.value}b")
+
+
+# ---- the reference's own C encoder (oracle/_ref/encode, built from /root/reference/c by `make ref`) -------
+REF_C_ENCODER = os.path.join(_HERE, "_ref", "encode")
+
+
+def ref_c_available():
+    return os.path.isfile(REF_C_ENCODER)
+
+
+def ref_c_compress(img, qfactor="med"):
+    """stdout of `encode <width> <height> <qfactor>` fed the raw rows of `img` from a FILE on stdin
+    (c/encode.c:13-66) — the reference binary itself, unmodified."""
+    import subprocess
+    import tempfile
+    import numpy as np
+    img = np.ascontiguousarray(img, dtype=np.uint8)
+    h, w = img.shape
+    with tempfile.NamedTemporaryFile(suffix=".raw") as f:
+        f.write(img.tobytes())
+        f.flush()
+        with open(f.name, "rb") as fin:
+            return subprocess.run([REF_C_ENCODER, str(w), str(h), qfactor], stdin=fin, stdout=subprocess.PIPE,
+                                  check=True).stdout

@@ -47,6 +47,20 @@ def _check_quality(quality):
     return int(quality)
 
 
+C_QFACTORS = {"best": 0, "high": 1, "med": 2, "low": 3}   # c/img.h:22, c/encode.c:19-30
+
+
+def _check_qfactor(qfactor):
+    if isinstance(qfactor, str):
+        if qfactor not in C_QFACTORS:
+            raise ValueError("Invalid quality factor")   # c/encode.c:28
+        return C_QFACTORS[qfactor]
+    q = int(qfactor)
+    if q not in (0, 1, 2, 3):
+        raise ValueError("Invalid quality factor")
+    return q
+
+
 def _as_u8_image(image):
     """`height, width = image.shape` (codec.py:27) then astype(int32) (codec.py:29)."""
     image = np.asarray(image)
@@ -113,6 +127,26 @@ class Encoder:
                 self._raise(rc)
         return out[: size.value].tobytes()
 
+    def compress_c(self, image, qfactor="med"):
+        """The stream of the reference's embedded C encoder (`c/encode <width> <height> [best|high|med|low]`
+        fed the raw pixel rows, c/encode.c:13-66): header flag bit 30, integer FDCT, byte-identical to that
+        binary's stdout for every block of the image.  (The binary then codes one more block row from a
+        clobbered stack buffer, c/encode.c:47 — different on every run — which is not produced.)"""
+        img, height, width = _as_u8_image(image)
+        q = _check_qfactor(qfactor)
+        if height % 8 or width % 8:
+            raise ValueError("Width and height must be multiples of 8")   # c/encode.c:38-41
+        cap = int(self.lib.tic_max_out_bytes(height, width))
+        out = np.empty(cap, dtype=np.uint8)
+        size = ctypes.c_int64(0)
+        status = ctypes.c_int32(0)
+        with self._lock:
+            rc = self.lib.tic_compress_host(self.handle, img.ctypes.data, height, width, q, _lib.TIC_FLAG_C_VARIANT,
+                                            out.ctypes.data, cap, ctypes.byref(size), ctypes.byref(status))
+            if rc != _lib.TIC_OK:
+                self._raise(rc)
+        return out[: size.value].tobytes()
+
     def encode(self, image, quality=50):
         import torch
         img, height, width = _as_u8_image(image)
@@ -134,11 +168,12 @@ class Encoder:
         return {"height": height, "width": width, "quality": quality, "dc": dc, "ac": ac}
 
     # -- batch, device buffers ----------------------------------------------------------------
-    def encode_batch_device(self, d_images, quality=50, out=None, stream=None, auto_generate_huffman_table=False):
+    def encode_batch_device(self, d_images, quality=50, out=None, stream=None, auto_generate_huffman_table=False,
+                            c_variant=False):
         """Encode a batch resident in HBM.  `d_images`: a CUDA uint8 tensor (N,H,W) or a list of
         2-D CUDA uint8 tensors.  Returns a DeviceBatchResult; nothing is copied to the host."""
         import torch
-        q = _check_quality(quality)
+        q = _check_qfactor(quality) if c_variant else _check_quality(quality)
         dev = torch.device("cuda", self.device)
         if isinstance(d_images, torch.Tensor):
             # (N, H, W) tensor: the pointer / size arrays are built with numpy, no per-image Python work
@@ -175,7 +210,8 @@ class Encoder:
             stat = meta[2 * max(n, 1):].view(torch.int32)[:n]
             stream = stream or torch.cuda.current_stream(dev)
             with self._lock:
-                flags = _lib.TIC_FLAG_AUTO_HUFFMAN if auto_generate_huffman_table else 0
+                flags = (_lib.TIC_FLAG_AUTO_HUFFMAN if auto_generate_huffman_table else 0) | \
+                        (_lib.TIC_FLAG_C_VARIANT if c_variant else 0)
                 rc = self.lib.tic_encode_batch(self.handle, ptrs, hs, ws, n, q, flags, out.data_ptr(), out.numel(),
                                                offs.data_ptr(), sizes.data_ptr(), stat.data_ptr(),
                                                stream.cuda_stream)
@@ -305,6 +341,11 @@ def compress(image, quality=50, auto_generate_huffman_table=False, device=None):
 def encode(image, quality=50, device=None):
     """Drop-in for tinyimgcodec.codec.encode (codec.py:26-43)."""
     return get_encoder(device).encode(image, quality)
+
+
+def compress_c(image, qfactor="med", device=None):
+    """The reference's embedded C encoder (c/encode.c) for one image: see Encoder.compress_c."""
+    return get_encoder(device).compress_c(image, qfactor)
 
 
 def compress_batch(images, quality=50, device=None, auto_generate_huffman_table=False):

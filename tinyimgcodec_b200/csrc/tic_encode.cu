@@ -34,7 +34,9 @@ __device__ __forceinline__ void load_tables(TileShared& sm, const HuffTables& g)
 // compress(), stage 1: every tile -> its bits in the arena + a TileRec.  Persistent CTAs, tiles
 // dealt round-robin; no tile waits for another.
 // ---------------------------------------------------------------------------------------------
-template <bool kAuto>
+// kMode: 0 = fixed Huffman tables, 1 = per-image tables (auto_generate_huffman_table), 2 = C-variant stream
+// (flag bit 30; `quality` is then the reference's IMG_Q_BEST .. IMG_Q_LOW = 0 .. 3)
+template <int kMode>
 __global__ void __launch_bounds__(kTile, kCtasPerSm)
 encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restrict__ descs, int n_images,
                     int uniform_tpi, long long ntiles, TileRec* __restrict__ recs, uint4* __restrict__ arena,
@@ -42,6 +44,7 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
                     int* __restrict__ status, int quality, const AutoTables* __restrict__ auto_tabs) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     TileShared& sm = *reinterpret_cast<TileShared*>(smem_raw);
+    constexpr bool kAuto = kMode == 1, kCVar = kMode == 2;
     const int t = threadIdx.x;
     const int lane = t & 31, warp = t >> 5;
     uint32_t sbase = smem_u32(smem_raw);   // kept in a register: the walk addresses shared memory directly
@@ -78,7 +81,8 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
         }
 
         // ---- per warp: coefficients, then the bits of every block into its private words ---------
-        transform_warp(ti, qp, sm, st);
+        if constexpr (kCVar) transform_warp_c(ti, quality, sm);
+        else transform_warp(ti, qp, sm, st);
         int err = 0, bits = 0, nwords = 0, diff = 0;
         if (t < ti.nb) {
             diff = sm.dcq[t] - dc_before(sm, t);                      // codec.py:34-35
@@ -111,6 +115,8 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
         const int hdr_bits = !ti.first ? 0 : (kAuto ? (int)auto_tabs[ti.img].hdr_bits : 128);
         const int bitpos = hdr_bits + warp_base + incl - bits;   // tile-relative bit offset of this block
         tile_bits += hdr_bits;
+        // C variant: IMG_encodeComplete always writes one more byte (c/img.h BB_flushBits) = one pad bit here
+        if constexpr (kCVar) tile_bits += ti.closing ? 1 : 0;
         const int nw_tile = (tile_bits + 31) >> 5;               // tile-relative words holding data
         const int n16_tile = (nw_tile + 3) >> 2;
         if (t == 0) {   // reserve the tile's slot in the arena; the latency hides behind the placement
@@ -136,7 +142,8 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
                     if constexpr (kAuto) {
                         w = auto_tabs[ti.img].hdr_words[i];
                     } else {   // struct.pack("III") is little-endian, the stream is MSB-first; flag word 0
-                        const uint32_t v = i == 0 ? (uint32_t)ti.h : (i == 1 ? (uint32_t)ti.w : (i == 2 ? (uint32_t)quality : 0u));
+                        // C variant: all four words are little-endian structs, flag = 1 << 30 (c/img.c:183-192)
+                        const uint32_t v = i == 0 ? (uint32_t)ti.h : (i == 1 ? (uint32_t)ti.w : (i == 2 ? (uint32_t)quality : (kCVar ? 0x40000000u : 0u)));
                         w = __byte_perm(v, 0, 0x0123);
                     }
                     if (w) atomicOr(&sm.stage[i - wbase], w);
@@ -683,16 +690,22 @@ static int ensure_tables(tic_handle h) {
     HuffTables t;
     build_default_tables(t);
     TIC_CUDA(h, cudaMemcpyToSymbol(c_default_tables, &t, sizeof t));
-    TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(TileShared)));
-    TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(TileShared)));
+    TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(TileShared)));
+    uint16_t sq[4][64];   // c/img.c:157-181
+    for (int f = 0; f < 4; f++)
+        for (int i = 0; i < 64; i++) sq[f][i] = (uint16_t)(65536 / (kQuantBase[i] << f));
+    TIC_CUDA(h, cudaMemcpyToSymbol(c_cvar_scaled_quant, sq, sizeof sq));
     TIC_CUDA(h, cudaFuncSetAttribute(coeffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(TileShared)));
     TIC_CUDA(h, cudaFuncSetAttribute(symbol_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(TileShared)));
     int per_sm = 0;
-    TIC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_tiles_kernel<false>, kTile, sizeof(TileShared)));
+    TIC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_tiles_kernel<0>, kTile, sizeof(TileShared)));
     cudaDeviceProp prop;
     TIC_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
     h->sm_count = prop.multiProcessorCount;
@@ -777,13 +790,21 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
         return TIC_E_INVALID;
     }
     const bool auto_mode = (flags & TIC_FLAG_AUTO_HUFFMAN) != 0;
+    const bool c_variant = (flags & TIC_FLAG_C_VARIANT) != 0;
+    if (auto_mode && c_variant) { h->err = "the C-variant stream has fixed tables"; return TIC_E_INVALID; }
     if ((reinterpret_cast<uintptr_t>(d_out) & 15) != 0) {
         h->err = "d_out must be 16-byte aligned";
         return TIC_E_INVALID;
     }
     QuantParams qp;
-    int rc = make_quant_params(quality, qp);
-    if (rc) { h->err = "quality must be in 1..99"; return rc; }
+    int rc = TIC_OK;
+    if (c_variant) {   // quality is IMG_Q_BEST .. IMG_Q_LOW (c/img.h:22); the float quantiser is unused
+        if (quality < 0 || quality > 3) { h->err = "C variant: quality must be 0..3 (IMG_Q_BEST..IMG_Q_LOW)"; return TIC_E_QUALITY; }
+        memset(&qp, 0, sizeof qp);
+    } else {
+        rc = make_quant_params(quality, qp);
+        if (rc) { h->err = "quality must be in 1..99"; return rc; }
+    }
     cudaStream_t stream = (cudaStream_t)stream_v;
     TIC_CUDA(h, cudaSetDevice(h->device));
     rc = ensure_tables(h);
@@ -801,6 +822,12 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     for (int i = 0; i < n_images; i++) {
         if (heights[i] < 0 || widths[i] < 0) { h->err = "negative image dimension"; return TIC_E_INVALID; }
         long long nblk = tic_num_blocks(heights[i], widths[i]);
+        if (c_variant) {
+            if ((heights[i] & 7) || (widths[i] & 7)) {   // c/encode.c:38-41
+                h->err = "C variant: width and height must be multiples of 8";
+                return TIC_E_INVALID;
+            }
+        }
         if (nblk > 0x7fffffffll - kTile) { h->err = "image too large"; return TIC_E_INVALID; }
         ImageDesc& d = h->h_descs[i];
         d.px = (const uint8_t*)d_pixels[i];
@@ -886,12 +913,17 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
         d_tabs = h->d_tabs;
         h->last_launches = 8;
         TIC_CUDA(h, cudaEventRecord(evq[0], stream));
-        encode_tiles_kernel<true><<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
+        encode_tiles_kernel<1><<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
+            qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_recs, h->d_arena, (unsigned long long)h->arena_cap16,
+            h->d_counters, d_status, quality, d_tabs);
+    } else if (c_variant) {
+        TIC_CUDA(h, cudaEventRecord(evq[0], stream));
+        encode_tiles_kernel<2><<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
             qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_recs, h->d_arena, (unsigned long long)h->arena_cap16,
             h->d_counters, d_status, quality, d_tabs);
     } else {
         TIC_CUDA(h, cudaEventRecord(evq[0], stream));
-        encode_tiles_kernel<false><<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
+        encode_tiles_kernel<0><<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
             qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_recs, h->d_arena, (unsigned long long)h->arena_cap16,
             h->d_counters, d_status, quality, d_tabs);
     }

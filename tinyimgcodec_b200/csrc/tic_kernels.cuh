@@ -89,6 +89,9 @@ enum { kCtrArena = 0, kCtrOverflow = 1, kCtrExactItems = 2, kCtrExactChanged = 3
 
 __device__ __constant__ uint8_t c_zigzag[64] = {TIC_ZIGZAG_LIST};
 __device__ __constant__ HuffTables c_default_tables;
+// C-variant stream (c/img.c of the reference): scaledQuant[qfactor][i] = 65536 / (QUANT[i] << qfactor)
+// (c/img.c:157-181), raster order
+__device__ __constant__ uint16_t c_cvar_scaled_quant[4][64];
 
 // ---------------------------------------------------------------------------------------------
 // small helpers
@@ -464,6 +467,145 @@ __device__ __forceinline__ void transform_block(const TileInfo& ti, const QuantP
     sm.nz_hi[t] = nz_hi;
     sm.dcq[t] = dc;
     if (!active) fl_lo = fl_hi = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C-variant stream (flag bit 30): the reference's embedded encoder c/img.c — integer AAN FDCT with 8-bit
+// fixed-point constants, rows first, every stage result truncated to int16 (c/img.c:47-125), quantiser
+// sign(d) * (((QUANT/2 + |d|) * scaledQuant) >> 16) (c/img.c:194-205).  Integer only: bit-exact by
+// construction, no guard band, no exact path.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int as_i16(int v) { return (int)(short)v; }
+
+__device__ __forceinline__ void aan8_c(int& d0, int& d1, int& d2, int& d3, int& d4, int& d5, int& d6, int& d7) {
+    int tmp0 = d0 + d7, tmp7 = d0 - d7, tmp1 = d1 + d6, tmp6 = d1 - d6;
+    int tmp2 = d2 + d5, tmp5 = d2 - d5, tmp3 = d3 + d4, tmp4 = d3 - d4;
+    int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    d0 = as_i16(tmp10 + tmp11);
+    d4 = as_i16(tmp10 - tmp11);
+    const int z1 = ((tmp12 + tmp13) * 181) >> 8;
+    d2 = as_i16(tmp13 + z1);
+    d6 = as_i16(tmp13 - z1);
+    tmp10 = tmp4 + tmp5;
+    tmp11 = tmp5 + tmp6;
+    tmp12 = tmp6 + tmp7;
+    const int z5 = (tmp10 - tmp12) * 98;
+    const int z2 = (z5 + tmp10 * 139) >> 8;
+    const int z4 = (z5 + tmp12 * 334) >> 8;
+    const int z3 = (tmp11 * 181) >> 8;
+    const int z11 = tmp7 + z3, z13 = tmp7 - z3;
+    d5 = as_i16(z13 + z2);
+    d3 = as_i16(z13 - z2);
+    d1 = as_i16(z11 + z4);
+    d7 = as_i16(z11 - z4);
+}
+
+template <int R>
+__device__ __forceinline__ int quantise_c(int d, int qfactor) {   // c/img.c:194-205
+    constexpr int q = kQuantBaseDev(R) >> 1;
+    const int sq = (int)c_cvar_scaled_quant[qfactor][R];
+    const int a = d < 0 ? -d : d;
+    const int m = ((q + a) * sq) >> 16;
+    return as_i16(d < 0 ? -m : m);
+}
+
+template <int P>
+__device__ __forceinline__ void quantise_pairs_c(const int (&d)[64], int qfactor, TileShared& sm, int t,
+                                                 uint32_t& nz_lo, uint32_t& nz_hi, int& dc) {
+    if constexpr (P < 32) {
+        constexpr int k0 = 2 * P, k1 = k0 + 1;
+        const int v0 = quantise_c<ZZ<k0>::r>(d[ZZ<k0>::r], qfactor), v1 = quantise_c<ZZ<k1>::r>(d[ZZ<k1>::r], qfactor);
+        if constexpr (k0 < 32) {
+            if (k0 != 0 && v0 != 0) nz_lo |= 0x80000000u >> k0;
+            if (v1 != 0) nz_lo |= 0x80000000u >> k1;
+        } else {
+            if (v0 != 0) nz_hi |= 0x80000000u >> (k0 - 32);
+            if (v1 != 0) nz_hi |= 0x80000000u >> (k1 - 32);
+        }
+        if constexpr (k0 == 0) dc = v0;
+        sm.coef[P][t] = __byte_perm((uint32_t)v0, (uint32_t)v1, 0x5410);
+        quantise_pairs_c<P + 1>(d, qfactor, sm, t, nz_lo, nz_hi, dc);
+    }
+}
+
+// Block coordinates in the C variant.  (c/encode.c:47 loops `while (!feof(in))` and therefore codes one more
+// block row after the image, from a stripe buffer whose tail the C library's stack frames have overwritten:
+// its bits differ from run to run of the reference binary itself.  That row is not part of the image and is
+// not produced here; everything before it is byte-identical.)
+__device__ __forceinline__ void block_origin_c(const TileInfo& ti, int b, int& y0, int& x0) {
+    int br, bc;
+    if (ti.bw_shift >= 0) {
+        br = b >> ti.bw_shift;
+        bc = b & (ti.bw - 1);
+    } else {
+        br = b / ti.bw;
+        bc = b - br * ti.bw;
+    }
+    y0 = br * 8;
+    x0 = bc * 8;
+}
+
+__device__ __forceinline__ void transform_block_c(const TileInfo& ti, int qfactor, TileShared& sm, int t, bool active) {
+    int y0, x0;
+    block_origin_c(ti, ti.blk0 + (active ? t : ti.nb - 1), y0, x0);
+    const uint8_t* p = ti.px + (size_t)y0 * ti.w + x0;
+    int d[64];
+    if ((reinterpret_cast<uintptr_t>(ti.px) & 7) == 0) {   // width is a multiple of 8 in this mode
+        uint2 rows[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) rows[i] = __ldg(reinterpret_cast<const uint2*>(p + (size_t)i * ti.w));
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {   // block[i] = (int8_t)(data[i] ^ 0x80), c/img.c:213
+                d[i * 8 + j] = (int)((rows[i].x >> (8 * j)) & 255u) - 128;
+                d[i * 8 + 4 + j] = (int)((rows[i].y >> (8 * j)) & 255u) - 128;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) d[i * 8 + j] = (int)__ldg(p + (size_t)i * ti.w + j) - 128;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++)   // rows first (c/img.c:54)
+        aan8_c(d[r * 8], d[r * 8 + 1], d[r * 8 + 2], d[r * 8 + 3], d[r * 8 + 4], d[r * 8 + 5], d[r * 8 + 6], d[r * 8 + 7]);
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+        aan8_c(d[c], d[8 + c], d[16 + c], d[24 + c], d[32 + c], d[40 + c], d[48 + c], d[56 + c]);
+    uint32_t nz_lo = 0, nz_hi = 0;
+    int dc = 0;
+    quantise_pairs_c<0>(d, qfactor, sm, t, nz_lo, nz_hi, dc);
+    sm.nz_lo[t] = nz_lo;
+    sm.nz_hi[t] = nz_hi;
+    sm.dcq[t] = dc;
+}
+
+// Phase 1 of the C variant for the 32 blocks of one warp.  The DC of the block in front of the warp is the
+// quantised (sum of pixels - 8192): the DC path of c/img.c has no rounding before the quantiser.
+__device__ __forceinline__ void transform_warp_c(const TileInfo& ti, int qfactor, TileShared& sm) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (warp * 32 >= ti.nb) return;   // warp-uniform
+    transform_block_c(ti, qfactor, sm, t, t < ti.nb);
+    int halo_dc = 0;
+    const int hb = ti.blk0 + warp * 32 - 1;
+    if (hb >= 0) {
+        int y0, x0;
+        block_origin_c(ti, hb, y0, x0);
+        int sum = 0;
+        if (lane < 8) {
+            const uint8_t* p = ti.px + (size_t)(y0 + lane) * ti.w + x0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) sum += (int)__ldg(p + j);
+        }
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+        halo_dc = quantise_c<0>(as_i16(sum - 8192), qfactor);
+    }
+    if (lane == 0) sm.dc_halo[warp] = halo_dc;
+    __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------

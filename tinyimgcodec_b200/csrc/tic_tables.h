@@ -16,6 +16,18 @@ static const int kQuantBase[64] = {
     18, 22, 37, 56, 68,  109, 103, 77,  24, 35, 55, 64, 81,  104, 113, 92,
     49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
 
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+constexpr int kQuantBaseDev(int r) {   // same table, usable in device code with a compile-time index
+    constexpr int q[64] = {
+        16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,
+        14, 13, 16, 24, 40,  57,  69,  56,  14, 17, 22, 29, 51,  87,  80,  62,
+        18, 22, 37, 56, 68,  109, 103, 77,  24, 35, 55, 64, 81,  104, 113, 92,
+        49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+    return q[r];
+}
+
 // zigzag index k -> raster index u*8+v (u vertical frequency)
 #define TIC_ZIGZAG_LIST                                                                     \
     0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34,  \
