@@ -51,6 +51,9 @@ constexpr int kPrivWords = TIC_PRIV;                           // private words 
 // The bits of a tile are assembled in a WINDOW of kWinWords 32-bit words of shared memory: a tile
 // whose stream is longer (worst case 128 x 1662 bits + a table header) is emitted in several rounds.
 constexpr int kWinWords = TIC_WIN;
+static_assert(kTile % 32 == 0 && kTile >= 64 && kTile <= 512, "a tile is 2..16 warps of blocks");
+static_assert(kWinWords % 4 == 0 && kWinWords >= 1056, "window: 16-byte copies; symbol_stats_kernel keeps 272 counters + 272 keys in it");
+static_assert(kPrivWords >= 2 && kPrivWords <= 52, "a block has at most 1662 bits");
 constexpr int kWarpWork = 32;                               // exact-path worklist entries per warp and round
 
 // Quality-dependent constants, passed BY VALUE so that every entry is a constant-bank operand.
