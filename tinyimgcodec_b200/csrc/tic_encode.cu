@@ -302,6 +302,51 @@ scan_apply_kernel(const TileRec* __restrict__ recs, long long ntiles, const long
     }
 }
 
+// Small batches (at most kSmallScan tiles: one 8K image, 50 x 512^2, ...): the three scan kernels and
+// finalize_kernel in ONE launch of one CTA — what counts there is launch latency, not throughput.
+constexpr int kSmallThreads = 1024, kSmallScan = kSmallThreads * kScanItems;
+__global__ void __launch_bounds__(kSmallThreads)
+scan_small_kernel(const TileRec* __restrict__ recs, int ntiles, long long* __restrict__ tile_pos, long long out_cap,
+                  long long* __restrict__ out_off, long long* __restrict__ out_end, long long* __restrict__ out_sizes,
+                  int n_images, const int* __restrict__ status, unsigned long long* __restrict__ counters) {
+    __shared__ Span warp_tot[kSmallThreads / 32];
+    const int base = (int)threadIdx.x * kScanItems;
+    uint32_t rb[kScanItems];
+    int img[kScanItems];
+    Span mine{0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        rb[i] = 0; img[i] = 0;
+        if (base + i < ntiles) {
+            const TileRec r = recs[base + i];
+            rb[i] = r.bits; img[i] = r.img;
+            mine = span_then(mine, span_of(r.bits));
+        }
+    }
+    Span total;
+    const Span before = cta_exclusive_span<kSmallThreads>(mine, warp_tot, total);
+    long long p = span_apply(0, before);
+#pragma unroll
+    for (int i = 0; i < kScanItems; i++) {
+        if (base + i >= ntiles) break;
+        tile_pos[base + i] = p;
+        const long long eb = p + (long long)(rb[i] & kRecBitsMask);
+        if (rb[i] & kRecFirst) out_off[img[i]] = p >> 3;
+        if (rb[i] & kRecClosing) {
+            const long long end_byte = (eb + 7) >> 3;
+            out_end[img[i]] = end_byte;
+            if (((end_byte + 3) & ~3ll) > out_cap) atomicExch(&counters[kCtrOverflow], 1ull);
+            atomicMax(&counters[kCtrTotalBits], (unsigned long long)(end_byte << 3));
+        }
+        p = span_apply(p, span_of(rb[i]));
+    }
+    __syncthreads();   // out_off / out_end of every image are in place (same CTA: visible after the barrier)
+    for (int i = threadIdx.x; i < n_images; i += kSmallThreads) {
+        out_sizes[i] = out_end[i] - out_off[i];
+        if (status[i]) atomicOr(&counters[kCtrAnyStatus], (unsigned long long)status[i]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // compress(), stage 3: arena -> dense output.  One warp per tile; every 32-bit output word is written
 // by exactly one lane: the tile that holds the word's LAST bit owns it (a closing tile also owns the
@@ -929,14 +974,23 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     }
     TIC_CUDA(h, cudaGetLastError());
     TIC_CUDA(h, cudaEventRecord(evq[1], stream));
-    scan_chunks_kernel<<<(unsigned)nchunks, kScanThreads, 0, stream>>>(h->d_recs, ntiles, h->d_chunk_span);
-    TIC_CUDA(h, cudaGetLastError());
-    scan_spine_kernel<<<1, kSpineThreads, 0, stream>>>(h->d_chunk_span, nchunks, h->d_chunk_pos);
-    TIC_CUDA(h, cudaGetLastError());
-    scan_apply_kernel<<<(unsigned)nchunks, kScanThreads, 0, stream>>>(h->d_recs, ntiles, h->d_chunk_pos, h->d_tile_pos,
-                                                                      (long long)out_capacity, (long long*)d_out_offsets,
-                                                                      h->d_out_end, h->d_counters);
-    TIC_CUDA(h, cudaGetLastError());
+    const bool small = ntiles <= kSmallScan;
+    if (small) {   // one launch instead of four
+        scan_small_kernel<<<1, kSmallThreads, 0, stream>>>(h->d_recs, (int)ntiles, h->d_tile_pos, (long long)out_capacity,
+                                                          (long long*)d_out_offsets, h->d_out_end, (long long*)d_out_sizes,
+                                                          n_images, d_status, h->d_counters);
+        TIC_CUDA(h, cudaGetLastError());
+        h->last_launches -= 3;
+    } else {
+        scan_chunks_kernel<<<(unsigned)nchunks, kScanThreads, 0, stream>>>(h->d_recs, ntiles, h->d_chunk_span);
+        TIC_CUDA(h, cudaGetLastError());
+        scan_spine_kernel<<<1, kSpineThreads, 0, stream>>>(h->d_chunk_span, nchunks, h->d_chunk_pos);
+        TIC_CUDA(h, cudaGetLastError());
+        scan_apply_kernel<<<(unsigned)nchunks, kScanThreads, 0, stream>>>(h->d_recs, ntiles, h->d_chunk_pos, h->d_tile_pos,
+                                                                          (long long)out_capacity, (long long*)d_out_offsets,
+                                                                          h->d_out_end, h->d_counters);
+        TIC_CUDA(h, cudaGetLastError());
+    }
     long long cgrid = (ntiles * 32 + kCompactThreads - 1) / kCompactThreads;
     const long long cmax = (long long)h->sm_count * 8 * 4;
     if (cgrid > cmax) cgrid = cmax;
@@ -947,10 +1001,12 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     TIC_CUDA(h, cudaGetLastError());
     TIC_CUDA(h, cudaEventRecord(evq[3], stream));
     h->ev_batches++;
-    finalize_kernel<<<(n_images + 255) / 256, 256, 0, stream>>>(n_images, (const long long*)d_out_offsets,
-                                                               h->d_out_end, (long long*)d_out_sizes, d_status,
-                                                               h->d_counters);
-    TIC_CUDA(h, cudaGetLastError());
+    if (!small) {
+        finalize_kernel<<<(n_images + 255) / 256, 256, 0, stream>>>(n_images, (const long long*)d_out_offsets,
+                                                                   h->d_out_end, (long long*)d_out_sizes, d_status,
+                                                                   h->d_counters);
+        TIC_CUDA(h, cudaGetLastError());
+    }
     h->last_tiles = ntiles;
     h->last_blocks = nblocks;
     return TIC_OK;

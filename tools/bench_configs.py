@@ -1,0 +1,74 @@
+#!/usr/bin/env python3
+"""Device-timed encode of the other BASELINE.json configurations (bench.py covers config 4):
+  C1  data/lenna.gif alone          C2  all 50 data/*.gif as one batch
+  C3  one 7680x4320 image           C5  one 32768x32768 image at q in {90,80,50,20,10,5}
+Pixels resident in HBM, CUDA events around tic_encode_batch, best and median of N runs; the C port of the
+reference path (oracle/, test infrastructure) is timed on the host next to it where that takes seconds.
+One JSON line per configuration."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def timed(enc, d_imgs, q, runs):
+    import torch
+    stream = torch.cuda.current_stream()
+    out = None
+    ms = []
+    for i in range(runs + 2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        res = enc.encode_batch_device(d_imgs, q, out=out, stream=stream)
+        e1.record(stream)
+        res.finish()
+        out = res.out
+        if i >= 2:
+            ms.append(e0.elapsed_time(e1))
+    st = enc.stats()
+    return res, float(np.min(ms)), float(np.median(ms)), st
+
+
+def main():
+    import torch
+    import tinyimgcodec_b200 as tic
+    from oracle import oracle_lib as O
+    from tests.cases import big_synthetic, synthetic_image
+    from tests.golden_io import Golden
+    enc = tic.get_encoder(0)
+    peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+    gifs = Golden().all_gifs()
+    configs = [
+        ("C1 lenna 512x512 q50", [gifs["lenna"]], [50]),
+        ("C2 50 x 512x512 gifs, one batch, q50", [gifs[k] for k in sorted(gifs)], [50]),
+        ("C3 7680x4320 synthetic q50", [synthetic_image(4320, 7680, seed=0)], [50]),
+        ("C5 32768x32768 synthetic", [big_synthetic(32768, 32768, seed=5)], [90, 80, 50, 20, 10, 5]),
+    ]
+    for name, imgs, qualities in configs:
+        d_imgs = [torch.from_numpy(im).cuda() for im in imgs]
+        px = sum(im.size for im in imgs)
+        for q in qualities:
+            res, best, med, st = timed(enc, d_imgs, q, 10 if px < (1 << 28) else 4)
+            nbytes = int(res.sizes.sum().item())
+            line = {"config": name, "quality": q, "pixels": px, "stream_bytes": nbytes, "bpp": 8.0 * nbytes / px,
+                    "ms_best": best, "ms_median": med, "mpixel_per_s": px / (med * 1e-3) / 1e6,
+                    "roofline_frac_whole_call": (px + nbytes) / (med * 1e-3) / 1e9 / peak,
+                    "encode_kernel_ms": st["encode_kernel_ms_sum"] / max(1, st["timed_batches"]),
+                    "tiles": st["tiles"]}
+            if px <= (1 << 26):
+                t0 = time.perf_counter()
+                ref = [O.compress(im, q) for im in imgs]
+                line["cpu_port_1_thread_ms"] = 1e3 * (time.perf_counter() - t0)
+                line["identical_to_oracle"] = ref == res.to_bytes()
+            print(json.dumps(line), flush=True)
+        del d_imgs
+        torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
