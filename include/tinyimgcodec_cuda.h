@@ -53,6 +53,12 @@ extern "C" {
                                     reference itself) is not produced.  Not combinable with
                                     TIC_FLAG_AUTO_HUFFMAN. */
 
+#define TIC_FLAG_AUTO_LE_FLAG 4u  /* opt-in, with TIC_FLAG_AUTO_HUFFMAN only: write the header's flag word as the
+                                    little-endian bytes 00 00 00 80.  The reference writes it MSB-first
+                                    (80 00 00 00, tinyimgcodec/codec.py:111) but reads it back with struct "I"
+                                    (codec.py:119), so its own decoder cannot open its auto-table streams; with
+                                    this flag it can.  Off by default: byte parity with compress() comes first. */
+
 /* per-image status bits written by the device */
 #define TIC_STATUS_CATEGORY 1 /* KeyError case above */
 #define TIC_STATUS_TABLE 2    /* auto table not serialisable (OverflowError in the reference,

@@ -63,8 +63,9 @@ def _as_u8(image):
     return np.ascontiguousarray(image.astype(np.uint8, copy=False))
 
 
-def compress(image, quality=50, auto_generate_huffman_table=False):
-    """Restatement of tinyimgcodec.codec.compress (codec.py:133-164) for uint8 input."""
+def compress(image, quality=50, auto_generate_huffman_table=False, le_flag_word=False):
+    """Restatement of tinyimgcodec.codec.compress (codec.py:133-164) for uint8 input.  le_flag_word: the
+    opt-in header form whose flag word the reference's own decoder can read (auto-table streams only)."""
     img = _as_u8(image)
     h, w = img.shape
     L = lib()
@@ -73,7 +74,8 @@ def compress(image, quality=50, auto_generate_huffman_table=False):
         cap = cap * 2
     out = np.empty(cap, dtype=np.uint8)
     status = ctypes.c_int(0)
-    n = L.tico_compress(img.ctypes.data, h, w, int(quality), int(bool(auto_generate_huffman_table)),
+    n = L.tico_compress(img.ctypes.data, h, w, int(quality),
+                        (2 if le_flag_word else 1) if auto_generate_huffman_table else 0,
                         out.ctypes.data, cap, ctypes.byref(status))
     if n < 0:
         raise OracleError(status.value)

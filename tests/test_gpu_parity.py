@@ -288,6 +288,19 @@ def test_auto_table_random_vs_oracle(tic):
             _assert_same(tic.compress(img, q, True), want, f"auto {kind} {h}x{w} q{q}")
 
 
+def test_auto_table_le_flag_word_vs_oracle(tic):
+    """TIC_FLAG_AUTO_LE_FLAG: only the four flag bytes change (decodability by the reference decoder is checked
+    in tests/test_oracle_vs_reference.py where the reference is mounted)."""
+    img = synthetic_image(200, 312, seed=4)
+    for q in (50, 10):
+        plain, compat = tic.compress(img, q, True), tic.compress(img, q, True, le_flag_word=True)
+        _assert_same(compat, O.compress(img, q, True, le_flag_word=True), f"le flag q{q}")
+        assert plain[12:16] == bytes([0x80, 0, 0, 0]) and compat[12:16] == bytes([0, 0, 0, 0x80])
+        assert plain[:12] == compat[:12] and plain[16:] == compat[16:]
+    with pytest.raises(ValueError):
+        tic.compress(img, 50, False, le_flag_word=True)
+
+
 def test_auto_table_batch_vs_oracle(tic):
     imgs = [synthetic_image(1024, 1024, seed=3), make_case({"kind": "noise", "shape": (200, 312), "seed": 5}),
             np.full((64, 64), 128, np.uint8), synthetic_image(8, 8, seed=1), synthetic_image(520, 1032, seed=9)]

@@ -86,3 +86,26 @@ def test_roundtrip_decodes_with_reference_decoder(ref):
     dec = ref.decompress(out)
     assert dec.shape == img.shape
     assert abs(psnr(img, dec) - 35.83) < 0.01
+
+
+def test_le_flag_word_makes_auto_streams_decodable(ref):
+    """SURVEY.md §8(f)4.  The reference writes the auto-table flag MSB-first (codec.py:111) and reads it
+    little-endian (codec.py:119): its decoder takes its own auto-table streams for fixed-table ones and fails
+    or returns garbage.  The opt-in little-endian flag word differs from the reference's stream in header
+    bytes 12..15 only, and the reference decoder then reconstructs exactly what it reconstructs from the
+    fixed-table stream of the same quality (same quantised coefficients)."""
+    img = _gif("lenna")
+    for q in (50, 10):
+        plain = O.compress(img, q, True)
+        compat = O.compress(img, q, True, le_flag_word=True)
+        assert plain == ref.compress(img, quality=q, auto_generate_huffman_table=True)
+        assert plain[12:16] == bytes([0x80, 0, 0, 0]) and compat[12:16] == bytes([0, 0, 0, 0x80])
+        assert plain[:12] == compat[:12] and plain[16:] == compat[16:]
+        want = ref.decompress(O.compress(img, q))
+        got = ref.decompress(compat)
+        assert np.array_equal(got, want)
+        try:
+            broken = ref.decompress(plain)
+            assert not np.array_equal(broken, want)
+        except Exception:
+            pass   # the reference decoder may also just fail on its own auto-table stream

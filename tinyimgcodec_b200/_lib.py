@@ -19,6 +19,7 @@ TIC_E_UNSUPPORTED = -6
 TIC_E_TABLE = -7
 TIC_FLAG_AUTO_HUFFMAN = 1
 TIC_FLAG_C_VARIANT = 2
+TIC_FLAG_AUTO_LE_FLAG = 4
 TIC_STATUS_CATEGORY = 1
 TIC_STATUS_TABLE = 2
 TIC_STATUS_LONGCODE = 4

@@ -109,10 +109,17 @@ class Encoder:
         raise TicError(rc, msg)
 
     # -- single image, host buffers ---------------------------------------------------------
-    def compress(self, image, quality=50, auto_generate_huffman_table=False):
+    def compress(self, image, quality=50, auto_generate_huffman_table=False, le_flag_word=False):
+        """le_flag_word (auto-table streams only, off by default): write the header's flag word little-endian
+        so that the reference's own decoder can open the stream (include/tinyimgcodec_cuda.h,
+        TIC_FLAG_AUTO_LE_FLAG); the default is byte identity with the reference's compress()."""
         img, height, width = _as_u8_image(image)
         quality = _check_quality(quality)
         flags = _lib.TIC_FLAG_AUTO_HUFFMAN if auto_generate_huffman_table else 0
+        if le_flag_word:
+            if not auto_generate_huffman_table:
+                raise ValueError("le_flag_word only applies to auto_generate_huffman_table=True")
+            flags |= _lib.TIC_FLAG_AUTO_LE_FLAG
         if flags and img.size == 0:
             # calc_huffman_table indexes an empty symbol array (huffman.py:102-103)
             raise IndexError("index 1 is out of bounds for axis 1 with size 0")
@@ -333,9 +340,9 @@ def get_encoder(device=None):
         return enc
 
 
-def compress(image, quality=50, auto_generate_huffman_table=False, device=None):
+def compress(image, quality=50, auto_generate_huffman_table=False, device=None, le_flag_word=False):
     """Drop-in for tinyimgcodec.codec.compress (codec.py:133-164)."""
-    return get_encoder(device).compress(image, quality, auto_generate_huffman_table)
+    return get_encoder(device).compress(image, quality, auto_generate_huffman_table, le_flag_word)
 
 
 def encode(image, quality=50, device=None):

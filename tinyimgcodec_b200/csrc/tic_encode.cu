@@ -554,7 +554,7 @@ __device__ int build_alphabet(TreeScratch& s, const uint32_t* hist, const unsign
     return status;
 }
 
-__global__ void build_tables_kernel(const ImageDesc* __restrict__ descs, int n_images, int quality,
+__global__ void build_tables_kernel(const ImageDesc* __restrict__ descs, int n_images, int quality, int le_flag,
                                     const uint32_t* __restrict__ g_hist,
                                     const unsigned long long* __restrict__ g_first,
                                     AutoTables* __restrict__ tabs, TreeScratch* __restrict__ scratch,
@@ -571,7 +571,9 @@ __global__ void build_tables_kernel(const ImageDesc* __restrict__ descs, int n_i
     hw.put(__byte_perm((uint32_t)d.h, 0, 0x0123), 32);           // struct.pack("III"), codec.py:103-109
     hw.put(__byte_perm((uint32_t)d.w, 0, 0x0123), 32);
     hw.put(__byte_perm((uint32_t)quality, 0, 0x0123), 32);
-    hw.put(0x80000000u, 32);                                     // codec.py:111
+    // codec.py:111 writes the flag MSB-first (80 00 00 00); le_flag: as the little-endian word the
+    // reference's parse_header (codec.py:119) can read
+    hw.put(le_flag ? 0x00000080u : 0x80000000u, 32);
     const uint32_t* hist = g_hist + (size_t)img * 272;
     const unsigned long long* first = g_first + (size_t)img * 272;
     int st = build_alphabet(s, hist, first, 256, 16, true, at.tab.dc, hw);    // table[DC] first, codec.py:74-78
@@ -837,6 +839,7 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     const bool auto_mode = (flags & TIC_FLAG_AUTO_HUFFMAN) != 0;
     const bool c_variant = (flags & TIC_FLAG_C_VARIANT) != 0;
     if (auto_mode && c_variant) { h->err = "the C-variant stream has fixed tables"; return TIC_E_INVALID; }
+    if ((flags & TIC_FLAG_AUTO_LE_FLAG) && !auto_mode) { h->err = "TIC_FLAG_AUTO_LE_FLAG needs TIC_FLAG_AUTO_HUFFMAN"; return TIC_E_INVALID; }
     if ((reinterpret_cast<uintptr_t>(d_out) & 15) != 0) {
         h->err = "d_out must be 16-byte aligned";
         return TIC_E_INVALID;
@@ -952,7 +955,8 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
         symbol_stats_kernel<<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
             qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_counters, h->d_hist, h->d_first, d_status);
         TIC_CUDA(h, cudaGetLastError());
-        build_tables_kernel<<<(n_images + 31) / 32, 32, 0, stream>>>(h->d_descs, n_images, quality, h->d_hist,
+        build_tables_kernel<<<(n_images + 31) / 32, 32, 0, stream>>>(h->d_descs, n_images, quality,
+                                                                    (flags & TIC_FLAG_AUTO_LE_FLAG) ? 1 : 0, h->d_hist,
                                                                     h->d_first, h->d_tabs, h->d_tree, d_status);
         TIC_CUDA(h, cudaGetLastError());
         d_tabs = h->d_tabs;
