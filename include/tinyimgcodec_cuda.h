@@ -70,9 +70,10 @@ typedef struct tic_handle_s *tic_handle;
 /* Library version string, e.g. "tinyimgcodec_cuda 0.1 sm_100a". */
 const char *tic_version(void);
 
-/* Create / destroy the per-GPU context (scratch buffers, constant tables, one stream-ordered
- * workspace).  Replaces nothing in the reference (which has no state); it is the price
- * of a device. */
+/* Create / destroy the per-GPU context (constant tables and a workspace that grows on demand and is
+ * reused across calls: per-tile records and positions, and the arena the tiles' bits pass through —
+ * never more than min(worst case, out_capacity) + 16 bytes per 128 blocks).  Replaces nothing in the
+ * reference (which has no state); it is the price of a device. */
 int tic_create(int device, tic_handle *out);
 int tic_destroy(tic_handle h);
 
@@ -98,7 +99,8 @@ int64_t tic_num_blocks(int32_t height, int32_t width);
  *   d_pixels      n_images device pointers... passed as a HOST array of device addresses;
  *                 image i is heights[i] x widths[i] uint8, row-major, contiguous.
  *   heights/widths HOST arrays, original (unpadded) dimensions; 0 is allowed.
- *   quality       1..99, the same for the whole batch.
+ *   quality       1..99, the same for the whole batch (0..3 = IMG_Q_BEST..IMG_Q_LOW with
+ *                 TIC_FLAG_C_VARIANT).
  *   flags         TIC_FLAG_* bits.
  *   d_out         device buffer of out_capacity bytes.  The n streams are written densely,
  *                 each starting on a 16-byte boundary, in image order.
