@@ -24,6 +24,7 @@
 // from the arena to its final bit position in the dense output (funnel shift + byte swap).
 // Quantised coefficients never touch HBM.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stddef.h>
 #include <stdint.h>
@@ -277,6 +278,20 @@ __device__ __noinline__ double dct8_exact(const double x0, const double x1, cons
     return sel < 4 ? __dmul_rn(0.5, __dadd_rn(t1, t2)) : __dmul_rn(0.5, __dsub_rn(t1, t2));
 }
 
+// The reference's quantised DC from the 8 column sums of the LEVEL-SHIFTED block alone.  In its float64 column
+// pass every operation before the last multiply acts on small integers and is exact, so column x contributes
+// RN(0.5 * colsum_x * HSQ); the row pass over those eight doubles is dct8_exact(.., 0).  Used where the fast
+// path finds the DC within the guard band of a tie (every block of a flat area whose DC lands on one).
+__device__ __noinline__ int dc_exact_from_colsums(double c0, double c1, double c2, double c3, double c4, double c5,
+                                                  double c6, double c7, double qt0) {
+    const double HSQ = 0x1.6a09e667f3bcdp-1;
+    const double y = dct8_exact(__dmul_rn(__dmul_rn(0.5, c0), HSQ), __dmul_rn(__dmul_rn(0.5, c1), HSQ),
+                                __dmul_rn(__dmul_rn(0.5, c2), HSQ), __dmul_rn(__dmul_rn(0.5, c3), HSQ),
+                                __dmul_rn(__dmul_rn(0.5, c4), HSQ), __dmul_rn(__dmul_rn(0.5, c5), HSQ),
+                                __dmul_rn(__dmul_rn(0.5, c6), HSQ), __dmul_rn(__dmul_rn(0.5, c7), HSQ), 0);
+    return __double2int_rn(__ddiv_rn(y, qt0));   // np.round(coeffs / qt), utils.py:53
+}
+
 struct TileInfo {
     const uint8_t* px;
     int h, w, bw, bw_shift;
@@ -419,13 +434,10 @@ __device__ __forceinline__ int coef_get(const TileShared& sm, int t, int k) {
     return (int)(short)((k & 1) ? (w >> 16) : w);
 }
 
-// One block, all 32 lanes of a warp that owns at least one block call (the group test votes); `active` =
-// this lane's block exists.
-__device__ __forceinline__ void transform_block(const TileInfo& ti, const QuantParams& qp, TileShared& sm,
-                                                int t, bool active, uint32_t& fl_lo, uint32_t& fl_hi) {
-    // a lane without a block of its own (last tile of an image) transforms a copy of the tile's last block:
-    // its results land in its own shared-memory column and are never read
-    const int b = ti.blk0 + (active ? t : ti.nb - 1);
+// Pixel origin of thread t's block.  A lane without a block of its own (last tile of an image) gets the
+// tile's last block: it transforms a copy whose results land in its own shared-memory column, never read.
+__device__ __forceinline__ void block_origin(const TileInfo& ti, int t, int& y0, int& x0) {
+    const int b = ti.blk0 + (t < ti.nb ? t : ti.nb - 1);
     int br, bc;
     if (ti.bw_shift >= 0) {   // blocks per row is a power of two (uniform branch)
         br = b >> ti.bw_shift;
@@ -434,9 +446,21 @@ __device__ __forceinline__ void transform_block(const TileInfo& ti, const QuantP
         br = b / ti.bw;
         bc = b - br * ti.bw;
     }
-    const int y0 = br * 8, x0 = bc * 8;
+    y0 = br * 8;
+    x0 = bc * 8;
+}
+__device__ __forceinline__ bool block_is_fast(const TileInfo& ti, int y0) {   // aligned interior block: 8 x LDG.64
+    return ((ti.w & 7) == 0) && ((reinterpret_cast<uintptr_t>(ti.px) & 7) == 0) && (y0 + 8 <= ti.h);
+}
+
+// One block, all 32 lanes of a warp that owns at least one block call (the group test votes); `active` =
+// this lane's block exists.
+__device__ __forceinline__ void transform_block(const TileInfo& ti, const QuantParams& qp, TileShared& sm,
+                                                int t, bool active, uint32_t& fl_lo, uint32_t& fl_hi) {
+    int y0, x0;
+    block_origin(ti, t, y0, x0);
     float d[64];
-    const bool fast = ((ti.w & 7) == 0) && ((reinterpret_cast<uintptr_t>(ti.px) & 7) == 0) && (y0 + 8 <= ti.h);
+    const bool fast = block_is_fast(ti, y0);
     if (fast) {
         const uint8_t* p = ti.px + (size_t)y0 * ti.w + x0;
         uint2 rows[8];
@@ -690,6 +714,35 @@ __device__ __forceinline__ void exact_round(const TileInfo& ti, const QuantParam
     }
 }
 
+// Out of line (rare): the thread's block has its DC on a rounding tie.  The 8 column sums of the block are
+// all the reference's DC depends on (dc_exact_from_colsums); the pixels are re-read — they are in L1/L2.
+// Returns false for blocks that need reflection padding: those stay with the worklist.
+// (Scalars by value: taking the TileInfo by reference would pin it in local memory for the whole kernel.)
+__device__ __noinline__ bool settle_dc_ties(const uint8_t* px, int w, int h, int bw, int blk0, int nb, double qt0,
+                                            uint32_t* coef0 /* &sm.coef[0][0] */, int* dcq, uint32_t fl_lo) {
+    const int t = threadIdx.x;
+    if (!(fl_lo & 0x80000000u)) return false;
+    const int b = blk0 + (t < nb ? t : nb - 1);
+    const int br = b / bw, bc = b - br * bw;
+    const int y0 = br * 8, x0 = bc * 8;
+    if ((w & 7) != 0 || (reinterpret_cast<uintptr_t>(px) & 7) != 0 || y0 + 8 > h) return false;
+    const uint8_t* p = px + (size_t)y0 * w + x0;
+    uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;   // column sums, two 16-bit lanes per word
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(p + (size_t)i * w));
+        w0 += __byte_perm(v.x, 0u, 0x4140); w1 += __byte_perm(v.x, 0u, 0x4342);
+        w2 += __byte_perm(v.y, 0u, 0x4140); w3 += __byte_perm(v.y, 0u, 0x4342);
+    }
+    const int dc = dc_exact_from_colsums(
+        (double)((int)(w0 & 0xffffu) - 1024), (double)((int)(w0 >> 16) - 1024), (double)((int)(w1 & 0xffffu) - 1024),
+        (double)((int)(w1 >> 16) - 1024), (double)((int)(w2 & 0xffffu) - 1024), (double)((int)(w2 >> 16) - 1024),
+        (double)((int)(w3 & 0xffffu) - 1024), (double)((int)(w3 >> 16) - 1024), qt0);
+    reinterpret_cast<unsigned short*>(&coef0[t])[0] = (unsigned short)dc;
+    dcq[t] = dc;
+    return true;
+}
+
 // Phases 1 and 2 for the 32 blocks of one warp; only warp-level synchronisation.  On return
 // sm.coef / nz / dcq / dc_halo hold the reference's quantised coefficients for those blocks.
 __device__ __forceinline__ void transform_warp(const TileInfo& ti, const QuantParams& qp, TileShared& sm,
@@ -703,6 +756,16 @@ __device__ __forceinline__ void transform_warp(const TileInfo& ti, const QuantPa
     __syncwarp();
     uint32_t fl_lo = 0, fl_hi = 0;
     if (warp * 32 < ti.nb) transform_block(ti, qp, sm, t, t < ti.nb, fl_lo, fl_hi);   // warp-uniform
+    // A DC in the guard band of a tie: 1 block in 128 on ordinary content — that one rides along in the
+    // exact-path worklist — but EVERY block of a flat area whose level lands on a tie (at quality 50: any odd
+    // pixel value, 255 included).  When several lanes of the warp are affected, each settles its own DC in
+    // float64 (settle_dc_ties, kept out of line): one pass for all of them instead of one entry per block.
+    if (__popc(__ballot_sync(0xffffffffu, (fl_lo & 0x80000000u) != 0)) >= 4) {   // warp-uniform
+        if (settle_dc_ties(ti.px, ti.w, ti.h, ti.bw, ti.blk0, ti.nb, qp.qt[0], &sm.coef[0][0], sm.dcq, fl_lo)) {
+            fl_lo &= 0x7fffffffu;
+            st.items++;
+        }
+    }
     // halo: quantised DC of the block in front of the warp's first block.  The DC coefficient is
     // (sum of pixels - 8192) / 8 exactly, so unless its quotient by qt lands within 1e-9 of a .5 tie
     // (where the reference's float64 rounding errors decide) one pixel sum settles it; otherwise, and
@@ -714,17 +777,31 @@ __device__ __forceinline__ void transform_warp(const TileInfo& ti, const QuantPa
         const int y0 = br * 8;
         halo_item = 1;
         if (((ti.w & 7) == 0) && ((reinterpret_cast<uintptr_t>(ti.px) & 7) == 0) && (y0 + 8 <= ti.h)) {
-            int sum = 0;
-            if (lane < 8) {
-                const uint2 v = __ldg(reinterpret_cast<const uint2*>(ti.px + (size_t)(y0 + lane) * ti.w + bc * 8));
-                sum = __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, 0u));
-            }
+            uint2 v = make_uint2(0u, 0u);   // lanes 0..7: one pixel row of that block each
+            if (lane < 8) v = __ldg(reinterpret_cast<const uint2*>(ti.px + (size_t)(y0 + lane) * ti.w + bc * 8));
+            int sum = __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, 0u));
             sum += __shfl_xor_sync(0xffffffffu, sum, 1);
             sum += __shfl_xor_sync(0xffffffffu, sum, 2);
             sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+            sum = __shfl_sync(0xffffffffu, sum, 0);   // lanes 8..31 summed zeros: every lane must take the same branch below
             const double tq = __dmul_rn((double)(sum - 8192), qp.dcinv);
             halo_dc = __double2int_rn(tq);
-            if (fabs(tq - (double)halo_dc) < 0.5 - 1.0e-9) halo_item = 0;
+            halo_item = 0;
+            if (!(fabs(tq - (double)halo_dc) < 0.5 - 1.0e-9)) {   // on a tie: the 8 column sums decide (warp-uniform)
+                uint32_t w0 = __byte_perm(v.x, 0u, 0x4140), w1 = __byte_perm(v.x, 0u, 0x4342);   // 16-bit lanes
+                uint32_t w2 = __byte_perm(v.y, 0u, 0x4140), w3 = __byte_perm(v.y, 0u, 0x4342);
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    w0 += __shfl_xor_sync(0xffffffffu, w0, o); w1 += __shfl_xor_sync(0xffffffffu, w1, o);
+                    w2 += __shfl_xor_sync(0xffffffffu, w2, o); w3 += __shfl_xor_sync(0xffffffffu, w3, o);
+                }
+                if (lane == 0)
+                    halo_dc = dc_exact_from_colsums((double)((int)(w0 & 0xffffu) - 1024), (double)((int)(w0 >> 16) - 1024),
+                                                    (double)((int)(w1 & 0xffffu) - 1024), (double)((int)(w1 >> 16) - 1024),
+                                                    (double)((int)(w2 & 0xffffu) - 1024), (double)((int)(w2 >> 16) - 1024),
+                                                    (double)((int)(w3 & 0xffffu) - 1024), (double)((int)(w3 >> 16) - 1024),
+                                                    qp.qt[0]);
+            }
         }
     }
     if (lane == 0) {
@@ -747,7 +824,7 @@ __device__ __forceinline__ void transform_warp(const TileInfo& ti, const QuantPa
         const int pending = sm.pending[warp];
         __syncwarp();
         if (count) {   // warp-uniform
-            if (lane == 0) st.items += (unsigned)count;
+            if (lane == 0) st.items += (unsigned)count;   // (DC ties settled above count too)
             exact_round(ti, qp, sm, warp, count, st);
         }
         if (pending == 0) break;

@@ -2,6 +2,7 @@
 """Device-timed encode of the other BASELINE.json configurations (bench.py covers config 4):
   C1  data/lenna.gif alone          C2  all 50 data/*.gif as one batch
   C3  one 7680x4320 image           C5  one 32768x32768 image at q in {90,80,50,20,10,5}
+  S1  16384^2 uniform noise (q 90/50/10)    S2  16384^2 flat image      [optional argv: config name prefixes]
 Pixels resident in HBM, CUDA events around tic_encode_batch, best and median of N runs; the C port of the
 reference path (oracle/, test infrastructure) is timed on the host next to it where that takes seconds.
 One JSON line per configuration."""
@@ -48,7 +49,14 @@ def main():
         ("C2 50 x 512x512 gifs, one batch, q50", [gifs[k] for k in sorted(gifs)], [50]),
         ("C3 7680x4320 synthetic q50", [synthetic_image(4320, 7680, seed=0)], [50]),
         ("C5 32768x32768 synthetic", [big_synthetic(32768, 32768, seed=5)], [90, 80, 50, 20, 10, 5]),
+        # stress distributions of SURVEY.md 8(d): the scan / pack worst case and the 6-bits-per-block floor
+        ("S1 16384x16384 uniform noise", [np.random.default_rng(7).integers(0, 256, (16384, 16384), dtype=np.uint8)],
+         [90, 50, 10]),
+        ("S2 16384x16384 flat (value 77)", [np.full((16384, 16384), 77, np.uint8)], [50]),
     ]
+    only = [a for a in sys.argv[1:] if not a.startswith("-")]
+    if only:
+        configs = [c for c in configs if any(c[0].startswith(o) for o in only)]
     for name, imgs, qualities in configs:
         d_imgs = [torch.from_numpy(im).cuda() for im in imgs]
         px = sum(im.size for im in imgs)

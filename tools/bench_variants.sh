@@ -8,7 +8,7 @@ import json,sys
 n=sys.argv[1]
 try:
     d=json.load(open(f"gpurun_out/var_{n}.json"))
-    print("VARIANT %-24s step_ms=%.3f kernel_ms=%.3f parity=%s" % (n, d["ms_per_step"], d["roofline"]["launch_ms"], d["parity"]))
+    print("VARIANT %-24s step_ms=%.3f kernel_ms=%.3f compact_ms=%.3f parity=%s" % (n, d["ms_per_step"], d["roofline"]["launch_ms"], d["roofline"]["other_kernels_ms"]["compact_kernel"], d["parity"]))
 except Exception as e:
     print("VARIANT", n, "failed", e)
 PY

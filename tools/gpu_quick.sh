@@ -3,8 +3,8 @@
 set -u
 TAG=${1:-}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
-timeout 600 python bench.py --no-cpu --no-e2e --steps 10 --warmup 3 > gpurun_out/quick.json 2> gpurun_out/quick.err || tail -5 gpurun_out/quick.err
+timeout 300 python -m pytest tests -m gpu -x -q --timeout=120 2>&1 | tail -15
+timeout 180 python bench.py --no-cpu --no-e2e --steps 10 --warmup 3 > gpurun_out/quick.json 2> gpurun_out/quick.err || tail -5 gpurun_out/quick.err
 python - <<'PY'
 import json
 d=json.load(open("gpurun_out/quick.json"))
