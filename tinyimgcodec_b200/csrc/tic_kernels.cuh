@@ -857,6 +857,9 @@ __device__ __forceinline__ uint2 lds_v2(uint32_t a) {
     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a) : "memory");
     return v;
 }
+// Same load, out of line: used on error paths only, so that the compiler branches around them instead of
+// predicating their instructions into the hot loop.
+__device__ __noinline__ uint2 lds_v2_cold(uint32_t a) { return lds_v2(a); }
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, int s) {   // 0 for s >= 32 (PTX semantics)
     uint32_t r;
     asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(s));
@@ -931,7 +934,9 @@ struct BitSink<true> {
 };
 
 __device__ __forceinline__ uint32_t value_bits(int v, int sz) {   // huffman.py:59-63
-    return (uint32_t)(v + (v >> 31)) & ((1u << sz) - 1u);
+    uint32_t mask;   // sz low bits set: one BMSK instead of a shifted -1
+    asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(mask) : "r"(0), "r"(sz));
+    return (uint32_t)(v + (v >> 31)) & mask;
 }
 
 template <bool kAuto, bool kToStage>
@@ -956,7 +961,7 @@ __device__ __forceinline__ int walk_block(const TileShared& sm, uint32_t sbase, 
     const uint32_t col = sbase + (uint32_t)offsetof(TileShared, coef) + (uint32_t)t * 4u;
     int sz = msb_index((uint32_t)(diff < 0 ? -diff : diff)) + 1;  // bits_required, utils.py:9-10
     uint2 e = lds_v2(dc_tab + (uint32_t)sz * 8u);
-    if (e.y == 0) { err = 1; sz = 0; e = lds_v2(dc_tab); }       // KeyError, huffman.py:62
+    if (e.y == 0) { err = 1; sz = 0; e = lds_v2_cold(dc_tab); }  // KeyError, huffman.py:62
     put_symbol<kAuto, kToStage>(s, e, diff, sz);
     int carry = 0;   // zeros since the last non-zero coefficient, not counting the current mask word
 #pragma unroll 1
@@ -980,7 +985,7 @@ __device__ __forceinline__ int walk_block(const TileShared& sm, uint32_t sbase, 
                 for (; run >= 16; run -= 16) s.put(zrl.x, (int)(zrl.y & kHuffLenMask));
             }
             e = lds_v2(ac_tab + (uint32_t)(run * 16 + sz) * 8u);
-            if (e.y == 0) { err = 1; sz = 1; v = 1; e = lds_v2(ac_tab + (uint32_t)(run * 16 + 1) * 8u); }
+            if (e.y == 0) { err = 1; sz = 1; v = 1; e = lds_v2_cold(ac_tab + (uint32_t)(run * 16 + 1) * 8u); }
             put_symbol<kAuto, kToStage>(s, e, v, sz);
         }
         carry += base + 32 - pos;
