@@ -217,6 +217,32 @@ def test_device_tensor_batch_and_stats(tic):
     assert st["timed_batches"] == 1 and st["encode_kernel_ms_sum"] > 0 and st["compact_kernel_ms_sum"] > 0
 
 
+def test_unaligned_pixel_pointers_and_output_alignment(tic):
+    """Pixels at odd device addresses take the byte-wise load path (and the worklist for every halo DC); the
+    output buffer must be 16-byte aligned (streams start on 16-byte boundaries)."""
+    import torch
+    enc = tic.get_encoder(0)
+    imgs = [synthetic_image(64, 128, seed=3), make_case({"kind": "noise", "shape": (40, 72), "seed": 8}),
+            np.full((256, 256), 255, np.uint8), synthetic_image(37, 51, seed=5)]
+    raw = torch.empty(sum(im.size for im in imgs) + 64, dtype=torch.uint8, device="cuda")
+    views, pos = [], 1
+    for im in imgs:
+        v = raw[pos: pos + im.size].view(im.shape)
+        v.copy_(torch.from_numpy(im))
+        assert v.data_ptr() % 8 != 0
+        views.append(v)
+        pos += im.size + (3 if (pos + im.size) % 8 == 5 else 2)   # keep every start off the 8-byte grid
+        pos += 1 if pos % 8 == 0 else 0
+    for q in (50, 90):
+        outs = enc.encode_batch_device(views, q).finish().to_bytes()
+        for im, out in zip(imgs, outs):
+            _assert_same(out, O.compress(im, q), f"unaligned {im.shape} q{q}")
+    buf = torch.empty(1 << 20, dtype=torch.uint8, device="cuda")
+    with pytest.raises(tic.TicError) as ei:
+        enc.encode_batch_device(views[:1], 50, out=buf[4:])
+    assert ei.value.code == -1
+
+
 def test_output_capacity_is_respected(tic):
     """TIC_E_CAPACITY: a too-small d_out is reported, and nothing past out_capacity is written."""
     import torch
