@@ -41,6 +41,11 @@ extern "C" {
 #define TIC_E_TABLE (-7)      /* auto table not serialisable: the reference raises OverflowError from
                                  int2ba (tinyimgcodec/codec.py:76-77,81-83) */
 
+#define TIC_E_STREAM (-8)     /* decode side: at least one stream of the batch is damaged, truncated or has a
+                                 header that does not match the caller's dimensions; per-stream detail
+                                 (TIC_DSTATUS_*) is in the status array.  The reference swallows these errors
+                                 block by block (try/except, tinyimgcodec/codec.py:177-185). */
+
 /* flags for tic_encode_batch */
 #define TIC_FLAG_AUTO_HUFFMAN 1u /* per-image tables, tinyimgcodec/codec.py:146-148 */
 #define TIC_FLAG_C_VARIANT 2u    /* the stream of the reference's embedded C encoder (c/encode.c, c/img.c:
@@ -150,6 +155,84 @@ int tic_compress_host(tic_handle h, const uint8_t *pixels, int32_t height, int32
  *       over the [7] batches enqueued since the previous tic_encode_finish (CUDA events recorded
  *       on the batches' stream around those two launches; the newest 64 batches at most) */
 int tic_last_stats(tic_handle h, int64_t stats[8]);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decode side: tinyimgcodec.codec.decompress(data) -> uint8 H x W
+ * (tinyimgcodec/codec.py:167-189) and everything under it — parse_header (codec.py:117-130),
+ * read_huffman_table (codec.py:87-99), decode_huffman / decode_run_length (tinyimgcodec/huffman.py:
+ * 77-98, 36-38), decode (codec.py:46-70: DC cumsum, de-zigzag, dequantise, scipy idct, +128, clip,
+ * crop, truncate to uint8).  Pixels are bit-identical to the reference decoder's for every stream the
+ * reference decodes without an internal exception, in all three stream forms it understands: fixed
+ * tables (flag 0), per-image tables (flag bit 31 as the reference READS it, i.e. the bytes 00 00 00 80),
+ * and the embedded C encoder's scaled integer DCT (flag bit 30).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* flags for tic_decode_batch */
+#define TIC_DFLAG_ACCEPT_BE_FLAG 1u /* opt-in: also treat the header bytes 80 00 00 00 — what compress(...,
+                                       auto_generate_huffman_table=True) writes (codec.py:111) and the
+                                       reference's own parse_header misreads (codec.py:119,124) — as
+                                       "per-image tables follow".  Off by default: the reference decodes such
+                                       a stream with the fixed tables (garbage), and so does this library. */
+
+/* per-stream status bits of the decode side */
+#define TIC_DSTATUS_HEADER 1     /* shorter than 16 bytes, or height / width differ from the caller's */
+#define TIC_DSTATUS_CODE 2       /* no codeword matches (ValueError, huffman.py:72-73) or a run passes
+                                    coefficient 63 */
+#define TIC_DSTATUS_TRUNCATED 4  /* the stream ends before the last block */
+#define TIC_DSTATUS_TABLE 8      /* per-image table too large for the device trie (1024 nodes) */
+#define TIC_DSTATUS_QUALITY 16   /* quality field 0: ZeroDivisionError in the reference (utils.py:50) */
+#define TIC_DSTATUS_RANGE 32     /* a DC value outside int16 (the reference keeps int32) */
+
+/* parse_header's fixed part (codec.py:117-122): the four little-endian words of the 16-byte header.
+ * Pure host arithmetic; TIC_E_INVALID when nbytes < 16 (struct.error in the reference). */
+int tic_parse_header(const uint8_t *data, int64_t nbytes, int32_t *height, int32_t *width,
+                     int32_t *quality, uint32_t *flag);
+
+/*
+ * decompress() for a batch of streams resident in device memory.
+ *
+ *   d_streams     HOST array of n device addresses, each 4-byte aligned; stream i is sizes[i] bytes and
+ *                 the buffer must be readable up to the next multiple of 4.
+ *   sizes         HOST array, bytes per stream (len(data)).
+ *   heights/widths HOST arrays: the dimensions the caller sized d_pixels[i] for (from tic_parse_header);
+ *                 a stream whose header disagrees gets TIC_DSTATUS_HEADER and is not written.
+ *   d_pixels      HOST array of n device addresses; image i is written as heights[i] x widths[i] uint8,
+ *                 row-major, contiguous.
+ *   d_status      device int32[n] of TIC_DSTATUS_* bits, or NULL.
+ *
+ * Enqueued on `stream`, but NOT fully asynchronous: the self-synchronising Huffman decode relaunches
+ * until no subsequence changes its entry state, and the host reads that flag once per round (typically
+ * 2-4 rounds).  Pixels are valid after tic_decode_finish().
+ */
+int tic_decode_batch(tic_handle h, const void *const *d_streams, const int64_t *sizes,
+                     const int32_t *heights, const int32_t *widths, int32_t n_images, uint32_t flags,
+                     void *const *d_pixels, int32_t *d_status, void *stream);
+
+/* Synchronise `stream` and report the last tic_decode_batch: TIC_OK or TIC_E_STREAM. */
+int tic_decode_finish(tic_handle h, void *stream);
+
+/* Host-buffer convenience: what a ctypes binding of decompress() for one `bytes` object calls.
+ * out needs height*width bytes (tic_parse_header).  Synchronous. */
+int tic_decompress_host(tic_handle h, const uint8_t *data, int64_t nbytes, uint32_t flags,
+                        uint8_t *out, int64_t out_capacity, int32_t *status);
+
+/*
+ * decode() for one image whose coefficients are resident in device memory — replaces
+ * tinyimgcodec/codec.py:46-70: the inverse of tic_encode_coeffs.
+ *   d_dc   device int32[nblk]     dc[0] absolute, dc[i>0] differences (np.cumsum, codec.py:53)
+ *   d_ac   device int32[nblk*63]  zigzag positions 1..63
+ *   scaled_dct  the "scaled_dct" key (codec.py:50,58-62): coefficients of the embedded C encoder,
+ *               quality = IMG_Q_BEST..LOW
+ *   d_pixels    device uint8[height*width]
+ * Errors the device sees (quality 0, a coefficient outside int16) are reported by tic_decode_finish().
+ */
+int tic_decode_coeffs(tic_handle h, const int32_t *d_dc, const int32_t *d_ac, int32_t height,
+                      int32_t width, int32_t quality, int32_t scaled_dct, void *d_pixels, void *stream);
+
+/* Counters of the last tic_decode_batch (valid after tic_decode_finish):
+ *   [0] kernels launched  [1] subsequences (1024 stream bits each)  [2] synchronisation rounds
+ *   [3] blocks  [4]-[7] device time in ns of: synchronisation rounds, scan, coefficient scatter, IDCT */
+int tic_decode_stats(tic_handle h, int64_t stats[8]);
 
 #ifdef __cplusplus
 }

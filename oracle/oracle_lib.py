@@ -51,6 +51,14 @@ def lib():
         L.tico_default_code.restype = ctypes.c_int
         L.tico_default_code.argtypes = [ctypes.c_int, ctypes.c_int,
                                         ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_int)]
+        L.tico_idct8_rows.restype = None
+        L.tico_idct8_rows.argtypes = [ctypes.c_void_p, ctypes.c_int64]
+        L.tico_parse_header.restype = ctypes.c_int
+        L.tico_parse_header.argtypes = [ctypes.c_void_p, ctypes.c_int64] + [ctypes.POINTER(ctypes.c_int64)] * 3 + [
+            ctypes.POINTER(ctypes.c_uint32)]
+        L.tico_decompress.restype = ctypes.c_int
+        L.tico_decompress.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p,
+                                      ctypes.POINTER(ctypes.c_int64)]
         del u8p
         _lib = L
     return _lib
@@ -93,6 +101,36 @@ def encode(image, quality=50):
     if rc:
         raise OracleError(rc)
     return {"height": h, "width": w, "quality": quality, "dc": dc, "ac": ac}
+
+
+def parse_header(data):
+    """Restatement of tinyimgcodec.codec.parse_header's fixed part (codec.py:117-122): (h, w, quality, flag)."""
+    buf = np.frombuffer(bytes(data[:16]), dtype=np.uint8)
+    h, w, q = ctypes.c_int64(0), ctypes.c_int64(0), ctypes.c_int64(0)
+    flag = ctypes.c_uint32(0)
+    if lib().tico_parse_header(buf.ctypes.data, buf.size, ctypes.byref(h), ctypes.byref(w), ctypes.byref(q),
+                               ctypes.byref(flag)):
+        raise OracleError(4)
+    return h.value, w.value, q.value, flag.value
+
+
+def decompress(data, return_errors=False):
+    """Restatement of tinyimgcodec.codec.decompress (codec.py:167-189) -> uint8 H x W."""
+    h, w, _, _ = parse_header(data)
+    buf = np.frombuffer(bytes(data), dtype=np.uint8)
+    out = np.zeros((h, w), dtype=np.uint8)
+    nerr = ctypes.c_int64(0)
+    rc = lib().tico_decompress(buf.ctypes.data, buf.size, out.ctypes.data, ctypes.byref(nerr))
+    if rc:
+        raise OracleError(rc)
+    return (out, nerr.value) if return_errors else out
+
+
+def idct8_rows(x):
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float64)).copy()
+    assert x.shape[-1] == 8
+    lib().tico_idct8_rows(x.ctypes.data, x.size // 8)
+    return x
 
 
 def dct8_rows(x):

@@ -18,6 +18,19 @@ class Golden:
         self.images = dict(np.load(os.path.join(GOLD, "images.npz")))
         self.streams = {k: v.tobytes() for k, v in np.load(os.path.join(GOLD, "streams.npz")).items()}
         self.coeffs = dict(np.load(os.path.join(GOLD, "coeffs.npz")))
+        # decode side (oracle/gen_golden_decode.py): pixels of the reference's decompress() by hash
+        with open(os.path.join(GOLD, "decoded.json")) as f:
+            self.decoded = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+        self.decode_streams = {k: v.tobytes()
+                               for k, v in np.load(os.path.join(GOLD, "decode_streams.npz")).items()}
+
+    def decode_cases(self, clean=True):
+        """Yield (key, stream bytes, shape, sha256 of the reference decoder's pixels).  clean: the reference
+        decoded every block without an internal exception (codec.py:177-185)."""
+        for key, info in sorted(self.decoded.items()):
+            if info["clean"] == clean:
+                data = self.streams.get(key) or self.decode_streams[key]
+                yield key, data, tuple(info["shape"]), info["sha256"]
 
     def all_gifs(self):
         """name -> pixels for all 50 data/*.gif (BASELINE config 2); loaded on demand (8 MB)."""

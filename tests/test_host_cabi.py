@@ -36,6 +36,20 @@ def test_host_arithmetic(lib):
         assert lib.tic_max_out_bytes(h, w) == O.lib().tico_max_out_bytes(h, w)
 
 
+def test_parse_header_is_pure_host(lib, golden):
+    from tinyimgcodec_b200 import parse_header
+    data = golden.streams["img_lenna_q50"]
+    h, w, q, f = (ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32(), ctypes.c_uint32())
+    buf = np.frombuffer(data, dtype=np.uint8)
+    assert lib.tic_parse_header(buf.ctypes.data, buf.size, ctypes.byref(h), ctypes.byref(w), ctypes.byref(q),
+                                ctypes.byref(f)) == 0
+    assert (h.value, w.value, q.value, f.value) == (512, 512, 50, 0) == parse_header(data)
+    assert lib.tic_parse_header(buf.ctypes.data, 15, None, None, None, None) != 0
+    import struct
+    with pytest.raises(struct.error):
+        parse_header(data[:15])
+
+
 def test_no_cpu_fallback(lib):
     """Without a GPU the product must fail loudly, never fall back to a CPU path."""
     import torch
@@ -44,6 +58,8 @@ def test_no_cpu_fallback(lib):
     import tinyimgcodec_b200 as tic
     with pytest.raises(tic.TicError):
         tic.compress(np.zeros((8, 8), np.uint8))
+    with pytest.raises(tic.TicError):
+        tic.decompress(bytes(16))
     h = ctypes.c_void_p()
     assert lib.tic_create(0, ctypes.byref(h)) != 0
 

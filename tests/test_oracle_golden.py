@@ -79,3 +79,26 @@ def test_quality_zero():
     with pytest.raises(O.OracleError) as ei:
         O.compress(np.zeros((8, 8), np.uint8), 0)
     assert ei.value.status == 3
+
+
+def test_decompress_matches_reference_decoder_hashes(golden):
+    """Oracle decompress() == the reference's decompress() (by the committed pixel hashes), including the
+    streams the reference only half-decodes (truncated, auto-table streams it misreads)."""
+    import hashlib
+    n = 0
+    for clean in (True, False):
+        for key, data, shape, sha in golden.decode_cases(clean):
+            px, nerr = O.decompress(data, return_errors=True)
+            assert px.shape == shape, key
+            assert hashlib.sha256(px.tobytes()).hexdigest() == sha, key
+            assert (nerr == 0) == clean, key
+            n += 1
+    assert n > 50
+
+
+def test_round_trip_psnr_is_sane(golden):
+    """decompress(compress(x)) is close to x: guards against a decoder that matches only by accident."""
+    img = golden.images["lenna"]
+    px = O.decompress(O.compress(img, 50)).astype(np.float64)
+    mse = np.mean((px - img.astype(np.float64)) ** 2)
+    assert 30.0 < 10 * np.log10(255.0 ** 2 / mse) < 40.0

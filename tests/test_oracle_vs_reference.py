@@ -109,3 +109,51 @@ def test_le_flag_word_makes_auto_streams_decodable(ref):
             assert not np.array_equal(broken, want)
         except Exception:
             pass   # the reference decoder may also just fail on its own auto-table stream
+
+
+@pytest.mark.parametrize("q", [97, 75, 50, 49, 20, 3, 1])
+def test_decompress_random_shapes(ref, q):
+    """Oracle decompress == the reference's decompress (codec.py:167-189) on its own streams."""
+    rng = np.random.default_rng(1000 + q)
+    for _ in range(4):
+        h, w = int(rng.integers(1, 70)), int(rng.integers(1, 70))
+        kind = ["noise", "synthetic", "binary", "impulse", "flat"][int(rng.integers(0, 5))]
+        img = make_case({"kind": kind, "shape": (h, w), "seed": int(rng.integers(0, 1 << 30)),
+                         "value": int(rng.integers(0, 256))})
+        try:
+            s = ref.compress(img, quality=q)
+        except KeyError:
+            continue
+        got, nerr = O.decompress(s, return_errors=True)
+        assert nerr == 0 and np.array_equal(ref.decompress(s), got), (h, w, kind, q)
+
+
+def test_decompress_data_images(ref):
+    for n in ("lenna", "5", "31"):
+        for q in (90, 50, 10):
+            s = ref.compress(_gif(n), quality=q)
+            assert np.array_equal(ref.decompress(s), O.decompress(s)), (n, q)
+
+
+def test_decompress_damaged_streams_like_the_reference(ref):
+    """Truncated streams, and auto-table streams whose flag word the reference misreads: the reference
+    swallows one exception per damaged block (codec.py:177-185); the restatement follows it bit for bit."""
+    img = make_case({"kind": "synthetic", "shape": (64, 96), "seed": 3})
+    s = ref.compress(img, quality=50)
+    for cut in (len(s) // 2, len(s) - 3, 20, 16):
+        got, nerr = O.decompress(s[:cut], return_errors=True)
+        assert nerr > 0 and np.array_equal(ref.decompress(s[:cut]), got), cut
+    s = ref.compress(img, quality=50, auto_generate_huffman_table=True)
+    assert np.array_equal(ref.decompress(s), O.decompress(s))
+
+
+def test_decompress_c_variant_streams(ref):
+    """Streams of the reference's C encoder binary (flag bit 30): decode() takes the scaled-DCT branch
+    (codec.py:58-62)."""
+    if not O.ref_c_available():
+        pytest.skip("oracle/_ref/encode not built")
+    img = make_case({"kind": "synthetic", "shape": (64, 64), "seed": 1})
+    for qf in ("best", "high", "med", "low"):
+        s = O.ref_c_compress(img, qf)
+        got, nerr = O.decompress(s, return_errors=True)
+        assert nerr == 0 and np.array_equal(ref.decompress(s), got), qf

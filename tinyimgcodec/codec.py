@@ -1,2 +1,2 @@
-"""`tinyimgcodec.codec` entry points of the encode path (tinyimgcodec/codec.py:26,133)."""
-from tinyimgcodec_b200.codec import compress, encode  # noqa: F401
+"""`tinyimgcodec.codec` entry points (tinyimgcodec/codec.py:26,46,133,167)."""
+from tinyimgcodec_b200.codec import compress, decode, decompress, encode  # noqa: F401

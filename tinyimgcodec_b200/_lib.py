@@ -17,18 +17,27 @@ TIC_E_CAPACITY = -4
 TIC_E_CATEGORY = -5
 TIC_E_UNSUPPORTED = -6
 TIC_E_TABLE = -7
+TIC_E_STREAM = -8
 TIC_FLAG_AUTO_HUFFMAN = 1
 TIC_FLAG_C_VARIANT = 2
 TIC_FLAG_AUTO_LE_FLAG = 4
 TIC_STATUS_CATEGORY = 1
 TIC_STATUS_TABLE = 2
 TIC_STATUS_LONGCODE = 4
+TIC_DFLAG_ACCEPT_BE_FLAG = 1
+TIC_DSTATUS_HEADER = 1
+TIC_DSTATUS_CODE = 2
+TIC_DSTATUS_TRUNCATED = 4
+TIC_DSTATUS_TABLE = 8
+TIC_DSTATUS_QUALITY = 16
+TIC_DSTATUS_RANGE = 32
 AUTO_HEADER_SLACK = 1664
 
 # every symbol include/tinyimgcodec_cuda.h declares
 EXPORTS = ["tic_version", "tic_create", "tic_destroy", "tic_last_error", "tic_max_out_bytes",
            "tic_num_blocks", "tic_encode_batch", "tic_encode_finish", "tic_encode_coeffs",
-           "tic_compress_host", "tic_last_stats"]
+           "tic_compress_host", "tic_last_stats", "tic_parse_header", "tic_decode_batch", "tic_decode_finish",
+           "tic_decompress_host", "tic_decode_coeffs", "tic_decode_stats"]
 
 _lib = None
 
@@ -66,5 +75,18 @@ def load():
                                     ctypes.POINTER(i32)]
     L.tic_last_stats.restype = ctypes.c_int
     L.tic_last_stats.argtypes = [vp, ctypes.POINTER(i64)]
+    L.tic_parse_header.restype = ctypes.c_int
+    L.tic_parse_header.argtypes = [vp, i64, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32),
+                                   ctypes.POINTER(u32)]
+    L.tic_decode_batch.restype = ctypes.c_int
+    L.tic_decode_batch.argtypes = [vp, vp, vp, vp, vp, i32, u32, vp, vp, vp]
+    L.tic_decode_finish.restype = ctypes.c_int
+    L.tic_decode_finish.argtypes = [vp, vp]
+    L.tic_decompress_host.restype = ctypes.c_int
+    L.tic_decompress_host.argtypes = [vp, vp, i64, u32, vp, i64, ctypes.POINTER(i32)]
+    L.tic_decode_coeffs.restype = ctypes.c_int
+    L.tic_decode_coeffs.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp, vp]
+    L.tic_decode_stats.restype = ctypes.c_int
+    L.tic_decode_stats.argtypes = [vp, ctypes.POINTER(i64)]
     _lib = L
     return L

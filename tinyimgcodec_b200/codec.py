@@ -1,9 +1,13 @@
-"""Host-side mirror of the reference's encode entry points, on top of the C ABI.
+"""Host-side mirror of the reference's codec entry points, on top of the C ABI.
 
     compress(image, quality=50, auto_generate_huffman_table=False) -> bytes
         mirrors tinyimgcodec/codec.py:133-164
     encode(image, quality=50) -> dict
         mirrors tinyimgcodec/codec.py:26-43
+    decompress(data) -> uint8 H x W
+        mirrors tinyimgcodec/codec.py:167-189
+    decode(data: dict) -> uint8 H x W
+        mirrors tinyimgcodec/codec.py:46-70
 
 Same names, argument meaning and error behaviour as the reference; the work runs in the
 sm_100a kernels behind libtinyimgcodec_cuda.so.  PyTorch is used only for device buffers
@@ -27,6 +31,24 @@ class TicError(RuntimeError):
     def __init__(self, code, message):
         super().__init__(f"libtinyimgcodec_cuda error {code}: {message}")
         self.code = code
+
+
+class TicStreamError(ValueError):
+    """A stream the decoder cannot parse cleanly.  The reference swallows the exception of every damaged
+    block (try/except, codec.py:177-185) and returns an image with those blocks zeroed; the B200 path reports
+    instead (pass strict=False to get whatever was decoded).  `.status`: TIC_DSTATUS_* bits per stream."""
+
+    def __init__(self, message, status):
+        super().__init__(message)
+        self.status = status
+
+
+def parse_header(data):
+    """(height, width, quality, flag) — the fixed part of parse_header (codec.py:117-122); struct.error for
+    fewer than 16 bytes, like struct.unpack in the reference."""
+    if len(data) < 16:
+        raise struct.error("unpack requires a buffer of 16 bytes")
+    return struct.unpack("IIII", bytes(data[:16]))
 
 
 def _default_device():
@@ -294,6 +316,133 @@ class Encoder:
                 index.extend((int(base + o), int(s)) for o, s in zip(offs, sizes))
         return h_out, index
 
+    # -- decode side ----------------------------------------------------------------------------------
+    def _raise_decode(self, rc, status):
+        msg = (self.lib.tic_last_error(self.handle) or b"").decode()
+        if rc == _lib.TIC_E_STREAM:
+            bits = int(np.bitwise_or.reduce(np.asarray(status, dtype=np.int64).reshape(-1))) if np.size(status) else 0
+            if bits & _lib.TIC_DSTATUS_QUALITY:
+                raise ZeroDivisionError("division by zero")   # utils.py:50: 5000 / quality
+            raise TicStreamError(msg, status)
+        raise TicError(rc, msg)
+
+    def decompress(self, data, strict=True, accept_be_flag=False):
+        """tinyimgcodec.codec.decompress (codec.py:167-189) for one stream in host memory."""
+        height, width, _, _ = parse_header(data)
+        buf = np.frombuffer(bytes(data), dtype=np.uint8)
+        out = np.empty((height, width), dtype=np.uint8)
+        status = ctypes.c_int32(0)
+        flags = _lib.TIC_DFLAG_ACCEPT_BE_FLAG if accept_be_flag else 0
+        with self._lock:
+            rc = self.lib.tic_decompress_host(self.handle, buf.ctypes.data, buf.size, flags, out.ctypes.data,
+                                              out.size, ctypes.byref(status))
+            if rc != _lib.TIC_OK and (strict or rc != _lib.TIC_E_STREAM):
+                self._raise_decode(rc, [status.value])
+        return out
+
+    def decode_batch_device(self, d_streams, sizes, heights, widths, pixels=None, stream=None,
+                            accept_be_flag=False, strict=True):
+        """Decode streams resident in HBM.  `d_streams`: list of CUDA uint8 tensors (each 4-byte aligned), or
+        one CUDA uint8 tensor plus `sizes` and byte offsets given as d_streams=(tensor, offsets).  Returns the
+        list of CUDA uint8 (H, W) tensors (views of one pixel buffer) and the status array (numpy int32)."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        if isinstance(d_streams, tuple):
+            base, offsets = d_streams
+            ptrs_np = np.uint64(base.data_ptr()) + np.asarray(offsets, dtype=np.uint64)
+            keep = base
+        else:
+            keep = list(d_streams)
+            ptrs_np = np.array([t.data_ptr() for t in keep], dtype=np.uint64).reshape(-1)
+        n = int(ptrs_np.size)
+        sizes_np = np.ascontiguousarray(sizes, dtype=np.int64).reshape(-1)
+        hs_np = np.ascontiguousarray(heights, dtype=np.int32).reshape(-1)
+        ws_np = np.ascontiguousarray(widths, dtype=np.int32).reshape(-1)
+        if not (sizes_np.size == hs_np.size == ws_np.size == n):
+            raise ValueError("d_streams, sizes, heights and widths must have one entry per stream")
+        npx = hs_np.astype(np.int64) * ws_np.astype(np.int64)
+        px_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum((npx + 15) & ~np.int64(15), out=px_off[1:])
+        with torch.cuda.device(dev):
+            if pixels is None:
+                pixels = torch.empty(int(px_off[-1]) + 16, dtype=torch.uint8, device=dev)
+            elif pixels.numel() < int(px_off[-1]):
+                raise ValueError("pixel buffer too small")
+            out_ptrs = np.uint64(pixels.data_ptr()) + px_off[:-1].astype(np.uint64)
+            d_status = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+            stream = stream or torch.cuda.current_stream(dev)
+            flags = _lib.TIC_DFLAG_ACCEPT_BE_FLAG if accept_be_flag else 0
+            if n == 0:
+                return [], np.zeros(0, dtype=np.int32)
+            with self._lock:
+                rc = self.lib.tic_decode_batch(self.handle, ptrs_np.ctypes.data, sizes_np.ctypes.data,
+                                               hs_np.ctypes.data, ws_np.ctypes.data, n, flags,
+                                               out_ptrs.ctypes.data, d_status.data_ptr(), stream.cuda_stream)
+                if rc == _lib.TIC_OK:
+                    rc = self.lib.tic_decode_finish(self.handle, stream.cuda_stream)
+                status = d_status[:n].cpu().numpy() if rc in (_lib.TIC_OK, _lib.TIC_E_STREAM) else None
+                if rc != _lib.TIC_OK and (strict or rc != _lib.TIC_E_STREAM):
+                    self._raise_decode(rc, status)
+        del keep
+        images = [pixels[int(px_off[i]): int(px_off[i]) + int(npx[i])].view(int(hs_np[i]), int(ws_np[i]))
+                  for i in range(n)]
+        return images, status
+
+    def decompress_batch(self, streams, strict=True, accept_be_flag=False):
+        """decompress() for a list of `bytes`: one pinned H2D copy of all streams, one decode, one D2H copy of all
+        pixels.  Returns a list of uint8 (H, W) arrays."""
+        import torch
+        dev = torch.device("cuda", self.device)
+        streams = [bytes(s) for s in streams]
+        hdrs = [parse_header(s) for s in streams]
+        sizes = np.array([len(s) for s in streams], dtype=np.int64)
+        offs = np.zeros(len(streams) + 1, dtype=np.int64)
+        np.cumsum((sizes + 15) & ~np.int64(15), out=offs[1:])
+        with torch.cuda.device(dev):
+            h_buf = torch.zeros(int(offs[-1]) + 16, dtype=torch.uint8).pin_memory()
+            h_np = h_buf.numpy()
+            for s, o in zip(streams, offs[:-1]):
+                h_np[o: o + len(s)] = np.frombuffer(s, dtype=np.uint8)
+            d_buf = h_buf.to(dev, non_blocking=True)
+            imgs, _ = self.decode_batch_device((d_buf, offs[:-1]), sizes, [h[0] for h in hdrs], [h[1] for h in hdrs],
+                                               strict=strict, accept_be_flag=accept_be_flag)
+            return [im.cpu().numpy() for im in imgs]
+
+    def decode(self, data):
+        """tinyimgcodec.codec.decode (codec.py:46-70): the dict encode() returns (plus the optional
+        "scaled_dct" key parse_header sets, codec.py:122) -> uint8 H x W."""
+        import torch
+        height, width, quality = int(data["height"]), int(data["width"]), data["quality"]
+        scaled = bool(data.get("scaled_dct", False))
+        struct.pack("I", quality)
+        if quality == 0 and not scaled:
+            raise ZeroDivisionError("division by zero")   # utils.py:50
+        nblk = int(self.lib.tic_num_blocks(height, width))
+        dc = np.ascontiguousarray(data["dc"], dtype=np.int32).reshape(-1)
+        ac = np.ascontiguousarray(data["ac"], dtype=np.int32).reshape(-1)
+        if dc.size != nblk or ac.size != nblk * 63:
+            raise ValueError(f"expected {nblk} dc and {nblk}x63 ac coefficients")
+        dev = torch.device("cuda", self.device)
+        with self._lock, torch.cuda.device(dev):
+            d_dc = torch.from_numpy(dc).to(dev) if nblk else torch.empty(1, dtype=torch.int32, device=dev)
+            d_ac = torch.from_numpy(ac).to(dev) if nblk else torch.empty(1, dtype=torch.int32, device=dev)
+            d_px = torch.empty(max(height * width, 1), dtype=torch.uint8, device=dev)
+            stream = torch.cuda.current_stream(dev)
+            rc = self.lib.tic_decode_coeffs(self.handle, d_dc.data_ptr(), d_ac.data_ptr(), height, width,
+                                            int(quality), int(scaled), d_px.data_ptr(), stream.cuda_stream)
+            if rc == _lib.TIC_OK:
+                rc = self.lib.tic_decode_finish(self.handle, stream.cuda_stream)
+            if rc != _lib.TIC_OK:
+                self._raise_decode(rc, [])
+            return d_px[: height * width].cpu().numpy().reshape(height, width)
+
+    def decode_stats(self):
+        arr = (ctypes.c_int64 * 8)()
+        self.lib.tic_decode_stats(self.handle, arr)
+        return {"launches": arr[0], "subsequences": arr[1], "sync_rounds": arr[2], "blocks": arr[3],
+                "sync_ms": arr[4] * 1e-6, "scan_ms": arr[5] * 1e-6, "scatter_ms": arr[6] * 1e-6,
+                "idct_ms": arr[7] * 1e-6}
+
     def stats(self):
         arr = (ctypes.c_int64 * 8)()
         self.lib.tic_last_stats(self.handle, arr)
@@ -348,6 +497,21 @@ def compress(image, quality=50, auto_generate_huffman_table=False, device=None, 
 def encode(image, quality=50, device=None):
     """Drop-in for tinyimgcodec.codec.encode (codec.py:26-43)."""
     return get_encoder(device).encode(image, quality)
+
+
+def decompress(data, device=None, strict=True, accept_be_flag=False):
+    """Drop-in for tinyimgcodec.codec.decompress (codec.py:167-189)."""
+    return get_encoder(device).decompress(data, strict=strict, accept_be_flag=accept_be_flag)
+
+
+def decode(data, device=None):
+    """Drop-in for tinyimgcodec.codec.decode (codec.py:46-70)."""
+    return get_encoder(device).decode(data)
+
+
+def decompress_batch(streams, device=None, strict=True, accept_be_flag=False):
+    """decompress() for a list of streams in one launch sequence."""
+    return get_encoder(device).decompress_batch(streams, strict=strict, accept_be_flag=accept_be_flag)
 
 
 def compress_c(image, qfactor="med", device=None):

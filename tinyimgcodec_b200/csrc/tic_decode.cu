@@ -1,0 +1,1041 @@
+// tic_decode.cu — the decode side of libtinyimgcodec_cuda.so for B200 (sm_100a): SURVEY.md §8(f)3.
+//
+// Replaces, for a batch of .img streams resident in device memory,
+//   tinyimgcodec.codec.decompress   tinyimgcodec/codec.py:167-189   (header, per-block Huffman decode)
+//   tinyimgcodec.codec.decode       tinyimgcodec/codec.py:46-70     (DC cumsum, de-zigzag, dequantise,
+//                                                                    IDCT, +128, clip, crop, uint8)
+//   parse_header / read_huffman_table   codec.py:117-130 / :87-99
+//   decode_huffman / read_huffman_code / decode_run_length   tinyimgcodec/huffman.py:77-98 / :66-74 / :36-38
+//   BitBuffer.read / read_uint / read_int   tinyimgcodec/bitbuffer.py:20-23 / :42-45 / :56-66
+//   block_idct, block_quantize(inverse=True), block_combine   tinyimgcodec/utils.py:40-45, :51-52, :23-29
+//
+// The stream has no markers, no restart intervals and no per-block lengths: block i can only be found by
+// decoding blocks 0..i-1.  The reference therefore decodes serially.  Here every stream is cut into
+// subsequences of kSubBits bits, one thread per subsequence, and the threads find their true entry
+// state by SELF-SYNCHRONISATION: a Huffman decoder started at a wrong bit falls back into step with the
+// true symbol sequence after a few symbols, so
+//   1. every thread decodes its subsequence from a guessed entry state (bit 0, "a DC symbol is next") and
+//      publishes the state in which it leaves (overshoot into the next subsequence, zigzag index);
+//   2. a thread whose published entry differs from the one it used decodes again; this repeats (inside a
+//      CTA through __syncthreads_or, across CTAs through relaunches) until nothing changes.  The first
+//      subsequence of a stream has a KNOWN entry, so by induction the fixed point is the serial parse;
+//   3. an exclusive scan over the subsequences' block counts and DC-difference sums gives each thread
+//      the index of its first block and the running DC predictor (np.cumsum, codec.py:53);
+//   4. the threads decode once more and scatter the coefficients (int16, raster order) to HBM;
+//   5. one thread per 8x8 block dequantises and runs the inverse DCT in float64, operation for operation
+//      what scipy.fftpack.idct (ducc0) executes, adds 128, clips, truncates — so pixels are
+//      bit-identical to the reference decoder's, including values that land on an integer boundary.
+//
+// FP64 on B200 runs at half the FP32 rate, so unlike the encoder no FP32 fast path is needed here.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/tinyimgcodec_cuda.h"
+#include "tic_tables.h"
+
+// hooks into the handle (defined in tic_encode.cu)
+void** tic_internal_dec_slot(tic_handle h);
+void tic_internal_set_error(tic_handle h, const std::string& msg);
+int tic_internal_device(tic_handle h);
+cudaStream_t tic_internal_own_stream(tic_handle h);
+
+namespace ticd {
+
+constexpr int kSubBits = 1024;      // bits per subsequence (one thread each)
+constexpr int kMaxNodes = 1024;     // trie nodes per table (a Huffman tree over <= 256 symbols has <= 255)
+constexpr int kMaxSymbols = 4096;   // symbols decoded per subsequence at most (zero-length codes)
+constexpr int kSyncThreads = 128;
+constexpr int kSyncIters = 64;      // in-CTA repair rounds per launch
+constexpr uint32_t kLeaf = 0x8000u;
+
+// Decode table of one alphabet: the reference's `table.inverse` dict (huffman.py:83) as a binary trie
+// (child[n][bit]: 0 = no code, kLeaf | symbol, else node index) plus a first-level table over the next
+// 8 bits (0 = no code, kLeaf | len << 8 | symbol for codes of <= 8 bits, else the node reached).
+struct DecTable {
+    uint16_t lut[256];
+    uint16_t child[kMaxNodes][2];
+};
+struct DecTables {
+    DecTable dc, ac;
+};
+
+struct DecImage {
+    // filled by the host
+    const uint32_t* words;   // stream, 4-byte aligned
+    long long nbits;         // 8 * size
+    long long sub_first;     // index of the stream's first subsequence in the batch
+    long long blk_first;     // index of the image's first block in the batch
+    uint8_t* pixels;
+    int height, width;       // as the caller expects them (checked against the header)
+    int nsubs, bw, nblk;
+    // filled by dec_setup_kernel
+    uint32_t quality, flag;
+    int mode;                // 0 fixed tables, 1 per-image tables, 2 scaled integer DCT (flag bit 30)
+    int skip_entropy;        // nothing to decode (error, no blocks, or every block is zero bits long)
+    int skip_pixels;         // header unusable: pixels are not written
+    int anchor_sub;          // subsequence in which the first block starts
+    int has_tables;
+    double two_q;            // 2**quality for mode 2 (codec.py:61)
+};
+
+enum { MODE_FIXED = 0, MODE_TABLES = 1, MODE_SCALED = 2 };
+
+__constant__ uint8_t c_zigzag[64] = {TIC_ZIGZAG_LIST};
+// tinyimgcodec/constants.py:37-51: ANNSCALES = these / 2048
+__constant__ double c_ann[64] = {
+    16384 / 2048.0, 22725 / 2048.0, 21407 / 2048.0, 19266 / 2048.0, 16384 / 2048.0, 12873 / 2048.0, 8867 / 2048.0,  4520 / 2048.0,
+    22725 / 2048.0, 31521 / 2048.0, 29692 / 2048.0, 26722 / 2048.0, 22725 / 2048.0, 17855 / 2048.0, 12299 / 2048.0, 6270 / 2048.0,
+    21407 / 2048.0, 29692 / 2048.0, 27969 / 2048.0, 25172 / 2048.0, 21407 / 2048.0, 16819 / 2048.0, 11585 / 2048.0, 5906 / 2048.0,
+    19266 / 2048.0, 26722 / 2048.0, 25172 / 2048.0, 22654 / 2048.0, 19266 / 2048.0, 15137 / 2048.0, 10426 / 2048.0, 5315 / 2048.0,
+    16384 / 2048.0, 22725 / 2048.0, 21407 / 2048.0, 19266 / 2048.0, 16384 / 2048.0, 12873 / 2048.0, 8867 / 2048.0,  4520 / 2048.0,
+    12873 / 2048.0, 17855 / 2048.0, 16819 / 2048.0, 15137 / 2048.0, 12873 / 2048.0, 10114 / 2048.0, 6967 / 2048.0,  3552 / 2048.0,
+    8867 / 2048.0,  12299 / 2048.0, 11585 / 2048.0, 10426 / 2048.0, 8867 / 2048.0,  6967 / 2048.0,  4799 / 2048.0,  2446 / 2048.0,
+    4520 / 2048.0,  6270 / 2048.0,  5906 / 2048.0,  5315 / 2048.0,  4520 / 2048.0,  3552 / 2048.0,  2446 / 2048.0,  1247 / 2048.0};
+__constant__ int c_qbase[64] = {
+    16, 11, 10, 16, 24,  40,  51,  61,  12, 12, 14, 19, 26,  58,  60,  55,
+    14, 13, 16, 24, 40,  57,  69,  56,  14, 17, 22, 29, 51,  87,  80,  62,
+    18, 22, 37, 56, 68,  109, 103, 77,  24, 35, 55, 64, 81,  104, 113, 92,
+    49, 64, 78, 87, 103, 121, 120, 101, 72, 92, 95, 98, 112, 100, 103, 99};
+
+// ---------------------------------------------------------------------------------------------------
+// Trie construction (host and device): insert one codeword; the shortest matching prefix wins, like
+// `while prefix not in table` (huffman.py:69).  Returns false when the node pool is exhausted.
+// ---------------------------------------------------------------------------------------------------
+__host__ __device__ inline void table_clear(DecTable& t, int& nodes) {
+    for (int i = 0; i < 256; i++) t.lut[i] = 0;
+    t.child[0][0] = t.child[0][1] = 0;
+    nodes = 1;
+}
+
+// `root_leaf`: a zero-length codeword (one-symbol alphabet, huffman.py:175-180) makes the root a leaf.
+__host__ __device__ inline bool table_insert(DecTable& t, int& nodes, int& root_leaf, uint32_t code, int len, int sym) {
+    if (len == 0) { root_leaf = sym; return true; }
+    int node = 0;
+    for (int i = 0; i < len; i++) {
+        int bit = (code >> (len - 1 - i)) & 1;
+        uint16_t c = t.child[node][bit];
+        if (i == len - 1) { t.child[node][bit] = (uint16_t)(kLeaf | (uint32_t)sym); return true; }
+        if (c & kLeaf) return true;   // a shorter codeword is a prefix of this one: unreachable
+        if (c == 0) {
+            if (nodes >= kMaxNodes) return false;
+            c = (uint16_t)nodes++;
+            t.child[c][0] = t.child[c][1] = 0;
+            t.child[node][bit] = c;
+        }
+        node = c;
+    }
+    return true;
+}
+
+__host__ __device__ inline void table_finish(DecTable& t, int root_leaf) {
+    for (int x = 0; x < 256; x++) {
+        if (root_leaf >= 0) { t.lut[x] = (uint16_t)(kLeaf | (uint32_t)root_leaf); continue; }
+        int node = 0;
+        uint16_t e = 0;
+        for (int d = 0; d < 8; d++) {
+            uint16_t c = t.child[node][(x >> (7 - d)) & 1];
+            if (c == 0) { e = 0; break; }
+            if (c & kLeaf) { e = (uint16_t)(kLeaf | ((uint32_t)(d + 1) << 8) | (c & 0xffu)); break; }
+            node = c;
+            e = c;   // after 8 steps: the node to continue from
+        }
+        t.lut[x] = e;
+    }
+}
+
+static void build_default_tables(DecTables& t) {
+    int nodes, root = -1;
+    table_clear(t.dc, nodes);
+    uint32_t code = 0;
+    int k = 0;
+    for (int l = 1; l <= 16; l++) {
+        for (int i = 0; i < tic::kDcBits[l]; i++) table_insert(t.dc, nodes, root, code++, l, tic::kDcVals[k++]);
+        code <<= 1;
+    }
+    table_finish(t.dc, -1);
+    table_clear(t.ac, nodes);
+    code = 0;
+    k = 0;
+    for (int l = 1; l <= 16; l++) {
+        for (int i = 0; i < tic::kAcBits[l]; i++) table_insert(t.ac, nodes, root, code++, l, tic::kAcVals[k++]);
+        code <<= 1;
+    }
+    table_finish(t.ac, -1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Bit access: the stream is MSB-first bytes (bitarray(endian="big"), bitbuffer.py:7); 32 bits starting at
+// bit p, zeros past the end (a slice past the end of a bitarray is empty).
+// ---------------------------------------------------------------------------------------------------
+struct BitSrc {
+    const uint32_t* words;
+    long long nwords;
+    uint32_t tailmask;   // valid bits of the last word (stream sizes need not be multiples of 4)
+};
+
+__device__ __forceinline__ BitSrc make_src(const DecImage& im) {
+    BitSrc s;
+    s.words = im.words;
+    s.nwords = (im.nbits + 31) >> 5;
+    int tail = (int)(im.nbits & 31);
+    s.tailmask = tail ? (0xffffffffu << (32 - tail)) : 0xffffffffu;
+    return s;
+}
+
+__device__ __forceinline__ uint32_t load_be(const BitSrc& s, long long i) {
+    if (i >= s.nwords) return 0u;
+    uint32_t w = __byte_perm(__ldg(s.words + i), 0, 0x0123);
+    return i == s.nwords - 1 ? (w & s.tailmask) : w;
+}
+
+__device__ __forceinline__ uint32_t peek32(const BitSrc& s, long long p) {
+    long long i = p >> 5;
+    return __funnelshift_l(load_be(s, i + 1), load_be(s, i), (uint32_t)(p & 31));
+}
+
+// One Huffman symbol from the 32 bits `v`: read_huffman_code (huffman.py:66-74).  len < 0: no codeword of
+// at most 16 bits matches (the reference raises ValueError).
+__device__ __forceinline__ void lookup(const DecTable* __restrict__ t, uint32_t v, int& sym, int& len) {
+    uint32_t e = __ldg(&t->lut[v >> 24]);
+    if (e & kLeaf) { sym = (int)(e & 0xffu); len = (int)((e >> 8) & 0x7fu); return; }
+    len = 8;
+    uint32_t node = e;
+    while (node != 0 && len < 16) {
+        uint32_t c = __ldg(&t->child[node][(v >> (31 - len)) & 1u]);
+        len++;
+        if (c & kLeaf) { sym = (int)(c & 0xffu); return; }
+        node = c;
+    }
+    sym = 0;
+    len = -1;
+}
+
+struct SubResult {
+    uint32_t exit;   // entry state of the next subsequence: overshoot bits | zigzag index << 16
+    int n;           // DC symbols (= blocks) that START in this subsequence
+    int dsum;        // sum of their DC differences
+    uint32_t err;
+};
+
+// Decode one subsequence from `entry`.  WRITE: also scatter coefficients; `blk` is the index (within the
+// image) of the next block to start, `dc_run` the DC predictor (sum of all earlier differences).
+template <bool WRITE>
+__device__ SubResult decode_sub(const DecImage& im, const BitSrc& src, const DecTable* __restrict__ tdc,
+                                const DecTable* __restrict__ tac, long long sub_bit0, uint32_t entry,
+                                int16_t* __restrict__ coef, int blk, int dc_run, const uint8_t* zz) {
+    long long p = sub_bit0 + (long long)(entry & 0xffffu);
+    int z = (int)((entry >> 16) & 0xffu);
+    const long long sub_end = sub_bit0 + kSubBits;
+    const long long end = sub_end < im.nbits ? sub_end : im.nbits;
+    SubResult r;
+    r.n = 0; r.dsum = 0; r.err = 0;
+    int cur = blk - 1;   // the block being filled when z > 0
+    int it = 0;
+    for (; p < end && it < kMaxSymbols; it++) {
+        if (WRITE && z == 0 && blk >= im.nblk) break;   // all blocks done: what follows is padding (bitbuffer.py:17-18)
+        uint32_t v = peek32(src, p);
+        int sym, len;
+        lookup(z == 0 ? tdc : tac, v, sym, len);
+        if (len < 0) {   // no codeword: a deterministic rule so that decode(entry) stays a function
+            r.err |= TIC_DSTATUS_CODE;
+            p += 1;
+            continue;
+        }
+        int size = sym & 15;   // DC: the category is the size; AC: (run, size), huffman.py:89-93
+        int val = 0;
+        if (size) {            // read_int, bitbuffer.py:56-66: leading 0 = negative, one's complement
+            uint32_t vb = (v << len) >> (32 - size);
+            val = (vb >> (size - 1)) ? (int)vb : (int)vb - (1 << size) + 1;
+        }
+        p += len + size;
+        if (z == 0) {
+            r.n++;
+            r.dsum += val;
+            if (WRITE) {
+                cur = blk++;
+                dc_run += val;
+                if (cur < im.nblk) {
+                    int s = dc_run < -32768 ? -32768 : (dc_run > 32767 ? 32767 : dc_run);
+                    if (s != dc_run) r.err |= TIC_DSTATUS_RANGE;
+                    coef[(long long)cur * 64] = (int16_t)s;
+                }
+            }
+            z = 1;
+        } else if (sym == 0) {   // EOB (huffman.py:94-95)
+            z = 0;
+        } else {
+            z += sym >> 4;       // decode_run_length (huffman.py:36-38): `run` zeros, then the value
+            if (WRITE) {
+                if (z > 63) r.err |= TIC_DSTATUS_CODE;   // the reference's ac[i, :len] assignment raises
+                else if (val != 0 && cur >= 0 && cur < im.nblk) coef[(long long)cur * 64 + zz[z]] = (int16_t)val;
+            }
+            z += 1;
+            if (z > 250) z = 250;
+        }
+    }
+    if (it >= kMaxSymbols) r.err |= TIC_DSTATUS_CODE;   // zero-length codewords that never advance
+    long long over = p - sub_end;
+    r.exit = (uint32_t)(over > 0 ? over : 0) | ((uint32_t)z << 16);
+    return r;
+}
+
+__device__ __forceinline__ int find_owner(const long long* __restrict__ first, int n, long long g) {
+    int lo = 0, hi = n;   // last i with first[i] <= g
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (__ldg(first + mid) <= g) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dec_setup_kernel: one warp per image.  parse_header (codec.py:117-130), read_huffman_table
+// (codec.py:87-99), the multiplier table of block_quantize(inverse=True) (utils.py:48-52).
+// ---------------------------------------------------------------------------------------------------
+// The multiplier table of block_quantize(inverse=True) (utils.py:48-52) — for mode 2 the table of quality 50
+// (codec.py:62) and 2**quality (codec.py:61).  Returns status bits.
+__device__ inline uint32_t fill_mul(DecImage& im, double* __restrict__ m) {
+    uint32_t q = im.quality;
+    if (im.mode == MODE_SCALED) {
+        if (q > 1000) return TIC_DSTATUS_QUALITY;
+        im.two_q = scalbn(1.0, (int)q);
+        for (int k = 0; k < 64; k++) m[k] = __ddiv_rn((double)((long long)c_qbase[k] * 100), 100.0);
+    } else if (q == 0) {
+        return TIC_DSTATUS_QUALITY;   // ZeroDivisionError, utils.py:50
+    } else if (q < 50) {
+        double factor = __ddiv_rn(5000.0, (double)q);
+        for (int k = 0; k < 64; k++) m[k] = __ddiv_rn(__dmul_rn((double)c_qbase[k], factor), 100.0);
+    } else {
+        long long factor = 200 - 2 * (long long)q;
+        for (int k = 0; k < 64; k++) m[k] = __ddiv_rn((double)((long long)c_qbase[k] * factor), 100.0);
+    }
+    return 0;
+}
+
+__device__ inline uint32_t get_bits(const BitSrc& s, long long& p, int n) {   // read_uint, n <= 16
+    uint32_t v = n ? (peek32(s, p) >> (32 - n)) : 0u;
+    p += n;
+    return v;
+}
+
+__global__ void __launch_bounds__(32) dec_setup_kernel(DecImage* __restrict__ imgs, int n_images, uint32_t flags,
+                                                       DecTables* __restrict__ tabs, double* __restrict__ mul,
+                                                       uint32_t* __restrict__ E, int* __restrict__ status,
+                                                       int* __restrict__ summary) {
+    __shared__ DecTables sh;
+    __shared__ int sh_build;
+    int i = blockIdx.x;
+    if (i >= n_images) return;
+    DecImage& im = imgs[i];
+    int lane = threadIdx.x;
+    if (lane == 0) {
+        sh_build = 0;
+        uint32_t st = 0;
+        im.mode = MODE_FIXED; im.skip_entropy = 0; im.skip_pixels = 0; im.anchor_sub = 0; im.has_tables = 0;
+        im.quality = 0; im.flag = 0; im.two_q = 1.0;
+        BitSrc src = make_src(im);
+        long long data_start = 128;
+        if (im.nbits < 128) {
+            st |= TIC_DSTATUS_HEADER;
+        } else {
+            // struct.unpack("IIII"): native little-endian words
+            uint32_t hh = __ldg(im.words + 0), ww = __ldg(im.words + 1);
+            im.quality = __ldg(im.words + 2);
+            im.flag = __ldg(im.words + 3);
+            if (hh != (uint32_t)im.height || ww != (uint32_t)im.width) st |= TIC_DSTATUS_HEADER;
+        }
+        if (st == 0) {
+            uint32_t f = im.flag;
+            if ((flags & TIC_DFLAG_ACCEPT_BE_FLAG) && f == 0x00000080u) f = 0x80000000u;
+            if (f & 0x80000000u) im.mode = MODE_TABLES;
+            else if (f & 0x40000000u) im.mode = MODE_SCALED;
+            st |= fill_mul(im, mul + (size_t)i * 64);
+        }
+        if (st == 0 && im.mode == MODE_TABLES) {
+            long long p = 128;
+            bool ok = true;
+            for (int pass = 0; pass < 2 && ok; pass++) {
+                DecTable& t = pass ? sh.ac : sh.dc;
+                int nodes, root = -1;
+                table_clear(t, nodes);
+                uint32_t cnt = get_bits(src, p, 16);
+                for (uint32_t e = 0; e < cnt && p < im.nbits; e++) {
+                    uint32_t a = get_bits(src, p, 4);
+                    uint32_t b = pass ? get_bits(src, p, 4) : 0u;
+                    uint32_t len = get_bits(src, p, pass ? 8 : 4);
+                    int sym = pass ? (int)(a * 16 + b) : (int)a;
+                    if (len <= 16) {
+                        uint32_t code = get_bits(src, p, (int)len);
+                        if (!table_insert(t, nodes, root, code, (int)len, sym)) ok = false;
+                    } else {
+                        p += len;   // can never match: read_huffman_code gives up after 17 bits
+                    }
+                }
+                table_finish(t, root);
+            }
+            if (!ok) st |= TIC_DSTATUS_TABLE;
+            data_start = p;
+            sh_build = 1;
+            im.has_tables = 1;
+            // every block is zero bits long: one-symbol alphabets with empty codewords on both sides
+            if (ok && sh.dc.lut[0] == (uint16_t)(kLeaf | 0u) && sh.ac.lut[0] == (uint16_t)(kLeaf | 0u)) im.skip_entropy = 1;
+        }
+        if (st & (TIC_DSTATUS_HEADER)) im.skip_pixels = 1;
+        if (st) im.skip_entropy = 1;
+        if (st & TIC_DSTATUS_QUALITY) im.skip_pixels = 1;
+        if (st == 0 && im.nblk > 0 && im.nsubs == 0) st |= TIC_DSTATUS_TRUNCATED;   // a header and nothing else
+        if (st || im.nblk == 0 || im.nsubs == 0) im.skip_entropy = 1;
+        if (!im.skip_entropy) {
+            long long rel = data_start - 128;
+            if (rel >= (long long)im.nsubs * kSubBits) {
+                im.skip_entropy = 1;   // tables run to the end of the stream: no block data at all
+                st |= TIC_DSTATUS_TRUNCATED;
+            } else {
+                im.anchor_sub = (int)(rel / kSubBits);
+                E[im.sub_first + im.anchor_sub] = (uint32_t)(rel % kSubBits);   // zigzag index 0: a DC symbol is next
+            }
+        }
+        if (st) { atomicOr(&status[i], (int)st); atomicOr(summary, (int)st); }
+    }
+    __syncwarp();
+    if (sh_build) {
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(&sh);
+        uint32_t* d = reinterpret_cast<uint32_t*>(tabs + i);
+        for (int k = lane; k < (int)(sizeof(DecTables) / 4); k += 32) d[k] = s[k];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dec_sync_kernel: phases 1 and 2.  E[g] = entry state of subsequence g (written by the thread of g-1),
+// U[g] = the entry the thread of g last decoded from, ND[g] = (blocks started, DC-difference sum) of
+// that decode.  Invariant: E[g+1] == decode(g, U[g]).exit; fixed point <=> U == E everywhere.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSyncThreads) dec_sync_kernel(const DecImage* __restrict__ imgs,
+                                                                const long long* __restrict__ sub_first, int n_images,
+                                                                long long total_subs, const DecTables* __restrict__ deftab,
+                                                                const DecTables* __restrict__ tabs, uint32_t* E,
+                                                                uint32_t* __restrict__ U, int2* __restrict__ ND,
+                                                                int* __restrict__ changed) {
+    long long g = (long long)blockIdx.x * kSyncThreads + threadIdx.x;
+    bool active = g < total_subs;
+    int idx = 0, k = 0;
+    bool has_next = false;
+    uint32_t used = 0xffffffffu;
+    const DecTables* tb = deftab;
+    BitSrc src = {};
+    if (active) {
+        idx = find_owner(sub_first, n_images, g);
+        const DecImage& im = imgs[idx];
+        k = (int)(g - im.sub_first);
+        active = !im.skip_entropy && k >= im.anchor_sub;
+        has_next = k + 1 < im.nsubs;
+        if (im.has_tables) tb = tabs + idx;
+        src = make_src(im);
+        used = U[g];
+    }
+    volatile uint32_t* Ev = E;
+    bool any = false;
+    for (int it = 0; it < kSyncIters; it++) {
+        bool wrote = false;
+        if (active) {
+            uint32_t e = Ev[g];
+            if (e != used) {
+                used = e;
+                SubResult r = decode_sub<false>(imgs[idx], src, &tb->dc, &tb->ac, 128 + (long long)k * kSubBits, e,
+                                                nullptr, 0, 0, nullptr);
+                ND[g] = make_int2(r.n, r.dsum);
+                if (has_next && Ev[g + 1] != r.exit) { Ev[g + 1] = r.exit; wrote = true; }
+            }
+        }
+        if (!__syncthreads_or(wrote)) break;
+        any = true;
+    }
+    if (active) U[g] = used;
+    if (any && threadIdx.x == 0) *changed = 1;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dec_scan_kernel: phase 3, one CTA per image: exclusive sums of ND over the image's subsequences.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) dec_scan_kernel(const DecImage* __restrict__ imgs, const int2* __restrict__ ND,
+                                                        int2* __restrict__ NB, int* __restrict__ status,
+                                                        int* __restrict__ summary) {
+    const DecImage& im = imgs[blockIdx.x];
+    if (im.skip_entropy) return;
+    __shared__ int2 warp_tot[32], warp_excl[32];
+    __shared__ int2 carry_sh, chunk_tot;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry_sh = make_int2(0, 0);
+    __syncthreads();
+    for (int base = im.anchor_sub; base < im.nsubs; base += 1024) {
+        int k = base + threadIdx.x;
+        int2 v = k < im.nsubs ? ND[im.sub_first + k] : make_int2(0, 0);
+        int2 inc = v;
+        for (int d = 1; d < 32; d <<= 1) {
+            int a = __shfl_up_sync(0xffffffffu, inc.x, d), b = __shfl_up_sync(0xffffffffu, inc.y, d);
+            if (lane >= d) { inc.x += a; inc.y += b; }
+        }
+        if (lane == 31) warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int2 w = warp_tot[lane], wi = w;
+            for (int d = 1; d < 32; d <<= 1) {
+                int a = __shfl_up_sync(0xffffffffu, wi.x, d), b = __shfl_up_sync(0xffffffffu, wi.y, d);
+                if (lane >= d) { wi.x += a; wi.y += b; }
+            }
+            warp_excl[lane] = make_int2(wi.x - w.x, wi.y - w.y);
+            if (lane == 31) chunk_tot = wi;
+        }
+        __syncthreads();
+        int2 c = carry_sh, wo = warp_excl[warp];
+        if (k < im.nsubs) NB[im.sub_first + k] = make_int2(c.x + wo.x + inc.x - v.x, c.y + wo.y + inc.y - v.y);
+        __syncthreads();
+        if (threadIdx.x == 0) carry_sh = make_int2(c.x + chunk_tot.x, c.y + chunk_tot.y);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && carry_sh.x < im.nblk) {
+        atomicOr(&status[blockIdx.x], TIC_DSTATUS_TRUNCATED);
+        atomicOr(summary, TIC_DSTATUS_TRUNCATED);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// dec_write_kernel: phase 4.  coef: int16[total_blocks][64] in RASTER order (u*8+v), zero-filled before.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kSyncThreads) dec_write_kernel(const DecImage* __restrict__ imgs,
+                                                                 const long long* __restrict__ sub_first, int n_images,
+                                                                 long long total_subs, const DecTables* __restrict__ deftab,
+                                                                 const DecTables* __restrict__ tabs,
+                                                                 const uint32_t* __restrict__ E, const int2* __restrict__ NB,
+                                                                 int16_t* __restrict__ coef, int* __restrict__ status,
+                                                                 int* __restrict__ summary) {
+    __shared__ uint8_t zz[64];
+    if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
+    __syncthreads();
+    long long g = (long long)blockIdx.x * kSyncThreads + threadIdx.x;
+    if (g >= total_subs) return;
+    int idx = find_owner(sub_first, n_images, g);
+    const DecImage& im = imgs[idx];
+    int k = (int)(g - im.sub_first);
+    if (im.skip_entropy || k < im.anchor_sub) return;
+    const DecTables* tb = im.has_tables ? tabs + idx : deftab;
+    BitSrc src = make_src(im);
+    int2 nb = NB[g];
+    if (nb.x > im.nblk) return;   // past the last block: padding bits (to_bytes, bitbuffer.py:17-18) or trailing bytes
+    SubResult r = decode_sub<true>(im, src, &tb->dc, &tb->ac, 128 + (long long)k * kSubBits, E[g],
+                                   coef + im.blk_first * 64, nb.x, nb.y, zz);
+    if (r.err) { atomicOr(&status[idx], (int)r.err); atomicOr(summary, (int)r.err); }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Phase 5: scipy.fftpack.idct(x, norm="ortho") for N = 8 in float64 = ducc0's DCT-III (T_dcst23, type 3):
+// c0 *= sqrt2; twiddle pre-pass; c4 *= 2 tw3; forward real FFT of length 8 (radf4, then radf2); scale
+// 1/sqrt(2N) = 0.25 (exact); minus/plus post-pass.  One IEEE operation per intrinsic, never contracted;
+// the constants are ducc0's, not the correctly rounded cosines.  The test suite
+// checks the same operation sequence against the installed SciPy bit for bit on the CPU.
+// ---------------------------------------------------------------------------------------------------
+#define DA(a, b) __dadd_rn((a), (b))
+#define DS(a, b) __dsub_rn((a), (b))
+#define DM(a, b) __dmul_rn((a), (b))
+
+__device__ __forceinline__ void idct8_exact(double& x0, double& x1, double& x2, double& x3, double& x4, double& x5,
+                                            double& x6, double& x7) {
+    const double TW0 = 0x1.f6297cff75cb0p-1, TW1 = 0x1.d906bcf328d46p-1, TW2 = 0x1.a9b66290ea1a3p-1,
+                 TW3 = 0x1.6a09e667f3bccp-1, TW4 = 0x1.1c73b39ae68c8p-1, TW5 = 0x1.87de2a6aea963p-2,
+                 TW6 = 0x1.8f8b83c69a60ap-3;
+    const double WR = 0x1.6a09e667f3bccp-1, WI = 0x1.6a09e667f3bcdp-1, SQ2 = 0x1.6a09e667f3bcdp+0;
+    double c0 = DM(x0, SQ2);
+    double t1 = DA(x1, x7), t2 = DS(x1, x7);
+    double c1 = DA(DM(TW0, t2), DM(TW6, t1)), c7 = DS(DM(TW0, t1), DM(TW6, t2));
+    t1 = DA(x2, x6); t2 = DS(x2, x6);
+    double c2 = DA(DM(TW1, t2), DM(TW5, t1)), c6 = DS(DM(TW1, t1), DM(TW5, t2));
+    t1 = DA(x3, x5); t2 = DS(x3, x5);
+    double c3 = DA(DM(TW2, t2), DM(TW4, t1)), c5 = DS(DM(TW2, t1), DM(TW4, t2));
+    double c4 = DM(x4, 2.0 * TW3);
+    // radf4
+    double atr1 = DA(c6, c2), h2 = DS(c6, c2), atr2 = DA(c0, c4), h1 = DS(c0, c4);
+    double h0 = DA(atr2, atr1), h3 = DS(atr2, atr1);
+    double btr1 = DA(c7, c3), h6 = DS(c7, c3), btr2 = DA(c1, c5), h5 = DS(c1, c5);
+    double h4 = DA(btr2, btr1), h7 = DS(btr2, btr1);
+    // radf2
+    double r0 = DA(h0, h4), r7 = DS(h0, h4);
+    double r4 = -h7, r3 = h3;
+    double tr2 = DA(DM(WR, h5), DM(WI, h6)), ti2 = DS(DM(WR, h6), DM(WI, h5));
+    double r1 = DA(h1, tr2), r5 = DS(h1, tr2);
+    double r2 = DA(ti2, h2), r6 = DS(ti2, h2);
+    // scale (exact) and post-pass
+    double s0 = DM(0.25, r0), s1 = DM(0.25, r1), s2 = DM(0.25, r2), s3 = DM(0.25, r3);
+    double s4 = DM(0.25, r4), s5 = DM(0.25, r5), s6 = DM(0.25, r6), s7 = DM(0.25, r7);
+    x0 = s0;
+    x1 = DS(s1, s2); x2 = DA(s1, s2);
+    x3 = DS(s3, s4); x4 = DA(s3, s4);
+    x5 = DS(s5, s6); x6 = DA(s5, s6);
+    x7 = s7;
+}
+
+__global__ void __launch_bounds__(128) dec_idct_kernel(const DecImage* __restrict__ imgs,
+                                                       const long long* __restrict__ blk_first, int n_images,
+                                                       long long total_blocks, const int16_t* __restrict__ coef,
+                                                       const double* __restrict__ mul) {
+    long long gb = (long long)blockIdx.x * 128 + threadIdx.x;
+    if (gb >= total_blocks) return;
+    int idx = find_owner(blk_first, n_images, gb);
+    const DecImage& im = imgs[idx];
+    if (im.skip_pixels) return;
+    int b = (int)(gb - im.blk_first);
+    int by = b / im.bw, bx = b - by * im.bw;
+    const double* __restrict__ m = mul + (size_t)idx * 64;
+    const bool scaled = im.mode == MODE_SCALED;
+    const double two_q = im.two_q;
+
+    double t[64];
+    const uint4* cp = reinterpret_cast<const uint4*>(coef + gb * 64);
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        uint4 q = __ldg(cp + u);
+        uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int v = 0; v < 8; v++) {
+            int c = (int)(int16_t)((w[v >> 1] >> ((v & 1) * 16)) & 0xffffu);
+            double d = (double)c;
+            if (scaled) d = DM(__ddiv_rn(d, c_ann[u * 8 + v]), two_q);   // codec.py:59-61
+            t[u * 8 + v] = DM(d, __ldg(m + u * 8 + v));                  // utils.py:51-52
+        }
+    }
+    // utils.py:40-45: axis -2 (down the columns) first, then axis -1 (along the rows)
+#pragma unroll
+    for (int v = 0; v < 8; v++)
+        idct8_exact(t[v], t[8 + v], t[16 + v], t[24 + v], t[32 + v], t[40 + v], t[48 + v], t[56 + v]);
+    const int y0 = by * 8, x0 = bx * 8;
+    const bool fast = x0 + 8 <= im.width && (((uintptr_t)im.pixels | (uintptr_t)im.width) & 7u) == 0;
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+        idct8_exact(t[u * 8], t[u * 8 + 1], t[u * 8 + 2], t[u * 8 + 3], t[u * 8 + 4], t[u * 8 + 5], t[u * 8 + 6],
+                    t[u * 8 + 7]);
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int v = 0; v < 8; v++) {
+            double p = DA(t[u * 8 + v], 128.0);             // np.clip(coeffs + 128, 0, 255), codec.py:68
+            p = p < 0.0 ? 0.0 : (p > 255.0 ? 255.0 : p);
+            uint32_t px = (uint32_t)__double2int_rz(p);     // astype(np.uint8): truncation, codec.py:70
+            if (v < 4) lo |= px << (8 * v); else hi |= px << (8 * (v - 4));
+        }
+        int y = y0 + u;
+        if (y < im.height) {
+            uint8_t* row = im.pixels + (size_t)y * (size_t)im.width + x0;
+            if (fast) {
+                *reinterpret_cast<uint2*>(row) = make_uint2(lo, hi);
+            } else {
+#pragma unroll
+                for (int v = 0; v < 8; v++)
+                    if (x0 + v < im.width) row[v] = (uint8_t)((v < 4 ? lo >> (8 * v) : hi >> (8 * (v - 4))) & 0xffu);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// decode() from coefficient arrays (codec.py:46-70): dc[nblk] differences, ac[nblk][63] in zigzag order.
+// The DC cumsum (codec.py:53) reuses dec_scan_kernel with one "subsequence" per block.
+// ---------------------------------------------------------------------------------------------------
+__global__ void dec_coeffs_prep_kernel(DecImage* __restrict__ im, double* __restrict__ mul,
+                                       const int32_t* __restrict__ dc, int2* __restrict__ ND, int nblk,
+                                       int* __restrict__ summary) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) {
+        uint32_t st = fill_mul(*im, mul);
+        if (st) { im->skip_pixels = 1; atomicOr(summary, (int)st); }
+    }
+    if (b < nblk) ND[b] = make_int2(1, dc[b]);
+}
+
+__global__ void dec_coeffs_pack_kernel(const int32_t* __restrict__ dc, const int32_t* __restrict__ ac,
+                                       const int2* __restrict__ NB, int16_t* __restrict__ coef, int nblk,
+                                       int* __restrict__ summary) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    int b = (int)(t >> 6), k = (int)(t & 63);
+    if (b >= nblk) return;
+    int v = k == 0 ? NB[b].y + dc[b] : ac[(long long)b * 63 + k - 1];
+    int s = v < -32768 ? -32768 : (v > 32767 ? 32767 : v);
+    if (s != v) atomicOr(summary, TIC_DSTATUS_RANGE);
+    coef[(long long)b * 64 + c_zigzag[k]] = (int16_t)s;   // coeffs[:, ZIGZAG_ORDER] = coeffs.copy(), codec.py:57
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+struct DecWs {
+    DecImage* d_imgs = nullptr; DecImage* h_imgs = nullptr; size_t imgs_cap = 0;
+    long long* d_first = nullptr; long long* h_first = nullptr;   // sub_first[n+1] then blk_first[n+1]
+    DecTables* d_tabs = nullptr; double* d_mul = nullptr;
+    DecTables* d_deftab = nullptr;
+    uint32_t* d_E = nullptr; uint32_t* d_U = nullptr; int2* d_ND = nullptr; int2* d_NB = nullptr; size_t subs_cap = 0;
+    int16_t* d_coef = nullptr; size_t blocks_cap = 0;
+    int* d_flags = nullptr;   // [0] changed, [1] summary
+    int* h_flags = nullptr;   // pinned
+    int* d_status_own = nullptr; size_t status_cap = 0;
+    // single-stream host path
+    uint8_t* d_stream = nullptr; size_t stream_cap = 0;
+    uint8_t* d_px = nullptr; size_t px_cap = 0;
+    cudaEvent_t ev[6] = {};
+    long long stats[8] = {};
+    bool pending_times = false;
+};
+
+}  // namespace ticd
+
+using namespace ticd;
+
+#define TICD_CUDA(h, call)                                                                           \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            tic_internal_set_error((h), std::string(#call) + ": " + cudaGetErrorString(e_));        \
+            return TIC_E_CUDA;                                                                       \
+        }                                                                                            \
+    } while (0)
+
+static DecWs* get_ws(tic_handle h) {
+    void** slot = tic_internal_dec_slot(h);
+    if (!*slot) *slot = new DecWs();
+    return static_cast<DecWs*>(*slot);
+}
+
+void tic_internal_dec_release(void* p) {
+    DecWs* w = static_cast<DecWs*>(p);
+    if (!w) return;
+    cudaFree(w->d_imgs); cudaFreeHost(w->h_imgs); cudaFree(w->d_first); cudaFreeHost(w->h_first);
+    cudaFree(w->d_tabs); cudaFree(w->d_mul); cudaFree(w->d_deftab); cudaFree(w->d_E); cudaFree(w->d_U);
+    cudaFree(w->d_ND); cudaFree(w->d_NB); cudaFree(w->d_coef); cudaFree(w->d_flags); cudaFreeHost(w->h_flags);
+    cudaFree(w->d_status_own); cudaFree(w->d_stream); cudaFree(w->d_px);
+    for (auto& e : w->ev) if (e) cudaEventDestroy(e);
+    delete w;
+}
+
+int tic_parse_header(const uint8_t* data, int64_t nbytes, int32_t* height, int32_t* width, int32_t* quality,
+                     uint32_t* flag) {
+    if (!data || nbytes < 16) return TIC_E_INVALID;   // struct.error in the reference (codec.py:119)
+    uint32_t f[4];
+    for (int i = 0; i < 4; i++)
+        f[i] = (uint32_t)data[4 * i] | ((uint32_t)data[4 * i + 1] << 8) | ((uint32_t)data[4 * i + 2] << 16) |
+               ((uint32_t)data[4 * i + 3] << 24);
+    if (f[0] > 0x7fffffffu || f[1] > 0x7fffffffu) return TIC_E_INVALID;
+    if (height) *height = (int32_t)f[0];
+    if (width) *width = (int32_t)f[1];
+    if (quality) *quality = (int32_t)f[2];
+    if (flag) *flag = f[3];
+    return TIC_OK;
+}
+
+static int ensure_base(tic_handle h, DecWs* w) {
+    if (w->d_flags) return TIC_OK;
+    TICD_CUDA(h, cudaMalloc(&w->d_flags, 2 * sizeof(int)));
+    TICD_CUDA(h, cudaMallocHost(&w->h_flags, 2 * sizeof(int)));
+    for (auto& e : w->ev) TICD_CUDA(h, cudaEventCreate(&e));
+    DecTables* def = new DecTables();
+    build_default_tables(*def);
+    cudaError_t e1 = cudaMalloc(&w->d_deftab, sizeof(DecTables));
+    if (e1 == cudaSuccess) e1 = cudaMemcpy(w->d_deftab, def, sizeof(DecTables), cudaMemcpyHostToDevice);
+    delete def;
+    TICD_CUDA(h, e1);
+    return TIC_OK;
+}
+
+template <typename T>
+static int grow(tic_handle h, T*& p, size_t n) {
+    cudaFree(p);
+    p = nullptr;
+    TICD_CUDA(h, cudaMalloc(&p, n * sizeof(T)));
+    return TIC_OK;
+}
+
+int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* sizes, const int32_t* heights,
+                     const int32_t* widths, int32_t n_images, uint32_t flags, void* const* d_pixels,
+                     int32_t* d_status, void* stream_v) {
+    if (!h) return TIC_E_INVALID;
+    if (n_images < 0 || (n_images > 0 && (!d_streams || !sizes || !heights || !widths || !d_pixels))) {
+        tic_internal_set_error(h, "tic_decode_batch: bad argument");
+        return TIC_E_INVALID;
+    }
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    TICD_CUDA(h, cudaSetDevice(tic_internal_device(h)));
+    DecWs* w = get_ws(h);
+    memset(w->stats, 0, sizeof w->stats);
+    w->pending_times = false;
+    if (int rc = ensure_base(h, w)) return rc;
+    w->h_flags[1] = 0;
+    TICD_CUDA(h, cudaMemsetAsync(w->d_flags, 0, 2 * sizeof(int), stream));
+    if (n_images == 0) return TIC_OK;
+    const size_t n = (size_t)n_images;
+    if (n > w->imgs_cap) {
+        size_t cap = n < 64 ? 64 : n * 2;
+        cudaFreeHost(w->h_imgs); cudaFreeHost(w->h_first);
+        w->h_imgs = nullptr; w->h_first = nullptr; w->imgs_cap = 0;
+        if (int rc = grow(h, w->d_imgs, cap)) return rc;
+        if (int rc = grow(h, w->d_first, 2 * (cap + 1))) return rc;
+        if (int rc = grow(h, w->d_tabs, cap)) return rc;
+        if (int rc = grow(h, w->d_mul, cap * 64)) return rc;
+        if (int rc = grow(h, w->d_status_own, cap)) return rc;
+        TICD_CUDA(h, cudaMallocHost(&w->h_imgs, cap * sizeof(DecImage)));
+        TICD_CUDA(h, cudaMallocHost(&w->h_first, 2 * (cap + 1) * sizeof(long long)));
+        w->imgs_cap = cap;
+    }
+    long long* sub_first = w->h_first;
+    long long* blk_first = w->h_first + (n + 1);
+    long long subs = 0, blocks = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (sizes[i] < 0 || heights[i] < 0 || widths[i] < 0 || (sizes[i] > 0 && !d_streams[i]) ||
+            ((uintptr_t)d_streams[i] & 3u)) {
+            tic_internal_set_error(h, "tic_decode_batch: stream " + std::to_string(i) +
+                                          ": negative size / dimension, NULL or not 4-byte aligned");
+            return TIC_E_INVALID;
+        }
+        DecImage& im = w->h_imgs[i];
+        memset(&im, 0, sizeof im);
+        im.words = static_cast<const uint32_t*>(d_streams[i]);
+        im.nbits = sizes[i] * 8;
+        im.height = heights[i];
+        im.width = widths[i];
+        im.bw = (widths[i] + 7) / 8;
+        long long nblk = (heights[i] == 0 || widths[i] == 0) ? 0 : (long long)((heights[i] + 7) / 8) * im.bw;
+        long long nsub = im.nbits > 128 ? (im.nbits - 128 + kSubBits - 1) / kSubBits : 0;
+        if (nblk > 0x7fffffffLL || nsub > 0x7fffffffLL) {
+            tic_internal_set_error(h, "tic_decode_batch: image too large");
+            return TIC_E_INVALID;
+        }
+        if (nblk > 0 && !d_pixels[i]) {
+            tic_internal_set_error(h, "tic_decode_batch: NULL pixel pointer");
+            return TIC_E_INVALID;
+        }
+        im.nblk = (int)nblk;
+        im.nsubs = (int)nsub;
+        im.pixels = static_cast<uint8_t*>(d_pixels[i]);
+        im.sub_first = subs;
+        im.blk_first = blocks;
+        sub_first[i] = subs;
+        blk_first[i] = blocks;
+        subs += nsub;
+        blocks += nblk;
+    }
+    sub_first[n] = subs;
+    blk_first[n] = blocks;
+    if ((size_t)subs > w->subs_cap) {
+        size_t cap = (size_t)subs + (size_t)subs / 4 + 1024;
+        w->subs_cap = 0;
+        if (int rc = grow(h, w->d_E, cap + 1)) return rc;
+        if (int rc = grow(h, w->d_U, cap + 1)) return rc;
+        if (int rc = grow(h, w->d_ND, cap + 1)) return rc;
+        if (int rc = grow(h, w->d_NB, cap + 1)) return rc;
+        w->subs_cap = cap;
+    }
+    if ((size_t)blocks > w->blocks_cap) {
+        size_t cap = (size_t)blocks + (size_t)blocks / 8 + 1024;
+        w->blocks_cap = 0;
+        if (int rc = grow(h, w->d_coef, cap * 64)) return rc;
+        w->blocks_cap = cap;
+    }
+    int* status = d_status ? d_status : w->d_status_own;
+    TICD_CUDA(h, cudaMemcpyAsync(w->d_imgs, w->h_imgs, n * sizeof(DecImage), cudaMemcpyHostToDevice, stream));
+    TICD_CUDA(h, cudaMemcpyAsync(w->d_first, w->h_first, 2 * (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    const long long* d_sub_first = w->d_first;
+    const long long* d_blk_first = w->d_first + (n + 1);
+    TICD_CUDA(h, cudaMemsetAsync(status, 0, n * sizeof(int), stream));
+    if (subs) {
+        TICD_CUDA(h, cudaMemsetAsync(w->d_E, 0, (size_t)subs * 4, stream));
+        TICD_CUDA(h, cudaMemsetAsync(w->d_U, 0xff, (size_t)subs * 4, stream));
+        TICD_CUDA(h, cudaMemsetAsync(w->d_ND, 0, (size_t)subs * sizeof(int2), stream));
+    }
+    TICD_CUDA(h, cudaEventRecord(w->ev[0], stream));
+    if (blocks) TICD_CUDA(h, cudaMemsetAsync(w->d_coef, 0, (size_t)blocks * 128, stream));
+    long long launches = 0;
+    dec_setup_kernel<<<n_images, 32, 0, stream>>>(w->d_imgs, n_images, flags, w->d_tabs, w->d_mul, w->d_E, status,
+                                                  w->d_flags + 1);
+    launches++;
+    TICD_CUDA(h, cudaGetLastError());
+    TICD_CUDA(h, cudaEventRecord(w->ev[1], stream));
+    long long rounds = 0;
+    if (subs) {
+        unsigned grid = (unsigned)((subs + kSyncThreads - 1) / kSyncThreads);
+        for (;;) {
+            dec_sync_kernel<<<grid, kSyncThreads, 0, stream>>>(w->d_imgs, d_sub_first, n_images, subs, w->d_deftab,
+                                                               w->d_tabs, w->d_E, w->d_U, w->d_ND, w->d_flags);
+            launches++;
+            rounds++;
+            TICD_CUDA(h, cudaGetLastError());
+            TICD_CUDA(h, cudaMemcpyAsync(w->h_flags, w->d_flags, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            TICD_CUDA(h, cudaMemsetAsync(w->d_flags, 0, sizeof(int), stream));
+            TICD_CUDA(h, cudaStreamSynchronize(stream));
+            if (!w->h_flags[0]) break;
+            if (rounds > subs + 2) {
+                tic_internal_set_error(h, "tic_decode_batch: synchronisation did not converge");
+                return TIC_E_CUDA;
+            }
+        }
+        TICD_CUDA(h, cudaEventRecord(w->ev[2], stream));
+        dec_scan_kernel<<<n_images, 1024, 0, stream>>>(w->d_imgs, w->d_ND, w->d_NB, status, w->d_flags + 1);
+        TICD_CUDA(h, cudaGetLastError());
+        TICD_CUDA(h, cudaEventRecord(w->ev[3], stream));
+        dec_write_kernel<<<grid, kSyncThreads, 0, stream>>>(w->d_imgs, d_sub_first, n_images, subs, w->d_deftab,
+                                                            w->d_tabs, w->d_E, w->d_NB, w->d_coef, status,
+                                                            w->d_flags + 1);
+        launches += 2;
+        TICD_CUDA(h, cudaGetLastError());
+    } else {
+        TICD_CUDA(h, cudaEventRecord(w->ev[2], stream));
+        TICD_CUDA(h, cudaEventRecord(w->ev[3], stream));
+    }
+    TICD_CUDA(h, cudaEventRecord(w->ev[4], stream));
+    if (blocks) {
+        unsigned grid = (unsigned)((blocks + 127) / 128);
+        dec_idct_kernel<<<grid, 128, 0, stream>>>(w->d_imgs, d_blk_first, n_images, blocks, w->d_coef, w->d_mul);
+        launches++;
+        TICD_CUDA(h, cudaGetLastError());
+    }
+    TICD_CUDA(h, cudaEventRecord(w->ev[5], stream));
+    TICD_CUDA(h, cudaMemcpyAsync(w->h_flags + 1, w->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    w->stats[0] = launches;
+    w->stats[1] = subs;
+    w->stats[2] = rounds;
+    w->stats[3] = blocks;
+    w->pending_times = true;
+    return TIC_OK;
+}
+
+int tic_decode_coeffs(tic_handle h, const int32_t* d_dc, const int32_t* d_ac, int32_t height, int32_t width,
+                      int32_t quality, int32_t scaled_dct, void* d_pixels, void* stream_v) {
+    if (!h || height < 0 || width < 0 || quality < 0) return TIC_E_INVALID;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    TICD_CUDA(h, cudaSetDevice(tic_internal_device(h)));
+    DecWs* w = get_ws(h);
+    if (int rc = ensure_base(h, w)) return rc;
+    memset(w->stats, 0, sizeof w->stats);
+    w->pending_times = false;
+    w->h_flags[1] = 0;
+    TICD_CUDA(h, cudaMemsetAsync(w->d_flags, 0, 2 * sizeof(int), stream));
+    long long nblk = (height == 0 || width == 0) ? 0 : (long long)((height + 7) / 8) * ((width + 7) / 8);
+    if (nblk == 0) return TIC_OK;
+    if (nblk > 0x7fffffffLL || !d_dc || !d_ac || !d_pixels) return TIC_E_INVALID;
+    if (w->imgs_cap == 0) {   // the same per-image arrays tic_decode_batch uses, sized for one image
+        const size_t cap = 64;
+        if (int rc = grow(h, w->d_imgs, cap)) return rc;
+        if (int rc = grow(h, w->d_first, 2 * (cap + 1))) return rc;
+        if (int rc = grow(h, w->d_tabs, cap)) return rc;
+        if (int rc = grow(h, w->d_mul, cap * 64)) return rc;
+        if (int rc = grow(h, w->d_status_own, cap)) return rc;
+        TICD_CUDA(h, cudaMallocHost(&w->h_imgs, cap * sizeof(DecImage)));
+        TICD_CUDA(h, cudaMallocHost(&w->h_first, 2 * (cap + 1) * sizeof(long long)));
+        w->imgs_cap = cap;
+    }
+    if ((size_t)nblk > w->subs_cap) {
+        size_t cap = (size_t)nblk + 1024;
+        w->subs_cap = 0;
+        if (int rc = grow(h, w->d_E, cap + 1)) return rc;
+        if (int rc = grow(h, w->d_U, cap + 1)) return rc;
+        if (int rc = grow(h, w->d_ND, cap + 1)) return rc;
+        if (int rc = grow(h, w->d_NB, cap + 1)) return rc;
+        w->subs_cap = cap;
+    }
+    if ((size_t)nblk > w->blocks_cap) {
+        size_t cap = (size_t)nblk + 1024;
+        w->blocks_cap = 0;
+        if (int rc = grow(h, w->d_coef, cap * 64)) return rc;
+        w->blocks_cap = cap;
+    }
+    DecImage& im = w->h_imgs[0];
+    memset(&im, 0, sizeof im);
+    im.pixels = static_cast<uint8_t*>(d_pixels);
+    im.height = height; im.width = width; im.bw = (width + 7) / 8;
+    im.nblk = (int)nblk; im.nsubs = (int)nblk;   // one scan element per block
+    im.quality = (uint32_t)quality;
+    im.mode = scaled_dct ? MODE_SCALED : MODE_FIXED;
+    im.two_q = 1.0;
+    w->h_first[0] = 0; w->h_first[1] = nblk;
+    TICD_CUDA(h, cudaMemcpyAsync(w->d_imgs, w->h_imgs, sizeof(DecImage), cudaMemcpyHostToDevice, stream));
+    TICD_CUDA(h, cudaMemcpyAsync(w->d_first, w->h_first, 2 * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    TICD_CUDA(h, cudaMemsetAsync(w->d_status_own, 0, sizeof(int), stream));
+    unsigned g1 = (unsigned)((nblk + 255) / 256), g2 = (unsigned)((nblk * 64 + 255) / 256);
+    dec_coeffs_prep_kernel<<<g1, 256, 0, stream>>>(w->d_imgs, w->d_mul, d_dc, w->d_ND, (int)nblk, w->d_flags + 1);
+    dec_scan_kernel<<<1, 1024, 0, stream>>>(w->d_imgs, w->d_ND, w->d_NB, w->d_status_own, w->d_flags + 1);
+    dec_coeffs_pack_kernel<<<g2, 256, 0, stream>>>(d_dc, d_ac, w->d_NB, w->d_coef, (int)nblk, w->d_flags + 1);
+    dec_idct_kernel<<<(unsigned)((nblk + 127) / 128), 128, 0, stream>>>(w->d_imgs, w->d_first, 1, nblk, w->d_coef,
+                                                                        w->d_mul);
+    TICD_CUDA(h, cudaGetLastError());
+    TICD_CUDA(h, cudaMemcpyAsync(w->h_flags + 1, w->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    w->stats[0] = 4;
+    w->stats[3] = nblk;
+    return TIC_OK;
+}
+
+int tic_decode_finish(tic_handle h, void* stream_v) {
+    if (!h) return TIC_E_INVALID;
+    DecWs* w = get_ws(h);
+    TICD_CUDA(h, cudaSetDevice(tic_internal_device(h)));
+    TICD_CUDA(h, cudaStreamSynchronize(static_cast<cudaStream_t>(stream_v)));
+    if (w->pending_times) {
+        float ms = 0.f;
+        // [4] synchronisation rounds, [5] scan, [6] coefficient scatter (+ its zero fill), [7] IDCT: device ns
+        if (cudaEventElapsedTime(&ms, w->ev[1], w->ev[2]) == cudaSuccess) w->stats[4] = (long long)(ms * 1e6);
+        if (cudaEventElapsedTime(&ms, w->ev[2], w->ev[3]) == cudaSuccess) w->stats[5] = (long long)(ms * 1e6);
+        if (cudaEventElapsedTime(&ms, w->ev[3], w->ev[4]) == cudaSuccess) w->stats[6] = (long long)(ms * 1e6);
+        if (cudaEventElapsedTime(&ms, w->ev[4], w->ev[5]) == cudaSuccess) w->stats[7] = (long long)(ms * 1e6);
+        w->pending_times = false;
+    }
+    if (w->h_flags && w->h_flags[1]) {
+        tic_internal_set_error(h, "tic_decode: stream errors, OR of status bits = " + std::to_string(w->h_flags[1]));
+        return TIC_E_STREAM;
+    }
+    return TIC_OK;
+}
+
+int tic_decode_stats(tic_handle h, int64_t stats[8]) {
+    if (!h || !stats) return TIC_E_INVALID;
+    DecWs* w = get_ws(h);
+    for (int i = 0; i < 8; i++) stats[i] = w->stats[i];
+    return TIC_OK;
+}
+
+int tic_decompress_host(tic_handle h, const uint8_t* data, int64_t nbytes, uint32_t flags, uint8_t* out,
+                        int64_t out_capacity, int32_t* status) {
+    if (!h || !data || nbytes < 0) return TIC_E_INVALID;
+    int32_t H, W, q;
+    uint32_t flag;
+    if (tic_parse_header(data, nbytes, &H, &W, &q, &flag)) {
+        tic_internal_set_error(h, "tic_decompress_host: header needs 16 bytes");
+        return TIC_E_INVALID;
+    }
+    long long npx = (long long)H * W;
+    if (npx > out_capacity || (npx > 0 && !out)) return TIC_E_CAPACITY;
+    TICD_CUDA(h, cudaSetDevice(tic_internal_device(h)));
+    DecWs* w = get_ws(h);
+    cudaStream_t s = tic_internal_own_stream(h);
+    size_t padded = ((size_t)nbytes + 3) & ~(size_t)3;
+    if (padded > w->stream_cap) {
+        size_t cap = padded * 2 + 1024;
+        w->stream_cap = 0;
+        if (int rc = grow(h, w->d_stream, cap)) return rc;
+        w->stream_cap = cap;
+    }
+    if ((size_t)npx > w->px_cap) {
+        size_t cap = (size_t)npx * 2 + 1024;
+        w->px_cap = 0;
+        if (int rc = grow(h, w->d_px, cap)) return rc;
+        w->px_cap = cap;
+    }
+    TICD_CUDA(h, cudaMemcpyAsync(w->d_stream, data, (size_t)nbytes, cudaMemcpyHostToDevice, s));
+    const void* sp = w->d_stream;
+    void* pp = w->d_px;
+    int64_t sz = nbytes;
+    int rc = tic_decode_batch(h, &sp, &sz, &H, &W, 1, flags, &pp, nullptr, s);
+    if (rc) return rc;
+    int st = 0;
+    TICD_CUDA(h, cudaMemcpyAsync(&st, w->d_status_own, sizeof(int), cudaMemcpyDeviceToHost, s));
+    if (npx) TICD_CUDA(h, cudaMemcpyAsync(out, w->d_px, (size_t)npx, cudaMemcpyDeviceToHost, s));
+    rc = tic_decode_finish(h, s);
+    if (status) *status = st;
+    return rc;
+}

@@ -659,7 +659,15 @@ struct tic_handle_s {
     long long last_tiles = 0, last_blocks = 0, last_launches = 0;
     bool tables_ready = false;
     int sm_count = 148, ctas_per_sm = kCtasPerSm;
+    void* dec_ws = nullptr;              // decode-side workspace, owned by tic_decode.cu
 };
+
+// hooks for tic_decode.cu (the decode side lives in its own translation unit)
+void tic_internal_dec_release(void* ws);
+void** tic_internal_dec_slot(tic_handle h) { return &h->dec_ws; }
+void tic_internal_set_error(tic_handle h, const std::string& msg) { h->err = msg; }
+int tic_internal_device(tic_handle h) { return h->device; }
+cudaStream_t tic_internal_own_stream(tic_handle h) { return h->own_stream; }
 
 #define TIC_CUDA(h, call)                                                                     \
     do {                                                                                      \
@@ -801,6 +809,7 @@ int tic_create(int device, tic_handle* out) {
 int tic_destroy(tic_handle h) {
     if (!h) return TIC_E_INVALID;
     cudaSetDevice(h->device);
+    tic_internal_dec_release(h->dec_ws);
     cudaFree(h->d_descs); cudaFreeHost(h->h_descs); cudaFree(h->d_recs); cudaFree(h->d_tile_pos); cudaFree(h->d_chunk_span); cudaFree(h->d_chunk_pos);
     cudaFree(h->d_arena); cudaFree(h->d_counters);
     cudaFree(h->d_hist); cudaFree(h->d_first); cudaFree(h->d_tabs); cudaFree(h->d_tree);
