@@ -429,6 +429,51 @@ def run_gpu_arm(args):
     except Exception as ex:
         c_variant = {"value": None, "error": f"{type(ex).__name__}: {ex}"}
 
+    # the decode side: the benchmarked batch's own streams, still in HBM, decoded back to
+    # pixels by tic_decode_batch (self-synchronising Huffman decode + float64 IDCT); CUDA events around the call
+    decode = None
+    try:
+        if args.no_decode:
+            raise RuntimeError("skipped (--no-decode)")
+        res = step().finish()
+        offs, sizes = res.offsets.cpu().numpy(), res.sizes.cpu().numpy()
+        d_px = torch.empty(n_local * IMG_H * IMG_W + 16, dtype=torch.uint8, device=dev)
+        hs, ws = [IMG_H] * n_local, [IMG_W] * n_local
+        for _ in range(2):
+            outs, _st = enc.decode_batch_device((res.out, offs), sizes, hs, ws, pixels=d_px, stream=stream)
+        dec_steps = max(1, min(args.steps, 5))
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(dec_steps):
+            outs, _st = enc.decode_batch_device((res.out, offs), sizes, hs, ws, pixels=d_px, stream=stream)
+        c1.record(stream)
+        barrier()
+        dms = c0.elapsed_time(c1) / dec_steps
+        if world > 1:
+            tt = torch.tensor([dms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dms = float(tt.item())
+        dst = enc.decode_stats()
+        mae = float((outs[0].float() - d_images[0].float()).abs().mean().item())
+        decode = {"value": total_px / (dms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": dms, "steps": dec_steps,
+                  "phases_ms": {k: dst[k] for k in ("sync_ms", "scan_ms", "scatter_ms", "idct_ms")},
+                  "sync_rounds": int(dst["sync_rounds"]), "subsequences": int(dst["subsequences"]),
+                  "launches": int(dst["launches"]), "mean_abs_error_image0": mae,
+                  "what": "tic_decode_batch on the batch's own q50 streams, device-resident, CUDA events around the "
+                          "call (the host reads one flag per synchronisation round inside it)"}
+        if rank == 0:
+            from oracle import oracle_lib as O
+            host = res.to_bytes()
+            ok = 0
+            for i in (0, n_local - 1):
+                ok += int(np.array_equal(outs[i].cpu().numpy(), O.decompress(host[i])))
+            decode["parity_vs_oracle"] = {"checked": 2, "identical": ok}
+            del host
+        del outs, d_px
+    except Exception as ex:
+        decode = {"value": None, "error": f"{type(ex).__name__}: {ex}"}
+
     line = None
     if rank == 0:
         cpu_baseline = None
@@ -458,7 +503,7 @@ def run_gpu_arm(args):
                        "stream_bytes": stream_bytes_total, "bits_per_pixel": 8.0 * stream_bytes_total / total_px,
                        "exact_path": {k: stats[k] for k in ("exact_items", "exact_changed", "blocks", "tiles")}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(stats["launches"]) * args.steps * n_gpus, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "parity": parity, "c_variant": c_variant,
+            "cpu_baseline": cpu_baseline, "parity": parity, "c_variant": c_variant, "decode": decode,
         }
         line.update(extra)
         print(json.dumps(line), flush=True)
@@ -477,6 +522,7 @@ def main():
     ap.add_argument("--images", type=int, default=TOTAL_IMAGES, help="total images in the batch (default 4096)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host end-to-end leg (profiling runs)")
+    ap.add_argument("--no-decode", action="store_true", help="skip the decode-side leg")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -486,7 +532,8 @@ def main():
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
-               "--images", str(args.images)] + (["--no-cpu"] if args.no_cpu else []) + (["--no-e2e"] if args.no_e2e else [])
+               "--images", str(args.images)] + (["--no-cpu"] if args.no_cpu else []) + (["--no-e2e"] if args.no_e2e else []) + \
+              (["--no-decode"] if args.no_decode else [])
         return subprocess.call(cmd)
     return run_gpu_arm(args)
 

@@ -173,8 +173,9 @@ def test_config4_images_on_device_round_trip(tic):
         for i in (0, 17, n - 1):
             _same(outs[i].cpu().numpy(), O.decompress(host[i]), f"q{q} image {i}")
         # every image, cheaply: a mis-synchronised decode is grossly wrong
-        err = (torch.stack(outs).float() - d_imgs.float()).abs().mean(dim=(1, 2)).cpu().numpy()
-        assert err.max() < (4.0 if q >= 50 else 8.0), err.max()
+        stacked = outs if isinstance(outs, torch.Tensor) else torch.stack(outs)
+        err = (stacked.float() - d_imgs.float()).abs().mean(dim=(1, 2)).cpu().numpy()
+        assert err.max() < {90: 3.0, 50: 6.0, 10: 10.0}[q], err.max()
 
 
 def test_config3_8k_image(tic):

@@ -344,7 +344,8 @@ class Encoder:
                             accept_be_flag=False, strict=True):
         """Decode streams resident in HBM.  `d_streams`: list of CUDA uint8 tensors (each 4-byte aligned), or
         one CUDA uint8 tensor plus `sizes` and byte offsets given as d_streams=(tensor, offsets).  Returns the
-        list of CUDA uint8 (H, W) tensors (views of one pixel buffer) and the status array (numpy int32)."""
+        CUDA uint8 (H, W) images (a list of views of one pixel buffer, or one (N, H, W) view when all shapes are
+        equal) and the status array (numpy int32)."""
         import torch
         dev = torch.device("cuda", self.device)
         if isinstance(d_streams, tuple):
@@ -384,8 +385,12 @@ class Encoder:
                 if rc != _lib.TIC_OK and (strict or rc != _lib.TIC_E_STREAM):
                     self._raise_decode(rc, status)
         del keep
-        images = [pixels[int(px_off[i]): int(px_off[i]) + int(npx[i])].view(int(hs_np[i]), int(ws_np[i]))
-                  for i in range(n)]
+        if n and (hs_np == hs_np[0]).all() and (ws_np == ws_np[0]).all() and int(npx[0]) % 16 == 0:
+            # equal shapes, densely packed: one (N, H, W) view instead of N slices (indexable like the list)
+            images = pixels[: n * int(npx[0])].view(n, int(hs_np[0]), int(ws_np[0]))
+        else:
+            images = [pixels[int(px_off[i]): int(px_off[i]) + int(npx[i])].view(int(hs_np[i]), int(ws_np[i]))
+                      for i in range(n)]
         return images, status
 
     def decompress_batch(self, streams, strict=True, accept_be_flag=False):

@@ -252,6 +252,7 @@ __device__ SubResult decode_sub(const DecImage& im, const BitSrc& src, const Dec
             uint32_t vb = (v << len) >> (32 - size);
             val = (vb >> (size - 1)) ? (int)vb : (int)vb - (1 << size) + 1;
         }
+        const long long p0 = p;
         p += len + size;
         if (z == 0) {
             r.n++;
@@ -270,12 +271,20 @@ __device__ SubResult decode_sub(const DecImage& im, const BitSrc& src, const Dec
             z = 0;
         } else {
             z += sym >> 4;       // decode_run_length (huffman.py:36-38): `run` zeros, then the value
-            if (WRITE) {
-                if (z > 63) r.err |= TIC_DSTATUS_CODE;   // the reference's ac[i, :len] assignment raises
-                else if (val != 0 && cur >= 0 && cur < im.nblk) coef[(long long)cur * 64 + zz[z]] = (int16_t)val;
+            if (z > 63) {
+                // More than 63 coefficients without an EOB: never on the true parse of a valid stream (the
+                // reference's ac[i, :len] assignment raises).  A guessed entry can fall into such a parse and
+                // stay in it for ever when the bits are periodic (a flat area is `00 1010` repeated, and from
+                // phase 4 that reads as the 6-bit AC symbol `100 010` again and again), so the rule that
+                // keeps decode(entry) a function also has to break the cycle: start over one bit further
+                // on, expecting a DC symbol.
+                r.err |= TIC_DSTATUS_CODE;
+                z = 0;
+                p = p0 + 1;
+                continue;
             }
+            if (WRITE && val != 0 && cur >= 0 && cur < im.nblk) coef[(long long)cur * 64 + zz[z]] = (int16_t)val;
             z += 1;
-            if (z > 250) z = 250;
         }
     }
     if (it >= kMaxSymbols) r.err |= TIC_DSTATUS_CODE;   // zero-length codewords that never advance
@@ -291,6 +300,20 @@ __device__ __forceinline__ int find_owner(const long long* __restrict__ first, i
         if (__ldg(first + mid) <= g) lo = mid; else hi = mid;
     }
     return lo;
+}
+
+// The same for a whole CTA whose threads hold consecutive indices g0 + threadIdx.x: one binary search (12
+// dependent loads for 4096 images) by thread 0, then a short walk forward for the threads behind an image
+// boundary.  Contains a barrier: every thread of the CTA must call it.
+__device__ __forceinline__ int find_owner_cta(const long long* __restrict__ first, int n, long long g0, long long g,
+                                              long long total) {
+    __shared__ int cta_owner;
+    if (threadIdx.x == 0) cta_owner = find_owner(first, n, g0 < total ? g0 : total - 1);
+    __syncthreads();
+    int idx = cta_owner;
+    if (g < total)
+        while (idx + 1 < n && __ldg(first + idx + 1) <= g) idx++;
+    return idx;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -428,8 +451,8 @@ __global__ void __launch_bounds__(kSyncThreads) dec_sync_kernel(const DecImage* 
     uint32_t used = 0xffffffffu;
     const DecTables* tb = deftab;
     BitSrc src = {};
+    idx = find_owner_cta(sub_first, n_images, (long long)blockIdx.x * kSyncThreads, g, total_subs);
     if (active) {
-        idx = find_owner(sub_first, n_images, g);
         const DecImage& im = imgs[idx];
         k = (int)(g - im.sub_first);
         active = !im.skip_entropy && k >= im.anchor_sub;
@@ -518,8 +541,8 @@ __global__ void __launch_bounds__(kSyncThreads) dec_write_kernel(const DecImage*
     if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
     __syncthreads();
     long long g = (long long)blockIdx.x * kSyncThreads + threadIdx.x;
+    int idx = find_owner_cta(sub_first, n_images, (long long)blockIdx.x * kSyncThreads, g, total_subs);
     if (g >= total_subs) return;
-    int idx = find_owner(sub_first, n_images, g);
     const DecImage& im = imgs[idx];
     int k = (int)(g - im.sub_first);
     if (im.skip_entropy || k < im.anchor_sub) return;
@@ -583,8 +606,8 @@ __global__ void __launch_bounds__(128) dec_idct_kernel(const DecImage* __restric
                                                        long long total_blocks, const int16_t* __restrict__ coef,
                                                        const double* __restrict__ mul) {
     long long gb = (long long)blockIdx.x * 128 + threadIdx.x;
+    int idx = find_owner_cta(blk_first, n_images, (long long)blockIdx.x * 128, gb, total_blocks);
     if (gb >= total_blocks) return;
-    int idx = find_owner(blk_first, n_images, gb);
     const DecImage& im = imgs[idx];
     if (im.skip_pixels) return;
     int b = (int)(gb - im.blk_first);
