@@ -87,7 +87,7 @@ enum { MODE_FIXED = 0, MODE_TABLES = 1, MODE_SCALED = 2 };
 
 __constant__ uint8_t c_zigzag[64] = {TIC_ZIGZAG_LIST};
 // tinyimgcodec/constants.py:37-51: ANNSCALES = these / 2048
-__constant__ double c_ann[64] = {
+__device__ const double d_ann[64] = {
     16384 / 2048.0, 22725 / 2048.0, 21407 / 2048.0, 19266 / 2048.0, 16384 / 2048.0, 12873 / 2048.0, 8867 / 2048.0,  4520 / 2048.0,
     22725 / 2048.0, 31521 / 2048.0, 29692 / 2048.0, 26722 / 2048.0, 22725 / 2048.0, 17855 / 2048.0, 12299 / 2048.0, 6270 / 2048.0,
     21407 / 2048.0, 29692 / 2048.0, 27969 / 2048.0, 25172 / 2048.0, 21407 / 2048.0, 16819 / 2048.0, 11585 / 2048.0, 5906 / 2048.0,
@@ -200,19 +200,47 @@ __device__ __forceinline__ uint32_t peek32(const BitSrc& s, long long p) {
 
 // One Huffman symbol from the 32 bits `v`: read_huffman_code (huffman.py:66-74).  len < 0: no codeword of
 // at most 16 bits matches (the reference raises ValueError).
-__device__ __forceinline__ void lookup(const DecTable* __restrict__ t, uint32_t v, int& sym, int& len) {
-    uint32_t e = __ldg(&t->lut[v >> 24]);
+__device__ __forceinline__ void lookup(const DecTable* t, uint32_t v, int& sym, int& len) {
+    uint32_t e = t->lut[v >> 24];
     if (e & kLeaf) { sym = (int)(e & 0xffu); len = (int)((e >> 8) & 0x7fu); return; }
     len = 8;
     uint32_t node = e;
     while (node != 0 && len < 16) {
-        uint32_t c = __ldg(&t->child[node][(v >> (31 - len)) & 1u]);
+        uint32_t c = t->child[node][(v >> (31 - len)) & 1u];
         len++;
         if (c & kLeaf) { sym = (int)(c & 0xffu); return; }
         node = c;
     }
     sym = 0;
     len = -1;
+}
+
+// A subsequence's bits staged in shared memory: kSubBits/32 words plus the two words a symbol that starts in
+// the last bit can reach (16 code bits + 15 value bits), MSB-first, zeros past the end of the stream.
+constexpr int kSubWords = kSubBits / 32;
+constexpr int kRowWords = kSubWords + 3;   // 34 used; odd stride: threads walk their rows at different speeds
+
+// Warp-cooperative, coalesced: for each of the warp's 32 subsequences the 32 lanes fetch its words together.
+__device__ __forceinline__ void stage_rows(uint32_t (*rows)[kRowWords], bool active, const BitSrc& src, long long word0) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int j = 0; j < 32; j++) {
+        if (!__shfl_sync(0xffffffffu, (int)active, j)) continue;
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(
+            __shfl_sync(0xffffffffu, (unsigned long long)reinterpret_cast<uintptr_t>(src.words), j));
+        long long nw = __shfl_sync(0xffffffffu, src.nwords, j);
+        uint32_t tm = __shfl_sync(0xffffffffu, src.tailmask, j);
+        long long first = __shfl_sync(0xffffffffu, word0, j);
+        for (int c = lane; c < kSubWords + 2; c += 32) {
+            long long i = first + c;
+            uint32_t w = 0;
+            if (i < nw) {
+                w = __byte_perm(__ldg(words + i), 0, 0x0123);
+                if (i == nw - 1) w &= tm;
+            }
+            rows[warp * 32 + j][c] = w;
+        }
+    }
+    __syncwarp();
 }
 
 struct SubResult {
@@ -222,23 +250,23 @@ struct SubResult {
     uint32_t err;
 };
 
-// Decode one subsequence from `entry`.  WRITE: also scatter coefficients; `blk` is the index (within the
-// image) of the next block to start, `dc_run` the DC predictor (sum of all earlier differences).
+// Decode one subsequence from `entry`, reading its bits from the staged row `sw`.  `end_rel`: bits of the
+// subsequence that belong to the stream (kSubBits except at the end).  WRITE: also scatter coefficients; `blk`
+// is the index (within the image) of the next block to start, `dc_run` the DC predictor (sum of all earlier
+// differences).
 template <bool WRITE>
-__device__ SubResult decode_sub(const DecImage& im, const BitSrc& src, const DecTable* __restrict__ tdc,
-                                const DecTable* __restrict__ tac, long long sub_bit0, uint32_t entry,
-                                int16_t* __restrict__ coef, int blk, int dc_run, const uint8_t* zz) {
-    long long p = sub_bit0 + (long long)(entry & 0xffffu);
+__device__ SubResult decode_sub(const uint32_t* sw, int end_rel, int nblk, const DecTable* tdc, const DecTable* tac,
+                                uint32_t entry, int16_t* __restrict__ coef, int blk, int dc_run, const uint8_t* zz) {
+    int p = (int)(entry & 0xffffu);
     int z = (int)((entry >> 16) & 0xffu);
-    const long long sub_end = sub_bit0 + kSubBits;
-    const long long end = sub_end < im.nbits ? sub_end : im.nbits;
     SubResult r;
     r.n = 0; r.dsum = 0; r.err = 0;
     int cur = blk - 1;   // the block being filled when z > 0
     int it = 0;
-    for (; p < end && it < kMaxSymbols; it++) {
-        if (WRITE && z == 0 && blk >= im.nblk) break;   // all blocks done: what follows is padding (bitbuffer.py:17-18)
-        uint32_t v = peek32(src, p);
+    for (; p < end_rel && it < kMaxSymbols; it++) {
+        if (WRITE && z == 0 && blk >= nblk) break;   // all blocks done: what follows is padding (bitbuffer.py:17-18)
+        const int wi = p >> 5;
+        uint32_t v = __funnelshift_l(sw[wi + 1], sw[wi], (uint32_t)(p & 31));
         int sym, len;
         lookup(z == 0 ? tdc : tac, v, sym, len);
         if (len < 0) {   // no codeword: a deterministic rule so that decode(entry) stays a function
@@ -252,7 +280,7 @@ __device__ SubResult decode_sub(const DecImage& im, const BitSrc& src, const Dec
             uint32_t vb = (v << len) >> (32 - size);
             val = (vb >> (size - 1)) ? (int)vb : (int)vb - (1 << size) + 1;
         }
-        const long long p0 = p;
+        const int p0 = p;
         p += len + size;
         if (z == 0) {
             r.n++;
@@ -260,7 +288,7 @@ __device__ SubResult decode_sub(const DecImage& im, const BitSrc& src, const Dec
             if (WRITE) {
                 cur = blk++;
                 dc_run += val;
-                if (cur < im.nblk) {
+                if (cur < nblk) {
                     int s = dc_run < -32768 ? -32768 : (dc_run > 32767 ? 32767 : dc_run);
                     if (s != dc_run) r.err |= TIC_DSTATUS_RANGE;
                     coef[(long long)cur * 64] = (int16_t)s;
@@ -283,12 +311,12 @@ __device__ SubResult decode_sub(const DecImage& im, const BitSrc& src, const Dec
                 p = p0 + 1;
                 continue;
             }
-            if (WRITE && val != 0 && cur >= 0 && cur < im.nblk) coef[(long long)cur * 64 + zz[z]] = (int16_t)val;
+            if (WRITE && val != 0 && cur >= 0 && cur < nblk) coef[(long long)cur * 64 + zz[z]] = (int16_t)val;
             z += 1;
         }
     }
     if (it >= kMaxSymbols) r.err |= TIC_DSTATUS_CODE;   // zero-length codewords that never advance
-    long long over = p - sub_end;
+    int over = p - kSubBits;
     r.exit = (uint32_t)(over > 0 ? over : 0) | ((uint32_t)z << 16);
     return r;
 }
@@ -444,14 +472,21 @@ __global__ void __launch_bounds__(kSyncThreads) dec_sync_kernel(const DecImage* 
                                                                 const DecTables* __restrict__ tabs, uint32_t* E,
                                                                 uint32_t* __restrict__ U, int2* __restrict__ ND,
                                                                 int* __restrict__ changed) {
+    __shared__ uint32_t rows[kSyncThreads][kRowWords];
+    __shared__ DecTables sh_def;   // the fixed tables; per-image tables stay in global memory
+    {
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(deftab);
+        uint32_t* d = reinterpret_cast<uint32_t*>(&sh_def);
+        for (int i = threadIdx.x; i < (int)(sizeof(DecTables) / 4); i += kSyncThreads) d[i] = __ldg(s + i);
+    }
     long long g = (long long)blockIdx.x * kSyncThreads + threadIdx.x;
     bool active = g < total_subs;
-    int idx = 0, k = 0;
+    int idx = 0, k = 0, end_rel = 0, nblk = 0;
     bool has_next = false;
     uint32_t used = 0xffffffffu;
-    const DecTables* tb = deftab;
+    const DecTables* tb = &sh_def;
     BitSrc src = {};
-    idx = find_owner_cta(sub_first, n_images, (long long)blockIdx.x * kSyncThreads, g, total_subs);
+    idx = find_owner_cta(sub_first, n_images, (long long)blockIdx.x * kSyncThreads, g, total_subs);   // barrier inside
     if (active) {
         const DecImage& im = imgs[idx];
         k = (int)(g - im.sub_first);
@@ -459,8 +494,13 @@ __global__ void __launch_bounds__(kSyncThreads) dec_sync_kernel(const DecImage* 
         has_next = k + 1 < im.nsubs;
         if (im.has_tables) tb = tabs + idx;
         src = make_src(im);
+        long long left = im.nbits - (128 + (long long)k * kSubBits);
+        end_rel = left < kSubBits ? (int)left : kSubBits;
+        nblk = im.nblk;
         used = U[g];
     }
+    stage_rows(rows, active, src, 4 + (long long)k * kSubWords);
+    const uint32_t* sw = rows[threadIdx.x];
     volatile uint32_t* Ev = E;
     bool any = false;
     for (int it = 0; it < kSyncIters; it++) {
@@ -469,8 +509,7 @@ __global__ void __launch_bounds__(kSyncThreads) dec_sync_kernel(const DecImage* 
             uint32_t e = Ev[g];
             if (e != used) {
                 used = e;
-                SubResult r = decode_sub<false>(imgs[idx], src, &tb->dc, &tb->ac, 128 + (long long)k * kSubBits, e,
-                                                nullptr, 0, 0, nullptr);
+                SubResult r = decode_sub<false>(sw, end_rel, nblk, &tb->dc, &tb->ac, e, nullptr, 0, 0, nullptr);
                 ND[g] = make_int2(r.n, r.dsum);
                 if (has_next && Ev[g + 1] != r.exit) { Ev[g + 1] = r.exit; wrote = true; }
             }
@@ -537,20 +576,40 @@ __global__ void __launch_bounds__(kSyncThreads) dec_write_kernel(const DecImage*
                                                                  const uint32_t* __restrict__ E, const int2* __restrict__ NB,
                                                                  int16_t* __restrict__ coef, int* __restrict__ status,
                                                                  int* __restrict__ summary) {
+    __shared__ uint32_t rows[kSyncThreads][kRowWords];
+    __shared__ DecTables sh_def;
     __shared__ uint8_t zz[64];
+    {
+        const uint32_t* s = reinterpret_cast<const uint32_t*>(deftab);
+        uint32_t* d = reinterpret_cast<uint32_t*>(&sh_def);
+        for (int i = threadIdx.x; i < (int)(sizeof(DecTables) / 4); i += kSyncThreads) d[i] = __ldg(s + i);
+    }
     if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
-    __syncthreads();
     long long g = (long long)blockIdx.x * kSyncThreads + threadIdx.x;
-    int idx = find_owner_cta(sub_first, n_images, (long long)blockIdx.x * kSyncThreads, g, total_subs);
-    if (g >= total_subs) return;
+    int idx = find_owner_cta(sub_first, n_images, (long long)blockIdx.x * kSyncThreads, g, total_subs);   // barrier inside
+    bool active = g < total_subs;
+    int k = 0, end_rel = 0;
+    int2 nb = make_int2(0, 0);
+    const DecTables* tb = &sh_def;
+    BitSrc src = {};
+    if (active) {
+        const DecImage& im = imgs[idx];
+        k = (int)(g - im.sub_first);
+        active = !im.skip_entropy && k >= im.anchor_sub;
+        if (active) {
+            nb = NB[g];
+            // past the last block: padding bits (to_bytes, bitbuffer.py:17-18) or trailing bytes
+            if (nb.x > im.nblk) active = false;
+        }
+        if (im.has_tables) tb = tabs + idx;
+        src = make_src(im);
+        long long left = im.nbits - (128 + (long long)k * kSubBits);
+        end_rel = left < kSubBits ? (int)left : kSubBits;
+    }
+    stage_rows(rows, active, src, 4 + (long long)k * kSubWords);
+    if (!active) return;
     const DecImage& im = imgs[idx];
-    int k = (int)(g - im.sub_first);
-    if (im.skip_entropy || k < im.anchor_sub) return;
-    const DecTables* tb = im.has_tables ? tabs + idx : deftab;
-    BitSrc src = make_src(im);
-    int2 nb = NB[g];
-    if (nb.x > im.nblk) return;   // past the last block: padding bits (to_bytes, bitbuffer.py:17-18) or trailing bytes
-    SubResult r = decode_sub<true>(im, src, &tb->dc, &tb->ac, 128 + (long long)k * kSubBits, E[g],
+    SubResult r = decode_sub<true>(rows[threadIdx.x], end_rel, im.nblk, &tb->dc, &tb->ac, E[g],
                                    coef + im.blk_first * 64, nb.x, nb.y, zz);
     if (r.err) { atomicOr(&status[idx], (int)r.err); atomicOr(summary, (int)r.err); }
 }
@@ -601,57 +660,72 @@ __device__ __forceinline__ void idct8_exact(double& x0, double& x1, double& x2, 
     x7 = s7;
 }
 
-__global__ void __launch_bounds__(128) dec_idct_kernel(const DecImage* __restrict__ imgs,
-                                                       const long long* __restrict__ blk_first, int n_images,
-                                                       long long total_blocks, const int16_t* __restrict__ coef,
-                                                       const double* __restrict__ mul) {
-    long long gb = (long long)blockIdx.x * 128 + threadIdx.x;
-    int idx = find_owner_cta(blk_first, n_images, (long long)blockIdx.x * 128, gb, total_blocks);
-    if (gb >= total_blocks) return;
-    const DecImage& im = imgs[idx];
-    if (im.skip_pixels) return;
-    int b = (int)(gb - im.blk_first);
-    int by = b / im.bw, bx = b - by * im.bw;
-    const double* __restrict__ m = mul + (size_t)idx * 64;
-    const bool scaled = im.mode == MODE_SCALED;
-    const double two_q = im.two_q;
+// 8 lanes per 8x8 block (4 blocks per warp, kIdctBlocks per CTA): lane t dequantises row t of the coefficients,
+// the block goes through a padded shared-memory tile, lane t transforms column t, back through the tile,
+// lane t transforms row t and stores its 8 pixels.  Two 8-point transforms of straight-line float64 code per
+// thread instead of sixteen: 50 registers instead of 162 and no instruction-cache misses (profiles/r1k_*).
+constexpr int kIdctBlocks = 32;   // blocks in flight per CTA (8 lanes each)
+constexpr int kIdctIters = 16;    // consecutive groups of kIdctBlocks per CTA: one owner search per 512 blocks
 
-    double t[64];
-    const uint4* cp = reinterpret_cast<const uint4*>(coef + gb * 64);
+__global__ void __launch_bounds__(kIdctBlocks * 8) dec_idct_kernel(const DecImage* __restrict__ imgs,
+                                                                   const long long* __restrict__ blk_first, int n_images,
+                                                                   long long total_blocks, const int16_t* __restrict__ coef,
+                                                                   const double* __restrict__ mul) {
+    __shared__ double tile[kIdctBlocks][8][9];   // 9: column and row accesses both conflict-free
+    const int lb = threadIdx.x >> 3, t = threadIdx.x & 7;
+    const long long cta0 = (long long)blockIdx.x * (kIdctBlocks * kIdctIters);
+    int idx = find_owner_cta(blk_first, n_images, cta0, cta0 + lb, total_blocks);   // barrier inside
+    const unsigned group = 0xffu << ((threadIdx.x & 31) & ~7);   // the 8 lanes of this block
+#pragma unroll 1
+    for (int iter = 0; iter < kIdctIters; iter++) {
+        const long long gb = cta0 + (long long)iter * kIdctBlocks + lb;
+        if (gb >= total_blocks) return;   // whole 8-lane groups leave together; only __syncwarp(group) follows
+        while (idx + 1 < n_images && __ldg(blk_first + idx + 1) <= gb) idx++;
+        const DecImage& im = imgs[idx];
+        if (im.skip_pixels) continue;
+        const int b = (int)(gb - im.blk_first);
+        const int by = b / im.bw, bx = b - by * im.bw;
+        const double* __restrict__ m = mul + (size_t)idx * 64 + t * 8;
+        const bool scaled = im.mode == MODE_SCALED;
+        const double two_q = im.two_q;
+
+        double x[8];
+        {
+            uint4 q = __ldg(reinterpret_cast<const uint4*>(coef + gb * 64) + t);   // row t: 8 int16
+            uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
-        uint4 q = __ldg(cp + u);
-        uint32_t w[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int v = 0; v < 8; v++) {
-            int c = (int)(int16_t)((w[v >> 1] >> ((v & 1) * 16)) & 0xffffu);
-            double d = (double)c;
-            if (scaled) d = DM(__ddiv_rn(d, c_ann[u * 8 + v]), two_q);   // codec.py:59-61
-            t[u * 8 + v] = DM(d, __ldg(m + u * 8 + v));                  // utils.py:51-52
+            for (int v = 0; v < 8; v++) {
+                int c = (int)(int16_t)((w[v >> 1] >> ((v & 1) * 16)) & 0xffffu);
+                double d = (double)c;
+                if (scaled) d = DM(__ddiv_rn(d, d_ann[t * 8 + v]), two_q);   // codec.py:59-61
+                tile[lb][t][v] = DM(d, __ldg(m + v));                        // utils.py:51-52
+            }
         }
-    }
-    // utils.py:40-45: axis -2 (down the columns) first, then axis -1 (along the rows)
+        __syncwarp(group);
+        // utils.py:40-45: axis -2 (down the columns) first, then axis -1 (along the rows)
 #pragma unroll
-    for (int v = 0; v < 8; v++)
-        idct8_exact(t[v], t[8 + v], t[16 + v], t[24 + v], t[32 + v], t[40 + v], t[48 + v], t[56 + v]);
-    const int y0 = by * 8, x0 = bx * 8;
-    const bool fast = x0 + 8 <= im.width && (((uintptr_t)im.pixels | (uintptr_t)im.width) & 7u) == 0;
+        for (int u = 0; u < 8; u++) x[u] = tile[lb][u][t];
+        idct8_exact(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
+        __syncwarp(group);
 #pragma unroll
-    for (int u = 0; u < 8; u++) {
-        idct8_exact(t[u * 8], t[u * 8 + 1], t[u * 8 + 2], t[u * 8 + 3], t[u * 8 + 4], t[u * 8 + 5], t[u * 8 + 6],
-                    t[u * 8 + 7]);
+        for (int u = 0; u < 8; u++) tile[lb][u][t] = x[u];
+        __syncwarp(group);
+#pragma unroll
+        for (int v = 0; v < 8; v++) x[v] = tile[lb][t][v];
+        __syncwarp(group);   // the tile is rewritten by the next iteration
+        idct8_exact(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
         uint32_t lo = 0, hi = 0;
 #pragma unroll
         for (int v = 0; v < 8; v++) {
-            double p = DA(t[u * 8 + v], 128.0);             // np.clip(coeffs + 128, 0, 255), codec.py:68
+            double p = DA(x[v], 128.0);                     // np.clip(coeffs + 128, 0, 255), codec.py:68
             p = p < 0.0 ? 0.0 : (p > 255.0 ? 255.0 : p);
             uint32_t px = (uint32_t)__double2int_rz(p);     // astype(np.uint8): truncation, codec.py:70
             if (v < 4) lo |= px << (8 * v); else hi |= px << (8 * (v - 4));
         }
-        int y = y0 + u;
+        const int y = by * 8 + t, x0 = bx * 8;
         if (y < im.height) {
             uint8_t* row = im.pixels + (size_t)y * (size_t)im.width + x0;
-            if (fast) {
+            if (x0 + 8 <= im.width && (((uintptr_t)im.pixels | (uintptr_t)im.width) & 7u) == 0) {
                 *reinterpret_cast<uint2*>(row) = make_uint2(lo, hi);
             } else {
 #pragma unroll
@@ -914,8 +988,8 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
     }
     TICD_CUDA(h, cudaEventRecord(w->ev[4], stream));
     if (blocks) {
-        unsigned grid = (unsigned)((blocks + 127) / 128);
-        dec_idct_kernel<<<grid, 128, 0, stream>>>(w->d_imgs, d_blk_first, n_images, blocks, w->d_coef, w->d_mul);
+        unsigned grid = (unsigned)((blocks + kIdctBlocks * kIdctIters - 1) / (kIdctBlocks * kIdctIters));
+        dec_idct_kernel<<<grid, kIdctBlocks * 8, 0, stream>>>(w->d_imgs, d_blk_first, n_images, blocks, w->d_coef, w->d_mul);
         launches++;
         TICD_CUDA(h, cudaGetLastError());
     }
@@ -985,7 +1059,7 @@ int tic_decode_coeffs(tic_handle h, const int32_t* d_dc, const int32_t* d_ac, in
     dec_coeffs_prep_kernel<<<g1, 256, 0, stream>>>(w->d_imgs, w->d_mul, d_dc, w->d_ND, (int)nblk, w->d_flags + 1);
     dec_scan_kernel<<<1, 1024, 0, stream>>>(w->d_imgs, w->d_ND, w->d_NB, w->d_status_own, w->d_flags + 1);
     dec_coeffs_pack_kernel<<<g2, 256, 0, stream>>>(d_dc, d_ac, w->d_NB, w->d_coef, (int)nblk, w->d_flags + 1);
-    dec_idct_kernel<<<(unsigned)((nblk + 127) / 128), 128, 0, stream>>>(w->d_imgs, w->d_first, 1, nblk, w->d_coef,
+    dec_idct_kernel<<<(unsigned)((nblk + kIdctBlocks * kIdctIters - 1) / (kIdctBlocks * kIdctIters)), kIdctBlocks * 8, 0, stream>>>(w->d_imgs, w->d_first, 1, nblk, w->d_coef,
                                                                         w->d_mul);
     TICD_CUDA(h, cudaGetLastError());
     TICD_CUDA(h, cudaMemcpyAsync(w->h_flags + 1, w->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
