@@ -690,6 +690,7 @@ __global__ void __launch_bounds__(kIdctBlocks * 8) dec_idct_kernel(const DecImag
         const double two_q = im.two_q;
 
         double x[8];
+        double (*tl)[9] = tile[lb];
         {
             uint4 q = __ldg(reinterpret_cast<const uint4*>(coef + gb * 64) + t);   // row t: 8 int16
             uint32_t w[4] = {q.x, q.y, q.z, q.w};
@@ -698,28 +699,29 @@ __global__ void __launch_bounds__(kIdctBlocks * 8) dec_idct_kernel(const DecImag
                 int c = (int)(int16_t)((w[v >> 1] >> ((v & 1) * 16)) & 0xffffu);
                 double d = (double)c;
                 if (scaled) d = DM(__ddiv_rn(d, d_ann[t * 8 + v]), two_q);   // codec.py:59-61
-                tile[lb][t][v] = DM(d, __ldg(m + v));                        // utils.py:51-52
+                tl[t][v] = DM(d, __ldg(m + v));                              // utils.py:51-52
             }
         }
         __syncwarp(group);
         // utils.py:40-45: axis -2 (down the columns) first, then axis -1 (along the rows)
 #pragma unroll
-        for (int u = 0; u < 8; u++) x[u] = tile[lb][u][t];
+        for (int u = 0; u < 8; u++) x[u] = tl[u][t];
         idct8_exact(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
         __syncwarp(group);
 #pragma unroll
-        for (int u = 0; u < 8; u++) tile[lb][u][t] = x[u];
+        for (int u = 0; u < 8; u++) tl[u][t] = x[u];
         __syncwarp(group);
 #pragma unroll
-        for (int v = 0; v < 8; v++) x[v] = tile[lb][t][v];
+        for (int v = 0; v < 8; v++) x[v] = tl[t][v];
         __syncwarp(group);   // the tile is rewritten by the next iteration
         idct8_exact(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7]);
         uint32_t lo = 0, hi = 0;
 #pragma unroll
         for (int v = 0; v < 8; v++) {
-            double p = DA(x[v], 128.0);                     // np.clip(coeffs + 128, 0, 255), codec.py:68
-            p = p < 0.0 ? 0.0 : (p > 255.0 ? 255.0 : p);
-            uint32_t px = (uint32_t)__double2int_rz(p);     // astype(np.uint8): truncation, codec.py:70
+            // np.clip(coeffs + 128, 0, 255) then astype(np.uint8) (codec.py:68-70) = truncate, then clamp: the two
+            // commute on [-inf, inf] (trunc is monotonic and fixes 0 and 255), and the clamp is integer work
+            int pi = __double2int_rz(DA(x[v], 128.0));
+            uint32_t px = (uint32_t)min(max(pi, 0), 255);
             if (v < 4) lo |= px << (8 * v); else hi |= px << (8 * (v - 4));
         }
         const int y = by * 8 + t, x0 = bx * 8;

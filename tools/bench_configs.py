@@ -1,10 +1,12 @@
 #!/usr/bin/env python3
-"""Device-timed encode of the other BASELINE.json configurations (bench.py covers config 4):
+"""Device-timed encode (and decode) of the other BASELINE.json configurations (bench.py covers config 4):
   C1  data/lenna.gif alone          C2  all 50 data/*.gif as one batch
   C3  one 7680x4320 image           C5  one 32768x32768 image at q in {90,80,50,20,10,5}
   S1  16384^2 uniform noise (q 90/50/10)    S2  16384^2 flat image      [optional argv: config name prefixes]
 Pixels resident in HBM, CUDA events around tic_encode_batch, best and median of N runs; the C port of the
 reference path (oracle/, test infrastructure) is timed on the host next to it where that takes seconds.
+Each line also carries the decode side: the streams just produced, still in HBM, decoded by tic_decode_batch
+(median ms, synchronisation rounds, pixel identity with the CPU restatement of the reference decoder).
 One JSON line per configuration."""
 import json
 import os
@@ -68,11 +70,33 @@ def main():
                     "roofline_frac_whole_call": (px + nbytes) / (med * 1e-3) / 1e9 / peak,
                     "encode_kernel_ms": st["encode_kernel_ms_sum"] / max(1, st["timed_batches"]),
                     "tiles": st["tiles"]}
+            offs, sizes = res.offsets.cpu().numpy(), res.sizes.cpu().numpy()
+            hs, ws = [im.shape[0] for im in imgs], [im.shape[1] for im in imgs]
+            stream = torch.cuda.current_stream()
+            dms = []
+            for i in range(5):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                outs, _ = enc.decode_batch_device((res.out, offs), sizes, hs, ws, stream=stream)
+                e1.record(stream)
+                torch.cuda.synchronize()
+                if i >= 1:
+                    dms.append(e0.elapsed_time(e1))
+            dst = enc.decode_stats()
+            line["decode"] = {"ms_median": float(np.median(dms)), "mpixel_per_s": px / (float(np.median(dms)) * 1e-3) / 1e6,
+                              "sync_rounds": int(dst["sync_rounds"]), "subsequences": int(dst["subsequences"]),
+                              "phases_ms": {k: dst[k] for k in ("sync_ms", "scan_ms", "scatter_ms", "idct_ms")}}
             if px <= (1 << 26):
                 t0 = time.perf_counter()
                 ref = [O.compress(im, q) for im in imgs]
                 line["cpu_port_1_thread_ms"] = 1e3 * (time.perf_counter() - t0)
                 line["identical_to_oracle"] = ref == res.to_bytes()
+                t0 = time.perf_counter()
+                want = [O.decompress(s) for s in ref]
+                line["decode"]["cpu_port_1_thread_ms"] = 1e3 * (time.perf_counter() - t0)
+                line["decode"]["identical_to_oracle"] = all(
+                    np.array_equal(outs[i].cpu().numpy(), want[i]) for i in range(len(imgs)))
+            del outs
             print(json.dumps(line), flush=True)
         del d_imgs
         torch.cuda.empty_cache()
