@@ -72,6 +72,30 @@ def synth_images_device(first, count, device, h=IMG_H, w=IMG_W, chunk=128):
 
 
 # ---------------------------------------------------------------------------------------------------
+# host side of a rank: run on the CPUs next to the rank's GPU, so that the pinned buffers of the end-to-end
+# leg are allocated on that NUMA node and each GPU's H2D / D2H traffic stays on its own socket
+# ---------------------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(index):
+    """Returns a short description for the bench line (or why it was not done)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        ideal = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = ideal & allowed
+        if not use:
+            return f"gpu {phys}: none of its {len(ideal)} local CPUs is in this process's cpuset ({len(allowed)} CPUs)"
+        os.sched_setaffinity(0, use)
+        return f"gpu {phys}: bound to {len(use)} of {len(ideal)} local CPUs"
+    except Exception as ex:
+        return f"not bound ({type(ex).__name__}: {ex})"
+
+
+# ---------------------------------------------------------------------------------------------------
 # clocks during the timed region (NVML, sampled from a thread)
 # ---------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
@@ -266,6 +290,7 @@ def run_gpu_arm(args):
             os.dup2(saved_stdout, 1)
             os.close(saved_stdout)
     n_gpus = world
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else "single rank: not bound"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     total = args.images
@@ -371,7 +396,7 @@ def run_gpu_arm(args):
         e2e = {"value": total_px * e2e_steps / dt / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": n_local * IMG_H * IMG_W * n_gpus, "d2h_bytes_per_step": d2h * n_gpus,
                "steps": e2e_steps, "api": "Encoder.compress_batch_pinned (chunked H2D / encode / D2H pipeline)",
-               "timing": "host wall clock around the API calls, max over ranks"}
+               "timing": "host wall clock around the API calls, max over ranks", "host_affinity_rank0": numa}
         del h_images
     except Exception as ex:  # keep the device-timed line even if the host leg cannot run
         e2e = {"value": None, "unit": UNIT, "error": f"{type(ex).__name__}: {ex}"}
