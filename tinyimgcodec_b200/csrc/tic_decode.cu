@@ -250,21 +250,16 @@ struct SubResult {
     uint32_t err;
 };
 
-// Decode one subsequence from `entry`, reading its bits from the staged row `sw`.  `end_rel`: bits of the
-// subsequence that belong to the stream (kSubBits except at the end).  WRITE: also scatter coefficients; `blk`
-// is the index (within the image) of the next block to start, `dc_run` the DC predictor (sum of all earlier
-// differences).
-template <bool WRITE>
-__device__ SubResult decode_sub(const uint32_t* sw, int end_rel, int nblk, const DecTable* tdc, const DecTable* tac,
-                                uint32_t entry, int16_t* __restrict__ coef, int blk, int dc_run, const uint8_t* zz) {
+// Decode one subsequence from `entry`, reading its bits from the staged row `sw`; nothing is stored (phases 1
+// and 2; dec_write_kernel walks the same parse once more with the stores).  `end_rel`: bits of the subsequence
+// that belong to the stream (kSubBits except at the end).
+__device__ SubResult decode_sub(const uint32_t* sw, int end_rel, const DecTable* tdc, const DecTable* tac, uint32_t entry) {
     int p = (int)(entry & 0xffffu);
     int z = (int)((entry >> 16) & 0xffu);
     SubResult r;
     r.n = 0; r.dsum = 0; r.err = 0;
-    int cur = blk - 1;   // the block being filled when z > 0
     int it = 0;
     for (; p < end_rel && it < kMaxSymbols; it++) {
-        if (WRITE && z == 0 && blk >= nblk) break;   // all blocks done: what follows is padding (bitbuffer.py:17-18)
         const int wi = p >> 5;
         uint32_t v = __funnelshift_l(sw[wi + 1], sw[wi], (uint32_t)(p & 31));
         int sym, len;
@@ -285,15 +280,6 @@ __device__ SubResult decode_sub(const uint32_t* sw, int end_rel, int nblk, const
         if (z == 0) {
             r.n++;
             r.dsum += val;
-            if (WRITE) {
-                cur = blk++;
-                dc_run += val;
-                if (cur < nblk) {
-                    int s = dc_run < -32768 ? -32768 : (dc_run > 32767 ? 32767 : dc_run);
-                    if (s != dc_run) r.err |= TIC_DSTATUS_RANGE;
-                    coef[(long long)cur * 64] = (int16_t)s;
-                }
-            }
             z = 1;
         } else if (sym == 0) {   // EOB (huffman.py:94-95)
             z = 0;
@@ -311,11 +297,9 @@ __device__ SubResult decode_sub(const uint32_t* sw, int end_rel, int nblk, const
                 p = p0 + 1;
                 continue;
             }
-            if (WRITE && val != 0 && cur >= 0 && cur < nblk) coef[(long long)cur * 64 + zz[z]] = (int16_t)val;
             z += 1;
         }
     }
-    if (it >= kMaxSymbols) r.err |= TIC_DSTATUS_CODE;   // zero-length codewords that never advance
     int over = p - kSubBits;
     r.exit = (uint32_t)(over > 0 ? over : 0) | ((uint32_t)z << 16);
     return r;
@@ -481,7 +465,7 @@ __global__ void __launch_bounds__(kSyncThreads) dec_sync_kernel(const DecImage* 
     }
     long long g = (long long)blockIdx.x * kSyncThreads + threadIdx.x;
     bool active = g < total_subs;
-    int idx = 0, k = 0, end_rel = 0, nblk = 0;
+    int idx = 0, k = 0, end_rel = 0;
     bool has_next = false;
     uint32_t used = 0xffffffffu;
     const DecTables* tb = &sh_def;
@@ -496,7 +480,6 @@ __global__ void __launch_bounds__(kSyncThreads) dec_sync_kernel(const DecImage* 
         src = make_src(im);
         long long left = im.nbits - (128 + (long long)k * kSubBits);
         end_rel = left < kSubBits ? (int)left : kSubBits;
-        nblk = im.nblk;
         used = U[g];
     }
     stage_rows(rows, active, src, 4 + (long long)k * kSubWords);
@@ -509,7 +492,7 @@ __global__ void __launch_bounds__(kSyncThreads) dec_sync_kernel(const DecImage* 
             uint32_t e = Ev[g];
             if (e != used) {
                 used = e;
-                SubResult r = decode_sub<false>(sw, end_rel, nblk, &tb->dc, &tb->ac, e, nullptr, 0, 0, nullptr);
+                SubResult r = decode_sub(sw, end_rel, &tb->dc, &tb->ac, e);
                 ND[g] = make_int2(r.n, r.dsum);
                 if (has_next && Ev[g + 1] != r.exit) { Ev[g + 1] = r.exit; wrote = true; }
             }
@@ -522,21 +505,77 @@ __global__ void __launch_bounds__(kSyncThreads) dec_sync_kernel(const DecImage* 
 }
 
 // ---------------------------------------------------------------------------------------------------
-// dec_scan_kernel: phase 3, one CTA per image: exclusive sums of ND over the image's subsequences.
+// Phase 3: exclusive sums of ND = (blocks started, sum of DC differences) over each stream's subsequences
+// (np.cumsum of the DC differences, codec.py:53, and the block index of every thread).  A stream is cut into
+// slices of at most kSliceSubs subsequences, one CTA each (the host builds the slice list); a stream that
+// needs several slices — a single large image — first gets its slice totals (dec_scan_totals_kernel), then
+// every slice starts from the sum of the totals in front of it.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) dec_scan_kernel(const DecImage* __restrict__ imgs, const int2* __restrict__ ND,
+constexpr int kSliceSubs = 32768;
+struct ScanSlice {
+    int img, first, count, index_in_img;
+};
+
+__device__ __forceinline__ int2 block_sum_1024(int2 v, int2* warp_buf) {   // sum over the CTA, result in every thread
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int d = 16; d > 0; d >>= 1) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, d);
+        v.y += __shfl_xor_sync(0xffffffffu, v.y, d);
+    }
+    if (lane == 0) warp_buf[warp] = v;
+    __syncthreads();
+    int2 t = warp_buf[lane];
+    for (int d = 16; d > 0; d >>= 1) {
+        t.x += __shfl_xor_sync(0xffffffffu, t.x, d);
+        t.y += __shfl_xor_sync(0xffffffffu, t.y, d);
+    }
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(1024) dec_scan_totals_kernel(const DecImage* __restrict__ imgs,
+                                                               const ScanSlice* __restrict__ slices,
+                                                               const int2* __restrict__ ND, int2* __restrict__ slice_tot) {
+    __shared__ int2 warp_buf[32];
+    const ScanSlice sl = slices[blockIdx.x];
+    const DecImage& im = imgs[sl.img];
+    int2 acc = make_int2(0, 0);
+    if (!im.skip_entropy)
+        for (int k = threadIdx.x; k < sl.count; k += 1024) {
+            int2 v = ND[im.sub_first + sl.first + k];
+            acc.x += v.x; acc.y += v.y;
+        }
+    acc = block_sum_1024(acc, warp_buf);
+    if (threadIdx.x == 0) slice_tot[blockIdx.x] = acc;
+}
+
+// E, coef: when given, the block a subsequence is entered in the middle of (zigzag index > 0 in its entry state)
+// is zeroed here, 128 bytes: those are the only blocks dec_write_kernel fills with partial stores.
+__global__ void __launch_bounds__(1024) dec_scan_kernel(const DecImage* __restrict__ imgs, const ScanSlice* __restrict__ slices,
+                                                        const int2* __restrict__ slice_tot, const int2* __restrict__ ND,
                                                         int2* __restrict__ NB, int* __restrict__ status,
-                                                        int* __restrict__ summary) {
-    const DecImage& im = imgs[blockIdx.x];
+                                                        int* __restrict__ summary, const uint32_t* __restrict__ E,
+                                                        int16_t* __restrict__ coef, int* __restrict__ ndec) {
+    const ScanSlice sl = slices[blockIdx.x];
+    const DecImage& im = imgs[sl.img];
     if (im.skip_entropy) return;
     __shared__ int2 warp_tot[32], warp_excl[32];
     __shared__ int2 carry_sh, chunk_tot;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry_sh = make_int2(0, 0);
+    {
+        int2 acc = make_int2(0, 0);   // the slices of this stream in front of this one
+        for (int j = threadIdx.x; j < sl.index_in_img; j += 1024) {
+            int2 v = slice_tot[blockIdx.x - sl.index_in_img + j];
+            acc.x += v.x; acc.y += v.y;
+        }
+        acc = block_sum_1024(acc, warp_tot);
+        if (threadIdx.x == 0) carry_sh = acc;
+    }
     __syncthreads();
-    for (int base = im.anchor_sub; base < im.nsubs; base += 1024) {
+    const long long base_g = im.sub_first + sl.first;
+    for (int base = 0; base < sl.count; base += 1024) {
         int k = base + threadIdx.x;
-        int2 v = k < im.nsubs ? ND[im.sub_first + k] : make_int2(0, 0);
+        int2 v = k < sl.count ? ND[base_g + k] : make_int2(0, 0);
         int2 inc = v;
         for (int d = 1; d < 32; d <<= 1) {
             int a = __shfl_up_sync(0xffffffffu, inc.x, d), b = __shfl_up_sync(0xffffffffu, inc.y, d);
@@ -555,14 +594,25 @@ __global__ void __launch_bounds__(1024) dec_scan_kernel(const DecImage* __restri
         }
         __syncthreads();
         int2 c = carry_sh, wo = warp_excl[warp];
-        if (k < im.nsubs) NB[im.sub_first + k] = make_int2(c.x + wo.x + inc.x - v.x, c.y + wo.y + inc.y - v.y);
+        if (k < sl.count) {
+            const int first_blk = c.x + wo.x + inc.x - v.x;
+            NB[base_g + k] = make_int2(first_blk, c.y + wo.y + inc.y - v.y);
+            if (E != nullptr && ((E[base_g + k] >> 16) & 0xffu) != 0 && first_blk >= 1 && first_blk <= im.nblk) {
+                uint4* dst = reinterpret_cast<uint4*>(coef + (im.blk_first + first_blk - 1) * 64);
+#pragma unroll
+                for (int i = 0; i < 8; i++) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
         __syncthreads();
         if (threadIdx.x == 0) carry_sh = make_int2(c.x + chunk_tot.x, c.y + chunk_tot.y);
         __syncthreads();
     }
-    if (threadIdx.x == 0 && carry_sh.x < im.nblk) {
-        atomicOr(&status[blockIdx.x], TIC_DSTATUS_TRUNCATED);
-        atomicOr(summary, TIC_DSTATUS_TRUNCATED);
+    if (threadIdx.x == 0 && sl.first + sl.count == im.nsubs) {
+        ndec[sl.img] = carry_sh.x < im.nblk ? carry_sh.x : im.nblk;
+        if (carry_sh.x < im.nblk) {
+            atomicOr(&status[sl.img], TIC_DSTATUS_TRUNCATED);
+            atomicOr(summary, TIC_DSTATUS_TRUNCATED);
+        }
     }
 }
 
@@ -579,6 +629,9 @@ __global__ void __launch_bounds__(kSyncThreads) dec_write_kernel(const DecImage*
     __shared__ uint32_t rows[kSyncThreads][kRowWords];
     __shared__ DecTables sh_def;
     __shared__ uint8_t zz[64];
+    __shared__ __align__(16) int16_t slots[kSyncThreads][64];   // one block under construction per thread
+    for (int i = threadIdx.x; i < kSyncThreads * 8; i += kSyncThreads)
+        reinterpret_cast<uint4*>(&slots[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
     {
         const uint32_t* s = reinterpret_cast<const uint32_t*>(deftab);
         uint32_t* d = reinterpret_cast<uint32_t*>(&sh_def);
@@ -588,10 +641,12 @@ __global__ void __launch_bounds__(kSyncThreads) dec_write_kernel(const DecImage*
     long long g = (long long)blockIdx.x * kSyncThreads + threadIdx.x;
     int idx = find_owner_cta(sub_first, n_images, (long long)blockIdx.x * kSyncThreads, g, total_subs);   // barrier inside
     bool active = g < total_subs;
-    int k = 0, end_rel = 0;
+    int k = 0, end_rel = 0, nblk = 0;
+    bool last_sub = false;
     int2 nb = make_int2(0, 0);
     const DecTables* tb = &sh_def;
     BitSrc src = {};
+    long long blk0 = 0;   // index of the image's first block in the batch
     if (active) {
         const DecImage& im = imgs[idx];
         k = (int)(g - im.sub_first);
@@ -605,13 +660,121 @@ __global__ void __launch_bounds__(kSyncThreads) dec_write_kernel(const DecImage*
         src = make_src(im);
         long long left = im.nbits - (128 + (long long)k * kSubBits);
         end_rel = left < kSubBits ? (int)left : kSubBits;
+        nblk = im.nblk;
+        last_sub = k + 1 >= im.nsubs;
+        blk0 = im.blk_first;
     }
     stage_rows(rows, active, src, 4 + (long long)k * kSubWords);
-    if (!active) return;
-    const DecImage& im = imgs[idx];
-    SubResult r = decode_sub<true>(rows[threadIdx.x], end_rel, im.nblk, &tb->dc, &tb->ac, E[g],
-                                   coef + im.blk_first * 64, nb.x, nb.y, zz);
-    if (r.err) { atomicOr(&status[idx], (int)r.err); atomicOr(summary, (int)r.err); }
+
+    // Phase 4 proper, warp-synchronous: every step each running lane decodes ONE symbol; the lanes whose symbol
+    // was the EOB of a block they started (the block sits in their slot) are then served by the whole warp,
+    // four blocks per pass, 8 lanes x 16 bytes per block: 128-byte coalesced stores, zeros included, so the
+    // coefficient buffer needs no zero fill and sees no partial-sector writes.  A block that spans subsequences is
+    // written with 2-byte stores by every thread that decodes a piece of it (the thread that entered in the middle
+    // of it directly, the thread that started it from its slot when its subsequence ends) into a block
+    // dec_scan_kernel zeroed beforehand; the pieces are disjoint coefficients.
+    const int lane = threadIdx.x & 31;
+    const uint32_t* sw = rows[threadIdx.x];
+    int16_t* slot = slots[threadIdx.x];
+    const DecTable* tdc = &tb->dc;
+    const DecTable* tac = &tb->ac;
+    uint32_t entry = active ? E[g] : 0u;
+    int p = (int)(entry & 0xffffu), z = (int)((entry >> 16) & 0xffu);
+    int blk = nb.x, dc_run = nb.y, cur = nb.x - 1, it = 0;
+    bool staged = false;
+    uint32_t err = 0;
+    for (;;) {
+        const bool running = active && p < end_rel && it < kMaxSymbols && !(z == 0 && blk >= nblk);
+        if (!__any_sync(0xffffffffu, running)) break;
+        bool ready = false;
+        if (running) {
+            it++;
+            const int wi = p >> 5;
+            uint32_t v = __funnelshift_l(sw[wi + 1], sw[wi], (uint32_t)(p & 31));
+            int sym, len;
+            lookup(z == 0 ? tdc : tac, v, sym, len);
+            if (len < 0) {   // the same rules as decode_sub: this pass must follow the parse the entries belong to
+                err |= TIC_DSTATUS_CODE;
+                p += 1;
+            } else {
+                int size = sym & 15;
+                int val = 0;
+                if (size) {
+                    uint32_t vb = (v << len) >> (32 - size);
+                    val = (vb >> (size - 1)) ? (int)vb : (int)vb - (1 << size) + 1;
+                }
+                const int p0 = p;
+                p += len + size;
+                if (z == 0) {
+                    cur = blk++;
+                    dc_run += val;
+                    int s = dc_run < -32768 ? -32768 : (dc_run > 32767 ? 32767 : dc_run);
+                    if (s != dc_run) err |= TIC_DSTATUS_RANGE;
+                    slot[0] = (int16_t)s;
+                    staged = true;
+                    z = 1;
+                } else if (sym == 0) {
+                    z = 0;
+                    ready = staged;
+                    staged = false;
+                } else {
+                    z += sym >> 4;
+                    if (z > 63) {
+                        err |= TIC_DSTATUS_CODE;
+                        z = 0;
+                        p = p0 + 1;
+                        if (staged) {   // damaged stream: the block reads as zero
+#pragma unroll
+                            for (int i = 0; i < 8; i++) reinterpret_cast<uint4*>(slot)[i] = make_uint4(0u, 0u, 0u, 0u);
+                            ready = true;
+                            staged = false;
+                        }
+                    } else {
+                        if (val != 0) {
+                            if (staged) slot[zz[z]] = (int16_t)val;
+                            else if (cur >= 0 && cur < nblk) coef[(blk0 + cur) * 64 + zz[z]] = (int16_t)val;
+                        }
+                        z += 1;
+                    }
+                }
+            }
+        }
+        unsigned m = __ballot_sync(0xffffffffu, ready);
+        const long long my_block = blk0 + cur;
+        while (m) {
+            // the (lane >> 3)-th of the lowest four ready lanes
+            unsigned mm = m;
+            int src_lane = -1;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                int b = mm ? __ffs(mm) - 1 : -1;
+                if (j == (lane >> 3)) src_lane = b;
+                mm &= mm - 1;
+            }
+            m = mm;
+            const long long dst_block = __shfl_sync(0xffffffffu, my_block, src_lane & 31);
+            if (src_lane >= 0) {
+                uint4* sp = reinterpret_cast<uint4*>(slots[(threadIdx.x & ~31) + src_lane]) + (lane & 7);
+                reinterpret_cast<uint4*>(coef + dst_block * 64)[lane & 7] = *sp;
+                *sp = make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        __syncwarp();
+    }
+    if (staged) {
+        if (last_sub) {   // the stream ends inside the block (truncated): nobody else writes it
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+                reinterpret_cast<uint4*>(coef + (blk0 + cur) * 64)[i] = reinterpret_cast<uint4*>(slot)[i];
+        } else {          // the block goes on in the next subsequence
+            for (int i = 0; i < 64; i++) {
+                int16_t c = slot[i];
+                if (c != 0) coef[(blk0 + cur) * 64 + i] = c;
+            }
+        }
+    }
+    if (active && it >= kMaxSymbols) err |= TIC_DSTATUS_CODE;
+    if (err) { atomicOr(&status[idx], (int)err); atomicOr(summary, (int)err); }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -670,7 +833,7 @@ constexpr int kIdctIters = 16;    // consecutive groups of kIdctBlocks per CTA: 
 __global__ void __launch_bounds__(kIdctBlocks * 8) dec_idct_kernel(const DecImage* __restrict__ imgs,
                                                                    const long long* __restrict__ blk_first, int n_images,
                                                                    long long total_blocks, const int16_t* __restrict__ coef,
-                                                                   const double* __restrict__ mul) {
+                                                                   const double* __restrict__ mul, const int* __restrict__ ndec) {
     __shared__ double tile[kIdctBlocks][8][9];   // 9: column and row accesses both conflict-free
     const int lb = threadIdx.x >> 3, t = threadIdx.x & 7;
     const long long cta0 = (long long)blockIdx.x * (kIdctBlocks * kIdctIters);
@@ -692,7 +855,9 @@ __global__ void __launch_bounds__(kIdctBlocks * 8) dec_idct_kernel(const DecImag
         double x[8];
         double (*tl)[9] = tile[lb];
         {
-            uint4 q = __ldg(reinterpret_cast<const uint4*>(coef + gb * 64) + t);   // row t: 8 int16
+            // row t: 8 int16; a block the stream never reached (truncated, or every block zero bits long) is zero
+            uint4 q = b < __ldg(ndec + idx) ? __ldg(reinterpret_cast<const uint4*>(coef + gb * 64) + t)
+                                            : make_uint4(0u, 0u, 0u, 0u);
             uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
             for (int v = 0; v < 8; v++) {
@@ -778,6 +943,9 @@ struct DecWs {
     int* d_flags = nullptr;   // [0] changed, [1] summary
     int* h_flags = nullptr;   // pinned
     int* d_status_own = nullptr; size_t status_cap = 0;
+    int* d_ndec = nullptr;    // per image: blocks whose coefficients were written (the rest read as zero)
+    ScanSlice* d_slices = nullptr; int2* d_slice_tot = nullptr; size_t slices_cap = 0;
+    std::vector<ScanSlice> h_slices;
     // single-stream host path
     uint8_t* d_stream = nullptr; size_t stream_cap = 0;
     uint8_t* d_px = nullptr; size_t px_cap = 0;
@@ -811,7 +979,7 @@ void tic_internal_dec_release(void* p) {
     cudaFree(w->d_imgs); cudaFreeHost(w->h_imgs); cudaFree(w->d_first); cudaFreeHost(w->h_first);
     cudaFree(w->d_tabs); cudaFree(w->d_mul); cudaFree(w->d_deftab); cudaFree(w->d_E); cudaFree(w->d_U);
     cudaFree(w->d_ND); cudaFree(w->d_NB); cudaFree(w->d_coef); cudaFree(w->d_flags); cudaFreeHost(w->h_flags);
-    cudaFree(w->d_status_own); cudaFree(w->d_stream); cudaFree(w->d_px);
+    cudaFree(w->d_status_own); cudaFree(w->d_stream); cudaFree(w->d_px); cudaFree(w->d_slices); cudaFree(w->d_slice_tot); cudaFree(w->d_ndec);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
     delete w;
 }
@@ -853,6 +1021,40 @@ static int grow(tic_handle h, T*& p, size_t n) {
     return TIC_OK;
 }
 
+// Phase 3 on `stream`: h_slices must list the slices of the images in image order.
+static int launch_scan(tic_handle h, DecWs* w, int* status, cudaStream_t stream, long long& launches,
+                       const uint32_t* E, int16_t* coef) {
+    const size_t ns = w->h_slices.size();
+    if (ns == 0) return TIC_OK;
+    if (ns > w->slices_cap) {
+        size_t cap = ns * 2 + 64;
+        w->slices_cap = 0;
+        if (int rc = grow(h, w->d_slices, cap)) return rc;
+        if (int rc = grow(h, w->d_slice_tot, cap)) return rc;
+        w->slices_cap = cap;
+    }
+    bool multi = false;
+    for (const ScanSlice& sl : w->h_slices) multi |= sl.index_in_img > 0;
+    TICD_CUDA(h, cudaMemcpyAsync(w->d_slices, w->h_slices.data(), ns * sizeof(ScanSlice), cudaMemcpyHostToDevice, stream));
+    if (multi) {
+        dec_scan_totals_kernel<<<(unsigned)ns, 1024, 0, stream>>>(w->d_imgs, w->d_slices, w->d_ND, w->d_slice_tot);
+        launches++;
+    }
+    dec_scan_kernel<<<(unsigned)ns, 1024, 0, stream>>>(w->d_imgs, w->d_slices, w->d_slice_tot, w->d_ND, w->d_NB, status,
+                                                       w->d_flags + 1, E, coef, w->d_ndec);
+    launches++;
+    TICD_CUDA(h, cudaGetLastError());
+    return TIC_OK;
+}
+
+static void push_slices(std::vector<ScanSlice>& v, int img, long long nsubs) {
+    int j = 0;
+    for (long long f = 0; f < nsubs; f += kSliceSubs, j++) {
+        long long c = nsubs - f < kSliceSubs ? nsubs - f : kSliceSubs;
+        v.push_back(ScanSlice{img, (int)f, (int)c, j});
+    }
+}
+
 int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* sizes, const int32_t* heights,
                      const int32_t* widths, int32_t n_images, uint32_t flags, void* const* d_pixels,
                      int32_t* d_status, void* stream_v) {
@@ -880,6 +1082,7 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
         if (int rc = grow(h, w->d_tabs, cap)) return rc;
         if (int rc = grow(h, w->d_mul, cap * 64)) return rc;
         if (int rc = grow(h, w->d_status_own, cap)) return rc;
+        if (int rc = grow(h, w->d_ndec, cap)) return rc;
         TICD_CUDA(h, cudaMallocHost(&w->h_imgs, cap * sizeof(DecImage)));
         TICD_CUDA(h, cudaMallocHost(&w->h_first, 2 * (cap + 1) * sizeof(long long)));
         w->imgs_cap = cap;
@@ -887,6 +1090,7 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
     long long* sub_first = w->h_first;
     long long* blk_first = w->h_first + (n + 1);
     long long subs = 0, blocks = 0;
+    w->h_slices.clear();
     for (size_t i = 0; i < n; i++) {
         if (sizes[i] < 0 || heights[i] < 0 || widths[i] < 0 || (sizes[i] > 0 && !d_streams[i]) ||
             ((uintptr_t)d_streams[i] & 3u)) {
@@ -920,6 +1124,7 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
         blk_first[i] = blocks;
         subs += nsub;
         blocks += nblk;
+        push_slices(w->h_slices, (int)i, nsub);
     }
     sub_first[n] = subs;
     blk_first[n] = blocks;
@@ -950,7 +1155,7 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
         TICD_CUDA(h, cudaMemsetAsync(w->d_ND, 0, (size_t)subs * sizeof(int2), stream));
     }
     TICD_CUDA(h, cudaEventRecord(w->ev[0], stream));
-    if (blocks) TICD_CUDA(h, cudaMemsetAsync(w->d_coef, 0, (size_t)blocks * 128, stream));
+    TICD_CUDA(h, cudaMemsetAsync(w->d_ndec, 0, n * sizeof(int), stream));   // the coefficient buffer itself needs no fill
     long long launches = 0;
     dec_setup_kernel<<<n_images, 32, 0, stream>>>(w->d_imgs, n_images, flags, w->d_tabs, w->d_mul, w->d_E, status,
                                                   w->d_flags + 1);
@@ -976,13 +1181,12 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
             }
         }
         TICD_CUDA(h, cudaEventRecord(w->ev[2], stream));
-        dec_scan_kernel<<<n_images, 1024, 0, stream>>>(w->d_imgs, w->d_ND, w->d_NB, status, w->d_flags + 1);
-        TICD_CUDA(h, cudaGetLastError());
+        if (int rc = launch_scan(h, w, status, stream, launches, w->d_E, w->d_coef)) return rc;
         TICD_CUDA(h, cudaEventRecord(w->ev[3], stream));
         dec_write_kernel<<<grid, kSyncThreads, 0, stream>>>(w->d_imgs, d_sub_first, n_images, subs, w->d_deftab,
                                                             w->d_tabs, w->d_E, w->d_NB, w->d_coef, status,
                                                             w->d_flags + 1);
-        launches += 2;
+        launches++;
         TICD_CUDA(h, cudaGetLastError());
     } else {
         TICD_CUDA(h, cudaEventRecord(w->ev[2], stream));
@@ -991,7 +1195,8 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
     TICD_CUDA(h, cudaEventRecord(w->ev[4], stream));
     if (blocks) {
         unsigned grid = (unsigned)((blocks + kIdctBlocks * kIdctIters - 1) / (kIdctBlocks * kIdctIters));
-        dec_idct_kernel<<<grid, kIdctBlocks * 8, 0, stream>>>(w->d_imgs, d_blk_first, n_images, blocks, w->d_coef, w->d_mul);
+        dec_idct_kernel<<<grid, kIdctBlocks * 8, 0, stream>>>(w->d_imgs, d_blk_first, n_images, blocks, w->d_coef, w->d_mul,
+                                                              w->d_ndec);
         launches++;
         TICD_CUDA(h, cudaGetLastError());
     }
@@ -1026,6 +1231,7 @@ int tic_decode_coeffs(tic_handle h, const int32_t* d_dc, const int32_t* d_ac, in
         if (int rc = grow(h, w->d_tabs, cap)) return rc;
         if (int rc = grow(h, w->d_mul, cap * 64)) return rc;
         if (int rc = grow(h, w->d_status_own, cap)) return rc;
+        if (int rc = grow(h, w->d_ndec, cap)) return rc;
         TICD_CUDA(h, cudaMallocHost(&w->h_imgs, cap * sizeof(DecImage)));
         TICD_CUDA(h, cudaMallocHost(&w->h_first, 2 * (cap + 1) * sizeof(long long)));
         w->imgs_cap = cap;
@@ -1057,15 +1263,19 @@ int tic_decode_coeffs(tic_handle h, const int32_t* d_dc, const int32_t* d_ac, in
     TICD_CUDA(h, cudaMemcpyAsync(w->d_imgs, w->h_imgs, sizeof(DecImage), cudaMemcpyHostToDevice, stream));
     TICD_CUDA(h, cudaMemcpyAsync(w->d_first, w->h_first, 2 * sizeof(long long), cudaMemcpyHostToDevice, stream));
     TICD_CUDA(h, cudaMemsetAsync(w->d_status_own, 0, sizeof(int), stream));
+    TICD_CUDA(h, cudaMemsetAsync(w->d_ndec, 0, sizeof(int), stream));
     unsigned g1 = (unsigned)((nblk + 255) / 256), g2 = (unsigned)((nblk * 64 + 255) / 256);
     dec_coeffs_prep_kernel<<<g1, 256, 0, stream>>>(w->d_imgs, w->d_mul, d_dc, w->d_ND, (int)nblk, w->d_flags + 1);
-    dec_scan_kernel<<<1, 1024, 0, stream>>>(w->d_imgs, w->d_ND, w->d_NB, w->d_status_own, w->d_flags + 1);
+    long long launches = 3;
+    w->h_slices.clear();
+    push_slices(w->h_slices, 0, nblk);
+    if (int rc = launch_scan(h, w, w->d_status_own, stream, launches, nullptr, nullptr)) return rc;
     dec_coeffs_pack_kernel<<<g2, 256, 0, stream>>>(d_dc, d_ac, w->d_NB, w->d_coef, (int)nblk, w->d_flags + 1);
     dec_idct_kernel<<<(unsigned)((nblk + kIdctBlocks * kIdctIters - 1) / (kIdctBlocks * kIdctIters)), kIdctBlocks * 8, 0, stream>>>(w->d_imgs, w->d_first, 1, nblk, w->d_coef,
-                                                                        w->d_mul);
+                                                                        w->d_mul, w->d_ndec);
     TICD_CUDA(h, cudaGetLastError());
     TICD_CUDA(h, cudaMemcpyAsync(w->h_flags + 1, w->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
-    w->stats[0] = 4;
+    w->stats[0] = launches;
     w->stats[3] = nblk;
     return TIC_OK;
 }
