@@ -174,6 +174,10 @@ int tic_last_stats(tic_handle h, int64_t stats[8]);
                                        "per-image tables follow".  Off by default: the reference decodes such
                                        a stream with the fixed tables (garbage), and so does this library. */
 
+#define TIC_DFLAG_EXACT_ONLY 2u     /* run the float64 IDCT on every block instead of the FP32 pass + float64 pass
+                                       over the blocks whose pixels the FP32 pass cannot guarantee.  Same pixels
+                                       either way (tests compare the two); for verification and profiling. */
+
 /* per-stream status bits of the decode side */
 #define TIC_DSTATUS_HEADER 1     /* shorter than 16 bytes, or height / width differ from the caller's */
 #define TIC_DSTATUS_CODE 2       /* no codeword matches (ValueError, huffman.py:72-73) or a run passes
@@ -231,8 +235,9 @@ int tic_decode_coeffs(tic_handle h, const int32_t *d_dc, const int32_t *d_ac, in
 
 /* Counters of the last tic_decode_batch (valid after tic_decode_finish):
  *   [0] kernels launched  [1] subsequences (1024 stream bits each)  [2] synchronisation rounds
- *   [3] blocks  [4]-[7] device time in ns of: synchronisation rounds, scan, coefficient scatter, IDCT */
-int tic_decode_stats(tic_handle h, int64_t stats[8]);
+ *   [3] blocks  [4]-[7] device time in ns of: synchronisation rounds, scan, coefficient pass, IDCT (both passes)
+ *   [8] blocks the FP32 IDCT pass handed to the exact float64 pass  [9]-[11] reserved */
+int tic_decode_stats(tic_handle h, int64_t stats[12]);
 
 #ifdef __cplusplus
 }

@@ -40,10 +40,12 @@ def test_golden_streams_decode_to_the_reference_pixels(tic, golden):
     assert n >= 60
 
 
-def test_golden_streams_as_one_batch(tic, golden):
-    """The same streams through tic_decode_batch in ONE call: ragged shapes, three stream forms mixed."""
+@pytest.mark.parametrize("exact_only", [False, True])
+def test_golden_streams_as_one_batch(tic, golden, exact_only):
+    """The same streams through tic_decode_batch in ONE call: ragged shapes, three stream forms mixed; with the
+    FP32 IDCT pass + exact work list (default) and with the float64 IDCT on every block."""
     cases = list(golden.decode_cases(clean=True))
-    outs = tic.decompress_batch([c[1] for c in cases])
+    outs = tic.decompress_batch([c[1] for c in cases], exact_only=exact_only)
     for (key, _, shape, sha), px in zip(cases, outs):
         assert px.shape == shape, key
         assert hashlib.sha256(np.ascontiguousarray(px).tobytes()).hexdigest() == sha, key
@@ -108,8 +110,11 @@ def test_round_trip_vs_oracle_qualities(tic, q):
         except O.OracleError:
             pass   # category outside the fixed tables (KeyError in the reference)
     outs = tic.decompress_batch(streams)
-    for i, (s, px) in enumerate(zip(streams, outs)):
-        _same(px, O.decompress(s), f"q{q} image {i}")
+    outs_exact = tic.decompress_batch(streams, exact_only=True)
+    for i, (s, px, pe) in enumerate(zip(streams, outs, outs_exact)):
+        want = O.decompress(s)
+        _same(px, want, f"q{q} image {i}")
+        _same(pe, want, f"q{q} image {i} (exact only)")
 
 
 def test_odd_shapes_and_edges(tic):
@@ -169,6 +174,13 @@ def test_config4_images_on_device_round_trip(tic):
         assert not status.any()
         st = enc.decode_stats()
         assert st["sync_rounds"] <= 8 and st["blocks"] == n * 16384, st
+        # the FP32 pass + exact work list against the float64 IDCT on every block: all 48 images, bit for bit
+        # (at q10 the multipliers are integers and no pixel of these images comes within the band: zero is real there)
+        assert (0 if q == 10 else 1) <= st["exact_blocks"] < 0.2 * st["blocks"], st
+        outs = outs.clone()
+        exact, _ = enc.decode_batch_device((res.out, offs), sizes, [1024] * n, [1024] * n, exact_only=True)
+        assert enc.decode_stats()["exact_blocks"] == 0
+        assert torch.equal(outs, exact), f"q{q}: {(outs != exact).sum().item()} pixels differ between the two IDCT paths"
         host = res.to_bytes()
         for i in (0, 17, n - 1):
             _same(outs[i].cpu().numpy(), O.decompress(host[i]), f"q{q} image {i}")
@@ -191,6 +203,39 @@ def test_long_single_stream_noise(tic):
     s = tic.compress(img, 90)
     assert len(s) * 8 > 1 << 26
     _same(tic.decompress(s), O.decompress(s), "noise 4096^2 q90")
+
+
+def test_fast_idct_guard_band_on_adversarial_blocks(tic):
+    """Images built to sit on the FP32 pass's decision boundary: blocks whose only coefficients are the rational
+    ones ((0,0), (0,4), (4,0), (4,4): pixel values on exact integers), saturated blocks (clipping at 0 and 255),
+    large-magnitude noise at q1/q99, and 8x8 checkerboards.  Both IDCT paths must agree with the CPU restatement."""
+    rng = np.random.default_rng(11)
+    imgs = []
+    base = np.zeros((64, 64), np.int64)
+    for by in range(8):
+        for bx in range(8):
+            yy, xx = np.mgrid[0:8, 0:8]
+            blk = 128 + 40 * rng.integers(-1, 2) + 24 * rng.integers(-1, 2) * np.where(yy < 4, 1, -1) \
+                + 16 * rng.integers(-1, 2) * np.where(xx < 4, 1, -1)
+            base[by * 8:by * 8 + 8, bx * 8:bx * 8 + 8] = blk
+    imgs.append(np.clip(base, 0, 255).astype(np.uint8))
+    imgs.append((rng.integers(0, 2, (96, 96)) * 255).astype(np.uint8))
+    imgs.append(np.kron(rng.integers(0, 2, (12, 12)), np.ones((8, 8), np.int64)).astype(np.uint8) * 255)
+    imgs.append(rng.integers(0, 256, (64, 64)).astype(np.uint8))
+    imgs.append(np.clip(rng.normal(128, 90, (128, 128)), 0, 255).astype(np.uint8))
+    for q in (1, 10, 50, 90, 99):
+        streams = []
+        for im in imgs:
+            try:
+                streams.append(O.compress(im, q))
+            except O.OracleError:
+                pass
+        a = tic.decompress_batch(streams)
+        b = tic.decompress_batch(streams, exact_only=True)
+        for i, s in enumerate(streams):
+            want = O.decompress(s)
+            _same(a[i], want, f"q{q} image {i}")
+            _same(b[i], want, f"q{q} image {i} (exact only)")
 
 
 def test_flat_and_periodic_streams_synchronise(tic):

@@ -326,13 +326,13 @@ class Encoder:
             raise TicStreamError(msg, status)
         raise TicError(rc, msg)
 
-    def decompress(self, data, strict=True, accept_be_flag=False):
+    def decompress(self, data, strict=True, accept_be_flag=False, exact_only=False):
         """tinyimgcodec.codec.decompress (codec.py:167-189) for one stream in host memory."""
         height, width, _, _ = parse_header(data)
         buf = np.frombuffer(bytes(data), dtype=np.uint8)
         out = np.empty((height, width), dtype=np.uint8)
         status = ctypes.c_int32(0)
-        flags = _lib.TIC_DFLAG_ACCEPT_BE_FLAG if accept_be_flag else 0
+        flags = (_lib.TIC_DFLAG_ACCEPT_BE_FLAG if accept_be_flag else 0) | (_lib.TIC_DFLAG_EXACT_ONLY if exact_only else 0)
         with self._lock:
             rc = self.lib.tic_decompress_host(self.handle, buf.ctypes.data, buf.size, flags, out.ctypes.data,
                                               out.size, ctypes.byref(status))
@@ -341,7 +341,7 @@ class Encoder:
         return out
 
     def decode_batch_device(self, d_streams, sizes, heights, widths, pixels=None, stream=None,
-                            accept_be_flag=False, strict=True):
+                            accept_be_flag=False, strict=True, exact_only=False):
         """Decode streams resident in HBM.  `d_streams`: list of CUDA uint8 tensors (each 4-byte aligned), or
         one CUDA uint8 tensor plus `sizes` and byte offsets given as d_streams=(tensor, offsets).  Returns the
         CUDA uint8 (H, W) images (a list of views of one pixel buffer, or one (N, H, W) view when all shapes are
@@ -372,7 +372,8 @@ class Encoder:
             out_ptrs = np.uint64(pixels.data_ptr()) + px_off[:-1].astype(np.uint64)
             d_status = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
             stream = stream or torch.cuda.current_stream(dev)
-            flags = _lib.TIC_DFLAG_ACCEPT_BE_FLAG if accept_be_flag else 0
+            flags = (_lib.TIC_DFLAG_ACCEPT_BE_FLAG if accept_be_flag else 0) | \
+                    (_lib.TIC_DFLAG_EXACT_ONLY if exact_only else 0)
             if n == 0:
                 return [], np.zeros(0, dtype=np.int32)
             with self._lock:
@@ -393,7 +394,7 @@ class Encoder:
                       for i in range(n)]
         return images, status
 
-    def decompress_batch(self, streams, strict=True, accept_be_flag=False):
+    def decompress_batch(self, streams, strict=True, accept_be_flag=False, exact_only=False):
         """decompress() for a list of `bytes`: one pinned H2D copy of all streams, one decode, one D2H copy of all
         pixels.  Returns a list of uint8 (H, W) arrays."""
         import torch
@@ -410,7 +411,7 @@ class Encoder:
                 h_np[o: o + len(s)] = np.frombuffer(s, dtype=np.uint8)
             d_buf = h_buf.to(dev, non_blocking=True)
             imgs, _ = self.decode_batch_device((d_buf, offs[:-1]), sizes, [h[0] for h in hdrs], [h[1] for h in hdrs],
-                                               strict=strict, accept_be_flag=accept_be_flag)
+                                               strict=strict, accept_be_flag=accept_be_flag, exact_only=exact_only)
             return [im.cpu().numpy() for im in imgs]
 
     def decode(self, data):
@@ -442,11 +443,11 @@ class Encoder:
             return d_px[: height * width].cpu().numpy().reshape(height, width)
 
     def decode_stats(self):
-        arr = (ctypes.c_int64 * 8)()
+        arr = (ctypes.c_int64 * 12)()
         self.lib.tic_decode_stats(self.handle, arr)
         return {"launches": arr[0], "subsequences": arr[1], "sync_rounds": arr[2], "blocks": arr[3],
                 "sync_ms": arr[4] * 1e-6, "scan_ms": arr[5] * 1e-6, "scatter_ms": arr[6] * 1e-6,
-                "idct_ms": arr[7] * 1e-6}
+                "idct_ms": arr[7] * 1e-6, "exact_blocks": arr[8]}
 
     def stats(self):
         arr = (ctypes.c_int64 * 8)()
@@ -504,9 +505,9 @@ def encode(image, quality=50, device=None):
     return get_encoder(device).encode(image, quality)
 
 
-def decompress(data, device=None, strict=True, accept_be_flag=False):
+def decompress(data, device=None, strict=True, accept_be_flag=False, exact_only=False):
     """Drop-in for tinyimgcodec.codec.decompress (codec.py:167-189)."""
-    return get_encoder(device).decompress(data, strict=strict, accept_be_flag=accept_be_flag)
+    return get_encoder(device).decompress(data, strict=strict, accept_be_flag=accept_be_flag, exact_only=exact_only)
 
 
 def decode(data, device=None):
@@ -514,9 +515,10 @@ def decode(data, device=None):
     return get_encoder(device).decode(data)
 
 
-def decompress_batch(streams, device=None, strict=True, accept_be_flag=False):
+def decompress_batch(streams, device=None, strict=True, accept_be_flag=False, exact_only=False):
     """decompress() for a list of streams in one launch sequence."""
-    return get_encoder(device).decompress_batch(streams, strict=strict, accept_be_flag=accept_be_flag)
+    return get_encoder(device).decompress_batch(streams, strict=strict, accept_be_flag=accept_be_flag,
+                                                exact_only=exact_only)
 
 
 def compress_c(image, qfactor="med", device=None):

@@ -334,7 +334,7 @@ __device__ __forceinline__ int find_owner_cta(const long long* __restrict__ firs
 // ---------------------------------------------------------------------------------------------------
 // The multiplier table of block_quantize(inverse=True) (utils.py:48-52) — for mode 2 the table of quality 50
 // (codec.py:62) and 2**quality (codec.py:61).  Returns status bits.
-__device__ inline uint32_t fill_mul(DecImage& im, double* __restrict__ m) {
+__device__ inline uint32_t fill_mul(DecImage& im, double* __restrict__ m, float* __restrict__ mf) {
     uint32_t q = im.quality;
     if (im.mode == MODE_SCALED) {
         if (q > 1000) return TIC_DSTATUS_QUALITY;
@@ -349,6 +349,8 @@ __device__ inline uint32_t fill_mul(DecImage& im, double* __restrict__ m) {
         long long factor = 200 - 2 * (long long)q;
         for (int k = 0; k < 64; k++) m[k] = __ddiv_rn((double)((long long)c_qbase[k] * factor), 100.0);
     }
+    // the fast pass's single-precision multiplier: one rounding of the whole factor (dec_idct_fast_kernel)
+    for (int k = 0; k < 64; k++) mf[k] = (float)(im.mode == MODE_SCALED ? m[k] * im.two_q / d_ann[k] : m[k]);
     return 0;
 }
 
@@ -360,7 +362,7 @@ __device__ inline uint32_t get_bits(const BitSrc& s, long long& p, int n) {   //
 
 __global__ void __launch_bounds__(32) dec_setup_kernel(DecImage* __restrict__ imgs, int n_images, uint32_t flags,
                                                        DecTables* __restrict__ tabs, double* __restrict__ mul,
-                                                       uint32_t* __restrict__ E, int* __restrict__ status,
+                                                       float* __restrict__ mulf, uint32_t* __restrict__ E, int* __restrict__ status,
                                                        int* __restrict__ summary) {
     __shared__ DecTables sh;
     __shared__ int sh_build;
@@ -389,7 +391,7 @@ __global__ void __launch_bounds__(32) dec_setup_kernel(DecImage* __restrict__ im
             if ((flags & TIC_DFLAG_ACCEPT_BE_FLAG) && f == 0x00000080u) f = 0x80000000u;
             if (f & 0x80000000u) im.mode = MODE_TABLES;
             else if (f & 0x40000000u) im.mode = MODE_SCALED;
-            st |= fill_mul(im, mul + (size_t)i * 64);
+            st |= fill_mul(im, mul + (size_t)i * 64, mulf + (size_t)i * 64);
         }
         if (st == 0 && im.mode == MODE_TABLES) {
             long long p = 128;
@@ -823,27 +825,159 @@ __device__ __forceinline__ void idct8_exact(double& x0, double& x1, double& x2, 
     x7 = s7;
 }
 
-// 8 lanes per 8x8 block (4 blocks per warp, kIdctBlocks per CTA): lane t dequantises row t of the coefficients,
-// the block goes through a padded shared-memory tile, lane t transforms column t, back through the tile,
-// lane t transforms row t and stores its 8 pixels.  Two 8-point transforms of straight-line float64 code per
-// thread instead of sixteen: 50 registers instead of 162 and no instruction-cache misses (profiles/r1k_*).
+// ---------------------------------------------------------------------------------------------------
+// Phase 5a, the fast pass: one thread per block, FP32.  Pixels are trunc(clip(X + 128)) of the reference's float64
+// result X, so an FP32 approximation Y gives the same pixel whenever no integer lies between Y + 128 and X + 128.
+// Y is the separable transform written as 4-term FMA dot products (even / odd halves), for which the classical
+// bound holds: with u = 2^-24, S = sum |dequantised coefficients| and all |cosine factors| <= 0.4904,
+//     |Y - X*| <= u S (9 * 0.2405 + 11.5 * 0.2405) = 4.93 u S = 2.94e-7 S          (X* = the exact real transform)
+// (per pass: gamma_8 for the accumulation, u for the rounded constant, 2.5 u for the FP32 dequantised input),
+// |X - X*| < 1e-11 for the float64 chain, and forming Y + 128 in FP32 adds at most 3.1e-5 below 512.  A pixel whose
+// FP32 value is further than delta = 6e-7 S + 4e-5 (twice the bound) from every integer is therefore final; a block
+// with any pixel inside the band goes to the exact float64 kernel through a work list (dec_idct_kernel below, which
+// with TIC_DFLAG_EXACT_ONLY transforms every block — tests compare the two paths bit for bit on whole batches).
+// Blocks with no AC coefficient at all (flat areas — where DC * 16 / 8 lands on an integer every time) are settled
+// here exactly: ducc0's operation sequence on (T, 0, ..., 0) collapses to two multiplications by sqrt2 and two
+// exact scalings by 0.25 per pass.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void idct8_fast(float& x0, float& x1, float& x2, float& x3, float& x4, float& x5, float& x6,
+                                           float& x7) {
+    // c(u) cos((2y+1) u pi / 16), c(0) = sqrt(1/8), c(u > 0) = 1/2: even columns u = 0,2,4,6 and odd u = 1,3,5,7
+    const float A = 0.35355339059327379f, B = 0.46193976625564337f, C = 0.19134171618254489f;
+    const float P = 0.49039264020161522f, Q = 0.41573480615127262f, R = 0.27778511650980111f, T = 0.09754516100806413f;
+    const float e0 = fmaf(C, x6, fmaf(A, x4, fmaf(B, x2, A * x0)));
+    const float e1 = fmaf(-B, x6, fmaf(-A, x4, fmaf(C, x2, A * x0)));
+    const float e2 = fmaf(B, x6, fmaf(-A, x4, fmaf(-C, x2, A * x0)));
+    const float e3 = fmaf(-C, x6, fmaf(A, x4, fmaf(-B, x2, A * x0)));
+    const float o0 = fmaf(T, x7, fmaf(R, x5, fmaf(Q, x3, P * x1)));
+    const float o1 = fmaf(-R, x7, fmaf(-P, x5, fmaf(-T, x3, Q * x1)));
+    const float o2 = fmaf(Q, x7, fmaf(T, x5, fmaf(-P, x3, R * x1)));
+    const float o3 = fmaf(-P, x7, fmaf(Q, x5, fmaf(-R, x3, T * x1)));
+    x0 = e0 + o0; x7 = e0 - o0;
+    x1 = e1 + o1; x6 = e1 - o1;
+    x2 = e2 + o2; x5 = e2 - o2;
+    x3 = e3 + o3; x4 = e3 - o3;
+}
+
+__device__ __forceinline__ void store_pixel_row(const DecImage& im, int y, int x0, uint32_t lo, uint32_t hi) {
+    if (y >= im.height) return;
+    uint8_t* row = im.pixels + (size_t)y * (size_t)im.width + x0;
+    if (x0 + 8 <= im.width && (((uintptr_t)im.pixels | (uintptr_t)im.width) & 7u) == 0) {
+        *reinterpret_cast<uint2*>(row) = make_uint2(lo, hi);
+    } else {
+#pragma unroll
+        for (int v = 0; v < 8; v++)
+            if (x0 + v < im.width) row[v] = (uint8_t)((v < 4 ? lo >> (8 * v) : hi >> (8 * (v - 4))) & 0xffu);
+    }
+}
+
+__global__ void __launch_bounds__(128) dec_idct_fast_kernel(const DecImage* __restrict__ imgs,
+                                                            const long long* __restrict__ blk_first, int n_images,
+                                                            long long total_blocks, const int16_t* __restrict__ coef,
+                                                            const double* __restrict__ mul, const float* __restrict__ mulf,
+                                                            const int* __restrict__ ndec, long long* __restrict__ list,
+                                                            int* __restrict__ list_count) {
+    const long long gb = (long long)blockIdx.x * 128 + threadIdx.x;
+    int idx = find_owner_cta(blk_first, n_images, (long long)blockIdx.x * 128, gb, total_blocks);   // barrier inside
+    if (gb >= total_blocks) return;
+    const DecImage& im = imgs[idx];
+    if (im.skip_pixels) return;
+    const int b = (int)(gb - im.blk_first);
+    const int by = b / im.bw, bx = b - by * im.bw;
+    const int y0 = by * 8, x0 = bx * 8;
+
+    uint32_t w[32];
+    {
+        const bool have = b < __ldg(ndec + idx);   // a block the stream never reached reads as zero
+        const uint4* cp = reinterpret_cast<const uint4*>(coef + gb * 64);
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            uint4 q = have ? __ldg(cp + u) : make_uint4(0u, 0u, 0u, 0u);
+            w[u * 4] = q.x; w[u * 4 + 1] = q.y; w[u * 4 + 2] = q.z; w[u * 4 + 3] = q.w;
+        }
+    }
+    uint32_t ac = w[0] & 0xffff0000u;
+#pragma unroll
+    for (int i = 1; i < 32; i++) ac |= w[i];
+    if (ac == 0) {
+        // DC only: idct8_exact on (T, 0, ..., 0) gives 0.25 RN(T sqrt2) everywhere; twice
+        const double SQ2 = 0x1.6a09e667f3bcdp+0;
+        double t = (double)(int)(short)(w[0] & 0xffffu);
+        if (im.mode == MODE_SCALED) t = DM(__ddiv_rn(t, d_ann[0]), im.two_q);
+        t = DM(t, __ldg(mul + (size_t)idx * 64));
+        t = DM(0.25, DM(t, SQ2));
+        t = DM(0.25, DM(t, SQ2));
+        const uint32_t px = (uint32_t)min(max(__double2int_rz(DA(t, 128.0)), 0), 255) * 0x01010101u;
+#pragma unroll
+        for (int u = 0; u < 8; u++) store_pixel_row(im, y0 + u, x0, px, px);
+        return;
+    }
+    const float* __restrict__ fm = mulf + (size_t)idx * 64;
+    float t[64];
+    float S = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 64; k++) {
+        const int c = (int)(short)((w[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
+        t[k] = (float)c * __ldg(fm + k);
+        S += fabsf(t[k]);
+    }
+#pragma unroll
+    for (int v = 0; v < 8; v++)   // down the columns
+        idct8_fast(t[v], t[8 + v], t[16 + v], t[24 + v], t[32 + v], t[40 + v], t[48 + v], t[56 + v]);
+    const float delta = fmaf(6e-7f, S, 4e-5f);
+    bool flag = !(delta < 0.25f);   // also catches magnitudes where the rounding trick below stops being valid
+    uint32_t lo[8], hi[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {   // along the rows
+        idct8_fast(t[u * 8], t[u * 8 + 1], t[u * 8 + 2], t[u * 8 + 3], t[u * 8 + 4], t[u * 8 + 5], t[u * 8 + 6], t[u * 8 + 7]);
+        lo[u] = 0; hi[u] = 0;
+#pragma unroll
+        for (int v = 0; v < 8; v++) {
+            const float W = t[u * 8 + v] + 128.0f;
+            const float r = W - ((W + 12582912.0f) - 12582912.0f);   // W - rint(W), exact below 2^22
+            flag |= fabsf(r) <= delta;
+            const uint32_t px = (uint32_t)min(max(__float2int_rz(W), 0), 255);
+            if (v < 4) lo[u] |= px << (8 * v); else hi[u] |= px << (8 * (v - 4));
+        }
+    }
+    if (flag) {
+        list[atomicAdd(list_count, 1)] = gb;
+        return;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) store_pixel_row(im, y0 + u, x0, lo[u], hi[u]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Phase 5b, the exact pass.  8 lanes per 8x8 block (4 blocks per warp, kIdctBlocks per CTA): lane t dequantises
+// row t of the coefficients, the block goes through a padded shared-memory tile, lane t transforms column t, back
+// through the tile, lane t transforms row t and stores its 8 pixels.  `list` given: only the blocks the fast pass
+// listed (their number is read from the device); otherwise every block.
+// ---------------------------------------------------------------------------------------------------
 constexpr int kIdctBlocks = 32;   // blocks in flight per CTA (8 lanes each)
 constexpr int kIdctIters = 16;    // consecutive groups of kIdctBlocks per CTA: one owner search per 512 blocks
 
 __global__ void __launch_bounds__(kIdctBlocks * 8) dec_idct_kernel(const DecImage* __restrict__ imgs,
                                                                    const long long* __restrict__ blk_first, int n_images,
                                                                    long long total_blocks, const int16_t* __restrict__ coef,
-                                                                   const double* __restrict__ mul, const int* __restrict__ ndec) {
+                                                                   const double* __restrict__ mul, const int* __restrict__ ndec,
+                                                                   const long long* __restrict__ list,
+                                                                   const int* __restrict__ list_count) {
     __shared__ double tile[kIdctBlocks][8][9];   // 9: column and row accesses both conflict-free
+    const bool listed = list != nullptr;
+    const long long total = listed ? (long long)*list_count : total_blocks;
     const int lb = threadIdx.x >> 3, t = threadIdx.x & 7;
     const long long cta0 = (long long)blockIdx.x * (kIdctBlocks * kIdctIters);
-    int idx = find_owner_cta(blk_first, n_images, cta0, cta0 + lb, total_blocks);   // barrier inside
+    if (cta0 >= total) return;
+    int idx = listed ? 0 : find_owner_cta(blk_first, n_images, cta0, cta0 + lb, total);   // barrier inside
     const unsigned group = 0xffu << ((threadIdx.x & 31) & ~7);   // the 8 lanes of this block
 #pragma unroll 1
     for (int iter = 0; iter < kIdctIters; iter++) {
-        const long long gb = cta0 + (long long)iter * kIdctBlocks + lb;
-        if (gb >= total_blocks) return;   // whole 8-lane groups leave together; only __syncwarp(group) follows
-        while (idx + 1 < n_images && __ldg(blk_first + idx + 1) <= gb) idx++;
+        const long long li = cta0 + (long long)iter * kIdctBlocks + lb;
+        if (li >= total) return;   // whole 8-lane groups leave together; only __syncwarp(group) follows
+        const long long gb = listed ? list[li] : li;
+        if (listed) idx = find_owner(blk_first, n_images, gb);
+        else while (idx + 1 < n_images && __ldg(blk_first + idx + 1) <= gb) idx++;
         const DecImage& im = imgs[idx];
         if (im.skip_pixels) continue;
         const int b = (int)(gb - im.blk_first);
@@ -889,17 +1023,7 @@ __global__ void __launch_bounds__(kIdctBlocks * 8) dec_idct_kernel(const DecImag
             uint32_t px = (uint32_t)min(max(pi, 0), 255);
             if (v < 4) lo |= px << (8 * v); else hi |= px << (8 * (v - 4));
         }
-        const int y = by * 8 + t, x0 = bx * 8;
-        if (y < im.height) {
-            uint8_t* row = im.pixels + (size_t)y * (size_t)im.width + x0;
-            if (x0 + 8 <= im.width && (((uintptr_t)im.pixels | (uintptr_t)im.width) & 7u) == 0) {
-                *reinterpret_cast<uint2*>(row) = make_uint2(lo, hi);
-            } else {
-#pragma unroll
-                for (int v = 0; v < 8; v++)
-                    if (x0 + v < im.width) row[v] = (uint8_t)((v < 4 ? lo >> (8 * v) : hi >> (8 * (v - 4))) & 0xffu);
-            }
-        }
+        store_pixel_row(im, by * 8 + t, bx * 8, lo, hi);
     }
 }
 
@@ -907,12 +1031,12 @@ __global__ void __launch_bounds__(kIdctBlocks * 8) dec_idct_kernel(const DecImag
 // decode() from coefficient arrays (codec.py:46-70): dc[nblk] differences, ac[nblk][63] in zigzag order.
 // The DC cumsum (codec.py:53) reuses dec_scan_kernel with one "subsequence" per block.
 // ---------------------------------------------------------------------------------------------------
-__global__ void dec_coeffs_prep_kernel(DecImage* __restrict__ im, double* __restrict__ mul,
+__global__ void dec_coeffs_prep_kernel(DecImage* __restrict__ im, double* __restrict__ mul, float* __restrict__ mulf,
                                        const int32_t* __restrict__ dc, int2* __restrict__ ND, int nblk,
                                        int* __restrict__ summary) {
     int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b == 0) {
-        uint32_t st = fill_mul(*im, mul);
+        uint32_t st = fill_mul(*im, mul, mulf);
         if (st) { im->skip_pixels = 1; atomicOr(summary, (int)st); }
     }
     if (b < nblk) ND[b] = make_int2(1, dc[b]);
@@ -936,11 +1060,11 @@ __global__ void dec_coeffs_pack_kernel(const int32_t* __restrict__ dc, const int
 struct DecWs {
     DecImage* d_imgs = nullptr; DecImage* h_imgs = nullptr; size_t imgs_cap = 0;
     long long* d_first = nullptr; long long* h_first = nullptr;   // sub_first[n+1] then blk_first[n+1]
-    DecTables* d_tabs = nullptr; double* d_mul = nullptr;
+    DecTables* d_tabs = nullptr; double* d_mul = nullptr; float* d_mulf = nullptr;
     DecTables* d_deftab = nullptr;
     uint32_t* d_E = nullptr; uint32_t* d_U = nullptr; int2* d_ND = nullptr; int2* d_NB = nullptr; size_t subs_cap = 0;
-    int16_t* d_coef = nullptr; size_t blocks_cap = 0;
-    int* d_flags = nullptr;   // [0] changed, [1] summary
+    int16_t* d_coef = nullptr; long long* d_list = nullptr; size_t blocks_cap = 0;   // coefficients; exact-pass work list
+    int* d_flags = nullptr;   // [0] changed, [1] summary, [2] blocks listed for the exact IDCT pass
     int* h_flags = nullptr;   // pinned
     int* d_status_own = nullptr; size_t status_cap = 0;
     int* d_ndec = nullptr;    // per image: blocks whose coefficients were written (the rest read as zero)
@@ -950,7 +1074,7 @@ struct DecWs {
     uint8_t* d_stream = nullptr; size_t stream_cap = 0;
     uint8_t* d_px = nullptr; size_t px_cap = 0;
     cudaEvent_t ev[6] = {};
-    long long stats[8] = {};
+    long long stats[12] = {};
     bool pending_times = false;
 };
 
@@ -977,7 +1101,7 @@ void tic_internal_dec_release(void* p) {
     DecWs* w = static_cast<DecWs*>(p);
     if (!w) return;
     cudaFree(w->d_imgs); cudaFreeHost(w->h_imgs); cudaFree(w->d_first); cudaFreeHost(w->h_first);
-    cudaFree(w->d_tabs); cudaFree(w->d_mul); cudaFree(w->d_deftab); cudaFree(w->d_E); cudaFree(w->d_U);
+    cudaFree(w->d_tabs); cudaFree(w->d_mul); cudaFree(w->d_mulf); cudaFree(w->d_list); cudaFree(w->d_deftab); cudaFree(w->d_E); cudaFree(w->d_U);
     cudaFree(w->d_ND); cudaFree(w->d_NB); cudaFree(w->d_coef); cudaFree(w->d_flags); cudaFreeHost(w->h_flags);
     cudaFree(w->d_status_own); cudaFree(w->d_stream); cudaFree(w->d_px); cudaFree(w->d_slices); cudaFree(w->d_slice_tot); cudaFree(w->d_ndec);
     for (auto& e : w->ev) if (e) cudaEventDestroy(e);
@@ -1001,8 +1125,8 @@ int tic_parse_header(const uint8_t* data, int64_t nbytes, int32_t* height, int32
 
 static int ensure_base(tic_handle h, DecWs* w) {
     if (w->d_flags) return TIC_OK;
-    TICD_CUDA(h, cudaMalloc(&w->d_flags, 2 * sizeof(int)));
-    TICD_CUDA(h, cudaMallocHost(&w->h_flags, 2 * sizeof(int)));
+    TICD_CUDA(h, cudaMalloc(&w->d_flags, 4 * sizeof(int)));
+    TICD_CUDA(h, cudaMallocHost(&w->h_flags, 4 * sizeof(int)));
     for (auto& e : w->ev) TICD_CUDA(h, cudaEventCreate(&e));
     DecTables* def = new DecTables();
     build_default_tables(*def);
@@ -1047,6 +1171,28 @@ static int launch_scan(tic_handle h, DecWs* w, int* status, cudaStream_t stream,
     return TIC_OK;
 }
 
+// Phase 5 on `stream`: the FP32 pass with its work list for the exact pass, or (TIC_DFLAG_EXACT_ONLY) the exact
+// float64 pass over every block.
+static int launch_idct(tic_handle h, DecWs* w, const long long* d_blk_first, int n_images, long long blocks, uint32_t flags,
+                       cudaStream_t stream, long long& launches) {
+    if (blocks == 0) return TIC_OK;
+    const unsigned exact_grid = (unsigned)((blocks + kIdctBlocks * kIdctIters - 1) / (kIdctBlocks * kIdctIters));
+    if (flags & TIC_DFLAG_EXACT_ONLY) {
+        dec_idct_kernel<<<exact_grid, kIdctBlocks * 8, 0, stream>>>(w->d_imgs, d_blk_first, n_images, blocks, w->d_coef, w->d_mul,
+                                                                    w->d_ndec, nullptr, nullptr);
+        launches++;
+    } else {
+        dec_idct_fast_kernel<<<(unsigned)((blocks + 127) / 128), 128, 0, stream>>>(w->d_imgs, d_blk_first, n_images, blocks,
+                                                                                 w->d_coef, w->d_mul, w->d_mulf, w->d_ndec,
+                                                                                 w->d_list, w->d_flags + 2);
+        dec_idct_kernel<<<exact_grid, kIdctBlocks * 8, 0, stream>>>(w->d_imgs, d_blk_first, n_images, blocks, w->d_coef, w->d_mul,
+                                                                    w->d_ndec, w->d_list, w->d_flags + 2);
+        launches += 2;
+    }
+    TICD_CUDA(h, cudaGetLastError());
+    return TIC_OK;
+}
+
 static void push_slices(std::vector<ScanSlice>& v, int img, long long nsubs) {
     int j = 0;
     for (long long f = 0; f < nsubs; f += kSliceSubs, j++) {
@@ -1069,8 +1215,8 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
     memset(w->stats, 0, sizeof w->stats);
     w->pending_times = false;
     if (int rc = ensure_base(h, w)) return rc;
-    w->h_flags[1] = 0;
-    TICD_CUDA(h, cudaMemsetAsync(w->d_flags, 0, 2 * sizeof(int), stream));
+    w->h_flags[1] = 0; w->h_flags[2] = 0;
+    TICD_CUDA(h, cudaMemsetAsync(w->d_flags, 0, 4 * sizeof(int), stream));
     if (n_images == 0) return TIC_OK;
     const size_t n = (size_t)n_images;
     if (n > w->imgs_cap) {
@@ -1081,6 +1227,7 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
         if (int rc = grow(h, w->d_first, 2 * (cap + 1))) return rc;
         if (int rc = grow(h, w->d_tabs, cap)) return rc;
         if (int rc = grow(h, w->d_mul, cap * 64)) return rc;
+        if (int rc = grow(h, w->d_mulf, cap * 64)) return rc;
         if (int rc = grow(h, w->d_status_own, cap)) return rc;
         if (int rc = grow(h, w->d_ndec, cap)) return rc;
         TICD_CUDA(h, cudaMallocHost(&w->h_imgs, cap * sizeof(DecImage)));
@@ -1141,6 +1288,7 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
         size_t cap = (size_t)blocks + (size_t)blocks / 8 + 1024;
         w->blocks_cap = 0;
         if (int rc = grow(h, w->d_coef, cap * 64)) return rc;
+        if (int rc = grow(h, w->d_list, cap)) return rc;
         w->blocks_cap = cap;
     }
     int* status = d_status ? d_status : w->d_status_own;
@@ -1157,7 +1305,7 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
     TICD_CUDA(h, cudaEventRecord(w->ev[0], stream));
     TICD_CUDA(h, cudaMemsetAsync(w->d_ndec, 0, n * sizeof(int), stream));   // the coefficient buffer itself needs no fill
     long long launches = 0;
-    dec_setup_kernel<<<n_images, 32, 0, stream>>>(w->d_imgs, n_images, flags, w->d_tabs, w->d_mul, w->d_E, status,
+    dec_setup_kernel<<<n_images, 32, 0, stream>>>(w->d_imgs, n_images, flags, w->d_tabs, w->d_mul, w->d_mulf, w->d_E, status,
                                                   w->d_flags + 1);
     launches++;
     TICD_CUDA(h, cudaGetLastError());
@@ -1193,15 +1341,9 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
         TICD_CUDA(h, cudaEventRecord(w->ev[3], stream));
     }
     TICD_CUDA(h, cudaEventRecord(w->ev[4], stream));
-    if (blocks) {
-        unsigned grid = (unsigned)((blocks + kIdctBlocks * kIdctIters - 1) / (kIdctBlocks * kIdctIters));
-        dec_idct_kernel<<<grid, kIdctBlocks * 8, 0, stream>>>(w->d_imgs, d_blk_first, n_images, blocks, w->d_coef, w->d_mul,
-                                                              w->d_ndec);
-        launches++;
-        TICD_CUDA(h, cudaGetLastError());
-    }
+    if (int rc = launch_idct(h, w, d_blk_first, n_images, blocks, flags, stream, launches)) return rc;
     TICD_CUDA(h, cudaEventRecord(w->ev[5], stream));
-    TICD_CUDA(h, cudaMemcpyAsync(w->h_flags + 1, w->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    TICD_CUDA(h, cudaMemcpyAsync(w->h_flags + 1, w->d_flags + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
     w->stats[0] = launches;
     w->stats[1] = subs;
     w->stats[2] = rounds;
@@ -1219,8 +1361,8 @@ int tic_decode_coeffs(tic_handle h, const int32_t* d_dc, const int32_t* d_ac, in
     if (int rc = ensure_base(h, w)) return rc;
     memset(w->stats, 0, sizeof w->stats);
     w->pending_times = false;
-    w->h_flags[1] = 0;
-    TICD_CUDA(h, cudaMemsetAsync(w->d_flags, 0, 2 * sizeof(int), stream));
+    w->h_flags[1] = 0; w->h_flags[2] = 0;
+    TICD_CUDA(h, cudaMemsetAsync(w->d_flags, 0, 4 * sizeof(int), stream));
     long long nblk = (height == 0 || width == 0) ? 0 : (long long)((height + 7) / 8) * ((width + 7) / 8);
     if (nblk == 0) return TIC_OK;
     if (nblk > 0x7fffffffLL || !d_dc || !d_ac || !d_pixels) return TIC_E_INVALID;
@@ -1230,6 +1372,7 @@ int tic_decode_coeffs(tic_handle h, const int32_t* d_dc, const int32_t* d_ac, in
         if (int rc = grow(h, w->d_first, 2 * (cap + 1))) return rc;
         if (int rc = grow(h, w->d_tabs, cap)) return rc;
         if (int rc = grow(h, w->d_mul, cap * 64)) return rc;
+        if (int rc = grow(h, w->d_mulf, cap * 64)) return rc;
         if (int rc = grow(h, w->d_status_own, cap)) return rc;
         if (int rc = grow(h, w->d_ndec, cap)) return rc;
         TICD_CUDA(h, cudaMallocHost(&w->h_imgs, cap * sizeof(DecImage)));
@@ -1249,6 +1392,7 @@ int tic_decode_coeffs(tic_handle h, const int32_t* d_dc, const int32_t* d_ac, in
         size_t cap = (size_t)nblk + 1024;
         w->blocks_cap = 0;
         if (int rc = grow(h, w->d_coef, cap * 64)) return rc;
+        if (int rc = grow(h, w->d_list, cap)) return rc;
         w->blocks_cap = cap;
     }
     DecImage& im = w->h_imgs[0];
@@ -1265,16 +1409,14 @@ int tic_decode_coeffs(tic_handle h, const int32_t* d_dc, const int32_t* d_ac, in
     TICD_CUDA(h, cudaMemsetAsync(w->d_status_own, 0, sizeof(int), stream));
     TICD_CUDA(h, cudaMemsetAsync(w->d_ndec, 0, sizeof(int), stream));
     unsigned g1 = (unsigned)((nblk + 255) / 256), g2 = (unsigned)((nblk * 64 + 255) / 256);
-    dec_coeffs_prep_kernel<<<g1, 256, 0, stream>>>(w->d_imgs, w->d_mul, d_dc, w->d_ND, (int)nblk, w->d_flags + 1);
+    dec_coeffs_prep_kernel<<<g1, 256, 0, stream>>>(w->d_imgs, w->d_mul, w->d_mulf, d_dc, w->d_ND, (int)nblk, w->d_flags + 1);
     long long launches = 3;
     w->h_slices.clear();
     push_slices(w->h_slices, 0, nblk);
     if (int rc = launch_scan(h, w, w->d_status_own, stream, launches, nullptr, nullptr)) return rc;
     dec_coeffs_pack_kernel<<<g2, 256, 0, stream>>>(d_dc, d_ac, w->d_NB, w->d_coef, (int)nblk, w->d_flags + 1);
-    dec_idct_kernel<<<(unsigned)((nblk + kIdctBlocks * kIdctIters - 1) / (kIdctBlocks * kIdctIters)), kIdctBlocks * 8, 0, stream>>>(w->d_imgs, w->d_first, 1, nblk, w->d_coef,
-                                                                        w->d_mul, w->d_ndec);
-    TICD_CUDA(h, cudaGetLastError());
-    TICD_CUDA(h, cudaMemcpyAsync(w->h_flags + 1, w->d_flags + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    if (int rc = launch_idct(h, w, w->d_first, 1, nblk, 0, stream, launches)) return rc;
+    TICD_CUDA(h, cudaMemcpyAsync(w->h_flags + 1, w->d_flags + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
     w->stats[0] = launches;
     w->stats[3] = nblk;
     return TIC_OK;
@@ -1301,10 +1443,11 @@ int tic_decode_finish(tic_handle h, void* stream_v) {
     return TIC_OK;
 }
 
-int tic_decode_stats(tic_handle h, int64_t stats[8]) {
+int tic_decode_stats(tic_handle h, int64_t stats[12]) {
     if (!h || !stats) return TIC_E_INVALID;
     DecWs* w = get_ws(h);
-    for (int i = 0; i < 8; i++) stats[i] = w->stats[i];
+    w->stats[8] = w->h_flags ? w->h_flags[2] : 0;
+    for (int i = 0; i < 12; i++) stats[i] = w->stats[i];
     return TIC_OK;
 }
 
