@@ -840,6 +840,50 @@ __device__ __forceinline__ void idct8_exact(double& x0, double& x1, double& x2, 
 // here exactly: ducc0's operation sequence on (T, 0, ..., 0) collapses to two multiplications by sqrt2 and two
 // exact scalings by 0.25 per pass.
 // ---------------------------------------------------------------------------------------------------
+// Two floats in an aligned register pair: the packed FP32 instructions of sm_100 (FADD2 / FMUL2 / FFMA2) do two
+// independent IEEE operations per issue slot — the same roundings as the scalar forms, so the error bound above
+// is unchanged.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float x, float y) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// idct8_fast (below) on two independent 8-point inputs at once
+__device__ __forceinline__ void idct8_fast2(f32x2& x0, f32x2& x1, f32x2& x2, f32x2& x3, f32x2& x4, f32x2& x5, f32x2& x6,
+                                            f32x2& x7) {
+    const f32x2 A = pk2(0.35355339059327379f, 0.35355339059327379f), B = pk2(0.46193976625564337f, 0.46193976625564337f),
+                C = pk2(0.19134171618254489f, 0.19134171618254489f), P = pk2(0.49039264020161522f, 0.49039264020161522f),
+                Q = pk2(0.41573480615127262f, 0.41573480615127262f), R = pk2(0.27778511650980111f, 0.27778511650980111f),
+                T = pk2(0.09754516100806413f, 0.09754516100806413f);
+    const f32x2 nA = pk2(-0.35355339059327379f, -0.35355339059327379f), nB = pk2(-0.46193976625564337f, -0.46193976625564337f),
+                nC = pk2(-0.19134171618254489f, -0.19134171618254489f), nP = pk2(-0.49039264020161522f, -0.49039264020161522f),
+                nR = pk2(-0.27778511650980111f, -0.27778511650980111f), nT = pk2(-0.09754516100806413f, -0.09754516100806413f);
+    const f32x2 a0 = mul2(A, x0);
+    const f32x2 e0 = fma2(C, x6, fma2(A, x4, fma2(B, x2, a0)));
+    const f32x2 e1 = fma2(nB, x6, fma2(nA, x4, fma2(C, x2, a0)));
+    const f32x2 e2 = fma2(B, x6, fma2(nA, x4, fma2(nC, x2, a0)));
+    const f32x2 e3 = fma2(nC, x6, fma2(A, x4, fma2(nB, x2, a0)));
+    const f32x2 o0 = fma2(T, x7, fma2(R, x5, fma2(Q, x3, mul2(P, x1))));
+    const f32x2 o1 = fma2(nR, x7, fma2(nP, x5, fma2(nT, x3, mul2(Q, x1))));
+    const f32x2 o2 = fma2(Q, x7, fma2(T, x5, fma2(nP, x3, mul2(R, x1))));
+    const f32x2 o3 = fma2(nP, x7, fma2(Q, x5, fma2(nR, x3, mul2(T, x1))));
+    x0 = add2(e0, o0); x7 = sub2(e0, o0);
+    x1 = add2(e1, o1); x6 = sub2(e1, o1);
+    x2 = add2(e2, o2); x5 = sub2(e2, o2);
+    x3 = add2(e3, o3); x4 = sub2(e3, o3);
+}
+
 __device__ __forceinline__ void idct8_fast(float& x0, float& x1, float& x2, float& x3, float& x4, float& x5, float& x6,
                                            float& x7) {
     // c(u) cos((2y+1) u pi / 16), c(0) = sqrt(1/8), c(u > 0) = 1/2: even columns u = 0,2,4,6 and odd u = 1,3,5,7
@@ -871,13 +915,27 @@ __device__ __forceinline__ void store_pixel_row(const DecImage& im, int y, int x
     }
 }
 
-__global__ void __launch_bounds__(128) dec_idct_fast_kernel(const DecImage* __restrict__ imgs,
+__global__ void __launch_bounds__(128, 5) dec_idct_fast_kernel(const DecImage* __restrict__ imgs,
                                                             const long long* __restrict__ blk_first, int n_images,
                                                             long long total_blocks, const int16_t* __restrict__ coef,
                                                             const double* __restrict__ mul, const float* __restrict__ mulf,
                                                             const int* __restrict__ ndec, long long* __restrict__ list,
                                                             int* __restrict__ list_count) {
+    // the warp's 32 blocks are 4 KB of consecutive coefficients: fetched with coalesced 16-byte loads into shared
+    // memory (rows padded to 9 x 16 bytes: conflict-free both ways), then every thread takes its own block
+    __shared__ uint4 stage[4][32][9];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long gb = (long long)blockIdx.x * 128 + threadIdx.x;
+    {
+        const long long warp_blk0 = (long long)blockIdx.x * 128 + warp * 32;
+        const uint4* src = reinterpret_cast<const uint4*>(coef) + warp_blk0 * 8;
+        const long long limit = (total_blocks - warp_blk0) * 8;   // 16-byte pieces that exist
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int i = j * 32 + lane;
+            stage[warp][i >> 3][i & 7] = i < limit ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
     int idx = find_owner_cta(blk_first, n_images, (long long)blockIdx.x * 128, gb, total_blocks);   // barrier inside
     if (gb >= total_blocks) return;
     const DecImage& im = imgs[idx];
@@ -889,10 +947,9 @@ __global__ void __launch_bounds__(128) dec_idct_fast_kernel(const DecImage* __re
     uint32_t w[32];
     {
         const bool have = b < __ldg(ndec + idx);   // a block the stream never reached reads as zero
-        const uint4* cp = reinterpret_cast<const uint4*>(coef + gb * 64);
 #pragma unroll
         for (int u = 0; u < 8; u++) {
-            uint4 q = have ? __ldg(cp + u) : make_uint4(0u, 0u, 0u, 0u);
+            uint4 q = have ? stage[warp][lane][u] : make_uint4(0u, 0u, 0u, 0u);
             w[u * 4] = q.x; w[u * 4 + 1] = q.y; w[u * 4 + 2] = q.z; w[u * 4 + 3] = q.w;
         }
     }
@@ -912,34 +969,59 @@ __global__ void __launch_bounds__(128) dec_idct_fast_kernel(const DecImage* __re
         for (int u = 0; u < 8; u++) store_pixel_row(im, y0 + u, x0, px, px);
         return;
     }
-    const float* __restrict__ fm = mulf + (size_t)idx * 64;
-    float t[64];
+    // pairs of horizontally adjacent coefficients — the two int16 of one coefficient word — through the column pass
+    const float2* __restrict__ fm = reinterpret_cast<const float2*>(mulf + (size_t)idx * 64);
+    f32x2 c2[8][4];
     float S = 0.0f;
 #pragma unroll
-    for (int k = 0; k < 64; k++) {
-        const int c = (int)(short)((w[k >> 1] >> ((k & 1) * 16)) & 0xffffu);
-        t[k] = (float)c * __ldg(fm + k);
-        S += fabsf(t[k]);
-    }
+    for (int u = 0; u < 8; u++) {
 #pragma unroll
-    for (int v = 0; v < 8; v++)   // down the columns
-        idct8_fast(t[v], t[8 + v], t[16 + v], t[24 + v], t[32 + v], t[40 + v], t[48 + v], t[56 + v]);
-    const float delta = fmaf(6e-7f, S, 4e-5f);
-    bool flag = !(delta < 0.25f);   // also catches magnitudes where the rounding trick below stops being valid
-    uint32_t lo[8], hi[8];
-#pragma unroll
-    for (int u = 0; u < 8; u++) {   // along the rows
-        idct8_fast(t[u * 8], t[u * 8 + 1], t[u * 8 + 2], t[u * 8 + 3], t[u * 8 + 4], t[u * 8 + 5], t[u * 8 + 6], t[u * 8 + 7]);
-        lo[u] = 0; hi[u] = 0;
-#pragma unroll
-        for (int v = 0; v < 8; v++) {
-            const float W = t[u * 8 + v] + 128.0f;
-            const float r = W - ((W + 12582912.0f) - 12582912.0f);   // W - rint(W), exact below 2^22
-            flag |= fabsf(r) <= delta;
-            const uint32_t px = (uint32_t)min(max(__float2int_rz(W), 0), 255);
-            if (v < 4) lo[u] |= px << (8 * v); else hi[u] |= px << (8 * (v - 4));
+        for (int vp = 0; vp < 4; vp++) {
+            const uint32_t word = w[u * 4 + vp];
+            const float2 m2 = __ldg(fm + u * 4 + vp);
+            const float a = (float)(int)(short)(word & 0xffffu) * m2.x, bb = (float)((int)word >> 16) * m2.y;
+            S += fabsf(a);
+            S += fabsf(bb);
+            c2[u][vp] = pk2(a, bb);
         }
     }
+#pragma unroll
+    for (int vp = 0; vp < 4; vp++)   // down the columns, two columns per instruction
+        idct8_fast2(c2[0][vp], c2[1][vp], c2[2][vp], c2[3][vp], c2[4][vp], c2[5][vp], c2[6][vp], c2[7][vp]);
+    const float delta = fmaf(6e-7f, S, 4e-5f);
+    bool flag = !(delta < 0.25f);   // also catches magnitudes where the rounding trick below stops being valid
+    float rmin = 1.0f;
+    uint32_t lo[8], hi[8];
+    const f32x2 k128 = pk2(128.0f, 128.0f), kmag = pk2(12582912.0f, 12582912.0f);
+#pragma unroll
+    for (int up = 0; up < 4; up++) {   // along the rows, two rows per instruction: re-pair (row 2up, row 2up+1)
+        f32x2 r2[8];
+#pragma unroll
+        for (int vp = 0; vp < 4; vp++) {
+            float a0, a1, b0, b1;
+            upk2(c2[2 * up][vp], a0, a1);
+            upk2(c2[2 * up + 1][vp], b0, b1);
+            r2[2 * vp] = pk2(a0, b0);
+            r2[2 * vp + 1] = pk2(a1, b1);
+        }
+        idct8_fast2(r2[0], r2[1], r2[2], r2[3], r2[4], r2[5], r2[6], r2[7]);
+        uint32_t l0 = 0, h0 = 0, l1 = 0, h1 = 0;
+#pragma unroll
+        for (int v = 0; v < 8; v++) {
+            const f32x2 W2 = add2(r2[v], k128);
+            const f32x2 d2 = sub2(W2, sub2(add2(W2, kmag), kmag));   // W - rint(W), exact below 2^22
+            float W0, W1, d0, d1;
+            upk2(W2, W0, W1);
+            upk2(d2, d0, d1);
+            rmin = fminf(rmin, fminf(fabsf(d0), fabsf(d1)));
+            const uint32_t p0 = (uint32_t)min(max(__float2int_rz(W0), 0), 255);
+            const uint32_t p1 = (uint32_t)min(max(__float2int_rz(W1), 0), 255);
+            if (v < 4) { l0 |= p0 << (8 * v); l1 |= p1 << (8 * v); }
+            else { h0 |= p0 << (8 * (v - 4)); h1 |= p1 << (8 * (v - 4)); }
+        }
+        lo[2 * up] = l0; hi[2 * up] = h0; lo[2 * up + 1] = l1; hi[2 * up + 1] = h1;
+    }
+    flag |= rmin <= delta;
     if (flag) {
         list[atomicAdd(list_count, 1)] = gb;
         return;
