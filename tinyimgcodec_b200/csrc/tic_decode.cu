@@ -21,12 +21,12 @@
 //      subsequence of a stream has a KNOWN entry, so by induction the fixed point is the serial parse;
 //   3. an exclusive scan over the subsequences' block counts and DC-difference sums gives each thread
 //      the index of its first block and the running DC predictor (np.cumsum, codec.py:53);
-//   4. the threads decode once more and scatter the coefficients (int16, raster order) to HBM;
-//   5. one thread per 8x8 block dequantises and runs the inverse DCT in float64, operation for operation
-//      what scipy.fftpack.idct (ducc0) executes, adds 128, clips, truncates — so pixels are
-//      bit-identical to the reference decoder's, including values that land on an integer boundary.
-//
-// FP64 on B200 runs at half the FP32 rate, so unlike the encoder no FP32 fast path is needed here.
+//   4. the threads walk the parse once more, warp-synchronously, and the warp stores every completed block's
+//      coefficients (int16, raster order) with coalesced 128-byte stores;
+//   5. one thread per 8x8 block dequantises and runs the inverse DCT in FP32 with a proven error bound; the
+//      blocks with a pixel too close to an integer for FP32 to decide are transformed again in float64,
+//      operation for operation what scipy.fftpack.idct (ducc0) executes — so pixels are bit-identical to the
+//      reference decoder's, including values that land on an integer boundary.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
