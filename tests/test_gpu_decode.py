@@ -250,3 +250,42 @@ def test_flat_and_periodic_streams_synchronise(tic):
     img = make_case({"kind": "blockalt", "shape": (1024, 1024)})
     s = tic.compress(img, 50)
     _same(tic.decompress(s), O.decompress(s), "blockalt")
+
+
+def test_damaged_and_random_streams_never_crash(tic):
+    """Bit flips, truncations and random bytes behind a valid header (with and without the per-image-table flag):
+    the decoder must come back with a status, a correctly shaped image and an intact GPU — whatever the bits say."""
+    import tinyimgcodec_b200._lib as L
+    rng = np.random.default_rng(2024)
+    img = synthetic_image(96, 136, 5)
+    good = {False: tic.compress(img, 50),
+            True: tic.compress(img, 50, auto_generate_huffman_table=True, le_flag_word=True)}
+    streams = []
+    for auto in (False, True):
+        s = np.frombuffer(good[auto], dtype=np.uint8)
+        for _ in range(40):
+            t = s.copy()
+            for pos in rng.integers(16, len(t), int(rng.integers(1, 6))):
+                t[pos] ^= np.uint8(1 << int(rng.integers(0, 8)))
+            streams.append(t.tobytes())
+        for cut in rng.integers(16, len(s), 10):
+            streams.append(s[: int(cut)].tobytes())
+        for _ in range(20):   # random payload behind the real header
+            t = s.copy()
+            t[16:] = rng.integers(0, 256, len(t) - 16, dtype=np.uint8)
+            streams.append(t.tobytes())
+    hdr = np.frombuffer(good[False], dtype=np.uint8)[:16].copy()
+    for n in (0, 1, 3, 64, 5000):
+        streams.append(hdr.tobytes() + rng.integers(0, 256, n, dtype=np.uint8).tobytes())
+    outs = tic.decompress_batch(streams, strict=False)
+    assert all(o.shape == (96, 136) and o.dtype == np.uint8 for o in outs)
+    flagged = 0
+    for s in streams:
+        try:
+            tic.decompress(s)
+        except tic.TicStreamError as ex:
+            flagged += 1
+            assert ex.status[0] & (L.TIC_DSTATUS_CODE | L.TIC_DSTATUS_TRUNCATED | L.TIC_DSTATUS_TABLE | L.TIC_DSTATUS_RANGE)
+    assert flagged > len(streams) // 2
+    # and the GPU still decodes a good stream correctly afterwards
+    _same(tic.decompress(good[False]), O.decompress(good[False]), "after the fuzz")
