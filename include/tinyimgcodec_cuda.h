@@ -1,5 +1,6 @@
 /*
- * tinyimgcodec_cuda.h — C ABI of libtinyimgcodec_cuda.so, the B200 (sm_100a) encode path.
+ * tinyimgcodec_cuda.h — C ABI of libtinyimgcodec_cuda.so, the B200 (sm_100a) encode path and the decode
+ * side that follows it.
  *
  * The reference (clysto/tinyimgcodec) has no FFI/plugin layer: its boundary for the
  * encode hot path is two Python functions,
@@ -7,8 +8,11 @@
  *         (tinyimgcodec/codec.py:133-164)
  *     tinyimgcodec.codec.encode(image, quality=50) -> dict
  *         (tinyimgcodec/codec.py:26-43)
- * and the CLI ./encode.py (encode.py:10-19).  This header is what a ctypes binding placed
- * UNDER those two functions calls (INTEGRATION.md shows the stub).  Every entry point
+ * and the CLI ./encode.py (encode.py:10-19); for the decode side (second half of this header)
+ *     tinyimgcodec.codec.decompress(data) -> uint8 H x W      (tinyimgcodec/codec.py:167-189)
+ *     tinyimgcodec.codec.decode(data: dict) -> uint8 H x W    (tinyimgcodec/codec.py:46-70).
+ * This header is what a ctypes binding placed
+ * UNDER those functions calls (INTEGRATION.md shows the stub).  Every entry point
  * returns 0 or a negative TIC_E_* code; no C++ exception, torch type or CUDA type
  * crosses the boundary (streams are passed as void*, i.e. a cudaStream_t value).
  * The caller owns every buffer; the library owns only the opaque handle and the
