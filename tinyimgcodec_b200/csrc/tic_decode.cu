@@ -484,9 +484,11 @@ __global__ void __launch_bounds__(kSyncThreads) dec_sync_kernel(const DecImage* 
         end_rel = left < kSubBits ? (int)left : kSubBits;
         used = U[g];
     }
+    volatile uint32_t* Ev = E;
+    // later rounds: most CTAs have nothing left to repair — leave before fetching the bits again
+    if (!__syncthreads_or(active && Ev[g] != used)) return;
     stage_rows(rows, active, src, 4 + (long long)k * kSubWords);
     const uint32_t* sw = rows[threadIdx.x];
-    volatile uint32_t* Ev = E;
     bool any = false;
     for (int it = 0; it < kSyncIters; it++) {
         bool wrote = false;
