@@ -46,7 +46,13 @@ cudaStream_t tic_internal_own_stream(tic_handle h);
 
 namespace ticd {
 
-constexpr int kSubBits = 1024;      // bits per subsequence (one thread each)
+#ifndef TICD_SUB_BITS
+#define TICD_SUB_BITS 1024
+#endif
+#ifndef TICD_FAST_MIN_CTAS
+#define TICD_FAST_MIN_CTAS 6
+#endif
+constexpr int kSubBits = TICD_SUB_BITS;   // bits per subsequence (one thread each)
 constexpr int kMaxNodes = 1024;     // trie nodes per table (a Huffman tree over <= 256 symbols has <= 255)
 constexpr int kMaxSymbols = 4096;   // symbols decoded per subsequence at most (zero-length codes)
 constexpr int kSyncThreads = 128;
@@ -917,7 +923,7 @@ __device__ __forceinline__ void store_pixel_row(const DecImage& im, int y, int x
     }
 }
 
-__global__ void __launch_bounds__(128, 5) dec_idct_fast_kernel(const DecImage* __restrict__ imgs,
+__global__ void __launch_bounds__(128, TICD_FAST_MIN_CTAS) dec_idct_fast_kernel(const DecImage* __restrict__ imgs,
                                                             const long long* __restrict__ blk_first, int n_images,
                                                             long long total_blocks, const int16_t* __restrict__ coef,
                                                             const double* __restrict__ mul, const float* __restrict__ mulf,
