@@ -50,6 +50,22 @@ def test_parse_header_is_pure_host(lib, golden):
         parse_header(data[:15])
 
 
+def test_null_handle_is_rejected_everywhere(lib):
+    """Every entry point that takes a handle returns TIC_E_INVALID for NULL before touching CUDA."""
+    from tinyimgcodec_b200 import _lib
+    z = ctypes.c_void_p(None)
+    i64 = (ctypes.c_int64 * 12)()
+    assert lib.tic_destroy(z) == _lib.TIC_E_INVALID
+    assert lib.tic_encode_finish(z, None, None) == _lib.TIC_E_INVALID
+    assert lib.tic_last_stats(z, i64) == _lib.TIC_E_INVALID
+    assert lib.tic_decode_batch(z, None, None, None, None, 0, 0, None, None, None) == _lib.TIC_E_INVALID
+    assert lib.tic_decode_finish(z, None) == _lib.TIC_E_INVALID
+    assert lib.tic_decode_stats(z, i64) == _lib.TIC_E_INVALID
+    assert lib.tic_decode_coeffs(z, None, None, 8, 8, 50, 0, None, None) == _lib.TIC_E_INVALID
+    assert lib.tic_decompress_host(z, None, 0, 0, None, 0, None) == _lib.TIC_E_INVALID
+    assert lib.tic_last_error(z) == b"null handle"
+
+
 def test_no_cpu_fallback(lib):
     """Without a GPU the product must fail loudly, never fall back to a CPU path."""
     import torch
