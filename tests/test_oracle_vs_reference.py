@@ -157,3 +157,24 @@ def test_decompress_c_variant_streams(ref):
         s = O.ref_c_compress(img, qf)
         got, nerr = O.decompress(s, return_errors=True)
         assert nerr == 0 and np.array_equal(ref.decompress(s), got), qf
+
+
+def test_decompress_random_sweep(ref):
+    """60 seeded random cases: 7 image kinds, shapes 1..90, qualities 1..99, a third with per-image tables (the
+    little-endian flag word, the only auto-table form the reference decoder can open)."""
+    rng = np.random.default_rng(99)
+    n = 0
+    while n < 60:
+        h, w = int(rng.integers(1, 90)), int(rng.integers(1, 90))
+        kind = ["noise", "synthetic", "binary", "impulse", "flat", "checker", "blockalt"][int(rng.integers(0, 7))]
+        q = int(rng.integers(1, 100))
+        img = make_case({"kind": kind, "shape": (h, w), "seed": int(rng.integers(0, 1 << 30)),
+                         "value": int(rng.integers(0, 256))})
+        auto = bool(rng.integers(0, 3) == 0)
+        try:
+            s = O.compress(img, q, auto, le_flag_word=auto) if auto else ref.compress(img, quality=q)
+        except (KeyError, O.OracleError):
+            continue
+        got, nerr = O.decompress(s, return_errors=True)
+        assert nerr == 0 and np.array_equal(ref.decompress(s), got), (kind, h, w, q, auto)
+        n += 1
