@@ -147,3 +147,100 @@ def test_without_the_restart_rule_a_flat_image_is_serial():
     without, _ = synchronise(bits, restart_rule=False)
     assert with_rule <= 4
     assert without >= nsubs // 2, (without, nsubs)
+
+
+# ---- the planned early stop of a repeated decode ("What comes next") ---------------------------------
+# A decode from a corrected entry meets the parse of the previous decode after a few dozen bits.  If the previous
+# decode left a mask of its DC-symbol starts, the repeat can stop at the first DC start the two parses share and
+# take the rest of its result from the previous one.  The model below checks the bookkeeping of that plan (the
+# mask update, the block count, the DC sum) against full decodes; the CUDA side does not use it yet.
+
+def _dc_value(padded, p):
+    sym, ln = _lookup(padded, p, DC_TAB)
+    size = sym & 15
+    if not size:
+        return 0
+    vb = int(padded[p + ln:p + ln + size], 2)
+    return vb if vb >> (size - 1) else vb - (1 << size) + 1
+
+
+def decode_sub_early(bits, start, entry, prev):
+    """prev: None or dict(mask=set of DC-start positions, n, dsum, exit) of the previous decode of this subsequence.
+    Returns the same dict for this decode, and the number of bits actually parsed."""
+    p, z = start + entry[0], entry[1]
+    end = min(start + SUB, len(bits))
+    padded = bits + "0" * 64
+    mask = set(prev["mask"]) if prev else set()
+    n = dsum = removed_n = removed_d = 0
+    first = p
+
+    def drop(lo, hi):   # DC starts of the previous parse that the new parse passes over
+        nonlocal removed_n, removed_d
+        for b in [b for b in mask if lo <= b < hi]:
+            mask.discard(b)
+            removed_n += 1
+            removed_d += _dc_value(padded, b)
+
+    drop(start, p)
+    it = 0
+    while p < end and it < 4096:
+        it += 1
+        if z == 0 and prev and p in mask:   # the two parses are in the same state: the rest is identical
+            return dict(mask=mask, n=n + prev["n"] - removed_n, dsum=dsum + prev["dsum"] - removed_d,
+                        exit=prev["exit"]), p - first
+        hit = _lookup(padded, p, DC_TAB if z == 0 else AC_TAB)
+        if hit is None:
+            drop(p, p + 1)
+            p += 1
+            continue
+        sym, ln = hit
+        size = sym & 15
+        val = 0
+        if size:
+            vb = int(padded[p + ln:p + ln + size], 2)
+            val = vb if vb >> (size - 1) else vb - (1 << size) + 1
+        p0 = p
+        p += ln + size
+        if z == 0:
+            drop(p0 + 1, p)
+            mask.add(p0)
+            n += 1
+            dsum += val
+            z = 1
+        elif sym == 0:
+            drop(p0, p)
+            z = 0
+        else:
+            z += sym >> 4
+            if z > 63:
+                z, p = 0, p0 + 1
+                drop(p0, p)
+                continue
+            drop(p0, p)
+            z += 1
+    drop(min(p, end), end)
+    return dict(mask=mask, n=n, dsum=dsum, exit=(max(p - (start + SUB), 0), z)), min(p, end) - first
+
+
+@pytest.mark.parametrize("kind,q", [("synthetic", 50), ("synthetic", 92), ("noise", 50), ("flat", 50), ("impulse", 30)])
+def test_early_stop_bookkeeping_matches_full_decodes(kind, q):
+    img = synthetic_image(128, 192, 7) if kind == "synthetic" else \
+        make_case({"kind": kind, "shape": (128, 192), "seed": 3, "value": 77})
+    bits = _bits(O.compress(img, q))
+    nsubs = (len(bits) - 128 + SUB - 1) // SUB
+    rng = np.random.default_rng(q)
+    parsed = full = 0
+    for g in range(1, nsubs):
+        start = 128 + g * SUB
+        state = None
+        # a chain of repeated decodes from different entries, the way repair rounds produce them: the guess first,
+        # then a few arbitrary (wrong) entries, then anything again
+        entries = [(0, 0)] + [(int(rng.integers(0, 31)), int(rng.integers(0, 20))) for _ in range(3)]
+        for e in entries:
+            state, nbits = decode_sub_early(bits, start, e, state)
+            ex, n, d = decode_sub(bits, start, e)
+            assert (state["exit"], state["n"], state["dsum"]) == (ex, n, d), (g, e)
+            if e != (0, 0):
+                parsed += nbits
+                full += min(SUB, len(bits) - start) - e[0]
+    assert parsed < 0.6 * full   # repeats stop early (on these small images; ~4-15 % on the benchmark's streams)
