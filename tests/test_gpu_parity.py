@@ -335,3 +335,37 @@ def test_auto_table_batch_vs_oracle(tic):
         _assert_same(out, O.compress(im, 50, True), f"auto batch {im.shape}")
     with pytest.raises(IndexError):
         tic.compress(np.zeros((0, 8), np.uint8), 50, True)
+
+
+@pytest.mark.parametrize("chunk", [1, 3, 4])
+def test_compress_batch_pinned_vs_oracle(tic, chunk):
+    """SURVEY §8(f)1, reference caller encode.py:10-19: the pipelined host API (pinned H2D / encode / D2H in
+    chunks) that produces bench.py's e2e number.  Every (offset, size) slice of the returned pinned buffer is
+    the reference's stream, for N below, at and above the chunk size (partial last chunk, more chunks than
+    buffers), twice in a row on the same encoder (buffer reuse)."""
+    import torch
+    enc = tic.get_encoder(0)
+    h, w = 64, 96
+    for n in sorted({1, max(chunk - 1, 1), chunk, 2 * chunk + 3, 5 * chunk + 1}):
+        imgs = np.stack([synthetic_image(h, w, seed=100 * chunk + i) for i in range(n)])
+        imgs[n // 2] = make_case({"kind": "noise", "shape": (h, w), "seed": n})   # one image far above the mean size
+        h_images = torch.from_numpy(imgs).pin_memory()
+        want = [O.compress(im, 50) for im in imgs]
+        for rep in range(2):
+            h_out, index = enc.compress_batch_pinned(h_images, 50, chunk=chunk, out_bytes_per_pixel=3.3)
+            assert len(index) == n
+            host = h_out.numpy()
+            for i, (off, size) in enumerate(index):
+                assert off % 16 == 0
+                _assert_same(host[off: off + size].tobytes(), want[i], f"chunk={chunk} n={n} rep={rep} image {i}")
+
+
+def test_compress_batch_pinned_capacity_error_names_the_knob(tic):
+    """A chunk that compresses worse than out_bytes_per_pixel must fail loudly (TIC_E_CAPACITY), not return a
+    truncated stream (codec.py:272)."""
+    import torch
+    enc = tic.get_encoder(0)
+    imgs = np.stack([make_case({"kind": "noise", "shape": (64, 64), "seed": i}) for i in range(6)])
+    with pytest.raises(Exception) as ei:
+        enc.compress_batch_pinned(torch.from_numpy(imgs).pin_memory(), 95, chunk=4, out_bytes_per_pixel=0.05)
+    assert "out_bytes_per_pixel" in str(ei.value) or "too small" in str(ei.value)
