@@ -68,6 +68,13 @@ extern "C" {
                                     (codec.py:119), so its own decoder cannot open its auto-table streams; with
                                     this flag it can.  Off by default: byte parity with compress() comes first. */
 
+#define TIC_FLAG_DEBUG_ALL_EXACT 8u /* test hook (tests/test_gpu_parity.py): EVERY coefficient is recomputed by the
+                                    float64 exact path, whether the tie guard flagged it or not, and
+                                    tic_last_guard_misses() counts the coefficients the exact path changed although
+                                    the guard had not flagged them — the guard band of the fast transform
+                                    (tensor-core f16 split GEMM, or FP32 butterflies) is sound iff that count is
+                                    0.  Same streams, many times slower.  Match: tinyimgcodec/utils.py:32-37,53. */
+
 /* per-image status bits written by the device */
 #define TIC_STATUS_CATEGORY 1 /* KeyError case above */
 #define TIC_STATUS_TABLE 2    /* auto table not serialisable (OverflowError in the reference,
@@ -159,6 +166,11 @@ int tic_compress_host(tic_handle h, const uint8_t *pixels, int32_t height, int32
  *       over the [7] batches enqueued since the previous tic_encode_finish (CUDA events recorded
  *       on the batches' stream around those two launches; the newest 64 batches at most) */
 int tic_last_stats(tic_handle h, int64_t stats[8]);
+
+/* After a batch encoded with TIC_FLAG_DEBUG_ALL_EXACT (and tic_encode_finish): the number of coefficients whose
+ * float64 exact value (the reference's, tinyimgcodec/utils.py:32-37,53) differs from the fast path's although the
+ * tie guard had not flagged them.  0 proves the guard band on that input; -1 for a null handle. */
+int64_t tic_last_guard_misses(tic_handle h);
 
 /* ------------------------------------------------------------------------------------------------
  * Decode side: tinyimgcodec.codec.decompress(data) -> uint8 H x W

@@ -369,3 +369,75 @@ def test_compress_batch_pinned_capacity_error_names_the_knob(tic):
     with pytest.raises(Exception) as ei:
         enc.compress_batch_pinned(torch.from_numpy(imgs).pin_memory(), 95, chunk=4, out_bytes_per_pixel=0.05)
     assert "out_bytes_per_pixel" in str(ei.value) or "too small" in str(ei.value)
+
+
+@pytest.mark.parametrize("q", [1, 50, 90, 95, 99])
+def test_tie_guard_is_sound_all_coefficients_exact(tic, q):
+    """SURVEY App. B (last bullet), VERDICT r1 weak #2: the guard band of the fast transform is ASSERTED, not
+    argued.  With TIC_FLAG_DEBUG_ALL_EXACT every coefficient — flagged or not, live group or not — is recomputed
+    by the float64 exact path (the reference's arithmetic, utils.py:32-37,53); `guard_misses` counts those whose
+    exact value differs from the fast value WITHOUT having been flagged.  Must be 0 on adversarial content."""
+    import torch
+    enc = tic.get_encoder(0)
+    h, w = 128, 256
+    kinds = [{"kind": "binary", "shape": (h, w), "seed": 3}, {"kind": "checker", "shape": (h, w)},
+             {"kind": "blockalt", "shape": (h, w)}, {"kind": "noise", "shape": (h, w), "seed": 5}]
+    imgs = [make_case(k) for k in kinds] + [synthetic_image(h, w, seed=s) for s in range(4)]
+    # blocks whose pixels follow the sign of one basis function each: the largest sum |pixel x basis| there is
+    yy, xx = np.mgrid[0:h, 0:w]
+    n = ((yy // 8) * (w // 8) + xx // 8) % 64
+    u, v = n // 8, n % 8
+    basis = np.cos((2 * (yy % 8) + 1) * u * np.pi / 16) * np.cos((2 * (xx % 8) + 1) * v * np.pi / 16)
+    imgs.append(np.where(basis > 0, 255, 0).astype(np.uint8))
+    d = torch.from_numpy(np.stack(imgs)).cuda()
+    try:
+        res = enc.encode_batch_device(d, q, debug_all_exact=True).finish()
+    except KeyError:
+        res = None   # q >= 97 on 0/255 content: category outside the fixed tables, like the reference (counted anyway)
+    st = enc.stats()
+    assert st["exact_items"] >= len(imgs) * (h // 8) * (w // 8) * 64      # every coefficient went through the exact path
+    assert enc.guard_misses() == 0
+    if res is not None:
+        for got, im in zip(res.to_bytes(), imgs):
+            _assert_same(got, O.compress(im, q), f"debug-all-exact stream q={q}")
+
+
+def test_bench_images_guard_is_sound(tic):
+    """The same assertion on 16 images of the benchmark's kind (1024 x 1024, BASELINE config 4) at q50."""
+    import torch
+    enc = tic.get_encoder(0)
+    imgs = np.stack([synthetic_image(1024, 1024, seed=s) for s in range(16)])
+    enc.encode_batch_device(torch.from_numpy(imgs).cuda(), 50, debug_all_exact=True).finish()
+    assert enc.guard_misses() == 0
+    assert enc.stats()["exact_items"] >= 16 * 16384 * 64
+
+
+def test_back_to_back_batches_without_finish(tic):
+    """ADVICE r1 (tic_encode.cu:943): two DIFFERENT batches enqueued back to back on a busy stream, one finish.
+    Both must be correct (the pinned descriptor staging is a ring), and an error of the FIRST batch must still be
+    reported by the finish that follows the second (sticky status)."""
+    import torch
+    enc = tic.get_encoder(0)
+    a = [synthetic_image(40 + 8 * i, 64 + 16 * i, seed=i) for i in range(5)]
+    b = [synthetic_image(96, 72 - 8 * i, seed=50 + i) for i in range(3)]
+    da = [torch.from_numpy(x).cuda() for x in a]
+    db = [torch.from_numpy(x).cuda() for x in b]
+    big = torch.from_numpy(np.stack([synthetic_image(1024, 1024, seed=s) for s in range(8)])).cuda()
+    for _ in range(3):
+        enc.encode_batch_device(big, 50)            # keeps the stream busy while the next two are enqueued
+    ra = enc.encode_batch_device(da, 50)
+    rb = enc.encode_batch_device(db, 60)
+    rb.finish()
+    ra.total_bytes = int((ra.offsets + ra.sizes).max().item())
+    for got, im in zip(ra.to_bytes(), a):
+        _assert_same(got, O.compress(im, 50), "first of two back-to-back batches")
+    for got, im in zip(rb.to_bytes(), b):
+        _assert_same(got, O.compress(im, 60), "second of two back-to-back batches")
+    # sticky error: the first batch overflows its (tiny) output buffer, the second is fine
+    small_out = torch.empty(64, dtype=torch.uint8, device="cuda")
+    enc.encode_batch_device(da, 50, out=small_out)
+    rb2 = enc.encode_batch_device(db, 60)
+    with pytest.raises(Exception) as ei:
+        rb2.finish()
+    assert "too small" in str(ei.value)
+    enc.encode_batch_device(db, 60).finish()        # and the handle is usable again

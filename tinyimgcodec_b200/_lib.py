@@ -21,6 +21,7 @@ TIC_E_STREAM = -8
 TIC_FLAG_AUTO_HUFFMAN = 1
 TIC_FLAG_C_VARIANT = 2
 TIC_FLAG_AUTO_LE_FLAG = 4
+TIC_FLAG_DEBUG_ALL_EXACT = 8
 TIC_STATUS_CATEGORY = 1
 TIC_STATUS_TABLE = 2
 TIC_STATUS_LONGCODE = 4
@@ -37,7 +38,7 @@ AUTO_HEADER_SLACK = 1664
 # every symbol include/tinyimgcodec_cuda.h declares
 EXPORTS = ["tic_version", "tic_create", "tic_destroy", "tic_last_error", "tic_max_out_bytes",
            "tic_num_blocks", "tic_encode_batch", "tic_encode_finish", "tic_encode_coeffs",
-           "tic_compress_host", "tic_last_stats", "tic_parse_header", "tic_decode_batch", "tic_decode_finish",
+           "tic_compress_host", "tic_last_stats", "tic_last_guard_misses", "tic_parse_header", "tic_decode_batch", "tic_decode_finish",
            "tic_decompress_host", "tic_decode_coeffs", "tic_decode_stats"]
 
 _lib = None
@@ -76,6 +77,8 @@ def load():
                                     ctypes.POINTER(i32)]
     L.tic_last_stats.restype = ctypes.c_int
     L.tic_last_stats.argtypes = [vp, ctypes.POINTER(i64)]
+    L.tic_last_guard_misses.restype = i64
+    L.tic_last_guard_misses.argtypes = [vp]
     L.tic_parse_header.restype = ctypes.c_int
     L.tic_parse_header.argtypes = [vp, i64, ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i32),
                                    ctypes.POINTER(u32)]

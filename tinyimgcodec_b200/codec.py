@@ -198,7 +198,7 @@ class Encoder:
 
     # -- batch, device buffers ----------------------------------------------------------------
     def encode_batch_device(self, d_images, quality=50, out=None, stream=None, auto_generate_huffman_table=False,
-                            c_variant=False):
+                            c_variant=False, debug_all_exact=False):
         """Encode a batch resident in HBM.  `d_images`: a CUDA uint8 tensor (N,H,W) or a list of
         2-D CUDA uint8 tensors.  Returns a DeviceBatchResult; nothing is copied to the host."""
         import torch
@@ -240,7 +240,8 @@ class Encoder:
             stream = stream or torch.cuda.current_stream(dev)
             with self._lock:
                 flags = (_lib.TIC_FLAG_AUTO_HUFFMAN if auto_generate_huffman_table else 0) | \
-                        (_lib.TIC_FLAG_C_VARIANT if c_variant else 0)
+                        (_lib.TIC_FLAG_C_VARIANT if c_variant else 0) | \
+                        (_lib.TIC_FLAG_DEBUG_ALL_EXACT if debug_all_exact else 0)
                 rc = self.lib.tic_encode_batch(self.handle, ptrs, hs, ws, n, q, flags, out.data_ptr(), out.numel(),
                                                offs.data_ptr(), sizes.data_ptr(), stat.data_ptr(),
                                                stream.cuda_stream)
@@ -448,6 +449,11 @@ class Encoder:
         return {"launches": arr[0], "subsequences": arr[1], "sync_rounds": arr[2], "blocks": arr[3],
                 "sync_ms": arr[4] * 1e-6, "scan_ms": arr[5] * 1e-6, "scatter_ms": arr[6] * 1e-6,
                 "idct_ms": arr[7] * 1e-6, "exact_blocks": arr[8]}
+
+    def guard_misses(self):
+        """After a batch encoded with debug_all_exact=True and finish(): coefficients whose float64 exact value
+        differs from the fast path's although the tie guard had not flagged them (must be 0)."""
+        return int(self.lib.tic_last_guard_misses(self.handle))
 
     def stats(self):
         arr = (ctypes.c_int64 * 8)()

@@ -14,16 +14,16 @@
 
 namespace tic {
 
-// Huffman tables -> shared memory in the form the walk wants (see TileShared::ac_tab).
+// Huffman tables -> shared memory in the form the walk wants (see TileShared::ac_tab).  All threads of a group call.
 template <bool kAuto>
 __device__ __forceinline__ void load_tables(TileShared& sm, const HuffTables& g) {
-    for (int i = threadIdx.x; i < 256; i += kTile) {
+    for (int i = tid(); i < 256; i += kTile) {
         const uint32_t len = g.ac[i].len, code = g.ac[i].code;
         if constexpr (kAuto) sm.ac_tab[i] = make_uint2(code, len);
         else sm.ac_tab[i] = len ? make_uint2(code << (i & 15), (len & kHuffLenMask) + (uint32_t)(i & 15)) : make_uint2(0u, 0u);
     }
-    if (threadIdx.x < 16) {
-        const int i = threadIdx.x;
+    if (tid() < 16) {
+        const int i = tid();
         const uint32_t len = g.dc[i].len, code = g.dc[i].code;
         if constexpr (kAuto) sm.dc_tab[i] = make_uint2(code, len);
         else sm.dc_tab[i] = len ? make_uint2(code << i, (len & kHuffLenMask) + (uint32_t)i) : make_uint2(0u, 0u);
@@ -31,57 +31,126 @@ __device__ __forceinline__ void load_tables(TileShared& sm, const HuffTables& g)
 }
 
 // ---------------------------------------------------------------------------------------------
-// compress(), stage 1: every tile -> its bits in the arena + a TileRec.  Persistent CTAs, tiles
-// dealt round-robin; no tile waits for another.
+// Shared memory of a CTA: [B operand | mbarriers + TMEM base] (tensor-core kernels only), then one TileShared
+// per group.  tc_cta_setup: B -> shared memory, one mbarrier per group, one TMEM allocation per CTA.
+// ---------------------------------------------------------------------------------------------
+constexpr size_t kTcCtlBytes = 128;   // G mbarriers (8 bytes each, G <= 8) + the TMEM base address at byte 64
+constexpr size_t kGroupStride = (sizeof(TileShared) + 127) & ~(size_t)127;
+template <int G, bool kTc>
+constexpr size_t cta_smem_bytes() { return (kTc ? (size_t)tc::kBBytes + kTcCtlBytes : 0) + (size_t)G * kGroupStride; }
+template <int G>
+struct TmemCols {   // TMEM allocations are powers of two >= 32 columns
+    static constexpr uint32_t value = G * tc::kColsPerGroup <= 64 ? 64u : (G * tc::kColsPerGroup <= 128 ? 128u : (G * tc::kColsPerGroup <= 256 ? 256u : 512u));
+};
+static_assert(kGroups >= 1 && kGroups <= 8 && kGroups * tc::kColsPerGroup <= 512, "TMEM has 512 columns");
+
+template <int G>
+__device__ __forceinline__ unsigned char* tc_cta_setup(unsigned char* smem_raw, const uint4* __restrict__ bmat, int g,
+                                                       TcGroup& tg, uint32_t& tmem_base) {
+    uint4* sB = reinterpret_cast<uint4*>(smem_raw);
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(smem_raw + tc::kBBytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem_raw + tc::kBBytes + 64);
+    for (int i = threadIdx.x; i < tc::kBBytes / 16; i += kTile * G) sB[i] = __ldg(bmat + i);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < G; i++) tc::mbar_init(tc::smem_addr(mbar + i), 1);
+        tc::fence_mbar_init();
+    }
+    if (threadIdx.x < 32) tc::tmem_alloc(tc::smem_addr(tmem_slot), TmemCols<G>::value);
+    tc::fence_proxy_async();   // the B operand is read through the async proxy
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    tmem_base = *tmem_slot;
+    tg.desc_b0 = tc::smem_desc(tc::smem_addr(sB), tc::kLboB, tc::kSboB);
+    tg.bar = tc::smem_addr(mbar + g);
+    // accumulator of group g: columns [64 g, 64 g + 64); a warp reads the lane quarter (warp % 4) * 32
+    tg.tmem = tmem_base + (uint32_t)(g * tc::kColsPerGroup) + ((uint32_t)(((threadIdx.x >> 5) & 3) * 32) << 16);
+    tg.phase = 0;
+    return smem_raw + tc::kBBytes + kTcCtlBytes;
+}
+template <int G>
+__device__ __forceinline__ void tc_cta_teardown(uint32_t tmem_base) {
+    tc::fence_before_sync();
+    __syncthreads();
+    if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base, TmemCols<G>::value);
+}
+
+// ---------------------------------------------------------------------------------------------
+// compress(), stage 1: every tile -> its bits in the arena + a TileRec.  Persistent CTAs of G groups, tiles
+// dealt round-robin to the groups; no tile waits for another.
 // ---------------------------------------------------------------------------------------------
 // kMode: 0 = fixed Huffman tables, 1 = per-image tables (auto_generate_huffman_table), 2 = C-variant stream
 // (flag bit 30; `quality` is then the reference's IMG_Q_BEST .. IMG_Q_LOW = 0 .. 3)
-template <int kMode>
-__global__ void __launch_bounds__(kTile, kCtasPerSm)
+template <int kMode, int G>
+__global__ void __launch_bounds__(kTile * G, G == 1 ? (kMode == 2 || !kFdctTc ? kCtasPerSm : 4) : 1)
 encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restrict__ descs, int n_images,
                     int uniform_tpi, long long ntiles, TileRec* __restrict__ recs, uint4* __restrict__ arena,
                     unsigned long long arena_cap16, unsigned long long* __restrict__ counters,
-                    int* __restrict__ status, int quality, const AutoTables* __restrict__ auto_tabs) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileShared& sm = *reinterpret_cast<TileShared*>(smem_raw);
-    constexpr bool kAuto = kMode == 1, kCVar = kMode == 2;
-    const int t = threadIdx.x;
+                    int* __restrict__ status, int quality, const AutoTables* __restrict__ auto_tabs,
+                    const uint4* __restrict__ bmat, uint32_t flags) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr bool kAuto = kMode == 1, kCVar = kMode == 2, kTc = kFdctTc && !kCVar;
+    const int t = tid(), g = (int)threadIdx.x / kTile;
     const int lane = t & 31, warp = t >> 5;
-    uint32_t sbase = smem_u32(smem_raw);   // kept in a register: the walk addresses shared memory directly
+    unsigned char* gbase = smem_raw;
+    TcGroup tg{};
+    uint32_t tmem_base = 0;
+    if constexpr (kTc) gbase = tc_cta_setup<G>(smem_raw, bmat, g, tg, tmem_base);
+    TileShared& sm = *reinterpret_cast<TileShared*>(gbase + (size_t)g * kGroupStride);
+    tg.desc_a0 = tc::smem_desc(tc::smem_addr(&sm.coef[0][0]), tc::kLboA, tc::kSboA);
+    uint32_t sbase = smem_u32(&sm);   // kept in a register: the walk addresses shared memory directly
     asm volatile("mov.u32 %0, %0;" : "+r"(sbase));
+    const bool debug_all = (flags & TIC_FLAG_DEBUG_ALL_EXACT) != 0;
 
     if constexpr (!kAuto) load_tables<false>(sm, c_default_tables);   // constants.py:53-242
     for (int i = t; i < kWinWords; i += kTile) sm.stage[i] = 0;
-    __syncthreads();
+    group_sync<G>(g);
 
-    ExactStats st{0u, 0u};
+    ExactStats st{0u, 0u, 0u};
+    bool timeout = false;
     int tab_img = -1;   // auto mode: image whose tables are in shared memory
+    const long long first = (long long)blockIdx.x * G + g, stride = (long long)gridDim.x * G;
     // uniform batch: (image, tile within image) advance by a fixed step, no division in the loop
     int u_img = 0, u_lt = 0, u_dq = 0, u_dr = 0;
     if (uniform_tpi > 0) {
-        u_img = (int)blockIdx.x / uniform_tpi; u_lt = (int)blockIdx.x - u_img * uniform_tpi;
-        u_dq = (int)gridDim.x / uniform_tpi;   u_dr = (int)gridDim.x - u_dq * uniform_tpi;
+        u_img = (int)(first / uniform_tpi);  u_lt = (int)(first - (long long)u_img * uniform_tpi);
+        u_dq = (int)(stride / uniform_tpi);  u_dr = (int)(stride - (long long)u_dq * uniform_tpi);
     }
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        TileInfo ti;
+    // the tile after `tile` in this group's sequence (the uniform counters run one tile ahead of the loop)
+    auto tile_at = [&](long long tl) -> TileInfo {
         if (uniform_tpi > 0) {
-            ti = tile_info(descs[u_img], u_img, u_lt);
+            const TileInfo r = tile_info(descs[u_img], u_img, u_lt);
             u_img += u_dq; u_lt += u_dr;
             if (u_lt >= uniform_tpi) { u_lt -= uniform_tpi; u_img++; }
-        } else {
-            ti = locate_tile(descs, n_images, tile, 0);
+            return r;
         }
+        return locate_tile(descs, n_images, tl, 0);
+    };
+    TileInfo ti{}, nti{};
+    uint2 rows[8] = {};   // tensor-core path: this thread's pixel rows, fetched one tile ahead
+    if (first < ntiles) {
+        ti = tile_at(first);
+        if constexpr (kTc) { if (TIC_PREFETCH && ti.nb > 0) load_block_rows(ti, t, rows); }
+    }
+    for (long long tile = first; tile < ntiles; tile += stride, ti = nti) {
+        const bool has_next = tile + stride < ntiles;
+        if (has_next) nti = tile_at(tile + stride);
         if constexpr (kAuto) {
-            if (tab_img != ti.img) {   // per-image tables (codec.py:146-148); CTA-uniform branch
-                __syncthreads();       // everyone is done with the previous image's tables
+            if (tab_img != ti.img) {   // per-image tables (codec.py:146-148); group-uniform branch
+                group_sync<G>(g);      // everyone is done with the previous image's tables
                 load_tables<true>(sm, auto_tabs[ti.img].tab);
                 tab_img = ti.img;
-                __syncthreads();
+                group_sync<G>(g);
             }
         }
 
-        // ---- per warp: coefficients, then the bits of every block into its private words ---------
+        // ---- coefficients of the tile, then the bits of every block into its private words ---------
         if constexpr (kCVar) transform_warp_c(ti, quality, sm);
+        else if constexpr (kTc) {
+            if (!TIC_PREFETCH && ti.nb > 0) load_block_rows(ti, t, rows);
+            if (ti.nb > 0) transform_tile_tc<G>(ti, qp, sm, tg, g, debug_all, st, timeout, rows, has_next && nti.nb > 0 ? &nti : nullptr);
+            else if (TIC_PREFETCH && has_next && nti.nb > 0) load_block_rows(nti, t, rows);
+        }
         else transform_warp(ti, qp, sm, st);
         int err = 0, bits = 0, nwords = 0, diff = 0;
         if (t < ti.nb) {
@@ -100,7 +169,7 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
         }
         const bool warp_err = __any_sync(0xffffffffu, err != 0);
         if (lane == 31) { sm.warp_bits[warp] = incl; sm.warp_err[warp] = warp_err ? 1 : 0; }
-        __syncthreads();   // B1: warp totals visible; the staging window is zero (previous copy-out done)
+        group_sync<G>(g);   // B1: warp totals visible; the staging window is zero (previous copy-out done)
 
         int warp_base = 0, tile_bits = 0, tile_err = 0;
 #pragma unroll
@@ -173,7 +242,7 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
                     walk_block<kAuto, true>(sm, sbase, t, diff, s, e2);
                 }
             }
-            __syncthreads();   // B2: window complete, arena offset visible
+            group_sync<G>(g);   // B2: window complete, arena offset visible
 
             // ---- window -> arena (16-byte stores), and the window is zero again -----------------
             const unsigned int aoff = sm.arena_off;
@@ -186,20 +255,24 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
             }
             wbase += kWinWords;
             if (wbase >= nw_tile) break;
-            __syncthreads();
+            group_sync<G>(g);
         }
     }
+    if constexpr (kTc) tc_cta_teardown<G>(tmem_base);
     // exact-path statistics: one atomic per warp at the very end
-    unsigned int items = st.items, changed = st.changed;
+    unsigned int items = st.items, changed = st.changed, unflagged = st.unflagged;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         items += __shfl_xor_sync(0xffffffffu, items, o);
         changed += __shfl_xor_sync(0xffffffffu, changed, o);
+        unflagged += __shfl_xor_sync(0xffffffffu, unflagged, o);
     }
     if (lane == 0) {
         if (items) atomicAdd(&counters[kCtrExactItems], (unsigned long long)items);
         if (changed) atomicAdd(&counters[kCtrExactChanged], (unsigned long long)changed);
+        if (unflagged) atomicAdd(&counters[kCtrUnflagged], (unsigned long long)unflagged);
     }
+    if (timeout) atomicExch(&counters[kCtrTcTimeout], 1ull);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -302,13 +375,27 @@ scan_apply_kernel(const TileRec* __restrict__ recs, long long ntiles, const long
     }
 }
 
+// What a batch leaves for tic_encode_finish: `sticky` accumulates over every batch enqueued since the last finish
+// (errors are ORed, so a later batch cannot hide an earlier batch's overflow; the byte total is the last batch's).
+// One thread, after every kernel that writes `counters` has completed (stream order) or behind a CTA barrier.
+__device__ __forceinline__ void fold_counters(unsigned long long* counters, unsigned long long* sticky) {
+    const unsigned long long overflow = atomicAdd(&counters[kCtrOverflow], 0ull), timeout = atomicAdd(&counters[kCtrTcTimeout], 0ull);
+    if (overflow) atomicOr(&sticky[kCtrOverflow], 1ull);
+    if (timeout) atomicOr(&sticky[kCtrTcTimeout], 1ull);
+    atomicExch(&sticky[kCtrExactItems], atomicAdd(&counters[kCtrExactItems], 0ull));     // statistics: the last batch's
+    atomicExch(&sticky[kCtrExactChanged], atomicAdd(&counters[kCtrExactChanged], 0ull));
+    atomicAdd(&sticky[kCtrUnflagged], atomicAdd(&counters[kCtrUnflagged], 0ull));        // guard misses: never lose one
+    atomicExch(&sticky[kCtrTotalBits], atomicAdd(&counters[kCtrTotalBits], 0ull));
+}
+
 // Small batches (at most kSmallScan tiles: one 8K image, 50 x 512^2, ...): the three scan kernels and
 // finalize_kernel in ONE launch of one CTA — what counts there is launch latency, not throughput.
 constexpr int kSmallThreads = 1024, kSmallScan = kSmallThreads * kScanItems;
 __global__ void __launch_bounds__(kSmallThreads)
 scan_small_kernel(const TileRec* __restrict__ recs, int ntiles, long long* __restrict__ tile_pos, long long out_cap,
                   long long* __restrict__ out_off, long long* __restrict__ out_end, long long* __restrict__ out_sizes,
-                  int n_images, const int* __restrict__ status, unsigned long long* __restrict__ counters) {
+                  int n_images, const int* __restrict__ status, unsigned long long* __restrict__ counters,
+                  unsigned long long* __restrict__ sticky) {
     __shared__ Span warp_tot[kSmallThreads / 32];
     const int base = (int)threadIdx.x * kScanItems;
     uint32_t rb[kScanItems];
@@ -343,8 +430,9 @@ scan_small_kernel(const TileRec* __restrict__ recs, int ntiles, long long* __res
     __syncthreads();   // out_off / out_end of every image are in place (same CTA: visible after the barrier)
     for (int i = threadIdx.x; i < n_images; i += kSmallThreads) {
         out_sizes[i] = out_end[i] - out_off[i];
-        if (status[i]) atomicOr(&counters[kCtrAnyStatus], (unsigned long long)status[i]);
+        if (status[i]) atomicOr(&sticky[kCtrAnyStatus], (unsigned long long)status[i]);
     }
+    if (threadIdx.x == 0) fold_counters(counters, sticky);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -404,24 +492,36 @@ compact_kernel(const TileRec* __restrict__ recs, const long long* __restrict__ t
 // ---------------------------------------------------------------------------------------------
 // auto_generate_huffman_table=True (codec.py:146-148): symbol statistics, then the tables
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTile, kCtasPerSm)
+__global__ void __launch_bounds__(kTile, kFdctTc ? 4 : kCtasPerSm)
 symbol_stats_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restrict__ descs, int n_images,
                     int uniform_tpi, long long ntiles, unsigned long long* __restrict__ counters,
                     uint32_t* __restrict__ g_hist, unsigned long long* __restrict__ g_first,
-                    int* __restrict__ status) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileShared& sm = *reinterpret_cast<TileShared*>(smem_raw);
+                    int* __restrict__ status, const uint4* __restrict__ bmat) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* gbase = smem_raw;
+    TcGroup tg{};
+    uint32_t tmem_base = 0;
+    if constexpr (kFdctTc) gbase = tc_cta_setup<1>(smem_raw, bmat, 0, tg, tmem_base);
+    TileShared& sm = *reinterpret_cast<TileShared*>(gbase);
+    tg.desc_a0 = tc::smem_desc(tc::smem_addr(&sm.coef[0][0]), tc::kLboA, tc::kSboA);
     const int t = threadIdx.x;
     uint32_t* hist = sm.stage;                                                       // 272 counters
     unsigned long long* first = reinterpret_cast<unsigned long long*>(sm.stage + 512); // 272 keys
-    ExactStats st{0u, 0u};
+    ExactStats st{0u, 0u, 0u};
+    bool timeout = false;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         __syncthreads();
         const TileInfo ti = locate_tile(descs, n_images, tile, uniform_tpi);
         for (int i = t; i < 272; i += kTile) { hist[i] = 0; first[i] = ~0ull; }
         if (t == 0) sm.warp_err[0] = 0;
         __syncthreads();
-        transform_warp(ti, qp, sm, st);
+        if constexpr (kFdctTc) {
+            if (ti.nb > 0) {
+                uint2 rows[8];
+                load_block_rows(ti, t, rows);
+                transform_tile_tc<1>(ti, qp, sm, tg, 0, false, st, timeout, rows, nullptr);
+            }
+        } else transform_warp(ti, qp, sm, st);
         int err = 0;
         if (t < ti.nb) block_stats(sm, t, (unsigned long long)(ti.blk0 + t), hist, first, err);
         if (err) sm.warp_err[0] = 1;
@@ -435,7 +535,8 @@ symbol_stats_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
         }
         if (t == 0 && sm.warp_err[0]) atomicOr(&status[ti.img], TIC_STATUS_TABLE);
     }
-    (void)counters;
+    if constexpr (kFdctTc) tc_cta_teardown<1>(tmem_base);
+    if (timeout) atomicExch(&counters[kCtrTcTimeout], 1ull);
 }
 
 // One thread per image: HuffmanTree (huffman.py:112-194) on CPython's heapq, which
@@ -587,26 +688,41 @@ __global__ void build_tables_kernel(const ImageDesc* __restrict__ descs, int n_i
 // sizes = end - offset, and the batch summary the host reads back in tic_encode_finish
 __global__ void finalize_kernel(int n_images, const long long* __restrict__ out_off,
                                 const long long* __restrict__ out_end, long long* __restrict__ out_sizes,
-                                const int* __restrict__ status, unsigned long long* __restrict__ counters) {
+                                const int* __restrict__ status, unsigned long long* __restrict__ counters,
+                                unsigned long long* __restrict__ sticky) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n_images) {
         out_sizes[i] = out_end[i] - out_off[i];
-        if (status[i]) atomicOr(&counters[kCtrAnyStatus], (unsigned long long)status[i]);
+        if (status[i]) atomicOr(&sticky[kCtrAnyStatus], (unsigned long long)status[i]);
     }
+    if (i == 0) fold_counters(counters, sticky);   // every writer of `counters` ran in an earlier kernel of the stream
 }
 
 // ---------------------------------------------------------------------------------------------
 // encode(): the same transform, coefficients written out (parity checkpoint for codec.py:26-43)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kTile, kCtasPerSm)
+__global__ void __launch_bounds__(kTile, kFdctTc ? 4 : kCtasPerSm)
 coeffs_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restrict__ descs,
-              unsigned long long* __restrict__ counters, int* __restrict__ dc, int* __restrict__ ac) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    TileShared& sm = *reinterpret_cast<TileShared*>(smem_raw);
+              unsigned long long* __restrict__ counters, int* __restrict__ dc, int* __restrict__ ac,
+              const uint4* __restrict__ bmat, uint32_t flags) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned char* gbase = smem_raw;
+    TcGroup tg{};
+    uint32_t tmem_base = 0;
+    if constexpr (kFdctTc) gbase = tc_cta_setup<1>(smem_raw, bmat, 0, tg, tmem_base);
+    TileShared& sm = *reinterpret_cast<TileShared*>(gbase);
+    tg.desc_a0 = tc::smem_desc(tc::smem_addr(&sm.coef[0][0]), tc::kLboA, tc::kSboA);
     const int t = threadIdx.x;
     const TileInfo ti = locate_tile(descs, 1, blockIdx.x, 0);
-    ExactStats st{0u, 0u};
-    transform_warp(ti, qp, sm, st);
+    ExactStats st{0u, 0u, 0u};
+    bool timeout = false;
+    if constexpr (kFdctTc) {
+        if (ti.nb > 0) {
+            uint2 rows[8];
+            load_block_rows(ti, t, rows);
+            transform_tile_tc<1>(ti, qp, sm, tg, 0, (flags & TIC_FLAG_DEBUG_ALL_EXACT) != 0, st, timeout, rows, nullptr);
+        }
+    } else transform_warp(ti, qp, sm, st);
     if (t < ti.nb) {
         const size_t b = (size_t)ti.blk0 + t;
         dc[b] = sm.dcq[t] - dc_before(sm, t);
@@ -617,8 +733,11 @@ coeffs_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restric
             row[k - 1] = nz ? coef_get(sm, t, k) : 0;
         }
     }
+    if constexpr (kFdctTc) tc_cta_teardown<1>(tmem_base);
     if (st.items) atomicAdd(&counters[kCtrExactItems], (unsigned long long)st.items);
     if (st.changed) atomicAdd(&counters[kCtrExactChanged], (unsigned long long)st.changed);
+    if (st.unflagged) atomicAdd(&counters[kCtrUnflagged], (unsigned long long)st.unflagged);
+    if (timeout) atomicExch(&counters[kCtrTcTimeout], 1ull);
 }
 
 }  // namespace tic
@@ -633,7 +752,15 @@ struct tic_handle_s {
     std::string err;
     // workspace (grown on demand)
     ImageDesc* d_descs = nullptr;       size_t descs_cap = 0;
-    ImageDesc* h_descs = nullptr;       // pinned
+    // pinned descriptor staging: one slot per batch in flight, guarded by an event recorded behind its H2D copy
+    static constexpr int kDescSlots = 4;
+    ImageDesc* h_descs_ring[kDescSlots] = {};
+    cudaEvent_t desc_ev[kDescSlots] = {};
+    long long desc_seq = 0;
+    ImageDesc* h_descs = nullptr;       // the slot of the batch being prepared
+    unsigned long long* d_sticky = nullptr;      // what tic_encode_finish reads: accumulated over batches (fold_counters)
+    uint4* d_bmat = nullptr;            // tensor-core B operands, one 16 KB matrix per quality (built on first use)
+    bool bmat_ready[100] = {};
     TileRec* d_recs = nullptr; long long* d_tile_pos = nullptr; size_t tiles_cap = 0;
     Span* d_chunk_span = nullptr; long long* d_chunk_pos = nullptr; size_t chunks_cap = 0;
     uint4* d_arena = nullptr;           size_t arena_cap16 = 0;          // 16-byte units
@@ -658,7 +785,7 @@ struct tic_handle_s {
     long long timed_batches = 0;
     long long last_tiles = 0, last_blocks = 0, last_launches = 0;
     bool tables_ready = false;
-    int sm_count = 148, ctas_per_sm = kCtasPerSm;
+    int sm_count = 148, ctas_per_sm = 1, ctas_per_sm_c = kCtasPerSm, ctas_per_sm_single = 4;
     void* dec_ws = nullptr;              // decode-side workspace, owned by tic_decode.cu
 };
 
@@ -730,42 +857,99 @@ static int make_quant_params(int quality, QuantParams& qp) {
         double m = 1.0 / (8.0 * aan[u] * aan[v] * qp.qt[i]);
         double w = kFastErr / qp.qt[i] + 2.4e-7 * (1024.0 / qp.qt[i]) + 1.0e-6;
         double hthr = 0.5 - w;
-        if (hthr < 0.0) hthr = 0.0;   // every coefficient goes to the exact path
+        if (hthr < 0.25) return TIC_E_QUALITY;   // unreachable for quality <= 99 (w <= 4.2e-3); the tensor-core scaling divides by hthr
         qp.qmul[k] = (float)m;
         qp.hthr[k] = (float)(hthr * (1.0 - 1.0e-6));
         // |d * zmul| < 1  =>  |t| < hthr: rounds to zero, and the residual test cannot fire
         qp.zmul[k] = hthr > 0.0 ? (float)(m / hthr * (1.0 + 1.0e-6)) : 3.0e38f;
     }
     qp.dcinv = 1.0 / (8.0 * qp.qt[0]);
+    // tensor-core path: the accumulator holds t / hthr * 2^E with ONE power of two per quality, chosen so that the
+    // largest entry of B = basis / (qt * hthr) * 2^E is in [2^13, 2^14): its f16 hi + lo split then carries >= 21 bits.
+    double mx = 0.0;
+    for (int k = 0; k < 64; k++) {
+        const int i = zigzag[k], u = i >> 3, v = i & 7;
+        const double cu = u ? 0.5 : sqrt(0.125), cv = v ? 0.5 : sqrt(0.125);
+        const double m = cu * cv / (qp.qt[i] * (double)qp.hthr[k]);   // |cos| <= 1
+        if (m > mx) mx = m;
+    }
+    int e = 0;
+    frexp(mx, &e);
+    qp.tc_exp = 14 - e;
+    qp.tc_live = (float)ldexp(1.0, qp.tc_exp);
+    for (int k = 0; k < 64; k++) qp.cn[k] = (float)ldexp((double)qp.hthr[k], -qp.tc_exp);   // exact: a power-of-two scaling
     return TIC_OK;
 }
+
+// B operand of the tensor-core FDCT for one quality, in the shared-memory layout of tic_tc.cuh:
+// B[n][k] = basis(zigzag[n], pixel k) / (qt * hthr) * 2^E as f16 hi (k) and lo (k + 64).
+static void build_bmat(const QuantParams& qp, __half* blob /* 64 x 128 */) {
+    static const int zigzag[64] = {TIC_ZIGZAG_LIST};
+    const double pi = 3.14159265358979323846;
+    for (int n = 0; n < 64; n++) {
+        const int i = zigzag[n], u = i >> 3, v = i & 7;
+        const double cu = u ? 0.5 : sqrt(0.125), cv = v ? 0.5 : sqrt(0.125);
+        const double scale = ldexp(cu * cv / (qp.qt[i] * (double)qp.hthr[n]), qp.tc_exp);
+        for (int k = 0; k < 64; k++) {
+            const int y = k >> 3, x = k & 7;
+            const double b = scale * cos((2 * y + 1) * u * pi / 16.0) * cos((2 * x + 1) * v * pi / 16.0);
+            const __half hi = __double2half(b);
+            const __half lo = __double2half(b - (double)__half2float(hi));
+            const int kl = k + 64;
+            blob[(size_t)(n / 8) * 64 + (size_t)(k / 8) * 512 + (size_t)(n % 8) * 8 + (size_t)(k % 8)] = hi;
+            blob[(size_t)(n / 8) * 64 + (size_t)(kl / 8) * 512 + (size_t)(n % 8) * 8 + (size_t)(kl % 8)] = lo;
+        }
+    }
+}
+
+constexpr size_t kSmemEncode = cta_smem_bytes<kGroups, kFdctTc>();       // persistent encode kernel, modes 0 and 1
+constexpr size_t kSmemEncodeC = cta_smem_bytes<1, false>();               // C variant: CUDA-core integer transform
+constexpr size_t kSmemSingle = cta_smem_bytes<1, kFdctTc>();              // symbol_stats_kernel, coeffs_kernel
+static_assert(kSmemEncode <= 232448, "shared memory of the persistent encode kernel exceeds 227 KB: lower TIC_GROUPS");
 
 static int ensure_tables(tic_handle h) {
     if (h->tables_ready) return TIC_OK;
     HuffTables t;
     build_default_tables(t);
     TIC_CUDA(h, cudaMemcpyToSymbol(c_default_tables, &t, sizeof t));
-    TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(TileShared)));
-    TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(TileShared)));
-    TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(TileShared)));
+    TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel<0, kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemEncode));
+    TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel<1, kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemEncode));
+    TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemEncodeC));
     uint16_t sq[4][64];   // c/img.c:157-181
     for (int f = 0; f < 4; f++)
         for (int i = 0; i < 64; i++) sq[f][i] = (uint16_t)(65536 / (kQuantBase[i] << f));
     TIC_CUDA(h, cudaMemcpyToSymbol(c_cvar_scaled_quant, sq, sizeof sq));
-    TIC_CUDA(h, cudaFuncSetAttribute(coeffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(TileShared)));
-    TIC_CUDA(h, cudaFuncSetAttribute(symbol_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(TileShared)));
-    int per_sm = 0;
-    TIC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_tiles_kernel<0>, kTile, sizeof(TileShared)));
+    TIC_CUDA(h, cudaFuncSetAttribute(coeffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSingle));
+    TIC_CUDA(h, cudaFuncSetAttribute(symbol_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSingle));
+    int per_sm = 0, per_sm_c = 0, per_sm_single = 0;
+    TIC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_tiles_kernel<0, kGroups>, kTile * kGroups, kSmemEncode));
+    TIC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, encode_tiles_kernel<2, 1>, kTile, kSmemEncodeC));
+    TIC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_single, symbol_stats_kernel, kTile, kSmemSingle));
     cudaDeviceProp prop;
     TIC_CUDA(h, cudaGetDeviceProperties(&prop, h->device));
     h->sm_count = prop.multiProcessorCount;
     h->ctas_per_sm = per_sm > 0 ? per_sm : 1;
+    h->ctas_per_sm_c = per_sm_c > 0 ? per_sm_c : 1;
+    h->ctas_per_sm_single = per_sm_single > 0 ? per_sm_single : 1;
     h->tables_ready = true;
+    return TIC_OK;
+}
+
+// The B operand of `quality` in device memory (built once per handle and quality).
+static int ensure_bmat(tic_handle h, int quality, const QuantParams& qp, const uint4** out) {
+    *out = nullptr;
+    if (!kFdctTc) return TIC_OK;
+    if (!h->d_bmat) TIC_CUDA(h, cudaMalloc(&h->d_bmat, (size_t)100 * tc::kBBytes));
+    uint4* dst = h->d_bmat + (size_t)quality * (tc::kBBytes / 16);
+    if (!h->bmat_ready[quality]) {
+        std::vector<__half> blob((size_t)64 * 128);
+        build_bmat(qp, blob.data());
+        // synchronous and device-wide: whatever stream a later batch of this quality runs on, the matrix is there
+        TIC_CUDA(h, cudaMemcpy(dst, blob.data(), tc::kBBytes, cudaMemcpyHostToDevice));
+        TIC_CUDA(h, cudaDeviceSynchronize());
+        h->bmat_ready[quality] = true;
+    }
+    *out = dst;
     return TIC_OK;
 }
 
@@ -793,6 +977,7 @@ int tic_create(int device, tic_handle* out) {
     tic_handle h = new tic_handle_s();
     h->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&h->d_counters, kCtrCount * 8) != cudaSuccess ||
+        cudaMalloc(&h->d_sticky, kCtrCount * 8) != cudaSuccess || cudaMemset(h->d_sticky, 0, kCtrCount * 8) != cudaSuccess ||
         cudaMallocHost(&h->h_counters, kCtrCount * 8) != cudaSuccess ||
         cudaMalloc(&h->d_meta, 64) != cudaSuccess || cudaMallocHost(&h->h_meta, 64) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -802,6 +987,8 @@ int tic_create(int device, tic_handle* out) {
     for (int i = 0; i < tic_handle_s::kEvRing; i++)
         for (int j = 0; j < 4; j++)
             if (cudaEventCreate(&h->ev[i][j]) != cudaSuccess) { tic_destroy(h); return TIC_E_CUDA; }
+    for (int i = 0; i < tic_handle_s::kDescSlots; i++)
+        if (cudaEventCreateWithFlags(&h->desc_ev[i], cudaEventDisableTiming) != cudaSuccess) { tic_destroy(h); return TIC_E_CUDA; }
     *out = h;
     return TIC_OK;
 }
@@ -810,7 +997,8 @@ int tic_destroy(tic_handle h) {
     if (!h) return TIC_E_INVALID;
     cudaSetDevice(h->device);
     tic_internal_dec_release(h->dec_ws);
-    cudaFree(h->d_descs); cudaFreeHost(h->h_descs); cudaFree(h->d_recs); cudaFree(h->d_tile_pos); cudaFree(h->d_chunk_span); cudaFree(h->d_chunk_pos);
+    cudaFree(h->d_descs); cudaFree(h->d_sticky); cudaFree(h->d_bmat); cudaFree(h->d_recs);
+    for (int i = 0; i < tic_handle_s::kDescSlots; i++) { cudaFreeHost(h->h_descs_ring[i]); if (h->desc_ev[i]) cudaEventDestroy(h->desc_ev[i]); } cudaFree(h->d_tile_pos); cudaFree(h->d_chunk_span); cudaFree(h->d_chunk_pos);
     cudaFree(h->d_arena); cudaFree(h->d_counters);
     cudaFree(h->d_hist); cudaFree(h->d_first); cudaFree(h->d_tabs); cudaFree(h->d_tree);
     cudaFreeHost(h->h_counters); cudaFree(h->d_out_end); cudaFree(h->d_px); cudaFree(h->d_out);
@@ -824,14 +1012,30 @@ int tic_destroy(tic_handle h) {
 
 const char* tic_last_error(tic_handle h) { return h ? h->err.c_str() : "null handle"; }
 
+// Room for n descriptors, and the pinned slot this batch stages them in.  A slot is reused only after the H2D copy
+// of the batch that used it last has completed (an event recorded behind that copy), so batches may be enqueued
+// back to back without tic_encode_finish in between.
 static int grow_descs(tic_handle h, size_t n) {
-    if (n <= h->descs_cap) return TIC_OK;
-    size_t cap = n < 64 ? 64 : n * 2;
-    cudaFree(h->d_descs); cudaFreeHost(h->h_descs);
-    h->d_descs = nullptr; h->h_descs = nullptr; h->descs_cap = 0;
-    TIC_CUDA(h, cudaMalloc(&h->d_descs, cap * sizeof(ImageDesc)));
-    TIC_CUDA(h, cudaMallocHost(&h->h_descs, cap * sizeof(ImageDesc)));
-    h->descs_cap = cap;
+    if (n > h->descs_cap) {
+        TIC_CUDA(h, cudaDeviceSynchronize());   // nothing in flight reads the old buffers
+        size_t cap = n < 64 ? 64 : n * 2;
+        cudaFree(h->d_descs);
+        h->d_descs = nullptr; h->descs_cap = 0;
+        for (int i = 0; i < tic_handle_s::kDescSlots; i++) { cudaFreeHost(h->h_descs_ring[i]); h->h_descs_ring[i] = nullptr; }
+        TIC_CUDA(h, cudaMalloc(&h->d_descs, cap * sizeof(ImageDesc)));
+        for (int i = 0; i < tic_handle_s::kDescSlots; i++) TIC_CUDA(h, cudaMallocHost(&h->h_descs_ring[i], cap * sizeof(ImageDesc)));
+        h->descs_cap = cap;
+    }
+    const int slot = (int)(h->desc_seq % tic_handle_s::kDescSlots);
+    TIC_CUDA(h, cudaEventSynchronize(h->desc_ev[slot]));   // returns at once for an event never recorded
+    h->h_descs = h->h_descs_ring[slot];
+    return TIC_OK;
+}
+// after the H2D copy of the staged descriptors has been enqueued on `stream`
+static int descs_staged(tic_handle h, cudaStream_t stream) {
+    const int slot = (int)(h->desc_seq % tic_handle_s::kDescSlots);
+    TIC_CUDA(h, cudaEventRecord(h->desc_ev[slot], stream));
+    h->desc_seq++;
     return TIC_OK;
 }
 
@@ -868,8 +1072,8 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     if (rc) return rc;
     h->last_tiles = h->last_blocks = h->last_launches = 0;
     cudaEvent_t* evq = h->ev[h->ev_batches % tic_handle_s::kEvRing];
-    if (n_images == 0) {
-        TIC_CUDA(h, cudaMemsetAsync(h->d_counters, 0, kCtrCount * 8, stream));
+    if (n_images == 0) {   // nothing to encode: the byte total of "the last batch" is 0
+        TIC_CUDA(h, cudaMemsetAsync(h->d_sticky + kCtrTotalBits, 0, 8, stream));
         return TIC_OK;
     }
     rc = grow_descs(h, (size_t)n_images);
@@ -942,10 +1146,23 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     }
     TIC_CUDA(h, cudaMemcpyAsync(h->d_descs, h->h_descs, (size_t)n_images * sizeof(ImageDesc),
                                 cudaMemcpyHostToDevice, stream));
+    rc = descs_staged(h, stream);
+    if (rc) return rc;
     TIC_CUDA(h, cudaMemsetAsync(h->d_counters, 0, kCtrCount * 8, stream));
     TIC_CUDA(h, cudaMemsetAsync(d_status, 0, (size_t)n_images * 4, stream));
+    const uint4* d_bmat = nullptr;
+    if (!c_variant) {
+        rc = ensure_bmat(h, quality, qp, &d_bmat);
+        if (rc) return rc;
+    }
+    // persistent kernel: one CTA of kGroups groups per SM; every group takes tiles round-robin
     long long grid = (long long)h->sm_count * h->ctas_per_sm;
-    if (grid > ntiles) grid = ntiles;
+    if (grid > (ntiles + kGroups - 1) / kGroups) grid = (ntiles + kGroups - 1) / kGroups;
+    long long grid_c = (long long)h->sm_count * h->ctas_per_sm_c;
+    if (grid_c > ntiles) grid_c = ntiles;
+    long long grid_single = (long long)h->sm_count * h->ctas_per_sm_single;
+    if (grid_single > ntiles) grid_single = ntiles;
+    const uint32_t kflags = flags & TIC_FLAG_DEBUG_ALL_EXACT;
     const AutoTables* d_tabs = nullptr;
     h->last_launches = 6;
     if (auto_mode) {   // calc_huffman_table (huffman.py:101-109) + write_huffman_table (codec.py:73-84)
@@ -961,8 +1178,8 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
         }
         TIC_CUDA(h, cudaMemsetAsync(h->d_hist, 0, (size_t)n_images * 272 * sizeof(uint32_t), stream));
         TIC_CUDA(h, cudaMemsetAsync(h->d_first, 0xff, (size_t)n_images * 272 * sizeof(unsigned long long), stream));
-        symbol_stats_kernel<<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
-            qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_counters, h->d_hist, h->d_first, d_status);
+        symbol_stats_kernel<<<(unsigned)grid_single, kTile, kSmemSingle, stream>>>(
+            qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_counters, h->d_hist, h->d_first, d_status, d_bmat);
         TIC_CUDA(h, cudaGetLastError());
         build_tables_kernel<<<(n_images + 31) / 32, 32, 0, stream>>>(h->d_descs, n_images, quality,
                                                                     (flags & TIC_FLAG_AUTO_LE_FLAG) ? 1 : 0, h->d_hist,
@@ -971,19 +1188,19 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
         d_tabs = h->d_tabs;
         h->last_launches = 8;
         TIC_CUDA(h, cudaEventRecord(evq[0], stream));
-        encode_tiles_kernel<1><<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
+        encode_tiles_kernel<1, kGroups><<<(unsigned)grid, kTile * kGroups, kSmemEncode, stream>>>(
             qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_recs, h->d_arena, (unsigned long long)h->arena_cap16,
-            h->d_counters, d_status, quality, d_tabs);
+            h->d_counters, d_status, quality, d_tabs, d_bmat, kflags);
     } else if (c_variant) {
         TIC_CUDA(h, cudaEventRecord(evq[0], stream));
-        encode_tiles_kernel<2><<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
+        encode_tiles_kernel<2, 1><<<(unsigned)grid_c, kTile, kSmemEncodeC, stream>>>(
             qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_recs, h->d_arena, (unsigned long long)h->arena_cap16,
-            h->d_counters, d_status, quality, d_tabs);
+            h->d_counters, d_status, quality, d_tabs, d_bmat, kflags);
     } else {
         TIC_CUDA(h, cudaEventRecord(evq[0], stream));
-        encode_tiles_kernel<0><<<(unsigned)grid, kTile, sizeof(TileShared), stream>>>(
+        encode_tiles_kernel<0, kGroups><<<(unsigned)grid, kTile * kGroups, kSmemEncode, stream>>>(
             qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_recs, h->d_arena, (unsigned long long)h->arena_cap16,
-            h->d_counters, d_status, quality, d_tabs);
+            h->d_counters, d_status, quality, d_tabs, d_bmat, kflags);
     }
     TIC_CUDA(h, cudaGetLastError());
     TIC_CUDA(h, cudaEventRecord(evq[1], stream));
@@ -991,7 +1208,7 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     if (small) {   // one launch instead of four
         scan_small_kernel<<<1, kSmallThreads, 0, stream>>>(h->d_recs, (int)ntiles, h->d_tile_pos, (long long)out_capacity,
                                                           (long long*)d_out_offsets, h->d_out_end, (long long*)d_out_sizes,
-                                                          n_images, d_status, h->d_counters);
+                                                          n_images, d_status, h->d_counters, h->d_sticky);
         TIC_CUDA(h, cudaGetLastError());
         h->last_launches -= 3;
     } else {
@@ -1017,7 +1234,7 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     if (!small) {
         finalize_kernel<<<(n_images + 255) / 256, 256, 0, stream>>>(n_images, (const long long*)d_out_offsets,
                                                                    h->d_out_end, (long long*)d_out_sizes, d_status,
-                                                                   h->d_counters);
+                                                                   h->d_counters, h->d_sticky);
         TIC_CUDA(h, cudaGetLastError());
     }
     h->last_tiles = ntiles;
@@ -1029,7 +1246,8 @@ int tic_encode_finish(tic_handle h, void* stream_v, int64_t* total_bytes) {
     if (!h) return TIC_E_INVALID;
     cudaStream_t stream = (cudaStream_t)stream_v;
     TIC_CUDA(h, cudaSetDevice(h->device));
-    TIC_CUDA(h, cudaMemcpyAsync(h->h_counters, h->d_counters, kCtrCount * 8, cudaMemcpyDeviceToHost, stream));
+    TIC_CUDA(h, cudaMemcpyAsync(h->h_counters, h->d_sticky, kCtrCount * 8, cudaMemcpyDeviceToHost, stream));
+    TIC_CUDA(h, cudaMemsetAsync(h->d_sticky, 0, kCtrCount * 8, stream));   // the next finish reports the batches after this one
     TIC_CUDA(h, cudaStreamSynchronize(stream));
     // device time of the two big kernels, summed over the batches enqueued since the last finish
     // (CUDA events recorded on the batches' stream; at most the newest kEvRing batches)
@@ -1044,6 +1262,7 @@ int tic_encode_finish(tic_handle h, void* stream_v, int64_t* total_bytes) {
     h->ev_batches = 0;
     (void)cudaGetLastError();
     if (total_bytes) *total_bytes = (int64_t)(h->h_counters[kCtrTotalBits] >> 3);
+    if (h->h_counters[kCtrTcTimeout]) { h->err = "tensor-core pipeline: an MMA completion never arrived"; return TIC_E_CUDA; }
     if (h->h_counters[kCtrOverflow]) { h->err = "output buffer too small"; return TIC_E_CAPACITY; }
     if (h->h_counters[kCtrAnyStatus] & TIC_STATUS_TABLE) {
         h->err = "auto-generated Huffman table cannot be serialised (reference: OverflowError)";
@@ -1074,6 +1293,8 @@ int tic_last_stats(tic_handle h, int64_t stats[8]) {
     return TIC_OK;
 }
 
+int64_t tic_last_guard_misses(tic_handle h) { return h ? (int64_t)h->h_counters[kCtrUnflagged] : -1; }
+
 int tic_encode_coeffs(tic_handle h, const void* d_pixels, int32_t height, int32_t width, int32_t quality,
                       int32_t* d_dc, int32_t* d_ac, void* stream_v) {
     if (!h) return TIC_E_INVALID;
@@ -1097,9 +1318,14 @@ int tic_encode_coeffs(tic_handle h, const void* d_pixels, int32_t height, int32_
     d.h = height; d.w = width; d.bw = (width + 7) / 8; d.nblk = (int)nblk; d.tile0 = 0;
     d.bw_shift = bw_shift_of(d.bw); d.pad = 0;
     TIC_CUDA(h, cudaMemcpyAsync(h->d_descs, h->h_descs, sizeof(ImageDesc), cudaMemcpyHostToDevice, stream));
+    rc = descs_staged(h, stream);
+    if (rc) return rc;
+    const uint4* d_bmat = nullptr;
+    rc = ensure_bmat(h, quality, qp, &d_bmat);
+    if (rc) return rc;
     TIC_CUDA(h, cudaMemsetAsync(h->d_counters, 0, kCtrCount * 8, stream));
     long long ntiles = (nblk + kTile - 1) / kTile;
-    coeffs_kernel<<<(unsigned)ntiles, kTile, sizeof(TileShared), stream>>>(qp, h->d_descs, h->d_counters, d_dc, d_ac);
+    coeffs_kernel<<<(unsigned)ntiles, kTile, kSmemSingle, stream>>>(qp, h->d_descs, h->d_counters, d_dc, d_ac, d_bmat, 0u);
     TIC_CUDA(h, cudaGetLastError());
     h->last_launches = 1;
     h->last_tiles = ntiles;

@@ -30,8 +30,24 @@
 #include <stdint.h>
 
 #include "tic_tables.h"
+#include "tic_tc.cuh"
 
 namespace tic {
+
+// 1 (default): the FDCT + quantiser scaling run on the tensor cores (tcgen05, tic_tc.cuh);
+// 0: the round-1 FP32 CUDA-core transform (kept for A/B measurements: tools/build_variants.sh)
+#ifndef TIC_FDCT_TC
+#define TIC_FDCT_TC 1
+#endif
+// 128-thread GROUPS per CTA of the persistent encode kernel: one CTA per SM, every group works on its own tile
+// with its own named barrier, TMEM columns and mbarrier; the B operand and the TMEM allocation are shared.
+#ifndef TIC_GROUPS
+#define TIC_GROUPS 6
+#endif
+// 1: the pixel rows of a group's NEXT tile are fetched into registers while the tensor core works on this one
+#ifndef TIC_PREFETCH
+#define TIC_PREFETCH 0
+#endif
 
 #ifndef TIC_TILE
 #define TIC_TILE 128
@@ -47,7 +63,11 @@ namespace tic {
 #endif
 constexpr int kTile = TIC_TILE;                             // blocks (= threads) per tile
 constexpr int kWarps = kTile / 32;
-constexpr int kCtasPerSm = TIC_CTAS;
+constexpr int kCtasPerSm = TIC_CTAS;                        // CTAs per SM of the single-group kernels
+constexpr int kGroups = TIC_GROUPS;
+constexpr bool kFdctTc = TIC_FDCT_TC != 0;
+static_assert(!kFdctTc || kTile == 128, "the tensor-core transform is M = 128: one tile = 128 blocks");
+static_assert((kTile & (kTile - 1)) == 0, "thread-in-group = threadIdx.x & (kTile - 1)");
 constexpr int kPrivWords = TIC_PRIV;                           // private words per block on the fast path (512 bits)
 // The bits of a tile are assembled in a WINDOW of kWinWords 32-bit words of shared memory: a tile
 // whose stream is longer (worst case 128 x 1662 bits + a table header) is emitted in several rounds.
@@ -64,6 +84,10 @@ struct QuantParams {
     float qmul[64];   // 1 / (8 * aan[u] * aan[v] * qt[u][v]):   t = d * qmul is coefficient / qt
     float zmul[64];   // qmul / hthr: |d * zmul| < 1  =>  rounds to 0 and is nowhere near a tie
     float hthr[64];   // 0.5 - w: |t - round(t)| > hthr  =>  within the guard band of a .5 tie
+    // tensor-core path: the accumulator holds D = t / hthr * 2^tc_exp (tic_tc.cuh), zigzag order
+    float cn[64];     // t = D * cn
+    float tc_live;    // 2^tc_exp: |D| < tc_live  =>  |t| < hthr: rounds to 0 and is nowhere near a tie
+    int tc_exp;
     double qt[64];    // [u*8+v]  the reference's float64 divisor (utils.py:50-53)
     double dcinv;     // 1 / (8 * qt[0]): quantised DC = (sum of pixels - 8192) * dcinv
 };
@@ -89,7 +113,8 @@ constexpr uint32_t kRecFirst = 1u << 30, kRecClosing = 1u << 31, kRecBitsMask = 
 
 // counters[] layout in the workspace
 enum { kCtrArena = 0, kCtrOverflow = 1, kCtrExactItems = 2, kCtrExactChanged = 3, kCtrTotalBits = 4,
-       kCtrAnyStatus = 5, kCtrCount = 8 };
+       kCtrAnyStatus = 5, kCtrUnflagged = 6 /* debug: exact != fast outside the guard band */,
+       kCtrTcTimeout = 7 /* an MMA completion never arrived */, kCtrCount = 8 };
 
 __device__ __constant__ uint8_t c_zigzag[64] = {TIC_ZIGZAG_LIST};
 __device__ __constant__ HuffTables c_default_tables;
@@ -100,6 +125,14 @@ __device__ __constant__ uint16_t c_cvar_scaled_quant[4][64];
 // ---------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------
+// thread within its group (= within the CTA for the single-group kernels)
+__device__ __forceinline__ int tid() { return (int)threadIdx.x & (kTile - 1); }
+template <int G>
+__device__ __forceinline__ void group_sync(int g) {   // barrier over the kTile threads of group g
+    if constexpr (G == 1) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(kTile) : "memory");
+}
+
 __device__ __forceinline__ int reflect_idx(int i, int n) {   // numpy "reflect", utils.py:56-61
     if (i < n) return i;
     if (n == 1) return 0;
@@ -313,6 +346,7 @@ struct TileShared {
     uint32_t nz_hi[kTile];           // bit 63-k set, k = 32..63
     int dcq[kTile];                  // quantised DC of thread t's block
     int dc_halo[kWarps];             // quantised DC of the block in front of the warp's first block
+    int blocksum[kWarps];            // tensor-core path: pixel sum of the warp's last block (the next warp's predictor)
     uint32_t work[kWarps][kWarpWork];// exact-path worklist: lane << 6 | zigzag index; bit 31: halo DC
     double colres[kWarps][4][8];
     int work_count[kWarps];
@@ -612,7 +646,7 @@ __device__ __forceinline__ void transform_block_c(const TileInfo& ti, int qfacto
 // Phase 1 of the C variant for the 32 blocks of one warp.  The DC of the block in front of the warp is the
 // quantised (sum of pixels - 8192): the DC path of c/img.c has no rounding before the quantiser.
 __device__ __forceinline__ void transform_warp_c(const TileInfo& ti, int qfactor, TileShared& sm) {
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int t = tid(), lane = t & 31, warp = t >> 5;
     if (warp * 32 >= ti.nb) return;   // warp-uniform
     transform_block_c(ti, qfactor, sm, t, t < ti.nb);
     int halo_dc = 0;
@@ -642,7 +676,11 @@ __device__ __forceinline__ void transform_warp_c(const TileInfo& ti, int qfactor
 // ---------------------------------------------------------------------------------------------
 struct ExactStats {
     unsigned int items, changed;
+    unsigned int unflagged;   // TIC_FLAG_DEBUG_ALL_EXACT: the exact value differs although the guard did not flag it
 };
+// worklist entry: lane << 6 | zigzag index; bit 31: the DC of the block in front of the tile / warp;
+// bit 30: flagged by the guard band (always set outside TIC_FLAG_DEBUG_ALL_EXACT)
+constexpr uint32_t kWorkHalo = 0x80000000u, kWorkGuard = 0x40000000u;
 
 __device__ __forceinline__ void exact_round(const TileInfo& ti, const QuantParams& qp, TileShared& sm,
                                             int warp, int count, ExactStats& st) {
@@ -707,6 +745,7 @@ __device__ __forceinline__ void exact_round(const TileInfo& ti, const QuantParam
                         if (q) atomicOr(m, bit); else atomicAnd(m, ~bit);
                     }
                     st.changed++;
+                    if (!(item & kWorkGuard)) st.unflagged++;
                 }
             }
         }
@@ -720,7 +759,7 @@ __device__ __forceinline__ void exact_round(const TileInfo& ti, const QuantParam
 // (Scalars by value: taking the TileInfo by reference would pin it in local memory for the whole kernel.)
 __device__ __noinline__ bool settle_dc_ties(const uint8_t* px, int w, int h, int bw, int blk0, int nb, double qt0,
                                             uint32_t* coef0 /* &sm.coef[0][0] */, int* dcq, uint32_t fl_lo) {
-    const int t = threadIdx.x;
+    const int t = tid();
     if (!(fl_lo & 0x80000000u)) return false;
     const int b = blk0 + (t < nb ? t : nb - 1);
     const int br = b / bw, bc = b - br * bw;
@@ -747,7 +786,7 @@ __device__ __noinline__ bool settle_dc_ties(const uint8_t* px, int w, int h, int
 // sm.coef / nz / dcq / dc_halo hold the reference's quantised coefficients for those blocks.
 __device__ __forceinline__ void transform_warp(const TileInfo& ti, const QuantParams& qp, TileShared& sm,
                                                ExactStats& st) {
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int t = tid(), lane = t & 31, warp = t >> 5;
     if (lane == 0) {
         sm.pending[warp] = 0;
         sm.dc_halo[warp] = 0;
@@ -815,7 +854,7 @@ __device__ __forceinline__ void transform_warp(const TileInfo& ti, const QuantPa
             const int k = fl_lo ? __clz(fl_lo) : 32 + __clz(fl_hi);
             const int slot = atomicAdd(&sm.work_count[warp], 1);
             if (slot >= kWarpWork) { atomicAdd(&sm.pending[warp], 1); break; }
-            sm.work[warp][slot] = ((uint32_t)lane << 6) | (uint32_t)k;
+            sm.work[warp][slot] = kWorkGuard | ((uint32_t)lane << 6) | (uint32_t)k;
             if (k < 32) fl_lo ^= 0x80000000u >> k; else fl_hi ^= 0x80000000u >> (k - 32);
         }
         __syncwarp();
@@ -825,6 +864,227 @@ __device__ __forceinline__ void transform_warp(const TileInfo& ti, const QuantPa
         __syncwarp();
         if (count) {   // warp-uniform
             if (lane == 0) st.items += (unsigned)count;   // (DC ties settled above count too)
+            exact_round(ti, qp, sm, warp, count, st);
+        }
+        if (pending == 0) break;
+        if (lane == 0) { sm.work_count[warp] = 0; sm.pending[warp] = 0; }
+        __syncwarp();
+    }
+    __syncwarp();
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// phases 1 + 2 on the tensor cores (tic_tc.cuh), for the kTile = 128 blocks of one tile; all threads of the
+// group call.  Pixels -> f16 A operand in shared memory (it aliases sm.coef: the quantised coefficients only
+// arrive after the MMA is complete) -> 8 MMAs issued by thread 0 -> the thread that owns a block reads its 64
+// scaled coefficients t / hthr * 2^E back from tensor memory, 16 columns at a time, and quantises them in
+// zigzag groups of 8 exactly like the FP32 path (group vote, magic-number rounding, residual test against the
+// guard band).  The exact path is unchanged.  On return (after a group barrier) sm.coef / nz / dcq hold the
+// reference's quantised coefficients of the whole tile and sm.dc_halo[0] the DC in front of its first block.
+// ---------------------------------------------------------------------------------------------
+struct TcGroup {
+    uint64_t desc_a0;  // shared-memory descriptor of the A operand's first K chunk (A aliases sm.coef)
+    uint64_t desc_b0;  // ... of the B operand (one per CTA)
+    uint32_t tmem;     // TMEM address of the group's accumulator columns, lane field = this warp's quarter
+    uint32_t bar;      // shared address of the group's mbarrier
+    uint32_t phase;
+};
+
+template <int G, int P>
+__device__ __forceinline__ void quantise_pairs_tc(const uint32_t* r /* 8 columns of group G */, const QuantParams& qp,
+                                                  TileShared& sm, int t, uint32_t& nz, uint32_t& fl, int& dc) {
+    if constexpr (P < 4) {
+        constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23
+        constexpr int k0 = 8 * G + 2 * P, k1 = k0 + 1;
+        const float d0 = __uint_as_float(r[2 * P]), d1 = __uint_as_float(r[2 * P + 1]);
+        const float b0 = fmaf(d0, qp.cn[k0], kMagic), b1 = fmaf(d1, qp.cn[k1], kMagic);
+        const float q0 = b0 - kMagic, q1 = b1 - kMagic;
+        const float e0 = fmaf(d0, qp.cn[k0], -q0), e1 = fmaf(d1, qp.cn[k1], -q1);   // t - round(t)
+        if (k0 != 0 && q0 != 0.0f) nz |= 0x80000000u >> (k0 & 31);
+        if (q1 != 0.0f) nz |= 0x80000000u >> (k1 & 31);
+        if (fabsf(e0) > qp.hthr[k0]) fl |= 0x80000000u >> (k0 & 31);   // the exact path decides
+        if (fabsf(e1) > qp.hthr[k1]) fl |= 0x80000000u >> (k1 & 31);
+        if constexpr (k0 == 0) dc = __float_as_int(b0) - 0x4B400000;
+        sm.coef[k0 >> 1][t] = __byte_perm(__float_as_uint(b0), __float_as_uint(b1), 0x5410);
+        quantise_pairs_tc<G, P + 1>(r, qp, sm, t, nz, fl, dc);
+    }
+}
+
+template <int G>
+__device__ __forceinline__ void quantise_group_tc(const uint32_t* r, const QuantParams& qp, TileShared& sm, int t,
+                                                  bool all_live, uint32_t& nz_lo, uint32_t& nz_hi, uint32_t& fl_lo,
+                                                  uint32_t& fl_hi, int& dc) {
+    bool live = true;
+    if constexpr (G > 0) {
+        float m = fmax3(fabsf(__uint_as_float(r[0])), fabsf(__uint_as_float(r[1])), fabsf(__uint_as_float(r[2])));
+        m = fmax3(m, fabsf(__uint_as_float(r[3])), fabsf(__uint_as_float(r[4])));
+        m = fmax3(m, fabsf(__uint_as_float(r[5])), fabsf(__uint_as_float(r[6])));
+        m = fmaxf(m, fabsf(__uint_as_float(r[7])));
+        live = __any_sync(0xffffffffu, m >= qp.tc_live) || all_live;
+    }
+    if (live) {   // warp-uniform
+        if constexpr (G < 4) quantise_pairs_tc<G, 0>(r, qp, sm, t, nz_lo, fl_lo, dc);
+        else quantise_pairs_tc<G, 0>(r, qp, sm, t, nz_hi, fl_hi, dc);
+    }
+}
+
+// Pixels of thread t's block as 8 rows of 8 bytes (reflection padding where the block leaves the image).
+__device__ __forceinline__ void load_block_rows(const TileInfo& ti, int t, uint2 (&rows)[8]) {
+    int y0, x0;
+    block_origin(ti, t, y0, x0);
+    if (block_is_fast(ti, y0)) {
+        const uint8_t* p = ti.px + (size_t)y0 * ti.w + x0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) rows[i] = __ldg(reinterpret_cast<const uint2*>(p + (size_t)i * ti.w));
+    } else {
+        int cx[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) cx[j] = reflect_idx(x0 + j, ti.w);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint8_t* row = ti.px + (size_t)reflect_idx(y0 + i, ti.h) * ti.w;
+            uint32_t lo = 0, hi = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                lo |= (uint32_t)__ldg(row + cx[j]) << (8 * j);
+                hi |= (uint32_t)__ldg(row + cx[4 + j]) << (8 * j);
+            }
+            rows[i] = make_uint2(lo, hi);
+        }
+    }
+}
+
+// rows: the pixel rows of this thread's block (load_block_rows), loaded by the caller — one tile ahead in the
+// persistent kernel; `next` (may be null): the tile whose rows are fetched into `rows` while the tensor core works.
+template <int G>
+__device__ __forceinline__ void transform_tile_tc(const TileInfo& ti, const QuantParams& qp, TileShared& sm,
+                                                  TcGroup& tg, int g, bool debug_all, ExactStats& st, bool& timeout,
+                                                  uint2 (&rows)[8], const TileInfo* next) {
+    const int t = tid(), lane = t & 31, warp = t >> 5;
+    if (lane == 0) {
+        sm.pending[warp] = 0;
+        sm.dc_halo[warp] = 0;
+        sm.work_count[warp] = 0;
+    }
+    // ---- pixels -> A operand ----------------------------------------------------------------------------
+    {
+        unsigned char* dst = reinterpret_cast<unsigned char*>(&sm.coef[0][0]) + (t >> 3) * 128 + (t & 7) * 16;
+#pragma unroll
+        for (int y = 0; y < 8; y++) *reinterpret_cast<uint4*>(dst + y * (int)tc::kLboA) = tc::row_to_f16(rows[y]);
+        if (lane == 31) {   // the next warp's DC predictor needs this block's DC: its pixel sum settles it (below)
+            uint32_t sum = 0;
+#pragma unroll
+            for (int y = 0; y < 8; y++) sum = __dp4a(rows[y].x, 0x01010101u, __dp4a(rows[y].y, 0x01010101u, sum));
+            sm.blocksum[warp] = (int)sum;
+        }
+    }
+    tc::fence_proxy_async();    // generic-proxy stores -> visible to the tensor core's async proxy
+    tc::fence_before_sync();    // this thread's TMEM reads of the previous tile are ordered before the barrier
+    group_sync<G>(g);
+    if (t == 0) {
+        tc::fence_after_sync();
+        tc::issue_tile_mma(tg.desc_a0, tg.desc_b0, tg.tmem & 0x0000ffffu, tg.bar);
+    }
+    if (TIC_PREFETCH && next) load_block_rows(*next, t, rows);   // in flight until the next tile is staged
+    // ---- while the tensor core works: quantised DC of the block in front of the warp's first block ------------
+    // (codec.py:34-35).  The DC coefficient is (sum of pixels - 8192) / 8 exactly, so unless its quotient by qt
+    // lands within 1e-9 of a .5 tie (where the reference's float64 rounding errors decide) one pixel sum settles
+    // it: the previous warp's last lane left it in shared memory; the block in front of the TILE belongs to
+    // another CTA and is summed here.  A tie, or a tile predecessor that needs reflection padding, becomes an
+    // exact-path item.
+    int halo_item = 0, halo_dc = 0;
+    const int hb = ti.blk0 + warp * 32 - 1;
+    if (hb >= 0 && warp * 32 < ti.nb) {   // warp-uniform
+        int sum = 0;
+        bool have_sum = true;
+        uint2 v = make_uint2(0u, 0u);
+        if (warp > 0) {
+            sum = sm.blocksum[warp - 1];
+        } else {
+            const int br = hb / ti.bw, bc = hb - br * ti.bw;
+            const int y0 = br * 8;
+            have_sum = ((ti.w & 7) == 0) && ((reinterpret_cast<uintptr_t>(ti.px) & 7) == 0) && (y0 + 8 <= ti.h);
+            if (have_sum) {
+                if (lane < 8) v = __ldg(reinterpret_cast<const uint2*>(ti.px + (size_t)(y0 + lane) * ti.w + bc * 8));
+                sum = __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, 0u));
+                sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+                sum += __shfl_xor_sync(0xffffffffu, sum, 4);
+                sum = __shfl_sync(0xffffffffu, sum, 0);
+            }
+        }
+        halo_item = 1;
+        if (have_sum) {
+            const double tq = __dmul_rn((double)(sum - 8192), qp.dcinv);
+            halo_dc = __double2int_rn(tq);
+            halo_item = (fabs(tq - (double)halo_dc) < 0.5 - 1.0e-9) ? 0 : 1;   // on a tie the exact path decides
+        }
+    }
+    // ---- accumulator -> quantised coefficients ------------------------------------------------------------
+    if (!tc::mbar_wait(tg.bar, tg.phase)) timeout = true;
+    tg.phase ^= 1u;
+    tc::fence_after_sync();
+    uint32_t fl_lo = 0, fl_hi = 0;
+    if (warp * 32 < ti.nb) {   // warp-uniform: the warp owns at least one block
+        uint32_t nz_lo = 0, nz_hi = 0;
+        int dc = 0;
+        uint32_t ra[16], rb[16];
+        tc::tmem_ld16(tg.tmem, ra);
+        tc::tmem_wait_ld(ra);
+        tc::tmem_ld16(tg.tmem + 16, rb);
+        quantise_group_tc<0>(ra, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
+        quantise_group_tc<1>(ra + 8, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
+        tc::tmem_wait_ld(rb);
+        tc::tmem_ld16(tg.tmem + 32, ra);
+        quantise_group_tc<2>(rb, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
+        quantise_group_tc<3>(rb + 8, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
+        tc::tmem_wait_ld(ra);
+        tc::tmem_ld16(tg.tmem + 48, rb);
+        quantise_group_tc<4>(ra, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
+        quantise_group_tc<5>(ra + 8, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
+        tc::tmem_wait_ld(rb);
+        quantise_group_tc<6>(rb, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
+        quantise_group_tc<7>(rb + 8, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
+        sm.nz_lo[t] = nz_lo;
+        sm.nz_hi[t] = nz_hi;
+        sm.dcq[t] = dc;
+        if (!(t < ti.nb)) fl_lo = fl_hi = 0;
+        // A DC in the guard band of a tie: 1 block in 128 on ordinary content, but EVERY block of a flat area whose
+        // level lands on a tie.  When several lanes are affected each settles its own DC in float64 (out of line).
+        if (__popc(__ballot_sync(0xffffffffu, (fl_lo & 0x80000000u) != 0)) >= 4) {   // warp-uniform
+            if (settle_dc_ties(ti.px, ti.w, ti.h, ti.bw, ti.blk0, ti.nb, qp.qt[0], &sm.coef[0][0], sm.dcq, fl_lo)) {
+                fl_lo &= 0x7fffffffu;
+                st.items++;
+            }
+        }
+    }
+    if (lane == 0) {
+        if (halo_item) sm.work[warp][atomicAdd(&sm.work_count[warp], 1)] = kWorkHalo | kWorkGuard;   // slot 0: nothing pushed yet
+        else sm.dc_halo[warp] = halo_dc;
+    }
+    __syncwarp();
+    // ---- exact path: flagged coefficients of the warp's 32 blocks (all of them under TIC_FLAG_DEBUG_ALL_EXACT) ----
+    uint32_t dbg_lo = 0, dbg_hi = 0;   // coefficients that go to the exact path although the guard did not flag them
+    if (debug_all && t < ti.nb) { dbg_lo = ~fl_lo; dbg_hi = ~fl_hi; }
+    while (true) {
+        while (fl_lo | fl_hi | dbg_lo | dbg_hi) {
+            const bool guard = (fl_lo | fl_hi) != 0;
+            uint32_t& lo = guard ? fl_lo : dbg_lo;
+            uint32_t& hi = guard ? fl_hi : dbg_hi;
+            const int k = lo ? __clz(lo) : 32 + __clz(hi);
+            const int slot = atomicAdd(&sm.work_count[warp], 1);
+            if (slot >= kWarpWork) { atomicAdd(&sm.pending[warp], 1); break; }
+            sm.work[warp][slot] = (guard ? kWorkGuard : 0u) | ((uint32_t)lane << 6) | (uint32_t)k;
+            if (k < 32) lo ^= 0x80000000u >> k; else hi ^= 0x80000000u >> (k - 32);
+        }
+        __syncwarp();
+        const int raw = sm.work_count[warp];
+        const int count = raw < kWarpWork ? raw : kWarpWork;
+        const int pending = sm.pending[warp];
+        __syncwarp();
+        if (count) {   // warp-uniform
+            if (lane == 0) st.items += (unsigned)count;
             exact_round(ti, qp, sm, warp, count, st);
         }
         if (pending == 0) break;

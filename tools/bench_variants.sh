@@ -2,7 +2,7 @@
 # run the short bench once per variant library in scratch/variants
 for f in scratch/variants/*.so; do
   n=$(basename $f .so)
-  TIC_LIB_PATH=$PWD/$f timeout 300 python bench.py --no-cpu --no-e2e --steps 10 --warmup 3 > gpurun_out/var_$n.json 2> gpurun_out/var_$n.err
+  TIC_LIB_PATH=$PWD/$f timeout 300 python bench.py --no-cpu --no-e2e --no-decode --steps 10 --warmup 3 > gpurun_out/var_$n.json 2> gpurun_out/var_$n.err
   python - "$n" <<'PY'
 import json,sys
 n=sys.argv[1]

@@ -5,8 +5,12 @@ rep_csv, lib, kernel = sys.argv[1], sys.argv[2], sys.argv[3]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
 td = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=td, stdout=subprocess.DEVNULL)
-cubin = [os.path.join(td, f) for f in os.listdir(td) if f.endswith(".cubin")][0]
-dis = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout.splitlines()
+dis = []
+for cubin in sorted(os.path.join(td, f) for f in os.listdir(td) if f.endswith(".cubin")):   # the one that holds the kernel
+    out = subprocess.run(["nvdisasm", "-g", "-c", cubin], capture_output=True, text=True).stdout
+    if kernel in out:
+        dis = out.splitlines()
+        break
 lines, cur, inside = [], None, False
 for ln in dis:
     if ln.startswith("//---") and ".text." in ln:
