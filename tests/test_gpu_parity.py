@@ -213,7 +213,7 @@ def test_device_tensor_batch_and_stats(tic):
     offs = res.offsets.cpu().numpy()
     assert np.all(offs % 16 == 0) and np.all(np.diff(offs) > 0)          # dense, 16-byte aligned, in order
     st = enc.stats()
-    assert st["launches"] == 3 and st["blocks"] == 9 * 32 * 48 and st["tiles"] == 9 * 12   # small batch: fused scan
+    assert st["launches"] == 4 and st["blocks"] == 9 * 32 * 48 and st["tiles"] == 9 * 12   # small (N,H,W) batch: prep, encode, fused scan, compact
     assert st["timed_batches"] == 1 and st["encode_kernel_ms_sum"] > 0 and st["compact_kernel_ms_sum"] > 0
 
 

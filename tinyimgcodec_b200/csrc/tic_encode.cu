@@ -17,16 +17,18 @@ namespace tic {
 // Huffman tables -> shared memory in the form the walk wants (see TileShared::ac_tab).  All threads of a group call.
 template <bool kAuto>
 __device__ __forceinline__ void load_tables(TileShared& sm, const HuffTables& g) {
+    uint32_t* ac32 = reinterpret_cast<uint32_t*>(sm.ac_tab);   // fixed tables: 32-bit entries (TileShared::ac_tab)
+    uint32_t* dc32 = reinterpret_cast<uint32_t*>(sm.dc_tab);
     for (int i = tid(); i < 256; i += kTile) {
         const uint32_t len = g.ac[i].len, code = g.ac[i].code;
         if constexpr (kAuto) sm.ac_tab[i] = make_uint2(code, len);
-        else sm.ac_tab[i] = len ? make_uint2(code << (i & 15), (len & kHuffLenMask) + (uint32_t)(i & 15)) : make_uint2(0u, 0u);
+        else ac32[i] = len ? (((len & kHuffLenMask) + (uint32_t)(i & 15)) << 27) | (code << (i & 15)) : 0u;
     }
     if (tid() < 16) {
         const int i = tid();
         const uint32_t len = g.dc[i].len, code = g.dc[i].code;
         if constexpr (kAuto) sm.dc_tab[i] = make_uint2(code, len);
-        else sm.dc_tab[i] = len ? make_uint2(code << i, (len & kHuffLenMask) + (uint32_t)i) : make_uint2(0u, 0u);
+        else dc32[i] = len ? (((len & kHuffLenMask) + (uint32_t)i) << 27) | (code << i) : 0u;
     }
 }
 
@@ -61,11 +63,9 @@ __device__ __forceinline__ unsigned char* tc_cta_setup(unsigned char* smem_raw, 
     __syncthreads();
     tc::fence_after_sync();
     tmem_base = *tmem_slot;
-    tg.desc_b0 = tc::smem_desc(tc::smem_addr(sB), tc::kLboB, tc::kSboB);
-    tg.bar = tc::smem_addr(mbar + g);
-    // accumulator of group g: columns [64 g, 64 g + 64); a warp reads the lane quarter (warp % 4) * 32
-    tg.tmem = tmem_base + (uint32_t)(g * tc::kColsPerGroup) + ((uint32_t)(((threadIdx.x >> 5) & 3) * 32) << 16);
+    tg.ctl = tc::smem_addr(mbar);
     tg.phase = 0;
+    (void)g;
     return smem_raw + tc::kBBytes + kTcCtlBytes;
 }
 template <int G>
@@ -97,7 +97,6 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
     uint32_t tmem_base = 0;
     if constexpr (kTc) gbase = tc_cta_setup<G>(smem_raw, bmat, g, tg, tmem_base);
     TileShared& sm = *reinterpret_cast<TileShared*>(gbase + (size_t)g * kGroupStride);
-    tg.desc_a0 = tc::smem_desc(tc::smem_addr(&sm.coef[0][0]), tc::kLboA, tc::kSboA);
     uint32_t sbase = smem_u32(&sm);   // kept in a register: the walk addresses shared memory directly
     asm volatile("mov.u32 %0, %0;" : "+r"(sbase));
     const bool debug_all = (flags & TIC_FLAG_DEBUG_ALL_EXACT) != 0;
@@ -106,35 +105,41 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
     for (int i = t; i < kWinWords; i += kTile) sm.stage[i] = 0;
     group_sync<G>(g);
 
-    ExactStats st{0u, 0u, 0u};
-    bool timeout = false;
+    const ExactStats st{&sm};
+    if (t == 0) sm.stat_items = sm.stat_changed = sm.stat_unflagged = sm.tc_timeout = 0u;
     int tab_img = -1;   // auto mode: image whose tables are in shared memory
-    const long long first = (long long)blockIdx.x * G + g, stride = (long long)gridDim.x * G;
-    // uniform batch: (image, tile within image) advance by a fixed step, no division in the loop
-    int u_img = 0, u_lt = 0, u_dq = 0, u_dr = 0;
-    if (uniform_tpi > 0) {
-        u_img = (int)(first / uniform_tpi);  u_lt = (int)(first - (long long)u_img * uniform_tpi);
-        u_dq = (int)(stride / uniform_tpi);  u_dr = (int)(stride - (long long)u_dq * uniform_tpi);
-    }
-    // the tile after `tile` in this group's sequence (the uniform counters run one tile ahead of the loop)
-    auto tile_at = [&](long long tl) -> TileInfo {
+    // tiles of this group: first, first + stride, ... (ntiles < 2^31: unsigned arithmetic cannot wrap)
+    const unsigned first = blockIdx.x * G + g, stride = gridDim.x * G, ntiles_u = (unsigned)ntiles;
+    // The description of tile `tl` into sm.tinfo[slot]: all lanes of warp 0 call (the search of a ragged batch is
+    // warp-cooperative); uniform batches step (image, tile in image) by a fixed amount, no division in the loop.
+    auto describe = [&](unsigned tl, int slot) {
         if (uniform_tpi > 0) {
-            const TileInfo r = tile_info(descs[u_img], u_img, u_lt);
-            u_img += u_dq; u_lt += u_dr;
-            if (u_lt >= uniform_tpi) { u_lt -= uniform_tpi; u_img++; }
-            return r;
+            if (lane == 0) {
+                int img = sm.u_img, lt = sm.u_lt;
+                sm.tinfo[slot] = tile_info(descs[img], img, lt);
+                const int dq = (int)(stride / (unsigned)uniform_tpi), dr = (int)(stride - (unsigned)dq * (unsigned)uniform_tpi);
+                img += dq; lt += dr;
+                if (lt >= uniform_tpi) { lt -= uniform_tpi; img++; }
+                sm.u_img = img; sm.u_lt = lt;
+            }
+        } else {
+            const TileInfo r = locate_tile(descs, n_images, (long long)tl, 0);
+            if (lane == 0) sm.tinfo[slot] = r;
         }
-        return locate_tile(descs, n_images, tl, 0);
     };
-    TileInfo ti{}, nti{};
-    uint2 rows[8] = {};   // tensor-core path: this thread's pixel rows, fetched one tile ahead
-    if (first < ntiles) {
-        ti = tile_at(first);
-        if constexpr (kTc) { if (TIC_PREFETCH && ti.nb > 0) load_block_rows(ti, t, rows); }
+    if (warp == 0 && first < ntiles_u) {
+        if (lane == 0 && uniform_tpi > 0) { sm.u_img = (int)(first / (unsigned)uniform_tpi); sm.u_lt = (int)(first - (unsigned)sm.u_img * (unsigned)uniform_tpi); }
+        describe(first, 0);
     }
-    for (long long tile = first; tile < ntiles; tile += stride, ti = nti) {
-        const bool has_next = tile + stride < ntiles;
-        if (has_next) nti = tile_at(tile + stride);
+    group_sync<G>(g);
+
+    int slot = 0;
+    constexpr int kDescWarp = (kTc && kWarps > 1) ? 1 : 0;   // warp 0 already issues the MMA and owns the tile's halo
+    for (unsigned tile = first; tile < ntiles_u; tile += stride, slot ^= 1) {
+        const TileInfo& ti = sm.tinfo[slot];
+        // one warp describes the group's next tile one tile ahead: in the tensor core's shadow (tensor-core path), or
+        // here; barrier B1 of this tile orders the write before every later read
+        auto describe_next = [&]() { if (warp == kDescWarp && tile + stride < ntiles_u) describe(tile + stride, slot ^ 1); };
         if constexpr (kAuto) {
             if (tab_img != ti.img) {   // per-image tables (codec.py:146-148); group-uniform branch
                 group_sync<G>(g);      // everyone is done with the previous image's tables
@@ -145,13 +150,18 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
         }
 
         // ---- coefficients of the tile, then the bits of every block into its private words ---------
-        if constexpr (kCVar) transform_warp_c(ti, quality, sm);
+        if constexpr (kCVar) { describe_next(); transform_warp_c(ti, quality, sm); }
         else if constexpr (kTc) {
-            if (!TIC_PREFETCH && ti.nb > 0) load_block_rows(ti, t, rows);
-            if (ti.nb > 0) transform_tile_tc<G>(ti, qp, sm, tg, g, debug_all, st, timeout, rows, has_next && nti.nb > 0 ? &nti : nullptr);
-            else if (TIC_PREFETCH && has_next && nti.nb > 0) load_block_rows(nti, t, rows);
+            if (ti.nb > 0) {
+                uint2 rows[8];
+                load_block_rows(ti, t, rows);
+                const uint2 halo_v = load_tile_halo(ti, t);   // with the tile's own rows: one DRAM latency, not two
+                transform_tile_tc<G>(ti, qp, sm, tg, g, debug_all, st, rows, halo_v, describe_next);
+            } else {
+                describe_next();
+            }
         }
-        else transform_warp(ti, qp, sm, st);
+        else { describe_next(); transform_warp(ti, qp, sm, st); }
         int err = 0, bits = 0, nwords = 0, diff = 0;
         if (t < ti.nb) {
             diff = sm.dcq[t] - dc_before(sm, t);                      // codec.py:34-35
@@ -259,29 +269,38 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
         }
     }
     if constexpr (kTc) tc_cta_teardown<G>(tmem_base);
-    // exact-path statistics: one atomic per warp at the very end
-    unsigned int items = st.items, changed = st.changed, unflagged = st.unflagged;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        items += __shfl_xor_sync(0xffffffffu, items, o);
-        changed += __shfl_xor_sync(0xffffffffu, changed, o);
-        unflagged += __shfl_xor_sync(0xffffffffu, unflagged, o);
+    // exact-path statistics of the group: one thread, at the very end
+    group_sync<G>(g);
+    if (t == 0) {
+        if (sm.stat_items) atomicAdd(&counters[kCtrExactItems], (unsigned long long)sm.stat_items);
+        if (sm.stat_changed) atomicAdd(&counters[kCtrExactChanged], (unsigned long long)sm.stat_changed);
+        if (sm.stat_unflagged) atomicAdd(&counters[kCtrUnflagged], (unsigned long long)sm.stat_unflagged);
+        if (sm.tc_timeout) atomicExch(&counters[kCtrTcTimeout], 1ull);
     }
-    if (lane == 0) {
-        if (items) atomicAdd(&counters[kCtrExactItems], (unsigned long long)items);
-        if (changed) atomicAdd(&counters[kCtrExactChanged], (unsigned long long)changed);
-        if (unflagged) atomicAdd(&counters[kCtrUnflagged], (unsigned long long)unflagged);
-    }
-    if (timeout) atomicExch(&counters[kCtrTcTimeout], 1ull);
 }
 
 // ---------------------------------------------------------------------------------------------
 // compress(), stage 2: absolute bit position of every tile.  Chunks of kScanChunk tiles:
-//   scan_chunks_kernel   what each chunk does to the position (a Span)
-//   scan_spine_kernel    one CTA: position at the start of every chunk
-//   scan_apply_kernel    position of every tile; stream offset / end of every image
+//   scan_chunks_kernel   what each chunk does to the position (a Span); its last CTA: position at the start of every chunk
+//   scan_apply_kernel    position of every tile; stream offset / end of every image; its last CTA: sizes and the
+//                        batch summary (what used to be two more launches: scan_spine_kernel, finalize_kernel)
 // ---------------------------------------------------------------------------------------------
 constexpr int kScanThreads = 256, kScanItems = 8, kScanChunk = kScanThreads * kScanItems;
+
+// What a batch leaves for tic_encode_finish: `sticky` accumulates over every batch enqueued since the last finish
+// (errors are ORed, so a later batch cannot hide an earlier batch's overflow; the byte total is the last batch's).
+// One thread, after every kernel that writes `counters` has completed (stream order) or behind a CTA barrier.
+__device__ __forceinline__ void fold_counters(unsigned long long* counters, unsigned long long* sticky) {
+    const unsigned long long overflow = atomicAdd(&counters[kCtrOverflow], 0ull), timeout = atomicAdd(&counters[kCtrTcTimeout], 0ull);
+    if (overflow) atomicOr(&sticky[kCtrOverflow], 1ull);
+    if (timeout) atomicOr(&sticky[kCtrTcTimeout], 1ull);
+    atomicExch(&sticky[kCtrExactItems], atomicAdd(&counters[kCtrExactItems], 0ull));     // statistics: the last batch's
+    atomicExch(&sticky[kCtrExactChanged], atomicAdd(&counters[kCtrExactChanged], 0ull));
+    atomicAdd(&sticky[kCtrUnflagged], atomicAdd(&counters[kCtrUnflagged], 0ull));        // guard misses: never lose one
+    atomicExch(&sticky[kCtrTotalBits], atomicAdd(&counters[kCtrTotalBits], 0ull));
+}
+
+
 
 // Exclusive scan of one Span per thread over the CTA (in thread order); `total` = all of them.
 template <int kThreads>
@@ -307,8 +326,27 @@ __device__ __forceinline__ Span cta_exclusive_span(const Span& mine, Span* warp_
     return span_then(before, up);
 }
 
+__device__ __forceinline__ Span span_ldcg(const Span* p) {   // written by another CTA of the same launch: read at L2
+    Span r;
+    r.a = __ldcg(&p->a); r.b = __ldcg(&p->b); r.closed = __ldcg(&p->closed);
+    return r;
+}
+// True in exactly one CTA of the launch: the last one to get here.  Everything the other CTAs wrote to global memory
+// before their call is visible to it (fence + ticket), provided it reads with __ldcg / atomics.
+__device__ __forceinline__ bool last_cta_done(unsigned long long* ticket) {
+    __shared__ int is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(ticket, 1ull) == (unsigned long long)gridDim.x - 1ull;
+    __syncthreads();
+    return is_last != 0;
+}
+
+// What each chunk of kScanChunk tiles does to the position; the last CTA to finish then scans the chunk spans
+// (the "spine": position at the start of every chunk) — one launch instead of two.
 __global__ void __launch_bounds__(kScanThreads)
-scan_chunks_kernel(const TileRec* __restrict__ recs, long long ntiles, Span* __restrict__ chunk_span) {
+scan_chunks_kernel(const TileRec* __restrict__ recs, long long ntiles, Span* __restrict__ chunk_span, long long nchunks,
+                   long long* __restrict__ chunk_pos, unsigned long long* __restrict__ counters) {
     __shared__ Span warp_tot[kScanThreads / 32];
     const long long base = (long long)blockIdx.x * kScanChunk + (long long)threadIdx.x * kScanItems;
     Span mine{0, 0, 0};
@@ -318,30 +356,25 @@ scan_chunks_kernel(const TileRec* __restrict__ recs, long long ntiles, Span* __r
     Span total;
     cta_exclusive_span<kScanThreads>(mine, warp_tot, total);
     if (threadIdx.x == 0) chunk_span[blockIdx.x] = total;
-}
-
-constexpr int kSpineThreads = 1024;
-__global__ void __launch_bounds__(kSpineThreads)
-scan_spine_kernel(const Span* __restrict__ chunk_span, long long nchunks, long long* __restrict__ chunk_pos) {
-    __shared__ Span warp_tot[kSpineThreads / 32];
-    const long long per = (nchunks + kSpineThreads - 1) / kSpineThreads;
+    if (!last_cta_done(&counters[kCtrTicketA])) return;
+    const long long per = (nchunks + kScanThreads - 1) / kScanThreads;
     const long long lo = (long long)threadIdx.x * per;
     const long long hi = lo + per < nchunks ? lo + per : nchunks;
-    Span mine{0, 0, 0};
-    for (long long c = lo; c < hi; c++) mine = span_then(mine, chunk_span[c]);
-    Span total;
-    const Span before = cta_exclusive_span<kSpineThreads>(mine, warp_tot, total);
+    mine = Span{0, 0, 0};
+    for (long long c = lo; c < hi; c++) mine = span_then(mine, span_ldcg(&chunk_span[c]));
+    const Span before = cta_exclusive_span<kScanThreads>(mine, warp_tot, total);
     long long p = span_apply(0, before);
     for (long long c = lo; c < hi; c++) {
         chunk_pos[c] = p;
-        p = span_apply(p, chunk_span[c]);
+        p = span_apply(p, span_ldcg(&chunk_span[c]));
     }
 }
 
 __global__ void __launch_bounds__(kScanThreads)
 scan_apply_kernel(const TileRec* __restrict__ recs, long long ntiles, const long long* __restrict__ chunk_pos,
                   long long* __restrict__ tile_pos, long long out_cap, long long* __restrict__ out_off,
-                  long long* __restrict__ out_end, unsigned long long* __restrict__ counters) {
+                  long long* __restrict__ out_end, unsigned long long* __restrict__ counters, int n_images,
+                  long long* __restrict__ out_sizes, const int* __restrict__ status, unsigned long long* __restrict__ sticky) {
     __shared__ Span warp_tot[kScanThreads / 32];
     const long long base = (long long)blockIdx.x * kScanChunk + (long long)threadIdx.x * kScanItems;
     uint32_t rb[kScanItems];
@@ -373,23 +406,18 @@ scan_apply_kernel(const TileRec* __restrict__ recs, long long ntiles, const long
         }
         p = span_apply(p, span_of(rb[i]));
     }
-}
-
-// What a batch leaves for tic_encode_finish: `sticky` accumulates over every batch enqueued since the last finish
-// (errors are ORed, so a later batch cannot hide an earlier batch's overflow; the byte total is the last batch's).
-// One thread, after every kernel that writes `counters` has completed (stream order) or behind a CTA barrier.
-__device__ __forceinline__ void fold_counters(unsigned long long* counters, unsigned long long* sticky) {
-    const unsigned long long overflow = atomicAdd(&counters[kCtrOverflow], 0ull), timeout = atomicAdd(&counters[kCtrTcTimeout], 0ull);
-    if (overflow) atomicOr(&sticky[kCtrOverflow], 1ull);
-    if (timeout) atomicOr(&sticky[kCtrTcTimeout], 1ull);
-    atomicExch(&sticky[kCtrExactItems], atomicAdd(&counters[kCtrExactItems], 0ull));     // statistics: the last batch's
-    atomicExch(&sticky[kCtrExactChanged], atomicAdd(&counters[kCtrExactChanged], 0ull));
-    atomicAdd(&sticky[kCtrUnflagged], atomicAdd(&counters[kCtrUnflagged], 0ull));        // guard misses: never lose one
-    atomicExch(&sticky[kCtrTotalBits], atomicAdd(&counters[kCtrTotalBits], 0ull));
+    // the last CTA to finish: sizes = end - offset, and the batch summary tic_encode_finish reads
+    if (!last_cta_done(&counters[kCtrTicketB])) return;
+    for (int i = threadIdx.x; i < n_images; i += kScanThreads) {
+        out_sizes[i] = __ldcg(&out_end[i]) - __ldcg(&out_off[i]);
+        const int st = status[i];
+        if (st) atomicOr(&sticky[kCtrAnyStatus], (unsigned long long)st);
+    }
+    if (threadIdx.x == 0) fold_counters(counters, sticky);
 }
 
 // Small batches (at most kSmallScan tiles: one 8K image, 50 x 512^2, ...): the three scan kernels and
-// finalize_kernel in ONE launch of one CTA — what counts there is launch latency, not throughput.
+// the size / summary pass in ONE launch of one CTA — what counts there is launch latency, not throughput.
 constexpr int kSmallThreads = 1024, kSmallScan = kSmallThreads * kScanItems;
 __global__ void __launch_bounds__(kSmallThreads)
 scan_small_kernel(const TileRec* __restrict__ recs, int ntiles, long long* __restrict__ tile_pos, long long out_cap,
@@ -503,12 +531,11 @@ symbol_stats_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
     uint32_t tmem_base = 0;
     if constexpr (kFdctTc) gbase = tc_cta_setup<1>(smem_raw, bmat, 0, tg, tmem_base);
     TileShared& sm = *reinterpret_cast<TileShared*>(gbase);
-    tg.desc_a0 = tc::smem_desc(tc::smem_addr(&sm.coef[0][0]), tc::kLboA, tc::kSboA);
     const int t = threadIdx.x;
     uint32_t* hist = sm.stage;                                                       // 272 counters
     unsigned long long* first = reinterpret_cast<unsigned long long*>(sm.stage + 512); // 272 keys
-    ExactStats st{0u, 0u, 0u};
-    bool timeout = false;
+    const ExactStats st{&sm};
+    if (t == 0) sm.stat_items = sm.stat_changed = sm.stat_unflagged = sm.tc_timeout = 0u;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         __syncthreads();
         const TileInfo ti = locate_tile(descs, n_images, tile, uniform_tpi);
@@ -519,7 +546,7 @@ symbol_stats_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
             if (ti.nb > 0) {
                 uint2 rows[8];
                 load_block_rows(ti, t, rows);
-                transform_tile_tc<1>(ti, qp, sm, tg, 0, false, st, timeout, rows, nullptr);
+                transform_tile_tc<1>(ti, qp, sm, tg, 0, false, st, rows, load_tile_halo(ti, t), [] {});
             }
         } else transform_warp(ti, qp, sm, st);
         int err = 0;
@@ -536,7 +563,8 @@ symbol_stats_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
         if (t == 0 && sm.warp_err[0]) atomicOr(&status[ti.img], TIC_STATUS_TABLE);
     }
     if constexpr (kFdctTc) tc_cta_teardown<1>(tmem_base);
-    if (timeout) atomicExch(&counters[kCtrTcTimeout], 1ull);
+    __syncthreads();
+    if (t == 0 && sm.tc_timeout) atomicExch(&counters[kCtrTcTimeout], 1ull);
 }
 
 // One thread per image: HuffmanTree (huffman.py:112-194) on CPython's heapq, which
@@ -685,17 +713,19 @@ __global__ void build_tables_kernel(const ImageDesc* __restrict__ descs, int n_i
     if (st) atomicOr(&status[img], st);
 }
 
-// sizes = end - offset, and the batch summary the host reads back in tic_encode_finish
-__global__ void finalize_kernel(int n_images, const long long* __restrict__ out_off,
-                                const long long* __restrict__ out_end, long long* __restrict__ out_sizes,
-                                const int* __restrict__ status, unsigned long long* __restrict__ counters,
-                                unsigned long long* __restrict__ sticky) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_images) {
-        out_sizes[i] = out_end[i] - out_off[i];
-        if (status[i]) atomicOr(&sticky[kCtrAnyStatus], (unsigned long long)status[i]);
-    }
-    if (i == 0) fold_counters(counters, sticky);   // every writer of `counters` ran in an earlier kernel of the stream
+// Uniform batch (every image H x W, equally spaced in memory): the descriptors are written on the device and the
+// per-batch status / counters are cleared by the same launch — instead of one H2D copy and two memsets.
+__global__ void prep_uniform_kernel(ImageDesc* __restrict__ descs, int n_images, const uint8_t* base, long long img_stride,
+                                    int h, int w, int bw, int bw_shift, int nblk, long long tiles_per_image,
+                                    int* __restrict__ status, unsigned long long* __restrict__ counters) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < kCtrCount) counters[i] = 0ull;
+    if (i >= n_images) return;
+    ImageDesc d;
+    d.px = base + (long long)i * img_stride;
+    d.h = h; d.w = w; d.bw = bw; d.nblk = nblk; d.tile0 = (long long)i * tiles_per_image; d.bw_shift = bw_shift; d.pad = 0;
+    descs[i] = d;
+    status[i] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -711,16 +741,16 @@ coeffs_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restric
     uint32_t tmem_base = 0;
     if constexpr (kFdctTc) gbase = tc_cta_setup<1>(smem_raw, bmat, 0, tg, tmem_base);
     TileShared& sm = *reinterpret_cast<TileShared*>(gbase);
-    tg.desc_a0 = tc::smem_desc(tc::smem_addr(&sm.coef[0][0]), tc::kLboA, tc::kSboA);
     const int t = threadIdx.x;
     const TileInfo ti = locate_tile(descs, 1, blockIdx.x, 0);
-    ExactStats st{0u, 0u, 0u};
-    bool timeout = false;
+    const ExactStats st{&sm};
+    if (t == 0) sm.stat_items = sm.stat_changed = sm.stat_unflagged = sm.tc_timeout = 0u;
+    __syncthreads();
     if constexpr (kFdctTc) {
         if (ti.nb > 0) {
             uint2 rows[8];
             load_block_rows(ti, t, rows);
-            transform_tile_tc<1>(ti, qp, sm, tg, 0, (flags & TIC_FLAG_DEBUG_ALL_EXACT) != 0, st, timeout, rows, nullptr);
+            transform_tile_tc<1>(ti, qp, sm, tg, 0, (flags & TIC_FLAG_DEBUG_ALL_EXACT) != 0, st, rows, load_tile_halo(ti, t), [] {});
         }
     } else transform_warp(ti, qp, sm, st);
     if (t < ti.nb) {
@@ -734,10 +764,13 @@ coeffs_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restric
         }
     }
     if constexpr (kFdctTc) tc_cta_teardown<1>(tmem_base);
-    if (st.items) atomicAdd(&counters[kCtrExactItems], (unsigned long long)st.items);
-    if (st.changed) atomicAdd(&counters[kCtrExactChanged], (unsigned long long)st.changed);
-    if (st.unflagged) atomicAdd(&counters[kCtrUnflagged], (unsigned long long)st.unflagged);
-    if (timeout) atomicExch(&counters[kCtrTcTimeout], 1ull);
+    __syncthreads();
+    if (t == 0) {
+        if (sm.stat_items) atomicAdd(&counters[kCtrExactItems], (unsigned long long)sm.stat_items);
+        if (sm.stat_changed) atomicAdd(&counters[kCtrExactChanged], (unsigned long long)sm.stat_changed);
+        if (sm.stat_unflagged) atomicAdd(&counters[kCtrUnflagged], (unsigned long long)sm.stat_unflagged);
+        if (sm.tc_timeout) atomicExch(&counters[kCtrTcTimeout], 1ull);
+    }
 }
 
 }  // namespace tic
@@ -883,9 +916,12 @@ static int make_quant_params(int quality, QuantParams& qp) {
 
 // B operand of the tensor-core FDCT for one quality, in the shared-memory layout of tic_tc.cuh:
 // B[n][k] = basis(zigzag[n], pixel k) / (qt * hthr) * 2^E as f16 hi (k) and lo (k + 64).
-static void build_bmat(const QuantParams& qp, __half* blob /* 64 x 128 */) {
+static void build_bmat(const QuantParams& qp, __half* blob /* tc::kN x 128, zero-filled */) {
     static const int zigzag[64] = {TIC_ZIGZAG_LIST};
     const double pi = 3.14159265358979323846;
+    auto at = [&](int n, int k) -> __half& {   // shared-memory layout of tic_tc.cuh, in f16 units
+        return blob[(size_t)(n / 8) * 64 + (size_t)(k / 8) * (tc::kLboB / 2) + (size_t)(n % 8) * 8 + (size_t)(k % 8)];
+    };
     for (int n = 0; n < 64; n++) {
         const int i = zigzag[n], u = i >> 3, v = i & 7;
         const double cu = u ? 0.5 : sqrt(0.125), cv = v ? 0.5 : sqrt(0.125);
@@ -894,12 +930,17 @@ static void build_bmat(const QuantParams& qp, __half* blob /* 64 x 128 */) {
             const int y = k >> 3, x = k & 7;
             const double b = scale * cos((2 * y + 1) * u * pi / 16.0) * cos((2 * x + 1) * v * pi / 16.0);
             const __half hi = __double2half(b);
-            const __half lo = __double2half(b - (double)__half2float(hi));
-            const int kl = k + 64;
-            blob[(size_t)(n / 8) * 64 + (size_t)(k / 8) * 512 + (size_t)(n % 8) * 8 + (size_t)(k % 8)] = hi;
-            blob[(size_t)(n / 8) * 64 + (size_t)(kl / 8) * 512 + (size_t)(n % 8) * 8 + (size_t)(kl % 8)] = lo;
+            at(n, k) = hi;
+            at(n, k + 64) = __double2half(b - (double)__half2float(hi));
         }
     }
+    // columns 64..71: S_x, columns 72..79: I_x (tic_tc.cuh); entries +-1 in the hi half, the lo half stays 0
+    static const int sgn[8] = {1, -1, -1, 1, 1, -1, -1, 1};
+    for (int x = 0; x < 8 && tc::kN >= tc::kColSums + 16; x++)
+        for (int y = 0; y < 8; y++) {
+            at(tc::kColSums + x, 8 * y + x) = __double2half(1.0);
+            at(tc::kColSums + 8 + x, 8 * y + x) = __double2half((double)sgn[y]);
+        }
 }
 
 constexpr size_t kSmemEncode = cta_smem_bytes<kGroups, kFdctTc>();       // persistent encode kernel, modes 0 and 1
@@ -942,7 +983,7 @@ static int ensure_bmat(tic_handle h, int quality, const QuantParams& qp, const u
     if (!h->d_bmat) TIC_CUDA(h, cudaMalloc(&h->d_bmat, (size_t)100 * tc::kBBytes));
     uint4* dst = h->d_bmat + (size_t)quality * (tc::kBBytes / 16);
     if (!h->bmat_ready[quality]) {
-        std::vector<__half> blob((size_t)64 * 128);
+        std::vector<__half> blob((size_t)tc::kN * 128, __double2half(0.0));
         build_bmat(qp, blob.data());
         // synchronous and device-wide: whatever stream a later batch of this quality runs on, the matrix is there
         TIC_CUDA(h, cudaMemcpy(dst, blob.data(), tc::kBBytes, cudaMemcpyHostToDevice));
@@ -1080,7 +1121,12 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     if (rc) return rc;
     long long ntiles = 0, nblocks = 0, worst = 16;
     int uniform_tpi = 0;
+    // same shape and equally spaced pointers (an (N, H, W) tensor): the descriptors can be built on the device
+    bool regular = n_images >= 1;
+    const long long img_stride = n_images >= 2 ? (long long)((const uint8_t*)d_pixels[1] - (const uint8_t*)d_pixels[0]) : 0;
     for (int i = 0; i < n_images; i++) {
+        if (heights[i] != heights[0] || widths[i] != widths[0] ||
+            (const uint8_t*)d_pixels[i] != (const uint8_t*)d_pixels[0] + (long long)i * img_stride) regular = false;
         if (heights[i] < 0 || widths[i] < 0) { h->err = "negative image dimension"; return TIC_E_INVALID; }
         long long nblk = tic_num_blocks(heights[i], widths[i]);
         if (c_variant) {
@@ -1144,12 +1190,21 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
         TIC_CUDA(h, cudaMalloc(&h->d_out_end, (size_t)n_images * 2 * 8));
         h->end_cap = (size_t)n_images * 2;
     }
-    TIC_CUDA(h, cudaMemcpyAsync(h->d_descs, h->h_descs, (size_t)n_images * sizeof(ImageDesc),
-                                cudaMemcpyHostToDevice, stream));
-    rc = descs_staged(h, stream);
-    if (rc) return rc;
-    TIC_CUDA(h, cudaMemsetAsync(h->d_counters, 0, kCtrCount * 8, stream));
-    TIC_CUDA(h, cudaMemsetAsync(d_status, 0, (size_t)n_images * 4, stream));
+    const bool prep_on_device = regular && uniform_tpi > 0;
+    if (prep_on_device) {
+        const ImageDesc& d0 = h->h_descs[0];
+        prep_uniform_kernel<<<(n_images + 255) / 256, 256, 0, stream>>>(h->d_descs, n_images, d0.px, img_stride, d0.h, d0.w, d0.bw,
+                                                                      d0.bw_shift, d0.nblk, (long long)uniform_tpi, d_status,
+                                                                      h->d_counters);
+        TIC_CUDA(h, cudaGetLastError());
+    } else {
+        TIC_CUDA(h, cudaMemcpyAsync(h->d_descs, h->h_descs, (size_t)n_images * sizeof(ImageDesc),
+                                    cudaMemcpyHostToDevice, stream));
+        rc = descs_staged(h, stream);
+        if (rc) return rc;
+        TIC_CUDA(h, cudaMemsetAsync(h->d_counters, 0, kCtrCount * 8, stream));
+        TIC_CUDA(h, cudaMemsetAsync(d_status, 0, (size_t)n_images * 4, stream));
+    }
     const uint4* d_bmat = nullptr;
     if (!c_variant) {
         rc = ensure_bmat(h, quality, qp, &d_bmat);
@@ -1212,14 +1267,15 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
         TIC_CUDA(h, cudaGetLastError());
         h->last_launches -= 3;
     } else {
-        scan_chunks_kernel<<<(unsigned)nchunks, kScanThreads, 0, stream>>>(h->d_recs, ntiles, h->d_chunk_span);
-        TIC_CUDA(h, cudaGetLastError());
-        scan_spine_kernel<<<1, kSpineThreads, 0, stream>>>(h->d_chunk_span, nchunks, h->d_chunk_pos);
+        scan_chunks_kernel<<<(unsigned)nchunks, kScanThreads, 0, stream>>>(h->d_recs, ntiles, h->d_chunk_span, nchunks,
+                                                                           h->d_chunk_pos, h->d_counters);
         TIC_CUDA(h, cudaGetLastError());
         scan_apply_kernel<<<(unsigned)nchunks, kScanThreads, 0, stream>>>(h->d_recs, ntiles, h->d_chunk_pos, h->d_tile_pos,
                                                                           (long long)out_capacity, (long long*)d_out_offsets,
-                                                                          h->d_out_end, h->d_counters);
+                                                                          h->d_out_end, h->d_counters, n_images,
+                                                                          (long long*)d_out_sizes, d_status, h->d_sticky);
         TIC_CUDA(h, cudaGetLastError());
+        h->last_launches -= 2;
     }
     long long cgrid = (ntiles * 32 + kCompactThreads - 1) / kCompactThreads;
     const long long cmax = (long long)h->sm_count * 8 * 4;
@@ -1231,12 +1287,7 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     TIC_CUDA(h, cudaGetLastError());
     TIC_CUDA(h, cudaEventRecord(evq[3], stream));
     h->ev_batches++;
-    if (!small) {
-        finalize_kernel<<<(n_images + 255) / 256, 256, 0, stream>>>(n_images, (const long long*)d_out_offsets,
-                                                                   h->d_out_end, (long long*)d_out_sizes, d_status,
-                                                                   h->d_counters, h->d_sticky);
-        TIC_CUDA(h, cudaGetLastError());
-    }
+    if (prep_on_device) h->last_launches += 1;
     h->last_tiles = ntiles;
     h->last_blocks = nblocks;
     return TIC_OK;

@@ -44,10 +44,9 @@ namespace tic {
 #ifndef TIC_GROUPS
 #define TIC_GROUPS 6
 #endif
-// 1: the pixel rows of a group's NEXT tile are fetched into registers while the tensor core works on this one
-#ifndef TIC_PREFETCH
-#define TIC_PREFETCH 0
-#endif
+// (Prefetching a group's next tile was measured and dropped: held in registers it spills — with 227 KB of shared
+// memory there is no L1 to catch a spill — and through cp.async + LDS it costs more than the latency it hides:
+// 5.52 ms against 5.01 ms for plain loads at the top of the tile, profiles/r2_variants.md.)
 
 #ifndef TIC_TILE
 #define TIC_TILE 128
@@ -56,7 +55,11 @@ namespace tic {
 #define TIC_CTAS 6
 #endif
 #ifndef TIC_PRIV
-#define TIC_PRIV 16
+#define TIC_PRIV 12
+#endif
+// 1: only warp 0 of a group polls the MMA's mbarrier, the other warps sleep at the group barrier
+#ifndef TIC_POLL_WARP0
+#define TIC_POLL_WARP0 0
 #endif
 #ifndef TIC_WIN
 #define TIC_WIN 1280
@@ -114,7 +117,8 @@ constexpr uint32_t kRecFirst = 1u << 30, kRecClosing = 1u << 31, kRecBitsMask = 
 // counters[] layout in the workspace
 enum { kCtrArena = 0, kCtrOverflow = 1, kCtrExactItems = 2, kCtrExactChanged = 3, kCtrTotalBits = 4,
        kCtrAnyStatus = 5, kCtrUnflagged = 6 /* debug: exact != fast outside the guard band */,
-       kCtrTcTimeout = 7 /* an MMA completion never arrived */, kCtrCount = 8 };
+       kCtrTcTimeout = 7 /* an MMA completion never arrived */,
+       kCtrTicketA = 8, kCtrTicketB = 9 /* last-CTA-done tickets of the two scan kernels */, kCtrCount = 10 };
 
 __device__ __constant__ uint8_t c_zigzag[64] = {TIC_ZIGZAG_LIST};
 __device__ __constant__ HuffTables c_default_tables;
@@ -351,11 +355,19 @@ struct TileShared {
     double colres[kWarps][4][8];
     int work_count[kWarps];
     int pending[kWarps];             // flagged coefficients that did not fit the worklist this round
-    uint2 ac_tab[256];               // per (run << 4 | size): fixed tables {code << size, len + size},
-    uint2 dc_tab[16];                //   auto tables {code, kHuffPresent | len};  .y == 0: not in the table
+    // per (run << 4 | size).  Fixed tables: ONE 32-bit word per entry, (len + size) << 27 | code << size (0: not in
+    // the table), in the first half of the array — a random-index 64-bit lookup cost 6.6 shared-memory wavefronts,
+    // a third of the kernel's LSU traffic (profiles/r2d).  Per-image tables: {code, kHuffPresent | len}, .y == 0: absent.
+    uint2 ac_tab[256];
+    uint2 dc_tab[16];
     int warp_bits[kWarps];
     int warp_err[kWarps];
     unsigned int arena_off;          // 16-byte units; 0xffffffff: arena exhausted
+    // The description of the tile in work and of the group's next tile: written ONE TILE AHEAD by warp 0 while the
+    // tensor core runs, read from shared memory where needed — a tile's geometry costs no registers.
+    TileInfo tinfo[2];
+    int u_img, u_lt;                 // uniform batches: (image, tile in image) of the tile after tinfo's newest (lane 0 of warp 0)
+    unsigned int stat_items, stat_changed, stat_unflagged, tc_timeout;   // flushed to the batch counters at the end
     alignas(16) uint32_t stage[kWinWords];   // window of the tile-relative MSB-first bit buffer (kept zeroed)
 };
 
@@ -674,16 +686,23 @@ __device__ __forceinline__ void transform_warp_c(const TileInfo& ti, int qfactor
 // of the block in front of them, which the DC difference of codec.py:34-35 needs).  8 lanes per
 // entry: lane c transforms column c of the block (axis -2 first, utils.py:33-34), lane 0 the row.
 // ---------------------------------------------------------------------------------------------
-struct ExactStats {
-    unsigned int items, changed;
-    unsigned int unflagged;   // TIC_FLAG_DEBUG_ALL_EXACT: the exact value differs although the guard did not flag it
+// Exact-path statistics live in shared memory (TileShared::stat_*): rare events, no registers.
+// stat_unflagged (TIC_FLAG_DEBUG_ALL_EXACT): the exact value differs although the guard did not flag it.
+struct ExactStats {   // handle passed around instead of three counters
+    TileShared* sm;
+    __device__ __forceinline__ void items(unsigned n) const;
+    __device__ __forceinline__ void changed(unsigned n) const;
+    __device__ __forceinline__ void unflagged(unsigned n) const;
 };
+__device__ __forceinline__ void ExactStats::items(unsigned n) const { atomicAdd(&sm->stat_items, n); }
+__device__ __forceinline__ void ExactStats::changed(unsigned n) const { atomicAdd(&sm->stat_changed, n); }
+__device__ __forceinline__ void ExactStats::unflagged(unsigned n) const { atomicAdd(&sm->stat_unflagged, n); }
 // worklist entry: lane << 6 | zigzag index; bit 31: the DC of the block in front of the tile / warp;
 // bit 30: flagged by the guard band (always set outside TIC_FLAG_DEBUG_ALL_EXACT)
 constexpr uint32_t kWorkHalo = 0x80000000u, kWorkGuard = 0x40000000u;
 
 __device__ __forceinline__ void exact_round(const TileInfo& ti, const QuantParams& qp, TileShared& sm,
-                                            int warp, int count, ExactStats& st) {
+                                            int warp, int count, const ExactStats& st) {
     const int lane = threadIdx.x & 31;
     const int grp = lane >> 3, c = lane & 7;
     const int wt0 = warp * 32;   // first thread of the warp
@@ -744,8 +763,8 @@ __device__ __forceinline__ void exact_round(const TileInfo& ti, const QuantParam
                         const uint32_t bit = 0x80000000u >> (k & 31);
                         if (q) atomicOr(m, bit); else atomicAnd(m, ~bit);
                     }
-                    st.changed++;
-                    if (!(item & kWorkGuard)) st.unflagged++;
+                    st.changed(1u);
+                    if (!(item & kWorkGuard)) st.unflagged(1u);
                 }
             }
         }
@@ -785,7 +804,7 @@ __device__ __noinline__ bool settle_dc_ties(const uint8_t* px, int w, int h, int
 // Phases 1 and 2 for the 32 blocks of one warp; only warp-level synchronisation.  On return
 // sm.coef / nz / dcq / dc_halo hold the reference's quantised coefficients for those blocks.
 __device__ __forceinline__ void transform_warp(const TileInfo& ti, const QuantParams& qp, TileShared& sm,
-                                               ExactStats& st) {
+                                               const ExactStats& st) {
     const int t = tid(), lane = t & 31, warp = t >> 5;
     if (lane == 0) {
         sm.pending[warp] = 0;
@@ -802,7 +821,7 @@ __device__ __forceinline__ void transform_warp(const TileInfo& ti, const QuantPa
     if (__popc(__ballot_sync(0xffffffffu, (fl_lo & 0x80000000u) != 0)) >= 4) {   // warp-uniform
         if (settle_dc_ties(ti.px, ti.w, ti.h, ti.bw, ti.blk0, ti.nb, qp.qt[0], &sm.coef[0][0], sm.dcq, fl_lo)) {
             fl_lo &= 0x7fffffffu;
-            st.items++;
+            st.items(1u);
         }
     }
     // halo: quantised DC of the block in front of the warp's first block.  The DC coefficient is
@@ -863,7 +882,7 @@ __device__ __forceinline__ void transform_warp(const TileInfo& ti, const QuantPa
         const int pending = sm.pending[warp];
         __syncwarp();
         if (count) {   // warp-uniform
-            if (lane == 0) st.items += (unsigned)count;   // (DC ties settled above count too)
+            if (lane == 0) st.items((unsigned)count);   // (DC ties settled above count too)
             exact_round(ti, qp, sm, warp, count, st);
         }
         if (pending == 0) break;
@@ -883,12 +902,20 @@ __device__ __forceinline__ void transform_warp(const TileInfo& ti, const QuantPa
 // guard band).  The exact path is unchanged.  On return (after a group barrier) sm.coef / nz / dcq hold the
 // reference's quantised coefficients of the whole tile and sm.dc_halo[0] the DC in front of its first block.
 // ---------------------------------------------------------------------------------------------
+// Everything but the mbarrier phase is recomputed where it is used (a handful of instructions per tile) instead
+// of living in registers across the whole tile loop.
 struct TcGroup {
-    uint64_t desc_a0;  // shared-memory descriptor of the A operand's first K chunk (A aliases sm.coef)
-    uint64_t desc_b0;  // ... of the B operand (one per CTA)
-    uint32_t tmem;     // TMEM address of the group's accumulator columns, lane field = this warp's quarter
-    uint32_t bar;      // shared address of the group's mbarrier
+    uint32_t ctl;      // shared address of the CTA's control block: mbarrier g at +8g, the TMEM base address at +64;
+                       // the B operand sits tc::kBBytes in front of it
     uint32_t phase;
+    __device__ __forceinline__ uint32_t bar(int g) const { return ctl + 8u * (uint32_t)g; }
+    __device__ __forceinline__ uint64_t desc_b0() const { return tc::smem_desc(ctl - (uint32_t)tc::kBBytes, tc::kLboB, tc::kSboB); }
+    // the group's accumulator columns, lane field = the calling warp's quarter of the 128 lanes
+    __device__ __forceinline__ uint32_t tmem(int g) const {
+        uint32_t base;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(base) : "r"(ctl + 64u));
+        return base + (uint32_t)(g * tc::kColsPerGroup) + ((uint32_t)(((threadIdx.x >> 5) & 3) * 32) << 16);
+    }
 };
 
 template <int G, int P>
@@ -955,12 +982,85 @@ __device__ __forceinline__ void load_block_rows(const TileInfo& ti, int t, uint2
     }
 }
 
+// Exact value of the coefficients of thread t's block that can sit on true .5 ties — (0,0), (4,0), (0,4), (4,4) =
+// zigzag 0, 10, 14, 39 — from the 16 column sums the tensor core left in the accumulator (tic_tc.cuh): the
+// reference's float64 column pass (axis -2 first, utils.py:33-34) for u = 0 is RN(0.5 * S_x * HSQ) and for u = 4
+// RN(0.5 * I_x * TW3), every earlier operation being exact on integers; the row pass is
+// dct8_exact over those eight doubles.  rat: bit 0 / 1 / 2 / 3 = zigzag 0 / 10 / 14 / 39 flagged.  Out of line, one
+// lane at a time in practice; only this thread touches its own column of sm.coef here.
+__device__ __noinline__ unsigned settle_rational(uint32_t taddr /* the lane's accumulator, column 0 */, uint32_t rat,
+                                                 const double* __restrict__ qt /* QuantParams::qt */, TileShared* smp, int t) {
+    uint32_t r[16];   // every lane of the warp calls (tcgen05.ld is warp-wide); lanes without a flag return below
+    tc::tmem_ld16(taddr + tc::kColSums, r);
+    tc::tmem_wait_ld(r);
+    if (!rat) return 0;
+    const float s0 = __uint_as_float(r[0]), s1 = __uint_as_float(r[1]), s2 = __uint_as_float(r[2]), s3 = __uint_as_float(r[3]);
+    const float s4 = __uint_as_float(r[4]), s5 = __uint_as_float(r[5]), s6 = __uint_as_float(r[6]), s7 = __uint_as_float(r[7]);
+    const float i0 = __uint_as_float(r[8]), i1 = __uint_as_float(r[9]), i2 = __uint_as_float(r[10]), i3 = __uint_as_float(r[11]);
+    const float i4 = __uint_as_float(r[12]), i5 = __uint_as_float(r[13]), i6 = __uint_as_float(r[14]), i7 = __uint_as_float(r[15]);
+    const double qt00 = qt[0], qt40 = qt[32], qt04 = qt[4], qt44 = qt[36];
+    uint32_t* coef_col = &smp->coef[0][t];
+    uint32_t* nz_lo = &smp->nz_lo[t];
+    uint32_t* nz_hi = &smp->nz_hi[t];
+    int* dcq = &smp->dcq[t];
+    const double HSQ = 0x1.6a09e667f3bcdp-1, TW3 = 0x1.6a09e667f3bccp-1;
+    unsigned changed = 0;
+#pragma unroll 1
+    for (int which = 0; which < 4; which++) {
+        if (!((rat >> which) & 1u)) continue;
+        const bool u4 = (which == 1 || which == 3), v4 = (which >= 2);
+        const double m = u4 ? TW3 : HSQ;
+        const double c0 = __dmul_rn(__dmul_rn(0.5, (double)(u4 ? i0 : s0)), m), c1 = __dmul_rn(__dmul_rn(0.5, (double)(u4 ? i1 : s1)), m);
+        const double c2 = __dmul_rn(__dmul_rn(0.5, (double)(u4 ? i2 : s2)), m), c3 = __dmul_rn(__dmul_rn(0.5, (double)(u4 ? i3 : s3)), m);
+        const double c4 = __dmul_rn(__dmul_rn(0.5, (double)(u4 ? i4 : s4)), m), c5 = __dmul_rn(__dmul_rn(0.5, (double)(u4 ? i5 : s5)), m);
+        const double c6 = __dmul_rn(__dmul_rn(0.5, (double)(u4 ? i6 : s6)), m), c7 = __dmul_rn(__dmul_rn(0.5, (double)(u4 ? i7 : s7)), m);
+        const double y = dct8_exact(c0, c1, c2, c3, c4, c5, c6, c7, v4 ? 4 : 0);
+        const double qt = which == 0 ? qt00 : (which == 1 ? qt40 : (which == 2 ? qt04 : qt44));
+        const int q = __double2int_rn(__ddiv_rn(y, qt));   // np.round(coeffs / qt), utils.py:53
+        const int k = which == 0 ? 0 : (which == 1 ? 10 : (which == 2 ? 14 : 39));
+        uint32_t* wp = coef_col + (k >> 1) * kTile;
+        const uint32_t w = *wp;
+        const int old = (int)(short)((k & 1) ? (w >> 16) : w);
+        if (old != q) {
+            const uint32_t qb = (uint32_t)q & 0xffffu;
+            *wp = (k & 1) ? ((w & 0x0000ffffu) | (qb << 16)) : ((w & 0xffff0000u) | qb);
+            if (k == 0) {
+                *dcq = q;
+            } else {
+                uint32_t* mp = k < 32 ? nz_lo : nz_hi;
+                const uint32_t bit = 0x80000000u >> (k & 31);
+                *mp = q ? (*mp | bit) : (*mp & ~bit);
+            }
+            changed++;
+        }
+    }
+    return changed;
+}
+
 // rows: the pixel rows of this thread's block (load_block_rows), loaded by the caller — one tile ahead in the
 // persistent kernel; `next` (may be null): the tile whose rows are fetched into `rows` while the tensor core works.
-template <int G>
+// The block in front of the tile (it belongs to another tile, i.e. another CTA): lanes 0..7 of warp 0 fetch one pixel
+// row of it each, TOGETHER with the tile's own rows, so that its DRAM latency is paid once, not again behind the MMA.
+__device__ __forceinline__ bool tile_halo_is_fast(const TileInfo& ti, int& y0, int& x0) {
+    const int hb = ti.blk0 - 1;
+    if (hb < 0) return false;
+    const int br = hb / ti.bw, bc = hb - br * ti.bw;
+    y0 = br * 8; x0 = bc * 8;
+    return ((ti.w & 7) == 0) && ((reinterpret_cast<uintptr_t>(ti.px) & 7) == 0) && (y0 + 8 <= ti.h);
+}
+__device__ __forceinline__ uint2 load_tile_halo(const TileInfo& ti, int t) {
+    uint2 v = make_uint2(0u, 0u);
+    int y0, x0;
+    if (t < 8 && tile_halo_is_fast(ti, y0, x0)) v = __ldg(reinterpret_cast<const uint2*>(ti.px + (size_t)(y0 + t) * ti.w + x0));
+    return v;
+}
+
+// after_issue(): called by every thread of the group right after the MMA has been issued (the kernel's tile loop
+// uses it to prepare the description of the group's next tile in the tensor core's shadow).
+template <int G, class AfterIssue>
 __device__ __forceinline__ void transform_tile_tc(const TileInfo& ti, const QuantParams& qp, TileShared& sm,
-                                                  TcGroup& tg, int g, bool debug_all, ExactStats& st, bool& timeout,
-                                                  uint2 (&rows)[8], const TileInfo* next) {
+                                                  TcGroup& tg, int g, bool debug_all, const ExactStats& st,
+                                                  uint2 (&rows)[8], uint2 halo_v, AfterIssue after_issue) {
     const int t = tid(), lane = t & 31, warp = t >> 5;
     if (lane == 0) {
         sm.pending[warp] = 0;
@@ -984,9 +1084,10 @@ __device__ __forceinline__ void transform_tile_tc(const TileInfo& ti, const Quan
     group_sync<G>(g);
     if (t == 0) {
         tc::fence_after_sync();
-        tc::issue_tile_mma(tg.desc_a0, tg.desc_b0, tg.tmem & 0x0000ffffu, tg.bar);
+        tc::issue_tile_mma(tc::smem_desc(tc::smem_addr(&sm.coef[0][0]), tc::kLboA, tc::kSboA), tg.desc_b0(),
+                           tg.tmem(g) & 0x0000ffffu, tg.bar(g));
     }
-    if (TIC_PREFETCH && next) load_block_rows(*next, t, rows);   // in flight until the next tile is staged
+    after_issue();
     // ---- while the tensor core works: quantised DC of the block in front of the warp's first block ------------
     // (codec.py:34-35).  The DC coefficient is (sum of pixels - 8192) / 8 exactly, so unless its quotient by qt
     // lands within 1e-9 of a .5 tie (where the reference's float64 rounding errors decide) one pixel sum settles
@@ -998,16 +1099,13 @@ __device__ __forceinline__ void transform_tile_tc(const TileInfo& ti, const Quan
     if (hb >= 0 && warp * 32 < ti.nb) {   // warp-uniform
         int sum = 0;
         bool have_sum = true;
-        uint2 v = make_uint2(0u, 0u);
         if (warp > 0) {
             sum = sm.blocksum[warp - 1];
         } else {
-            const int br = hb / ti.bw, bc = hb - br * ti.bw;
-            const int y0 = br * 8;
-            have_sum = ((ti.w & 7) == 0) && ((reinterpret_cast<uintptr_t>(ti.px) & 7) == 0) && (y0 + 8 <= ti.h);
+            int y0, x0;
+            have_sum = tile_halo_is_fast(ti, y0, x0);
             if (have_sum) {
-                if (lane < 8) v = __ldg(reinterpret_cast<const uint2*>(ti.px + (size_t)(y0 + lane) * ti.w + bc * 8));
-                sum = __dp4a(v.x, 0x01010101u, __dp4a(v.y, 0x01010101u, 0u));
+                sum = __dp4a(halo_v.x, 0x01010101u, __dp4a(halo_v.y, 0x01010101u, 0u));   // lanes 8..31 hold zeros
                 sum += __shfl_xor_sync(0xffffffffu, sum, 1);
                 sum += __shfl_xor_sync(0xffffffffu, sum, 2);
                 sum += __shfl_xor_sync(0xffffffffu, sum, 4);
@@ -1022,40 +1120,69 @@ __device__ __forceinline__ void transform_tile_tc(const TileInfo& ti, const Quan
         }
     }
     // ---- accumulator -> quantised coefficients ------------------------------------------------------------
-    if (!tc::mbar_wait(tg.bar, tg.phase)) timeout = true;
+    // warp 0 waits for the MMA; the other warps sleep at the group barrier instead of polling
+    if (TIC_POLL_WARP0) {
+        if (warp == 0) { if (!tc::mbar_wait(tg.bar(g), tg.phase)) sm.tc_timeout = 1u; }
+        group_sync<G>(g);
+    } else {
+        if (!tc::mbar_wait(tg.bar(g), tg.phase)) sm.tc_timeout = 1u;
+    }
     tg.phase ^= 1u;
     tc::fence_after_sync();
     uint32_t fl_lo = 0, fl_hi = 0;
     if (warp * 32 < ti.nb) {   // warp-uniform: the warp owns at least one block
         uint32_t nz_lo = 0, nz_hi = 0;
         int dc = 0;
-        uint32_t ra[16], rb[16];
-        tc::tmem_ld16(tg.tmem, ra);
-        tc::tmem_wait_ld(ra);
-        tc::tmem_ld16(tg.tmem + 16, rb);
+        uint32_t ra[8], rb[8];   // 8 columns = one zigzag group; the next group's load is in flight while this one is quantised
+        const uint32_t tmem = tg.tmem(g);
+        tc::tmem_ld8(tmem, ra);
+        tc::tmem_wait_ld8(ra);
+        tc::tmem_ld8(tmem + 8, rb);
         quantise_group_tc<0>(ra, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
-        quantise_group_tc<1>(ra + 8, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
-        tc::tmem_wait_ld(rb);
-        tc::tmem_ld16(tg.tmem + 32, ra);
-        quantise_group_tc<2>(rb, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
-        quantise_group_tc<3>(rb + 8, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
-        tc::tmem_wait_ld(ra);
-        tc::tmem_ld16(tg.tmem + 48, rb);
+        tc::tmem_wait_ld8(rb);
+        tc::tmem_ld8(tmem + 16, ra);
+        quantise_group_tc<1>(rb, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
+        tc::tmem_wait_ld8(ra);
+        tc::tmem_ld8(tmem + 24, rb);
+        quantise_group_tc<2>(ra, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
+        tc::tmem_wait_ld8(rb);
+        tc::tmem_ld8(tmem + 32, ra);
+        quantise_group_tc<3>(rb, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
+        tc::tmem_wait_ld8(ra);
+        tc::tmem_ld8(tmem + 40, rb);
         quantise_group_tc<4>(ra, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
-        quantise_group_tc<5>(ra + 8, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
-        tc::tmem_wait_ld(rb);
-        quantise_group_tc<6>(rb, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
-        quantise_group_tc<7>(rb + 8, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
+        tc::tmem_wait_ld8(rb);
+        tc::tmem_ld8(tmem + 48, ra);
+        quantise_group_tc<5>(rb, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
+        tc::tmem_wait_ld8(ra);
+        tc::tmem_ld8(tmem + 56, rb);
+        quantise_group_tc<6>(ra, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
+        tc::tmem_wait_ld8(rb);
+        quantise_group_tc<7>(rb, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
         sm.nz_lo[t] = nz_lo;
         sm.nz_hi[t] = nz_hi;
         sm.dcq[t] = dc;
         if (!(t < ti.nb)) fl_lo = fl_hi = 0;
-        // A DC in the guard band of a tie: 1 block in 128 on ordinary content, but EVERY block of a flat area whose
-        // level lands on a tie.  When several lanes are affected each settles its own DC in float64 (out of line).
-        if (__popc(__ballot_sync(0xffffffffu, (fl_lo & 0x80000000u) != 0)) >= 4) {   // warp-uniform
-            if (settle_dc_ties(ti.px, ti.w, ti.h, ti.bw, ti.blk0, ti.nb, qp.qt[0], &sm.coef[0][0], sm.dcq, fl_lo)) {
-                fl_lo &= 0x7fffffffu;
-                st.items++;
+        // Flagged coefficients at the four positions where exact .5 ties occur (9 in 10 of all flagged ones; every
+        // block of a flat area whose level lands on a tie): settled by the lane itself from the accumulator's
+        // column sums.  Everything else that is flagged goes to the warp's worklist below.
+        constexpr uint32_t kRatLo = 0x80000000u | (0x80000000u >> 10) | (0x80000000u >> 14), kRatHi = 0x80000000u >> (39 - 32);
+        if (!TIC_RATIONAL) {
+            if (__popc(__ballot_sync(0xffffffffu, (fl_lo & 0x80000000u) != 0)) >= 4) {   // warp-uniform
+                if (settle_dc_ties(ti.px, ti.w, ti.h, ti.bw, ti.blk0, ti.nb, qp.qt[0], &sm.coef[0][0], sm.dcq, fl_lo)) {
+                    fl_lo &= 0x7fffffffu;
+                    st.items(1u);
+                }
+            }
+        } else if (!debug_all && __any_sync(0xffffffffu, ((fl_lo & kRatLo) | (fl_hi & kRatHi)) != 0)) {   // warp-uniform
+            const uint32_t rat = (fl_lo >> 31) | (((fl_lo >> (31 - 10)) & 1u) << 1) | (((fl_lo >> (31 - 14)) & 1u) << 2) |
+                                 (((fl_hi >> (31 - 7)) & 1u) << 3);
+            const unsigned ch = settle_rational(tmem, rat, qp.qt, &sm, t);
+            if (rat) {
+                st.items((unsigned)__popc(rat));
+                if (ch) st.changed(ch);
+                fl_lo &= ~kRatLo;
+                fl_hi &= ~kRatHi;
             }
         }
     }
@@ -1084,7 +1211,7 @@ __device__ __forceinline__ void transform_tile_tc(const TileInfo& ti, const Quan
         const int pending = sm.pending[warp];
         __syncwarp();
         if (count) {   // warp-uniform
-            if (lane == 0) st.items += (unsigned)count;
+            if (lane == 0) st.items((unsigned)count);
             exact_round(ti, qp, sm, warp, count, st);
         }
         if (pending == 0) break;
@@ -1204,10 +1331,24 @@ __device__ __forceinline__ void put_symbol(BitSink<kToStage>& s, uint2 e, int v,
     if constexpr (kAuto) {   // e = {code, kHuffPresent | length}: code up to 32 bits + value up to 15
         s.put(e.x, (int)(e.y & kHuffLenMask));
         s.put(value_bits(v, sz), sz);
-    } else {                 // e = {code << size, code length + size <= 26}
-        s.put(e.x | value_bits(v, sz), (int)e.y);
+    } else {                 // e.x = (code length + size) << 27 | code << size;  length + size <= 26, code << size < 2^26
+        s.put((e.x & 0x07ffffffu) | value_bits(v, sz), (int)(e.x >> 27));
     }
 }
+// one table entry: fixed tables 32 bits (returned in .x, .y = .x so that "absent" is .y == 0 in both forms)
+template <bool kAuto>
+__device__ __forceinline__ uint2 tab_entry(uint32_t tab, uint32_t idx) {
+    if constexpr (kAuto) return lds_v2(tab + idx * 8u);
+    uint32_t w;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(tab + idx * 4u) : "memory");
+    return make_uint2(w, w);
+}
+template <bool kAuto>
+__device__ __noinline__ uint2 tab_entry_cold(uint32_t tab, uint32_t idx) { return tab_entry<kAuto>(tab, idx); }
+template <bool kAuto>
+__device__ __forceinline__ int tab_len(uint2 e) { return kAuto ? (int)(e.y & kHuffLenMask) : (int)(e.x >> 27); }
+template <bool kAuto>
+__device__ __forceinline__ uint32_t tab_code(uint2 e) { return kAuto ? e.x : (e.x & 0x07ffffffu); }
 
 // Emits the bits of thread t's block (DC difference `diff`, AC from sm.coef / nz masks) and returns
 // their number.  |quantised value| <= 1024 / 0.2 (quality 99), so a size never exceeds 14 and the
@@ -1220,8 +1361,8 @@ __device__ __forceinline__ int walk_block(const TileShared& sm, uint32_t sbase, 
     const uint32_t ac_tab = sbase + (uint32_t)offsetof(TileShared, ac_tab);
     const uint32_t col = sbase + (uint32_t)offsetof(TileShared, coef) + (uint32_t)t * 4u;
     int sz = msb_index((uint32_t)(diff < 0 ? -diff : diff)) + 1;  // bits_required, utils.py:9-10
-    uint2 e = lds_v2(dc_tab + (uint32_t)sz * 8u);
-    if (e.y == 0) { err = 1; sz = 0; e = lds_v2_cold(dc_tab); }  // KeyError, huffman.py:62
+    uint2 e = tab_entry<kAuto>(dc_tab, (uint32_t)sz);
+    if (e.y == 0) { err = 1; sz = 0; e = tab_entry_cold<kAuto>(dc_tab, 0u); }  // KeyError, huffman.py:62
     put_symbol<kAuto, kToStage>(s, e, diff, sz);
     int carry = 0;   // zeros since the last non-zero coefficient, not counting the current mask word
 #pragma unroll 1
@@ -1241,17 +1382,17 @@ __device__ __forceinline__ int walk_block(const TileShared& sm, uint32_t sbase, 
             int v = lds_s16(col + (((uint32_t)k * (kTile * 2u + 2u)) & (63u * kTile * 4u | 2u)));
             sz = msb_index((uint32_t)(v < 0 ? -v : v)) + 1;
             if (run >= 16) {                                      // ZRL, huffman.py:25-29
-                const uint2 zrl = lds_v2(ac_tab + 0xF0u * 8u);
-                for (; run >= 16; run -= 16) s.put(zrl.x, (int)(zrl.y & kHuffLenMask));
+                const uint2 zrl = tab_entry<kAuto>(ac_tab, 0xF0u);
+                for (; run >= 16; run -= 16) s.put(tab_code<kAuto>(zrl), tab_len<kAuto>(zrl));
             }
-            e = lds_v2(ac_tab + (uint32_t)(run * 16 + sz) * 8u);
-            if (e.y == 0) { err = 1; sz = 1; v = 1; e = lds_v2_cold(ac_tab + (uint32_t)(run * 16 + 1) * 8u); }
+            e = tab_entry<kAuto>(ac_tab, (uint32_t)(run * 16 + sz));
+            if (e.y == 0) { err = 1; sz = 1; v = 1; e = tab_entry_cold<kAuto>(ac_tab, (uint32_t)(run * 16 + 1)); }
             put_symbol<kAuto, kToStage>(s, e, v, sz);
         }
         carry += base + 32 - pos;
     }
-    e = lds_v2(ac_tab);
-    s.put(e.x, (int)(e.y & kHuffLenMask));                       // EOB always, huffman.py:33
+    e = tab_entry<kAuto>(ac_tab, 0u);
+    s.put(tab_code<kAuto>(e), tab_len<kAuto>(e));                // EOB always, huffman.py:33
     return s.finish();
 }
 

@@ -20,13 +20,23 @@ namespace tic {
 namespace tc {
 
 constexpr int kABytes = 128 * 64 * 2;   // A operand of one tile: 128 blocks x 64 f16 (aliases TileShared::coef)
-constexpr int kBBytes = 64 * 128 * 2;   // B operand: 64 columns x (64 hi + 64 lo) f16
-constexpr int kColsPerGroup = 64;       // TMEM columns per tile accumulator (f32)
+// N = 80 output columns: 64 scaled zigzag coefficients, then 8 column sums S_x = sum_y (p - 128)[y][x] and 8 signed
+// column sums I_x = sum_y s_y (p - 128)[y][x], s = + for y in {0,3,4,7}, - for y in {1,2,5,6} — exact small integers.
+// They are everything the reference's float64 column pass needs for u = 0 and u = 4 (every
+// operation before the last multiply acts on integers), i.e. for the four coefficients whose quotients can sit on
+// exact .5 ties: (0,0), (4,0), (0,4), (4,4).  A lane with such a tie reads them from tensor memory.
+#ifndef TIC_RATIONAL
+#define TIC_RATIONAL 1   // 1: the 16 column-sum outputs exist and ties at the four rational positions are settled from them
+#endif
+constexpr int kN = TIC_RATIONAL ? 80 : 64;
+constexpr int kBBytes = kN * 128 * 2;   // B operand: 80 columns x (64 hi + 64 lo) f16
+constexpr int kColsPerGroup = kN;       // TMEM columns per tile accumulator (f32)
+constexpr int kColSums = 64;            // first of the 16 sum columns
 
 // Shared-memory layouts (canonical K-major, no swizzle: core matrix = 8 rows x 16 bytes, contiguous 128 bytes)
 //   A[m][k = 8y + x]: (m / 8) * 128 + y * 2048 + (m % 8) * 16 + x * 2     SBO = 128 (next 8 blocks), LBO = 2048 (next 8 k)
-//   B[n][k]         : (n / 8) * 128 + (k / 8) * 1024 + (n % 8) * 16 + (k % 8) * 2     SBO = 128, LBO = 1024
-constexpr uint32_t kLboA = 2048, kSboA = 128, kLboB = 1024, kSboB = 128;
+//   B[n][k]         : (n / 8) * 128 + (k / 8) * 1280 + (n % 8) * 16 + (k % 8) * 2     SBO = 128, LBO = 1280 (10 row groups)
+constexpr uint32_t kLboA = 2048, kSboA = 128, kLboB = (kN / 8) * 128, kSboB = 128;
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -37,7 +47,7 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint3
            ((uint64_t)((sbo >> 4) & 0x3fffu) << 32) | (1ull << 46);
 }
 // cute::UMMA::InstrDescriptor: D = f32 (1 at [4,6)), A = B = f16 (0), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
-constexpr uint32_t kIdescF16M128N64 = (1u << 4) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kIdescF16M128 = (1u << 4) | ((uint32_t)(kN >> 3) << 17) | ((128u >> 4) << 24);
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -57,10 +67,15 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 }
 // Bounded (the MMA of a tile completes within microseconds): a fault in the asynchronous pipe must surface as a
 // status, never as a hung GPU.  Returns false on timeout.
+#ifndef TIC_POLL_SLEEP_NS
+#define TIC_POLL_SLEEP_NS 0   // > 0: sleep between two polls of the MMA's mbarrier (fewer issue slots spent polling)
+#endif
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
 #pragma unroll 1
-    for (int i = 0; i < (1 << 16); i++)
+    for (int i = 0; i < (1 << 16); i++) {
         if (mbar_try_wait(bar, parity)) return true;
+        if (TIC_POLL_SLEEP_NS > 0) __nanosleep(TIC_POLL_SLEEP_NS);
+    }
     return false;
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -92,6 +107,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
                  : "r"(taddr)
                  : "memory");
 }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld8(uint32_t (&r)[8]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :
+                 : "memory");
+}
 // The registers of every tcgen05.ld issued so far are valid after this.  They are passed through the statement
 // ("+r") so that the compiler cannot move a use of them above the wait.
 __device__ __forceinline__ void tmem_wait_ld(uint32_t (&r)[16]) {
@@ -111,7 +138,7 @@ __device__ __forceinline__ void issue_tile_mma(uint64_t desc_a0, uint64_t desc_b
         const int j = i & 3;             // pixel rows 2j, 2j+1 of every block
         const uint64_t da = desc_a0 + (uint64_t)((uint32_t)j * 2u * kLboA >> 4);
         const uint64_t db = desc_b0 + (uint64_t)((uint32_t)(half * 4 + j) * 2u * kLboB >> 4);
-        mma_f16(tmem_d, da, db, kIdescF16M128N64, i > 0 ? 1u : 0u);
+        mma_f16(tmem_d, da, db, kIdescF16M128, i > 0 ? 1u : 0u);
     }
     commit(bar);
 }

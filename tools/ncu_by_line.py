@@ -38,7 +38,7 @@ tot_e, tot_s = sum(ex.values()), sum(sm.values())
 src = {}
 def text(f, l):
     if f not in src:
-        p = [os.path.join(d, f) for d in ("tinyimgcodec_b200/csrc",) if os.path.exists(os.path.join(d, f))]
+        p = [os.path.join(d, f) for d in (os.environ.get("TIC_SRC_DIR", "tinyimgcodec_b200/csrc"),) if os.path.exists(os.path.join(d, f))]
         src[f] = open(p[0]).read().splitlines() if p else []
     return src[f][l - 1].strip()[:90] if 0 < l <= len(src[f]) else ""
 print(f"total warp-inst {tot_e:.3e}, samples {tot_s:.0f}")
