@@ -165,7 +165,32 @@ def _numpy_sample_images(count):
     return [synthetic_image(IMG_H, IMG_W, seed=i) for i in range(count)]
 
 
-def time_reference_c_encoder(cores, images_per_core, distinct=4):
+def time_reference_python(cores, images_per_core):
+    """The reference's PYTHON encoder — tinyimgcodec.codec.compress, the path BASELINE.json's north_star names — one
+    process per host core on distinct synthetic 1024x1024 images (precedent: tests/benchmark.py:12-28).  Unmodified
+    reference code (oracle/ref_py_worker.py: sources in the build container, their bytecode on the GPU box), with the
+    pure-Python bidict / bitarray stand-ins.  None if the reference is not available."""
+    from oracle.ref_harness import reference_python_available
+    if not reference_python_available():
+        return None
+    worker = os.path.join(ROOT, "oracle", "ref_py_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(images_per_core), str(IMG_H), str(IMG_W), str(1000 * i)],
+                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL) for i in range(cores)]
+    outs = []
+    for p in procs:
+        o, _ = p.communicate()
+        if p.returncode == 0 and o.strip():
+            outs.append(json.loads(o.decode().strip().splitlines()[-1]))
+    if len(outs) != cores:
+        return None
+    px, slowest = sum(o["pixels"] for o in outs), max(o["seconds"] for o in outs)
+    return {"value": px / slowest / 1e6, "unit": UNIT, "cores": cores, "kind": "reference",
+            "per_core": px / sum(o["seconds"] for o in outs) / 1e6,
+            "sample": f"{cores} procs x {images_per_core} distinct synthetic {IMG_H}x{IMG_W} images, q{QUALITY}, unmodified "
+                      f"tinyimgcodec.codec.compress (Python; pure-Python bitarray/bidict stand-ins), slowest process {slowest:.1f} s"}
+
+
+def time_reference_c_encoder(cores, images_per_core, distinct=64):
     """The reference's own C encoder (c/encode.c), one process per core, raw rows on stdin,
     `med` quality, exactly how tests/cbenchmark.py:24-26 drives it — but with the input in a file
     so that the pipe is not the test.  Emits the flag-bit-30 stream variant (integer AAN DCT)."""
@@ -189,7 +214,7 @@ def time_reference_c_encoder(cores, images_per_core, distinct=4):
     return cores * images_per_core * IMG_H * IMG_W / dt / 1e6, dt
 
 
-def time_oracle_port(cores, images_per_core, distinct=4):
+def time_oracle_port(cores, images_per_core, distinct=16):
     """The C restatement of the Python path (oracle/tic_oracle.c), one thread per core."""
     from concurrent.futures import ThreadPoolExecutor
     from oracle import oracle_lib as O
@@ -227,9 +252,10 @@ def run_reference_arm(args):
     total_px = steps * cores * per_core * IMG_H * IMG_W
     total_t = sum(dt for _, dt in vals)
     value = total_px / total_t / 1e6
-    sample = (f"{cores} procs x {per_core} synthetic 1024x1024 images per step "
-              + ("(reference C encoder c/encode.c, quality 'med', flag-bit-30 stream variant)" if kind == "reference"
-                 else "(C port of the Python path, q50)"))
+    sample = (f"{cores} procs x {per_core} synthetic 1024x1024 images per step ({min(per_core, 64)} distinct per process) "
+              + ("(reference C encoder c/encode.c, quality 'med', flag-bit-30 stream variant: compare with the GPU arm's "
+                 "c_variant figures)" if kind == "reference" else "(C port of the Python path, q50)"))
+    py = time_reference_python(cores, 4)   # the path north_star names, on the same host cores
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_t / steps, "higher_is_better": True, "scaling": "strong",
@@ -238,7 +264,7 @@ def run_reference_arm(args):
                    "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "python_reference": py, "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
@@ -363,41 +389,69 @@ def run_gpu_arm(args):
                 "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": kernel_ms, "launches_timed": nb,
                 "step_ms": float(np.mean(step_ms)), "step_ms_min": float(np.min(step_ms)),
                 "other_kernels_ms": {"compact_kernel": compact_ms,
-                                     "scan_chunks+scan_spine+scan_apply+finalize (by difference, with launch gaps)":
+                                     "prep + scan_chunks (+ spine) + scan_apply (+ sizes, summary) (by difference, with launch gaps)":
                                          float(np.mean(step_ms)) - kernel_ms - compact_ms},
                 "whole_step": {"achieved": alg_bytes / (float(np.mean(step_ms)) * 1e-3) / 1e9,
                                "frac": alg_bytes / (float(np.mean(step_ms)) * 1e-3) / 1e9 / peak},
                 "note": "launch_ms = CUDA events around encode_tiles_kernel alone, on its stream, averaged over the "
-                        "timed steps; step_ms = events around one whole tic_encode_batch (2 memsets, 1 small H2D, "
-                        "6 kernels); algorithmic bytes = pixels read once + stream bytes written once"}
+                        "timed steps; step_ms = events around one whole tic_encode_batch (5 kernels: prep, encode, two scan "
+                        "kernels, compact; no copy, no memset); algorithmic bytes = pixels read once + stream bytes written once"}
 
-    # end to end through the public host API: pinned host pixels in, streams back on the host
+    # end to end through the public host API: pinned host pixels in, streams back on the host.  Next to it the plain
+    # H2D ceiling of the same pinned buffer at the same N (all ranks copy at the same time): the pipeline moves 14 x
+    # more bytes in than out, so the end-to-end figure is a host-link number and is reported as a fraction of that ceiling.
     e2e = None
+    e2e_parity = None
+    h_images = None
     try:
         if args.no_e2e:
             raise RuntimeError("skipped (--no-e2e)")
-        h_images = torch.empty((n_local, IMG_H, IMG_W), dtype=torch.uint8).pin_memory()
+        h_images = torch.empty((n_local, IMG_H, IMG_W), dtype=torch.uint8).pin_memory()   # after bind_to_gpu_numa_node
         h_images.copy_(d_images)
         torch.cuda.synchronize()
-        enc.compress_batch_pinned(h_images, QUALITY)   # warm-up (allocates the pipeline buffers)
+        chunk, nbuf = 64, 4
+        enc.compress_batch_pinned(h_images, QUALITY, chunk=chunk, nbuf=nbuf)   # warm-up (allocates the pipeline buffers)
         e2e_steps = max(1, min(args.steps, 3))
         barrier()
         t0 = time.perf_counter()
         d2h = 0
         for _ in range(e2e_steps):
-            h_out, index = enc.compress_batch_pinned(h_images, QUALITY)
+            h_out, index = enc.compress_batch_pinned(h_images, QUALITY, chunk=chunk, nbuf=nbuf)
             d2h = sum(s for _, s in index)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        if rank == 0:   # parity of what the pipeline returned (host buffer + index), outside the timed region
+            from oracle import oracle_lib as O
+            host = h_out.numpy()
+            picks = sorted({0, 1, chunk - 1, chunk, n_local // 2, n_local - 1} & set(range(n_local)))
+            ok = sum(int(host[index[i][0]: index[i][0] + index[i][1]].tobytes() == O.compress(h_images[i].numpy(), QUALITY)) for i in picks)
+            e2e_parity = {"checked": len(picks), "identical": ok}
+        # plain H2D of the same bytes, same chunking, one stream
+        d_tmp = torch.empty((chunk, IMG_H, IMG_W), dtype=torch.uint8, device=dev)
+        barrier()
+        c0 = time.perf_counter()
+        for lo_ in range(0, n_local, chunk):
+            hi_ = min(n_local, lo_ + chunk)
+            d_tmp[: hi_ - lo_].copy_(h_images[lo_:hi_], non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_dt = time.perf_counter() - c0
+        del d_tmp
         if world > 1:
-            tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+            tt = torch.tensor([dt, h2d_dt], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
+            dt, h2d_dt = float(tt[0].item()), float(tt[1].item())
+        h2d_bytes = n_local * IMG_H * IMG_W * n_gpus
+        e2e_gbs = h2d_bytes * e2e_steps / dt / 1e9
+        ceil_gbs = h2d_bytes / h2d_dt / 1e9
         e2e = {"value": total_px * e2e_steps / dt / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": n_local * IMG_H * IMG_W * n_gpus, "d2h_bytes_per_step": d2h * n_gpus,
-               "steps": e2e_steps, "api": "Encoder.compress_batch_pinned (chunked H2D / encode / D2H pipeline)",
-               "timing": "host wall clock around the API calls, max over ranks", "host_affinity_rank0": numa}
-        del h_images
+               "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h * n_gpus,
+               "steps": e2e_steps, "api": f"Encoder.compress_batch_pinned(chunk={chunk}, nbuf={nbuf}): H2D / encode / D2H on three streams, "
+                                          "no host synchronisation in front of the GPU",
+               "timing": "host wall clock around the API calls, max over ranks", "host_affinity_rank0": numa,
+               "h2d_gbs_all_gpus": e2e_gbs, "h2d_ceiling_gbs_all_gpus": ceil_gbs, "frac_of_h2d_ceiling": e2e_gbs / ceil_gbs,
+               "saturating_link": "host -> device (PCIe Gen5 x16 per GPU; the ceiling is a plain chunked cudaMemcpyAsync of the same "
+                                  "pinned buffer, all ranks at once)",
+               "parity": e2e_parity}
     except Exception as ex:  # keep the device-timed line even if the host leg cannot run
         e2e = {"value": None, "unit": UNIT, "error": f"{type(ex).__name__}: {ex}"}
 
@@ -441,6 +495,19 @@ def run_gpu_arm(args):
                      "encode_kernel_ms": cst["encode_kernel_ms_sum"] / max(1, int(cst["timed_batches"])),
                      "stream_bytes_rank0": int(cres.sizes.sum().item()),
                      "what": "integer-FDCT stream of c/encode.c, quality 'med', device-resident, CUDA events"}
+        if h_images is not None:   # the same through the host pipeline: what the reference arm's ratio should be read against
+            enc.compress_batch_pinned(h_images, "med", c_variant=True)
+            barrier()
+            t0 = time.perf_counter()
+            enc.compress_batch_pinned(h_images, "med", c_variant=True)
+            torch.cuda.synchronize()
+            cdt = time.perf_counter() - t0
+            if world > 1:
+                tt = torch.tensor([cdt], device=dev, dtype=torch.float64)
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+                cdt = float(tt.item())
+            c_variant["e2e"] = {"value": total_px / cdt / 1e6, "unit": UNIT, "steps": 1,
+                                "api": "Encoder.compress_batch_pinned(c_variant=True), host wall clock, max over ranks"}
         if rank == 0:
             from oracle import oracle_lib as O
             if O.ref_c_available():   # the reference binary itself, 2 images (outside every timed region)
@@ -453,6 +520,45 @@ def run_gpu_arm(args):
         del cres
     except Exception as ex:
         c_variant = {"value": None, "error": f"{type(ex).__name__}: {ex}"}
+    h_images = None
+
+    # the same batch with per-image Huffman tables (auto_generate_huffman_table=True, codec.py:146-148): symbol statistics
+    # + table construction + encode, all on the device
+    auto = None
+    try:
+        a_steps = max(1, min(args.steps, 5))
+        for _ in range(2):
+            ares = enc.encode_batch_device(d_images, QUALITY, out=d_out, stream=stream, auto_generate_huffman_table=True)
+        ares.finish()
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record(stream)
+        for _ in range(a_steps):
+            ares = enc.encode_batch_device(d_images, QUALITY, out=d_out, stream=stream, auto_generate_huffman_table=True)
+        c1.record(stream)
+        barrier()
+        ares.finish()
+        ams = c0.elapsed_time(c1) / a_steps
+        if world > 1:
+            tt = torch.tensor([ams], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ams = float(tt.item())
+        ast_ = enc.stats()
+        auto = {"value": total_px / (ams * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ams, "steps": a_steps,
+                "encode_kernel_ms": ast_["encode_kernel_ms_sum"] / max(1, int(ast_["timed_batches"])),
+                "launches": int(ast_["launches"]), "stream_bytes_rank0": int(ares.sizes.sum().item()),
+                "what": "per-image Huffman tables: symbol_stats_kernel + build_tables_kernel + encode_tiles_kernel<1>, "
+                        "device-resident, CUDA events around the whole call"}
+        if rank == 0:
+            from oracle import oracle_lib as O
+            outs = ares.to_bytes()
+            picks = (0, n_local - 1)
+            auto["parity_vs_oracle"] = {"checked": len(picks), "identical": sum(
+                int(outs[i] == O.compress(d_images[i].cpu().numpy(), QUALITY, True)) for i in picks)}
+            del outs
+        del ares
+    except Exception as ex:
+        auto = {"value": None, "error": f"{type(ex).__name__}: {ex}"}
 
     # the decode side: the benchmarked batch's own streams, still in HBM, decoded back to
     # pixels by tic_decode_batch (self-synchronising Huffman decode + float64 IDCT); CUDA events around the call
@@ -516,10 +622,14 @@ def run_gpu_arm(args):
                                                     f"Python path (oracle/tic_oracle.c, q50, byte-identical streams), {p[1]:.1f} s"}
             if cpu_baseline is None:
                 cpu_baseline = extra.pop("cpu_baseline_port")
+            py = time_reference_python(cores, 4)
+            if py is not None:
+                extra["cpu_baseline_python_reference"] = py
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "f32 fdct + f64 exact ties, int32 entropy",
+            "scaling": "strong", "vs_baseline": None,
+            "dtype": "f16 x f16 -> f32 tensor-core fdct (hi/lo split), f64 exact ties, int32 entropy",
             "data": "synthetic",
             "config": {"workload": f"{total} synthetic {IMG_H}x{IMG_W} grayscale images, quality {QUALITY}, "
                                    f"default Huffman tables, sharded by image over {n_gpus} GPU(s)",
@@ -528,7 +638,7 @@ def run_gpu_arm(args):
                        "stream_bytes": stream_bytes_total, "bits_per_pixel": 8.0 * stream_bytes_total / total_px,
                        "exact_path": {k: stats[k] for k in ("exact_items", "exact_changed", "blocks", "tiles")}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(stats["launches"]) * args.steps * n_gpus, "roofline": roofline,
-            "cpu_baseline": cpu_baseline, "parity": parity, "c_variant": c_variant, "decode": decode,
+            "cpu_baseline": cpu_baseline, "parity": parity, "c_variant": c_variant, "auto_tables": auto, "decode": decode,
         }
         line.update(extra)
         print(json.dumps(line), flush=True)

@@ -11,12 +11,25 @@ import importlib
 import os
 import sys
 
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_STANDINS = os.path.join(_HERE, "standins")
+# the build container has the reference itself; the GPU box only has its bytecode (oracle/Makefile `refpy`:
+# oracle/_ref/py/tinyimgcodec/*.pyc, a sourceless package — the encoder only, for CPU timing)
 REFERENCE_ROOT = os.environ.get("TIC_REFERENCE_ROOT", "/root/reference")
-_STANDINS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "standins")
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, "tinyimgcodec", "codec.py")) and \
+        os.path.isfile(os.path.join(_HERE, "_ref", "py", "tinyimgcodec", "codec.pyc")):
+    REFERENCE_ROOT = os.path.join(_HERE, "_ref", "py")
 
 
 def reference_available():
+    """The reference SOURCES (needed by the tests that also use its data/ and tests/ files)."""
     return os.path.isfile(os.path.join(REFERENCE_ROOT, "tinyimgcodec", "codec.py"))
+
+
+def reference_python_available():
+    """The reference's Python package, as source or as bytecode: enough to call compress() / decompress()."""
+    d = os.path.join(REFERENCE_ROOT, "tinyimgcodec")
+    return os.path.isfile(os.path.join(d, "codec.py")) or os.path.isfile(os.path.join(d, "codec.pyc"))
 
 
 def load_reference():
@@ -29,7 +42,7 @@ def load_reference():
     """
     if "tinyimgcodec_reference" in sys.modules:
         return sys.modules["tinyimgcodec_reference"]
-    if not reference_available():
+    if not reference_python_available():
         raise ImportError(f"reference not present at {REFERENCE_ROOT}")
     saved_path = list(sys.path)
     saved_mods = {k: v for k, v in sys.modules.items()

@@ -312,3 +312,23 @@ def test_random_sweep_vs_oracle(tic):
         outs = tic.decompress_batch(streams, exact_only=exact_only)
         for i, (px, ref_px) in enumerate(zip(outs, want)):
             _same(px, ref_px, f"case {i} exact_only={exact_only}")
+
+
+@pytest.mark.parametrize("chunk", [1, 3, 8])
+def test_pinned_pipeline_round_trip(chunk):
+    """SURVEY §8(f)1 on the decode side (reference callers: encode.py:10-19, viewer.py's read-and-decompress): the
+    pinned, chunked encode pipeline feeds the pinned, chunked decode pipeline; every decoded image equals the CPU
+    restatement of the reference decoder on the same stream."""
+    import torch
+    import tinyimgcodec_b200 as tic
+    from tests.cases import synthetic_image
+    enc = tic.get_encoder(0)
+    h, w, n = 64, 96, 2 * chunk + 3
+    imgs = np.stack([synthetic_image(h, w, seed=7 * chunk + i) for i in range(n)])
+    h_out, index = enc.compress_batch_pinned(torch.from_numpy(imgs).pin_memory(), 50, chunk=chunk, out_bytes_per_pixel=3.3)
+    px, pidx = enc.decompress_batch_pinned(h_out, index, [h] * n, [w] * n, chunk=chunk)
+    assert tuple(px.shape) == (n, h, w) and len(pidx) == n
+    host = h_out.numpy()
+    for i, (off, size) in enumerate(index):
+        want = O.decompress(host[off: off + size].tobytes())
+        assert np.array_equal(px[i].numpy(), want), f"image {i}"

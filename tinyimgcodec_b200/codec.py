@@ -250,71 +250,110 @@ class Encoder:
         return DeviceBatchResult(self, out, offs, sizes, stat, stream, n, keep)
 
     # -- batch, host buffers, pipelined -----------------------------------------------------------
-    def compress_batch_pinned(self, h_images, quality=50, chunk=256, out_bytes_per_pixel=0.75):
-        """End-to-end encode of an (N,H,W) uint8 tensor in PINNED host memory: chunked H2D on a copy
-        stream overlapped with the encode of the previous chunk, streams copied back to pinned host
-        memory.  Returns (host_buffer, [(offset, size)] per image) with offsets into host_buffer."""
+    def compress_batch_pinned(self, h_images, quality=50, chunk=64, out_bytes_per_pixel=0.75, nbuf=4, c_variant=False):
+        """End-to-end encode of an (N,H,W) uint8 tensor in PINNED host memory — the batch form of the reference's
+        caller (encode.py:10-19: read pixels, compress, write bytes).  Three streams: H2D of chunk c+1 and c+2,
+        encode of chunk c and D2H of chunk c-1 run concurrently over `nbuf` device buffer pairs; the host never
+        blocks the GPU (it waits for chunk c-1's sizes while chunk c encodes and the next copies are queued).
+        Returns (host_buffer, [(offset, size)] per image) with offsets into host_buffer (16-byte aligned).
+        out_bytes_per_pixel bounds the compressed size of a CHUNK (device buffer) and of the whole batch (host
+        buffer); a batch that compresses worse raises TicError(TIC_E_CAPACITY) naming it.  c_variant: the stream of
+        the reference's C encoder (compress_c), `quality` is then "best" | "high" | "med" | "low"."""
         import torch
-        n, hgt, wid = h_images.shape
+        n, hgt, wid = (int(v) for v in h_images.shape)
         dev = torch.device("cuda", self.device)
-        chunk = max(1, min(chunk, n))
-        cap = int(chunk * hgt * wid * out_bytes_per_pixel) + 4096
-        cap = (cap + 15) & ~15
+        q = _check_qfactor(quality) if c_variant else _check_quality(quality)
+        chunk = max(1, min(int(chunk), max(n, 1)))
+        nbuf = max(3, int(nbuf))
+        cap = (int(chunk * hgt * wid * out_bytes_per_pixel) + 4096 + 15) & ~15
+        nchunks = (n + chunk - 1) // chunk
         with torch.cuda.device(dev):
-            if getattr(self, "_pipe_key", None) != (chunk, hgt, wid, cap):
+            key = (chunk, hgt, wid, cap, nbuf)
+            if getattr(self, "_pipe_key", None) != key:
                 self._pipe = {
-                    "d_in": [torch.empty((chunk, hgt, wid), dtype=torch.uint8, device=dev) for _ in range(2)],
-                    "d_out": [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(2)],
+                    "d_in": [torch.empty((chunk, hgt, wid), dtype=torch.uint8, device=dev) for _ in range(nbuf)],
+                    "d_out": [torch.empty(cap, dtype=torch.uint8, device=dev) for _ in range(nbuf)],
                     "s_in": torch.cuda.Stream(dev), "s_comp": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
                 }
-                self._pipe_key = (chunk, hgt, wid, cap)
+                self._pipe_key = key
             P = self._pipe
+            need = int(n * hgt * wid * out_bytes_per_pixel) + 4096 * max(nchunks, 1)
             h_out = getattr(self, "_h_out", None)
-            need = int(n * hgt * wid * out_bytes_per_pixel) + 4096 * ((n + chunk - 1) // chunk)
             if h_out is None or h_out.numel() < need:
                 h_out = self._h_out = torch.empty(need, dtype=torch.uint8).pin_memory()
-            nchunks = (n + chunk - 1) // chunk
-            h_meta = getattr(self, "_h_meta", None)
+            h_meta = getattr(self, "_h_meta", None)   # per chunk: offsets, sizes (int64) and status (int32 in an int64 slot)
             if h_meta is None or h_meta.shape[0] < nchunks or h_meta.shape[2] < chunk:
-                h_meta = self._h_meta = torch.empty((nchunks, 2, chunk), dtype=torch.int64).pin_memory()
+                h_meta = self._h_meta = torch.empty((max(nchunks, 1), 3, chunk), dtype=torch.int64).pin_memory()
             ev_in = [torch.cuda.Event() for _ in range(nchunks)]
             ev_comp = [torch.cuda.Event() for _ in range(nchunks)]
             ev_out = [torch.cuda.Event() for _ in range(nchunks)]
-            results, index, h_pos = [], [], 0
+            keep, index, h_pos = {}, [], 0
+
+            def span(c):
+                return c * chunk, min(n, (c + 1) * chunk)
 
             def issue_h2d(c):
-                lo, hi = c * chunk, min(n, (c + 1) * chunk)
+                lo, hi = span(c)
                 with torch.cuda.stream(P["s_in"]):
-                    if c >= 2:
-                        P["s_in"].wait_event(ev_comp[c - 2])   # input buffer free again
-                    P["d_in"][c & 1][: hi - lo].copy_(h_images[lo:hi], non_blocking=True)
+                    if c >= nbuf:
+                        P["s_in"].wait_event(ev_comp[c - nbuf])   # input buffer free again
+                    P["d_in"][c % nbuf][: hi - lo].copy_(h_images[lo:hi], non_blocking=True)
                     ev_in[c].record(P["s_in"])
 
-            issue_h2d(0)
-            for c in range(nchunks):
-                lo, hi = c * chunk, min(n, (c + 1) * chunk)
-                if c + 1 < nchunks:
-                    issue_h2d(c + 1)
+            def issue_encode(c):
+                lo, hi = span(c)
                 P["s_comp"].wait_event(ev_in[c])
-                if c >= 2:
-                    P["s_comp"].wait_event(ev_out[c - 2])      # output buffer drained
-                res = self.encode_batch_device(P["d_in"][c & 1][: hi - lo], quality, out=P["d_out"][c & 1],
-                                               stream=P["s_comp"])
+                if c >= nbuf:
+                    P["s_comp"].wait_event(ev_out[c - nbuf])      # output buffer drained
+                res = self.encode_batch_device(P["d_in"][c % nbuf][: hi - lo], q, out=P["d_out"][c % nbuf], stream=P["s_comp"],
+                                               c_variant=c_variant)
                 with torch.cuda.stream(P["s_comp"]):
                     h_meta[c, 0, : hi - lo].copy_(res.offsets, non_blocking=True)
                     h_meta[c, 1, : hi - lo].copy_(res.sizes, non_blocking=True)
-                ev_comp[c].record(P["s_comp"])
-                res.finish()                                     # waits for chunk c only; chunk c+1's H2D is in flight
+                    h_meta[c, 2, : hi - lo].view(torch.int32)[: hi - lo].copy_(res.status, non_blocking=True)
+                    ev_comp[c].record(P["s_comp"])
+                keep[c] = res
+
+            def drain(c):
+                nonlocal h_pos
+                lo, hi = span(c)
+                ev_comp[c].synchronize()       # chunk c only: chunk c+1 is encoding, the next H2D copies are queued
+                offs, sizes = h_meta[c, 0, : hi - lo].numpy(), h_meta[c, 1, : hi - lo].numpy()
+                status = h_meta[c, 2, : hi - lo].view(torch.int32)[: hi - lo].numpy()
+                total = int((offs + sizes).max()) if hi > lo else 0
+                if total > cap or h_pos + total > h_out.numel():
+                    raise TicError(_lib.TIC_E_CAPACITY, f"output buffer too small: images {lo}..{hi - 1} need {total} bytes; "
+                                                        f"raise out_bytes_per_pixel (now {out_bytes_per_pixel})")
+                if hi > lo and (int(np.bitwise_or.reduce(status)) & _lib.TIC_STATUS_CATEGORY):
+                    raise KeyError("coefficient category outside the fixed Huffman tables (reference: KeyError)")
                 with torch.cuda.stream(P["s_out"]):
                     P["s_out"].wait_event(ev_comp[c])
-                    h_out[h_pos: h_pos + res.total_bytes].copy_(P["d_out"][c & 1][: res.total_bytes], non_blocking=True)
+                    h_out[h_pos: h_pos + total].copy_(P["d_out"][c % nbuf][:total], non_blocking=True)
                     ev_out[c].record(P["s_out"])
-                results.append((h_pos, h_meta[c, :, : hi - lo]))
-                h_pos += (res.total_bytes + 15) & ~15
-            P["s_out"].synchronize()
-            for base, meta in results:
-                offs, sizes = meta[0].numpy(), meta[1].numpy()
-                index.extend((int(base + o), int(s)) for o, s in zip(offs, sizes))
+                index.extend((int(h_pos + o), int(s)) for o, s in zip(offs, sizes))
+                h_pos += (total + 15) & ~15
+                del keep[c]
+
+            try:
+                for c in range(min(2, nchunks)):
+                    issue_h2d(c)
+                for c in range(nchunks):
+                    issue_encode(c)
+                    if c + 2 < nchunks:
+                        issue_h2d(c + 2)
+                    if c >= 1:
+                        drain(c - 1)
+                if nchunks:
+                    drain(nchunks - 1)
+                P["s_out"].synchronize()
+            finally:
+                # one finish for the whole batch: collects whatever the device flagged (sticky) and leaves the handle clean
+                total = ctypes.c_int64(0)
+                with self._lock:
+                    rc = self.lib.tic_encode_finish(self.handle, P["s_comp"].cuda_stream, ctypes.byref(total))
+                keep.clear()
+            if rc not in (_lib.TIC_OK,):
+                self._raise(rc)
         return h_out, index
 
     # -- decode side ----------------------------------------------------------------------------------
@@ -414,6 +453,82 @@ class Encoder:
             imgs, _ = self.decode_batch_device((d_buf, offs[:-1]), sizes, [h[0] for h in hdrs], [h[1] for h in hdrs],
                                                strict=strict, accept_be_flag=accept_be_flag, exact_only=exact_only)
             return [im.cpu().numpy() for im in imgs]
+
+    def decompress_batch_pinned(self, h_streams, index, heights, widths, chunk=64, nbuf=3, strict=True):
+        """The mirror of compress_batch_pinned for the decode side (decompress, codec.py:167-189, for a batch): `h_streams`
+        is a PINNED uint8 tensor holding the streams, `index` the [(offset, size)] list compress_batch_pinned returns
+        (offsets 16-byte aligned, ascending).  Chunks of `chunk` streams go H2D on a copy stream while the previous chunk
+        decodes and the one before returns its pixels.  Returns (pinned pixel buffer, [(offset, height, width)]); for
+        equal shapes the buffer is an (N, H, W) tensor."""
+        import torch
+        n = len(index)
+        dev = torch.device("cuda", self.device)
+        hs = np.ascontiguousarray(heights, dtype=np.int64).reshape(-1)
+        ws = np.ascontiguousarray(widths, dtype=np.int64).reshape(-1)
+        if hs.size != n or ws.size != n:
+            raise ValueError("index, heights and widths must have one entry per stream")
+        offs = np.array([o for o, _ in index], dtype=np.int64)
+        sizes = np.array([s for _, s in index], dtype=np.int64)
+        if n and (np.any(offs % 4) or np.any(np.diff(offs) < 0)):
+            raise ValueError("stream offsets must be 4-byte aligned and ascending")
+        npx = hs * ws
+        px_off = np.zeros(n + 1, dtype=np.int64)
+        np.cumsum((npx + 15) & ~np.int64(15), out=px_off[1:])
+        chunk = max(1, min(int(chunk), max(n, 1)))
+        nbuf = max(2, int(nbuf))
+        nchunks = (n + chunk - 1) // chunk
+        spans = [(c * chunk, min(n, (c + 1) * chunk)) for c in range(nchunks)]
+        brange = [(int(offs[lo]), int((offs[hi - 1] + sizes[hi - 1] + 15) & ~15)) for lo, hi in spans]
+        in_cap = max([b1 - b0 for b0, b1 in brange] or [16]) + 16
+        px_cap = max([int(px_off[hi] - px_off[lo]) for lo, hi in spans] or [16]) + 16
+        with torch.cuda.device(dev):
+            key = ("dec", in_cap, px_cap, nbuf)
+            if getattr(self, "_dpipe_key", None) != key:
+                self._dpipe = {
+                    "d_in": [torch.zeros(in_cap, dtype=torch.uint8, device=dev) for _ in range(nbuf)],
+                    "d_px": [torch.empty(px_cap, dtype=torch.uint8, device=dev) for _ in range(nbuf)],
+                    "s_in": torch.cuda.Stream(dev), "s_comp": torch.cuda.Stream(dev), "s_out": torch.cuda.Stream(dev),
+                }
+                self._dpipe_key = key
+            P = self._dpipe
+            h_px = getattr(self, "_h_px", None)
+            if h_px is None or h_px.numel() < int(px_off[-1]) + 16:
+                h_px = self._h_px = torch.empty(int(px_off[-1]) + 16, dtype=torch.uint8).pin_memory()
+            ev_in = [torch.cuda.Event() for _ in range(nchunks)]
+            ev_comp = [torch.cuda.Event() for _ in range(nchunks)]
+            ev_out = [torch.cuda.Event() for _ in range(nchunks)]
+
+            def issue_h2d(c):
+                b0, b1 = brange[c]
+                b1 = min(b1, h_streams.numel())
+                with torch.cuda.stream(P["s_in"]):
+                    if c >= nbuf:
+                        P["s_in"].wait_event(ev_comp[c - nbuf])
+                    P["d_in"][c % nbuf][: b1 - b0].copy_(h_streams[b0:b1], non_blocking=True)
+                    ev_in[c].record(P["s_in"])
+
+            if nchunks:
+                issue_h2d(0)
+            for c, (lo, hi) in enumerate(spans):
+                if c + 1 < nchunks:
+                    issue_h2d(c + 1)
+                P["s_comp"].wait_event(ev_in[c])
+                if c >= nbuf:
+                    P["s_comp"].wait_event(ev_out[c - nbuf])
+                # tic_decode_batch reads one flag per synchronisation round on the host: the call returns when chunk c is
+                # decoded; the copies of its neighbours run meanwhile on their own streams
+                self.decode_batch_device((P["d_in"][c % nbuf], offs[lo:hi] - brange[c][0]), sizes[lo:hi], hs[lo:hi], ws[lo:hi],
+                                         pixels=P["d_px"][c % nbuf], stream=P["s_comp"], strict=strict)
+                ev_comp[c].record(P["s_comp"])
+                with torch.cuda.stream(P["s_out"]):
+                    P["s_out"].wait_event(ev_comp[c])
+                    nb = int(px_off[hi] - px_off[lo])
+                    h_px[int(px_off[lo]): int(px_off[lo]) + nb].copy_(P["d_px"][c % nbuf][:nb], non_blocking=True)
+                    ev_out[c].record(P["s_out"])
+            P["s_out"].synchronize()
+        if n and (hs == hs[0]).all() and (ws == ws[0]).all() and int(npx[0]) % 16 == 0:
+            return h_px[: n * int(npx[0])].view(n, int(hs[0]), int(ws[0])), [(int(px_off[i]), int(hs[i]), int(ws[i])) for i in range(n)]
+        return h_px, [(int(px_off[i]), int(hs[i]), int(ws[i])) for i in range(n)]
 
     def decode(self, data):
         """tinyimgcodec.codec.decode (codec.py:46-70): the dict encode() returns (plus the optional

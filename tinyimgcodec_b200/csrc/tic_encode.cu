@@ -163,12 +163,12 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
         }
         else { describe_next(); transform_warp(ti, qp, sm, st); }
         int err = 0, bits = 0, nwords = 0, diff = 0;
-        if (t < ti.nb) {
-            diff = sm.dcq[t] - dc_before(sm, t);                      // codec.py:34-35
+        if (const int tw = tid_now(); tw < ti.nb) {
+            diff = sm.dcq[tw] - dc_before(sm, tw);                    // codec.py:34-35
             BitSink<false> s;
-            s.ptr = sbase + (uint32_t)offsetof(TileShared, priv) + (uint32_t)t * 4u;
+            s.ptr = sbase + (uint32_t)offsetof(TileShared, priv) + (uint32_t)tw * 4u;
             s.ptr_end = s.ptr + (uint32_t)kPrivWords * kTile * 4u;
-            bits = walk_block<kAuto, false>(sm, sbase, t, diff, s, err);
+            bits = walk_block<kAuto, false>(sm, sbase, tw, diff, s, err);
             nwords = (bits + 31) >> 5;
         }
         int incl = bits;

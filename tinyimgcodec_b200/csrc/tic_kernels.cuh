@@ -131,6 +131,13 @@ __device__ __constant__ uint16_t c_cvar_scaled_quant[4][64];
 // ---------------------------------------------------------------------------------------------
 // thread within its group (= within the CTA for the single-group kernels)
 __device__ __forceinline__ int tid() { return (int)threadIdx.x & (kTile - 1); }
+// The same, re-read from the special register every time: costs an S2R where a cached copy would cost a register
+// that lives across the whole tile loop (and, with none to spare, a reload from local memory = an L2 round trip).
+__device__ __forceinline__ int tid_now() {
+    unsigned x;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(x));
+    return (int)x & (kTile - 1);
+}
 template <int G>
 __device__ __forceinline__ void group_sync(int g) {   // barrier over the kTile threads of group g
     if constexpr (G == 1) __syncthreads();
