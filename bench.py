@@ -175,14 +175,16 @@ def time_reference_python(cores, images_per_core):
         return None
     worker = os.path.join(ROOT, "oracle", "ref_py_worker.py")
     procs = [subprocess.Popen([sys.executable, worker, str(images_per_core), str(IMG_H), str(IMG_W), str(1000 * i)],
-                              stdout=subprocess.PIPE, stderr=subprocess.DEVNULL) for i in range(cores)]
-    outs = []
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE) for i in range(cores)]
+    outs, errs = [], []
     for p in procs:
-        o, _ = p.communicate()
+        o, e = p.communicate()
         if p.returncode == 0 and o.strip():
             outs.append(json.loads(o.decode().strip().splitlines()[-1]))
+        else:
+            errs.append(e.decode(errors="replace").strip().splitlines()[-1:] or [f"rc={p.returncode}"])
     if len(outs) != cores:
-        return None
+        return {"value": None, "error": f"{len(errs)} of {cores} workers failed: {errs[0][0][:200]}"}
     px, slowest = sum(o["pixels"] for o in outs), max(o["seconds"] for o in outs)
     return {"value": px / slowest / 1e6, "unit": UNIT, "cores": cores, "kind": "reference",
             "per_core": px / sum(o["seconds"] for o in outs) / 1e6,

@@ -14,11 +14,11 @@ import sys
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _STANDINS = os.path.join(_HERE, "standins")
 # the build container has the reference itself; the GPU box only has its bytecode (oracle/Makefile `refpy`:
-# oracle/_ref/py/tinyimgcodec/*.pyc, a sourceless package — the encoder only, for CPU timing)
+# oracle/_ref/py/tinyimgcodec_ref.zip, a sourceless package — the encoder only, for CPU timing)
 REFERENCE_ROOT = os.environ.get("TIC_REFERENCE_ROOT", "/root/reference")
-if not os.path.isfile(os.path.join(REFERENCE_ROOT, "tinyimgcodec", "codec.py")) and \
-        os.path.isfile(os.path.join(_HERE, "_ref", "py", "tinyimgcodec", "codec.pyc")):
-    REFERENCE_ROOT = os.path.join(_HERE, "_ref", "py")
+_STAGED_ZIP = os.path.join(_HERE, "_ref", "py", "tinyimgcodec_ref.zip")
+if not os.path.isfile(os.path.join(REFERENCE_ROOT, "tinyimgcodec", "codec.py")) and os.path.isfile(_STAGED_ZIP):
+    REFERENCE_ROOT = _STAGED_ZIP   # zipimport: tinyimgcodec/*.pyc inside
 
 
 def reference_available():
@@ -28,8 +28,7 @@ def reference_available():
 
 def reference_python_available():
     """The reference's Python package, as source or as bytecode: enough to call compress() / decompress()."""
-    d = os.path.join(REFERENCE_ROOT, "tinyimgcodec")
-    return os.path.isfile(os.path.join(d, "codec.py")) or os.path.isfile(os.path.join(d, "codec.pyc"))
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "tinyimgcodec", "codec.py")) or REFERENCE_ROOT == _STAGED_ZIP
 
 
 def load_reference():

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY — one CPU worker of bench.py's Python-reference timing.
 
 Runs the UNMODIFIED reference encoder tinyimgcodec.codec.compress (codec.py:133-164; from /root/reference in the build
-container, from its bytecode under oracle/_ref/py on the GPU box — oracle/Makefile `refpy`) on `count` synthetic
+container, from its bytecode under oracle/_ref/py/tinyimgcodec_ref.zip on the GPU box — oracle/Makefile `refpy`) on `count` synthetic
 images and prints {"pixels", "seconds", "bytes"} as JSON.  bidict / bitarray are the pure-Python stand-ins of
 oracle/standins: the real bitarray is a C extension, so the reference with its real
 dependencies would be somewhat faster than what this measures.

@@ -536,12 +536,35 @@ symbol_stats_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
     unsigned long long* first = reinterpret_cast<unsigned long long*>(sm.stage + 512); // 272 keys
     const ExactStats st{&sm};
     if (t == 0) sm.stat_items = sm.stat_changed = sm.stat_unflagged = sm.tc_timeout = 0u;
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // Every CTA takes a CONTIGUOUS range of tiles and keeps one image's statistics in shared memory until the image
+    // changes: the per-image bins in global memory see a few atomics per CTA and image, not 2 x 272 per tile from
+    // hundreds of CTAs at once (which serialised in L2: this kernel took 4x the encode kernel).
+    const long long per = (ntiles + gridDim.x - 1) / gridDim.x;
+    const long long t_lo = (long long)blockIdx.x * per, t_hi = t_lo + per < ntiles ? t_lo + per : ntiles;
+    int cur_img = -1;
+    auto flush = [&]() {   // all threads; barriers inside
         __syncthreads();
-        const TileInfo ti = locate_tile(descs, n_images, tile, uniform_tpi);
+        if (cur_img >= 0) {
+            for (int i = t; i < 272; i += kTile) {
+                const uint32_t c = hist[i];
+                if (c) {
+                    atomicAdd(&g_hist[(size_t)cur_img * 272 + i], c);
+                    atomicMin(&g_first[(size_t)cur_img * 272 + i], first[i]);
+                }
+            }
+            if (t == 0 && sm.warp_err[0]) atomicOr(&status[cur_img], TIC_STATUS_TABLE);
+        }
+        __syncthreads();
         for (int i = t; i < 272; i += kTile) { hist[i] = 0; first[i] = ~0ull; }
         if (t == 0) sm.warp_err[0] = 0;
         __syncthreads();
+    };
+    for (long long tile = t_lo; tile < t_hi; tile++) {
+        const TileInfo ti = locate_tile(descs, n_images, tile, uniform_tpi);
+        if (ti.img != cur_img) {   // CTA-uniform
+            flush();
+            cur_img = ti.img;
+        }
         if constexpr (kFdctTc) {
             if (ti.nb > 0) {
                 uint2 rows[8];
@@ -550,26 +573,22 @@ symbol_stats_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
             }
         } else transform_warp(ti, qp, sm, st);
         int err = 0;
-        if (t < ti.nb) block_stats(sm, t, (unsigned long long)(ti.blk0 + t), hist, first, err);
+        if ((t & ~31) < ti.nb) warp_block_stats(sm, t, t < ti.nb, (unsigned long long)ti.blk0, hist, first, err);   // warp-uniform
         if (err) sm.warp_err[0] = 1;
-        __syncthreads();
-        for (int i = t; i < 272; i += kTile) {
-            uint32_t c = hist[i] + (i == 0 ? (uint32_t)ti.nb : 0u);   // one EOB per block (huffman.py:33)
-            if (c) {
-                atomicAdd(&g_hist[(size_t)ti.img * 272 + i], c);
-                atomicMin(&g_first[(size_t)ti.img * 272 + i], first[i]);
-            }
-        }
-        if (t == 0 && sm.warp_err[0]) atomicOr(&status[ti.img], TIC_STATUS_TABLE);
+        __syncthreads();   // the next tile's staging overwrites the coefficients this tile's statistics read
     }
+    flush();
     if constexpr (kFdctTc) tc_cta_teardown<1>(tmem_base);
     __syncthreads();
     if (t == 0 && sm.tc_timeout) atomicExch(&counters[kCtrTcTimeout], 1ull);
 }
 
-// One thread per image: HuffmanTree (huffman.py:112-194) on CPython's heapq, which
+// One warp per image, everything in shared memory: HuffmanTree (huffman.py:112-194) on CPython's heapq, which
 // queue.PriorityQueue uses — leaves pushed in first-occurrence order, nodes compared by frequency
-// only, DFS with left = "0" — then write_huffman_table (codec.py:73-84) into the header words.
+// only, DFS with left = "0" — then write_huffman_table (codec.py:73-84) into the header words.  The heap and the
+// DFS are sequential by nature (lane 0); loading, ordering the symbols by first occurrence (a rank sort over
+// the 32 lanes) and writing the tables back are warp-wide.  (Round 1 ran one THREAD per image on scratch in
+// global memory: 18 ms for 4096 images, three times the encode kernel.)
 struct TreeScratch {
     unsigned long long freq[544];
     short left[544], right[544], sym[544];
@@ -607,26 +626,21 @@ __device__ void heap_siftup(TreeScratch& s, int hlen, int pos) {   // heapq._sif
 struct HdrWriter {
     uint32_t* words;
     int nbits;
-    __device__ void put(uint32_t v, int n) {   // n <= 32, MSB-first
-        for (int i = n - 1; i >= 0; i--) {
-            if (nbits < kMaxHdrWords * 32 && ((v >> i) & 1)) words[nbits >> 5] |= 0x80000000u >> (nbits & 31);
-            nbits++;
-        }
+    __device__ void put(uint32_t v, int n) {   // n <= 32, MSB-first; bits past the buffer are counted, not stored
+        if (n <= 0) return;
+        if (n < 32) v &= (1u << n) - 1u;
+        const int w = nbits >> 5, sh = nbits & 31;                   // the value occupies bits [sh, sh + n) of words w, w + 1
+        const unsigned long long x = ((unsigned long long)v << (64 - n)) >> sh;   // left-aligned at bit sh of a 64-bit window
+        if (w < kMaxHdrWords) words[w] |= (uint32_t)(x >> 32);
+        if (w + 1 < kMaxHdrWords && (uint32_t)x) words[w + 1] |= (uint32_t)x;
+        nbits += n;
     }
 };
 
 // Builds one alphabet: symbols base..base+count-1 of hist/first.  Returns status bits.
-__device__ int build_alphabet(TreeScratch& s, const uint32_t* hist, const unsigned long long* first, int base,
-                              int count, bool is_dc, HuffEntry* table, HdrWriter& hw) {
-    // present symbols in first-occurrence order (dict insertion order, huffman.py:187-194)
-    short order[256];
-    int n = 0;
-    for (int i = 0; i < count; i++) {
-        if (hist[base + i] == 0) continue;
-        int j = n++;
-        while (j > 0 && first[base + order[j - 1]] > first[base + i]) { order[j] = order[j - 1]; j--; }
-        order[j] = (short)i;
-    }
+// order[0..n): the present symbols in first-occurrence order (dict insertion order, huffman.py:187-194)
+__device__ int build_alphabet(TreeScratch& s, const uint32_t* hist, int base, const short* order, int n, bool is_dc,
+                              HuffEntry* table, HdrWriter& hw) {
     int status = 0;
     hw.put((uint32_t)n, 16);                                     // codec.py:74,79
     if (n == 0) return status;
@@ -683,34 +697,66 @@ __device__ int build_alphabet(TreeScratch& s, const uint32_t* hist, const unsign
     return status;
 }
 
-__global__ void build_tables_kernel(const ImageDesc* __restrict__ descs, int n_images, int quality, int le_flag,
-                                    const uint32_t* __restrict__ g_hist,
-                                    const unsigned long long* __restrict__ g_first,
-                                    AutoTables* __restrict__ tabs, TreeScratch* __restrict__ scratch,
-                                    int* __restrict__ status) {
-    const int img = blockIdx.x * blockDim.x + threadIdx.x;
+struct TableShared {
+    TreeScratch s;
+    AutoTables at;
+    uint32_t hist[272];
+    unsigned long long first[272];
+    short order[2][256];
+    int n[2];
+};
+
+// Warp-wide rank sort of the present symbols of one alphabet by first occurrence (the keys are distinct).
+__device__ void order_alphabet(const uint32_t* hist, const unsigned long long* first, int base, int count, short* order, int* n_out) {
+    const int lane = threadIdx.x;
+    int n = 0;
+    for (int i0 = 0; i0 < count; i0 += 32) {
+        const int i = i0 + lane;
+        const bool present = i < count && hist[base + i] != 0;
+        if (present) {
+            const unsigned long long key = first[base + i];
+            int rank = 0;
+            for (int j = 0; j < count; j++) rank += (hist[base + j] != 0 && first[base + j] < key) ? 1 : 0;
+            order[rank] = (short)i;
+        }
+        n += __popc(__ballot_sync(0xffffffffu, present));
+    }
+    if (lane == 0) *n_out = n;
+}
+
+__global__ void __launch_bounds__(32)
+build_tables_kernel(const ImageDesc* __restrict__ descs, int n_images, int quality, int le_flag,
+                    const uint32_t* __restrict__ g_hist, const unsigned long long* __restrict__ g_first,
+                    AutoTables* __restrict__ tabs, int* __restrict__ status) {
+    __shared__ TableShared ts;
+    const int img = blockIdx.x, lane = threadIdx.x;
     if (img >= n_images) return;
-    AutoTables& at = tabs[img];
-    TreeScratch& s = scratch[img];
-    for (int i = 0; i < 256; i++) at.tab.ac[i].code = at.tab.ac[i].len = 0;
-    for (int i = 0; i < 16; i++) at.tab.dc[i].code = at.tab.dc[i].len = 0;
-    for (int i = 0; i < kMaxHdrWords; i++) at.hdr_words[i] = 0;
-    HdrWriter hw{at.hdr_words, 0};
-    const ImageDesc d = descs[img];
-    hw.put(__byte_perm((uint32_t)d.h, 0, 0x0123), 32);           // struct.pack("III"), codec.py:103-109
-    hw.put(__byte_perm((uint32_t)d.w, 0, 0x0123), 32);
-    hw.put(__byte_perm((uint32_t)quality, 0, 0x0123), 32);
-    // codec.py:111 writes the flag MSB-first (80 00 00 00); le_flag: as the little-endian word the
-    // reference's parse_header (codec.py:119) can read
-    hw.put(le_flag ? 0x00000080u : 0x80000000u, 32);
-    const uint32_t* hist = g_hist + (size_t)img * 272;
-    const unsigned long long* first = g_first + (size_t)img * 272;
-    int st = build_alphabet(s, hist, first, 256, 16, true, at.tab.dc, hw);    // table[DC] first, codec.py:74-78
-    st |= build_alphabet(s, hist, first, 0, 256, false, at.tab.ac, hw);        // then table[AC], codec.py:79-84
-    if (hw.nbits > kMaxHdrWords * 32) st |= TIC_STATUS_LONGCODE;
-    at.hdr_bits = (uint32_t)hw.nbits;
-    at.status = (uint32_t)st;
-    if (st) atomicOr(&status[img], st);
+    for (int i = lane; i < 272; i += 32) { ts.hist[i] = g_hist[(size_t)img * 272 + i]; ts.first[i] = g_first[(size_t)img * 272 + i]; }
+    uint32_t* atw = reinterpret_cast<uint32_t*>(&ts.at);
+    for (int i = lane; i < (int)(sizeof(AutoTables) / 4); i += 32) atw[i] = 0u;
+    __syncwarp();
+    order_alphabet(ts.hist, ts.first, 256, 16, ts.order[0], &ts.n[0]);    // DC sizes
+    order_alphabet(ts.hist, ts.first, 0, 256, ts.order[1], &ts.n[1]);     // AC (run, size)
+    __syncwarp();
+    if (lane == 0) {
+        HdrWriter hw{ts.at.hdr_words, 0};
+        const ImageDesc d = descs[img];
+        hw.put(__byte_perm((uint32_t)d.h, 0, 0x0123), 32);           // struct.pack("III"), codec.py:103-109
+        hw.put(__byte_perm((uint32_t)d.w, 0, 0x0123), 32);
+        hw.put(__byte_perm((uint32_t)quality, 0, 0x0123), 32);
+        // codec.py:111 writes the flag MSB-first (80 00 00 00); le_flag: as the little-endian word the
+        // reference's parse_header (codec.py:119) can read
+        hw.put(le_flag ? 0x00000080u : 0x80000000u, 32);
+        int st = build_alphabet(ts.s, ts.hist, 256, ts.order[0], ts.n[0], true, ts.at.tab.dc, hw);    // table[DC] first, codec.py:74-78
+        st |= build_alphabet(ts.s, ts.hist, 0, ts.order[1], ts.n[1], false, ts.at.tab.ac, hw);         // then table[AC], codec.py:79-84
+        if (hw.nbits > kMaxHdrWords * 32) st |= TIC_STATUS_LONGCODE;
+        ts.at.hdr_bits = (uint32_t)hw.nbits;
+        ts.at.status = (uint32_t)st;
+        if (st) atomicOr(&status[img], st);
+    }
+    __syncwarp();
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&tabs[img]);
+    for (int i = lane; i < (int)(sizeof(AutoTables) / 4); i += 32) dst[i] = atw[i];
 }
 
 // Uniform batch (every image H x W, equally spaced in memory): the descriptors are written on the device and the
@@ -802,7 +848,7 @@ struct tic_handle_s {
     long long* d_out_end = nullptr;     size_t end_cap = 0;
     // auto-table mode: per-image statistics, tables, tree scratch
     uint32_t* d_hist = nullptr; unsigned long long* d_first = nullptr; AutoTables* d_tabs = nullptr;
-    TreeScratch* d_tree = nullptr;      size_t auto_cap = 0;
+    size_t auto_cap = 0;
     // single-image host path
     uint8_t* d_px = nullptr;            size_t px_cap = 0;
     uint8_t* d_out = nullptr;           size_t out_cap = 0;
@@ -971,7 +1017,7 @@ static int ensure_tables(tic_handle h) {
     h->sm_count = prop.multiProcessorCount;
     h->ctas_per_sm = per_sm > 0 ? per_sm : 1;
     h->ctas_per_sm_c = per_sm_c > 0 ? per_sm_c : 1;
-    h->ctas_per_sm_single = per_sm_single > 0 ? per_sm_single : 1;
+    h->ctas_per_sm_single = per_sm_single > 4 ? per_sm_single : 4;   // launch bounds: 4 CTAs of 128 threads per SM (54 KB, 128 registers)
     h->tables_ready = true;
     return TIC_OK;
 }
@@ -1041,7 +1087,7 @@ int tic_destroy(tic_handle h) {
     cudaFree(h->d_descs); cudaFree(h->d_sticky); cudaFree(h->d_bmat); cudaFree(h->d_recs);
     for (int i = 0; i < tic_handle_s::kDescSlots; i++) { cudaFreeHost(h->h_descs_ring[i]); if (h->desc_ev[i]) cudaEventDestroy(h->desc_ev[i]); } cudaFree(h->d_tile_pos); cudaFree(h->d_chunk_span); cudaFree(h->d_chunk_pos);
     cudaFree(h->d_arena); cudaFree(h->d_counters);
-    cudaFree(h->d_hist); cudaFree(h->d_first); cudaFree(h->d_tabs); cudaFree(h->d_tree);
+    cudaFree(h->d_hist); cudaFree(h->d_first); cudaFree(h->d_tabs);
     cudaFreeHost(h->h_counters); cudaFree(h->d_out_end); cudaFree(h->d_px); cudaFree(h->d_out);
     cudaFreeHost(h->h_stage); cudaFree(h->d_meta); cudaFreeHost(h->h_meta);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -1222,13 +1268,12 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     h->last_launches = 6;
     if (auto_mode) {   // calc_huffman_table (huffman.py:101-109) + write_huffman_table (codec.py:73-84)
         if ((size_t)n_images > h->auto_cap) {
-            cudaFree(h->d_hist); cudaFree(h->d_first); cudaFree(h->d_tabs); cudaFree(h->d_tree);
-            h->d_hist = nullptr; h->d_first = nullptr; h->d_tabs = nullptr; h->d_tree = nullptr; h->auto_cap = 0;
+            cudaFree(h->d_hist); cudaFree(h->d_first); cudaFree(h->d_tabs);
+            h->d_hist = nullptr; h->d_first = nullptr; h->d_tabs = nullptr; h->auto_cap = 0;
             size_t cap = (size_t)n_images + (size_t)n_images / 4 + 8;
             TIC_CUDA(h, cudaMalloc(&h->d_hist, cap * 272 * sizeof(uint32_t)));
             TIC_CUDA(h, cudaMalloc(&h->d_first, cap * 272 * sizeof(unsigned long long)));
             TIC_CUDA(h, cudaMalloc(&h->d_tabs, cap * sizeof(AutoTables)));
-            TIC_CUDA(h, cudaMalloc(&h->d_tree, cap * sizeof(TreeScratch)));
             h->auto_cap = cap;
         }
         TIC_CUDA(h, cudaMemsetAsync(h->d_hist, 0, (size_t)n_images * 272 * sizeof(uint32_t), stream));
@@ -1236,9 +1281,8 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
         symbol_stats_kernel<<<(unsigned)grid_single, kTile, kSmemSingle, stream>>>(
             qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_counters, h->d_hist, h->d_first, d_status, d_bmat);
         TIC_CUDA(h, cudaGetLastError());
-        build_tables_kernel<<<(n_images + 31) / 32, 32, 0, stream>>>(h->d_descs, n_images, quality,
-                                                                    (flags & TIC_FLAG_AUTO_LE_FLAG) ? 1 : 0, h->d_hist,
-                                                                    h->d_first, h->d_tabs, h->d_tree, d_status);
+        build_tables_kernel<<<n_images, 32, 0, stream>>>(h->d_descs, n_images, quality, (flags & TIC_FLAG_AUTO_LE_FLAG) ? 1 : 0,
+                                                         h->d_hist, h->d_first, h->d_tabs, d_status);
         TIC_CUDA(h, cudaGetLastError());
         d_tabs = h->d_tabs;
         h->last_launches = 8;

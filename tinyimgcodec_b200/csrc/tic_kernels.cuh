@@ -1403,37 +1403,64 @@ __device__ __forceinline__ int walk_block(const TileShared& sm, uint32_t sbase, 
     return s.finish();
 }
 
-// Symbol statistics of one block for the per-image tables (huffman.py:101-109, 187-194): counts
-// and, for the dict-insertion order the reference's tree depends on, the first occurrence of every
-// symbol as key = block index * 256 + ordinal of the symbol inside the block's list.
-// hist/first: 272 entries, [0,256) AC (run*16+size), [256,272) DC size.
-__device__ __forceinline__ void block_stats(const TileShared& sm, int t, unsigned long long blk,
-                                            uint32_t* hist, unsigned long long* first, int& err) {
-    int diff = sm.dcq[t] - dc_before(sm, t);
-    int s = bitlen(diff);
-    if (s > 15) { err = 1; s = 15; }   // int2ba(category, 4) overflows in the reference (codec.py:76)
-    atomicAdd(&hist[256 + s], 1u);
-    atomicMin(&first[256 + s], blk << 8);
-    uint32_t lo = sm.nz_lo[t], hi = sm.nz_hi[t];
-    int prev = 0, ord = 0;
-    while (lo | hi) {
-        int k;
-        if (lo) { k = __clz(lo); lo ^= 0x80000000u >> k; } else { k = __clz(hi); hi ^= 0x80000000u >> k; k += 32; }
-        int run = k - prev - 1;
-        prev = k;
-        int sz = bitlen(coef_get(sm, t, k));
-        if (sz > 15) { err = 1; sz = 15; }
-        if (run >> 4) {
-            atomicAdd(&hist[0xF0], (uint32_t)(run >> 4));
-            atomicMin(&first[0xF0], (blk << 8) | (unsigned)ord);
-            ord += run >> 4;
-        }
-        int sym = ((run & 15) << 4) | sz;
-        atomicAdd(&hist[sym], 1u);
-        atomicMin(&first[sym], (blk << 8) | (unsigned)ord);
-        ord++;
+// Symbol statistics of the warp's 32 blocks for the per-image tables (huffman.py:101-109, 187-194): counts and, for
+// the dict-insertion order the reference's tree depends on, the first occurrence of every symbol as key = block
+// index * 256 + ordinal of the symbol inside the block's list.  hist/first: 272 entries in shared memory, [0,256) AC
+// (run*16+size), [256,272) DC size.  All 32 lanes call.  The lanes step through their symbol lists together; equal
+// symbols of one step are combined (match.any) so that one lane adds their number and offers their smallest key —
+// one thread per symbol with a shared-memory atomicAdd + 64-bit atomicMin each made this kernel four times as slow
+// as the encode kernel (the few frequent symbols serialise).
+// rel: (thread in tile) << 8 | ordinal — the key relative to the tile's first block; key0 = first block << 8
+__device__ __forceinline__ void stats_step(int sym, unsigned rel, unsigned long long key0, uint32_t* hist, unsigned long long* first) {
+    const unsigned act = __ballot_sync(0xffffffffu, sym >= 0);
+    if (sym < 0) return;
+    const unsigned peers = __match_any_sync(act, sym);
+    if ((peers & (0u - peers)) == (1u << (threadIdx.x & 31))) {          // the lowest lane of the group: rel's high bits are
+        atomicAdd(&hist[sym], (uint32_t)__popc(peers));                  // the thread index, so its key is the group's smallest
+        const unsigned long long k = key0 + rel;
+        if (k < first[sym]) atomicMin(&first[sym], k);                   // only until the symbol's first occurrence is settled
     }
-    atomicMin(&first[0], (blk << 8) | (unsigned)ord);   // EOB; its count is the number of blocks
+}
+__device__ __forceinline__ void warp_block_stats(const TileShared& sm, int t, bool active, unsigned long long blk0,
+                                                 uint32_t* hist, unsigned long long* first, int& err) {
+    const unsigned long long key0 = blk0 << 8;
+    const unsigned rel0 = (unsigned)t << 8;
+    // DC symbol: ordinal 0
+    int s = 0;
+    if (active) {
+        s = bitlen(sm.dcq[t] - dc_before(sm, t));
+        if (s > 15) { err = 1; s = 15; }   // int2ba(category, 4) overflows in the reference (codec.py:76)
+    }
+    stats_step(active ? 256 + s : -1, rel0, key0, hist, first);
+    uint32_t lo = active ? sm.nz_lo[t] : 0u, hi = active ? sm.nz_hi[t] : 0u;
+    int prev = 0, ord = 0;
+    int zrl_left = 0;   // ZRL symbols still to be counted in front of the pending coefficient symbol
+    int pend_sym = -1;
+    while (__any_sync(0xffffffffu, (lo | hi) != 0u || zrl_left > 0 || pend_sym >= 0)) {
+        if (zrl_left == 0 && pend_sym < 0 && (lo | hi)) {   // next non-zero coefficient of this lane's block
+            int k;
+            if (lo) { k = __clz(lo); lo ^= 0x80000000u >> k; } else { k = __clz(hi); hi ^= 0x80000000u >> k; k += 32; }
+            const int run = k - prev - 1;
+            prev = k;
+            int sz = bitlen(coef_get(sm, t, k));
+            if (sz > 15) { err = 1; sz = 15; }
+            zrl_left = run >> 4;
+            pend_sym = ((run & 15) << 4) | sz;
+        }
+        int sym = -1;
+        const unsigned rel = rel0 | (unsigned)ord;
+        if (zrl_left > 0) {   // every ZRL of a run has the same symbol; the first one carries the smallest ordinal
+            sym = 0xF0;
+            ord += 1;
+            zrl_left -= 1;
+        } else if (pend_sym >= 0) {
+            sym = pend_sym;
+            pend_sym = -1;
+            ord += 1;
+        }
+        stats_step(sym, rel, key0, hist, first);
+    }
+    stats_step(active ? 0 : -1, rel0 | (unsigned)ord, key0, hist, first);   // EOB (huffman.py:33)
 }
 
 // ---------------------------------------------------------------------------------------------
