@@ -332,3 +332,18 @@ def test_pinned_pipeline_round_trip(chunk):
     for i, (off, size) in enumerate(index):
         want = O.decompress(host[off: off + size].tobytes())
         assert np.array_equal(px[i].numpy(), want), f"image {i}"
+
+
+def test_undecodable_streams_read_as_zero_when_not_strict(tic):
+    """ADVICE r1 (tic_decode.cu:1579): a stream the device refuses as a whole (quality 0: the reference raises
+    ZeroDivisionError, utils.py:50) must not come back, under strict=False, as whatever the reused pixel workspace
+    held from the previous decode."""
+    img = synthetic_image(32, 40, seed=3)
+    good = tic.compress(img, 50)
+    bad = bytearray(good)
+    bad[8:12] = (0).to_bytes(4, "little")          # quality field 0
+    first = tic.decompress(good)                    # leaves its pixels in the handle's workspace
+    px = tic.decompress(bytes(bad), strict=False)
+    assert px.shape == first.shape and not px.any()
+    outs = tic.decompress_batch([good, bytes(bad)], strict=False)
+    assert np.array_equal(outs[0], first) and not outs[1].any()

@@ -370,7 +370,7 @@ class Encoder:
         """tinyimgcodec.codec.decompress (codec.py:167-189) for one stream in host memory."""
         height, width, _, _ = parse_header(data)
         buf = np.frombuffer(bytes(data), dtype=np.uint8)
-        out = np.empty((height, width), dtype=np.uint8)
+        out = np.zeros((height, width), dtype=np.uint8)   # a stream the device does not decode at all (strict=False) reads as 0
         status = ctypes.c_int32(0)
         flags = (_lib.TIC_DFLAG_ACCEPT_BE_FLAG if accept_be_flag else 0) | (_lib.TIC_DFLAG_EXACT_ONLY if exact_only else 0)
         with self._lock:
@@ -425,6 +425,10 @@ class Encoder:
                 status = d_status[:n].cpu().numpy() if rc in (_lib.TIC_OK, _lib.TIC_E_STREAM) else None
                 if rc != _lib.TIC_OK and (strict or rc != _lib.TIC_E_STREAM):
                     self._raise_decode(rc, status)
+                if rc == _lib.TIC_E_STREAM:   # strict=False: streams the device did not decode at all (header mismatch,
+                    # quality 0) must not come back as whatever the pixel buffer held before
+                    for i in np.nonzero(status & (_lib.TIC_DSTATUS_HEADER | _lib.TIC_DSTATUS_QUALITY))[0]:
+                        pixels[int(px_off[i]): int(px_off[i]) + int(npx[i])].zero_()
         del keep
         if n and (hs_np == hs_np[0]).all() and (ws_np == ws_np[0]).all() and int(npx[0]) % 16 == 0:
             # equal shapes, densely packed: one (N, H, W) view instead of N slices (indexable like the list)

@@ -750,6 +750,8 @@ __global__ void __launch_bounds__(kSyncThreads) dec_write_kernel(const DecImage*
             }
         }
         unsigned m = __ballot_sync(0xffffffffu, ready);
+        __syncwarp();   // the lanes' stores into their slots are ordered before the other lanes' reads below (vote and
+                        // shuffle do not order memory)
         const long long my_block = blk0 + cur;
         while (m) {
             // the (lane >> 3)-th of the lowest four ready lanes
@@ -1578,6 +1580,9 @@ int tic_decompress_host(tic_handle h, const uint8_t* data, int64_t nbytes, uint3
     TICD_CUDA(h, cudaMemcpyAsync(&st, w->d_status_own, sizeof(int), cudaMemcpyDeviceToHost, s));
     if (npx) TICD_CUDA(h, cudaMemcpyAsync(out, w->d_px, (size_t)npx, cudaMemcpyDeviceToHost, s));
     rc = tic_decode_finish(h, s);
+    // A stream the device refuses as a whole (header mismatch, quality 0) writes no pixel: the reused workspace
+    // still holds the previous decode.  The caller gets zeros, not somebody else's image.
+    if (npx && (st & (TIC_DSTATUS_HEADER | TIC_DSTATUS_QUALITY))) memset(out, 0, (size_t)npx);
     if (status) *status = st;
     return rc;
 }

@@ -55,14 +55,14 @@ namespace tic {
 #define TIC_CTAS 6
 #endif
 #ifndef TIC_PRIV
-#define TIC_PRIV 12
+#define TIC_PRIV 16
 #endif
 // 1: only warp 0 of a group polls the MMA's mbarrier, the other warps sleep at the group barrier
 #ifndef TIC_POLL_WARP0
 #define TIC_POLL_WARP0 0
 #endif
 #ifndef TIC_WIN
-#define TIC_WIN 1280
+#define TIC_WIN 1152
 #endif
 constexpr int kTile = TIC_TILE;                             // blocks (= threads) per tile
 constexpr int kWarps = kTile / 32;
