@@ -139,7 +139,15 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
         const TileInfo& ti = sm.tinfo[slot];
         // one warp describes the group's next tile one tile ahead: in the tensor core's shadow (tensor-core path), or
         // here; barrier B1 of this tile orders the write before every later read
-        auto describe_next = [&]() { if (warp == kDescWarp && tile + stride < ntiles_u) describe(tile + stride, slot ^ 1); };
+        auto describe_next = [&]() {
+            if (warp == kDescWarp && tile + stride < ntiles_u) {
+                describe(tile + stride, slot ^ 1);
+                if constexpr (TIC_PREFETCH_L2 != 0 && kTc) {
+                    __syncwarp();   // lane 0 wrote the description
+                    prefetch_tile_l2(sm.tinfo[slot ^ 1], lane);
+                }
+            }
+        };
         if constexpr (kAuto) {
             if (tab_img != ti.img) {   // per-image tables (codec.py:146-148); group-uniform branch
                 group_sync<G>(g);      // everyone is done with the previous image's tables

@@ -64,6 +64,18 @@ namespace tic {
 #ifndef TIC_WIN
 #define TIC_WIN 1152
 #endif
+#ifndef TIC_QUANT_F32X2
+#define TIC_QUANT_F32X2 1  // the tensor-core quantiser rounds coefficient pairs with packed FP32 instructions
+#endif
+#ifndef TIC_PREFETCH_L2
+#define TIC_PREFETCH_L2 1  // the pixel rows of a group's next tile are pulled into L2 one tile ahead (one bulk prefetch per row)
+#endif
+#ifndef TIC_RAT_FAST
+#define TIC_RAT_FAST 1     // ties at the four rational positions: the float64 sequence with its power-of-two factors moved to the end
+#endif
+#ifndef TIC_WALK_PIPE
+#define TIC_WALK_PIPE 1   // the walk fetches the next coefficient before it codes the current one
+#endif
 constexpr int kTile = TIC_TILE;                             // blocks (= threads) per tile
 constexpr int kWarps = kTile / 32;
 constexpr int kCtasPerSm = TIC_CTAS;                        // CTAs per SM of the single-group kernels
@@ -932,9 +944,19 @@ __device__ __forceinline__ void quantise_pairs_tc(const uint32_t* r /* 8 columns
         constexpr float kMagic = 12582912.0f;   // 1.5 * 2^23
         constexpr int k0 = 8 * G + 2 * P, k1 = k0 + 1;
         const float d0 = __uint_as_float(r[2 * P]), d1 = __uint_as_float(r[2 * P + 1]);
+#if TIC_QUANT_F32X2
+        // packed FP32 (FFMA2 / FADD2): the pair's three operations in three issue slots instead of six
+        const f32x2 d01 = pk2(d0, d1), cn01 = pk2(qp.cn[k0], qp.cn[k1]), mg = pk2(kMagic, kMagic);
+        const f32x2 b01 = fma2(d01, cn01, mg);
+        const f32x2 nq01 = sub2(mg, b01);             // -(round(t))
+        const f32x2 e01 = fma2(d01, cn01, nq01);      // t - round(t)
+        float b0, b1, q0, q1, e0, e1;
+        upk2(b01, b0, b1); upk2(nq01, q0, q1); upk2(e01, e0, e1);
+#else
         const float b0 = fmaf(d0, qp.cn[k0], kMagic), b1 = fmaf(d1, qp.cn[k1], kMagic);
         const float q0 = b0 - kMagic, q1 = b1 - kMagic;
         const float e0 = fmaf(d0, qp.cn[k0], -q0), e1 = fmaf(d1, qp.cn[k1], -q1);   // t - round(t)
+#endif
         if (k0 != 0 && q0 != 0.0f) nz |= 0x80000000u >> (k0 & 31);
         if (q1 != 0.0f) nz |= 0x80000000u >> (k1 & 31);
         if (fabsf(e0) > qp.hthr[k0]) fl |= 0x80000000u >> (k0 & 31);   // the exact path decides
@@ -1017,11 +1039,24 @@ __device__ __noinline__ unsigned settle_rational(uint32_t taddr /* the lane's ac
         if (!((rat >> which) & 1u)) continue;
         const bool u4 = (which == 1 || which == 3), v4 = (which >= 2);
         const double m = u4 ? TW3 : HSQ;
+#if TIC_RAT_FAST
+        // dct8_exact(.., 0 or 4) over c_x = RN(RN(0.5 s_x) m), with every multiplication by a power of two moved to
+        // the end (exact: they commute with rounding, nothing here is near overflow or underflow):
+        // y = 0.25 RN(RN(RN(RN(X0 + X7) + RN(X3 + X4)) +- RN(RN(X1 + X2) + RN(X5 + X6))) K), X_x = RN(s_x m).
+        // Checked bit for bit against the long form on 8e7 random column-sum vectors (tools/rat_check.c).
+        const double X0 = __dmul_rn((double)(u4 ? i0 : s0), m), X1 = __dmul_rn((double)(u4 ? i1 : s1), m);
+        const double X2 = __dmul_rn((double)(u4 ? i2 : s2), m), X3 = __dmul_rn((double)(u4 ? i3 : s3), m);
+        const double X4 = __dmul_rn((double)(u4 ? i4 : s4), m), X5 = __dmul_rn((double)(u4 ? i5 : s5), m);
+        const double X6 = __dmul_rn((double)(u4 ? i6 : s6), m), X7 = __dmul_rn((double)(u4 ? i7 : s7), m);
+        const double A = __dadd_rn(__dadd_rn(X0, X7), __dadd_rn(X3, X4)), H = __dadd_rn(__dadd_rn(X1, X2), __dadd_rn(X5, X6));
+        const double y = __dmul_rn(0.25, __dmul_rn(v4 ? __dsub_rn(A, H) : __dadd_rn(A, H), v4 ? TW3 : HSQ));
+#else
         const double c0 = __dmul_rn(__dmul_rn(0.5, (double)(u4 ? i0 : s0)), m), c1 = __dmul_rn(__dmul_rn(0.5, (double)(u4 ? i1 : s1)), m);
         const double c2 = __dmul_rn(__dmul_rn(0.5, (double)(u4 ? i2 : s2)), m), c3 = __dmul_rn(__dmul_rn(0.5, (double)(u4 ? i3 : s3)), m);
         const double c4 = __dmul_rn(__dmul_rn(0.5, (double)(u4 ? i4 : s4)), m), c5 = __dmul_rn(__dmul_rn(0.5, (double)(u4 ? i5 : s5)), m);
         const double c6 = __dmul_rn(__dmul_rn(0.5, (double)(u4 ? i6 : s6)), m), c7 = __dmul_rn(__dmul_rn(0.5, (double)(u4 ? i7 : s7)), m);
         const double y = dct8_exact(c0, c1, c2, c3, c4, c5, c6, c7, v4 ? 4 : 0);
+#endif
         const double qt = which == 0 ? qt00 : (which == 1 ? qt40 : (which == 2 ? qt04 : qt44));
         const int q = __double2int_rn(__ddiv_rn(y, qt));   // np.round(coeffs / qt), utils.py:53
         const int k = which == 0 ? 0 : (which == 1 ? 10 : (which == 2 ? 14 : 39));
@@ -1060,6 +1095,40 @@ __device__ __forceinline__ uint2 load_tile_halo(const TileInfo& ti, int t) {
     int y0, x0;
     if (t < 8 && tile_halo_is_fast(ti, y0, x0)) v = __ldg(reinterpret_cast<const uint2*>(ti.px + (size_t)(y0 + t) * ti.w + x0));
     return v;
+}
+
+// The pixel rows of tile `ti` -> L2, one cp.async.bulk.prefetch per pixel row and block row of the tile (lane = block
+// row of the tile * 8 + pixel row): called by one warp for the group's NEXT tile while the tensor core works on the
+// current one, so that the 8 x LDG.64 of load_block_rows find their lines in L2 instead of in HBM (the kernel keeps
+// 6 warps per scheduler: a DRAM round trip at the top of every tile is not hidden, profiles/r2e: 8.5 % of all stall
+// samples).  Rows that are not 16-byte aligned, and tiles that span more than four block rows, are left alone.
+__device__ __forceinline__ void prefetch_tile_l2(const TileInfo& ti, int lane) {
+    if (ti.nb <= 0 || (ti.w & 15) != 0 || (reinterpret_cast<uintptr_t>(ti.px) & 15) != 0) return;
+    const int last = ti.blk0 + ti.nb - 1;
+    int br0, br1;
+    if (ti.bw_shift >= 0) { br0 = ti.blk0 >> ti.bw_shift; br1 = last >> ti.bw_shift; }
+    else { br0 = ti.blk0 / ti.bw; br1 = last / ti.bw; }
+    const int nrows = br1 - br0 + 1;
+    const int r = lane >> 3, y = lane & 7;
+    if (nrows > 4 || r >= nrows) return;
+    const int Y = (br0 + r) * 8 + y;
+    if (Y >= ti.h) return;
+    int xa = r == 0 ? (ti.blk0 - br0 * ti.bw) * 8 : 0;
+    int xb = r == nrows - 1 ? (last - br1 * ti.bw + 1) * 8 : ti.w;
+    xa &= ~15;
+    xb = (xb + 15) & ~15;
+    if (xb > ti.w) xb = ti.w;
+    if (xb <= xa) return;
+    const uint8_t* p = ti.px + (size_t)Y * ti.w + xa;
+#if TIC_PREFETCH_L2 == 2
+    // one 128-byte line per instruction and lane (the bulk form takes its operands from uniform registers: the
+    // compiler serialises the lanes)
+    const uint8_t* pe = p + (xb - xa);
+    for (p = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(p) & ~(uintptr_t)127); p < pe; p += 128)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p) : "memory");
+#else
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"((uint32_t)(xb - xa)) : "memory");
+#endif
 }
 
 // after_issue(): called by every thread of the group right after the MMA has been issued (the kernel's tile loop
@@ -1356,6 +1425,8 @@ template <bool kAuto>
 __device__ __forceinline__ int tab_len(uint2 e) { return kAuto ? (int)(e.y & kHuffLenMask) : (int)(e.x >> 27); }
 template <bool kAuto>
 __device__ __forceinline__ uint32_t tab_code(uint2 e) { return kAuto ? e.x : (e.x & 0x07ffffffu); }
+template <bool kAuto>
+__device__ __forceinline__ uint32_t tab_present(uint2 e) { return e.y; }   // 0: the symbol is not in the table
 
 // Emits the bits of thread t's block (DC difference `diff`, AC from sm.coef / nz masks) and returns
 // their number.  |quantised value| <= 1024 / 0.2 (quality 99), so a size never exceeds 14 and the
@@ -1371,33 +1442,61 @@ __device__ __forceinline__ int walk_block(const TileShared& sm, uint32_t sbase, 
     uint2 e = tab_entry<kAuto>(dc_tab, (uint32_t)sz);
     if (e.y == 0) { err = 1; sz = 0; e = tab_entry_cold<kAuto>(dc_tab, 0u); }  // KeyError, huffman.py:62
     put_symbol<kAuto, kToStage>(s, e, diff, sz);
-    int carry = 0;   // zeros since the last non-zero coefficient, not counting the current mask word
+    // AC coefficients.  The walk works on BIT indices of the non-zero masks (bit b of a mask word = zigzag coefficient
+    // 31 - b resp. 63 - b = b ^ 31 resp. b ^ 63): the run is the distance to the previous symbol's bit, and the byte
+    // offset of coefficient k in the thread's column, (k >> 1) * P + (k & 1) * 2 with P = kTile * 4, places the bits of
+    // k one by one, so offset(b ^ c) = offset(b) ^ offset(c): one multiply, one AND-XOR, no subtraction.  A run of
+    // 16 or more emits ZRL (huffman.py:25-29) as an iteration of its own — same code path, coefficient not consumed —
+    // so that the loop body has no inner branch (the two convergence barriers around the ZRL loop and the
+    // KeyError call cost 9 of 45 instructions per symbol, profiles/r2e).
+    constexpr uint32_t kOffMul = kTile * 2u + 2u, kOffMask = 63u * kTile * 4u | 2u;
+    int prev = 31;   // bit index of the last coded coefficient in the current word's numbering (the DC is bit 31 of word 0)
+    uint32_t present = 0xffffffffu;   // AND-like minimum over the table entries used: 0 = a symbol outside the table
 #pragma unroll 1
-    for (int base = 0; base < 64; base += 32) {
-        uint32_t m = base ? sm.nz_hi[t] : sm.nz_lo[t];           // bit 31 - j: coefficient base + j
-        int pos = base;
-        if (base == 0) { m <<= 1; pos = 1; }                      // k = 0 is the DC
+    for (int word = 0; word < 2; word++) {
+        uint32_t m = word ? sm.nz_hi[t] : (sm.nz_lo[t] & 0x7fffffffu);   // k = 0 is the DC
+        const uint32_t flip = word ? ((63u * kOffMul) & kOffMask) : ((31u * kOffMul) & kOffMask);
+#if TIC_WALK_PIPE
+        // software-pipelined: the next coefficient is fetched before this one is coded, so that one shared-memory
+        // latency per symbol (the table entry) is exposed instead of two
+        int b = msb_index(m) & 31;
+        int v = lds_s16(col + ((((uint32_t)b * kOffMul) & kOffMask) ^ flip));
         while (m) {
-            const int z = 31 - msb_index(m);
-            const int k = pos + z;
-            int run = carry + z;
-            carry = 0;
-            pos = k + 1;
-            m = shl_clamp(m, z + 1);
-            // coefficient k: 16-bit half (k & 1) of word sm.coef[k >> 1][t], i.e. byte offset
-            // (k >> 1) * P + (k & 1) * 2 with P = kTile * 4: one multiply and one mask (k < 64, P >= 256)
-            int v = lds_s16(col + (((uint32_t)k * (kTile * 2u + 2u)) & (63u * kTile * 4u | 2u)));
-            sz = msb_index((uint32_t)(v < 0 ? -v : v)) + 1;
-            if (run >= 16) {                                      // ZRL, huffman.py:25-29
-                const uint2 zrl = tab_entry<kAuto>(ac_tab, 0xF0u);
-                for (; run >= 16; run -= 16) s.put(tab_code<kAuto>(zrl), tab_len<kAuto>(zrl));
-            }
-            e = tab_entry<kAuto>(ac_tab, (uint32_t)(run * 16 + sz));
-            if (e.y == 0) { err = 1; sz = 1; v = 1; e = tab_entry_cold<kAuto>(ac_tab, (uint32_t)(run * 16 + 1)); }
+            const int run = prev - b - 1;
+            const bool zrl = run >= 16;
+            uint32_t below;   // bits below b
+            asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(below) : "r"(0), "r"(b));
+            const uint32_t m2 = zrl ? m : (m & below);
+            const int b2 = msb_index(m2) & 31;
+            const int v2 = lds_s16(col + ((((uint32_t)b2 * kOffMul) & kOffMask) ^ flip));
+            const int szv = msb_index((uint32_t)(v < 0 ? -v : v)) + 1;
+            sz = zrl ? 0 : szv;
+            e = tab_entry<kAuto>(ac_tab, (uint32_t)((zrl ? 15 : run) * 16 + sz));
+            present = present < tab_present<kAuto>(e) ? present : tab_present<kAuto>(e);
             put_symbol<kAuto, kToStage>(s, e, v, sz);
+            prev = zrl ? prev - 16 : b;
+            m = m2; b = b2; v = v2;
         }
-        carry += base + 32 - pos;
+#else
+        while (m) {
+            const int b = msb_index(m);
+            const int run = prev - b - 1;
+            const bool zrl = run >= 16;
+            int v = lds_s16(col + ((((uint32_t)b * kOffMul) & kOffMask) ^ flip));
+            const int szv = msb_index((uint32_t)(v < 0 ? -v : v)) + 1;
+            sz = zrl ? 0 : szv;
+            e = tab_entry<kAuto>(ac_tab, (uint32_t)((zrl ? 15 : run) * 16 + sz));
+            present = present < tab_present<kAuto>(e) ? present : tab_present<kAuto>(e);
+            put_symbol<kAuto, kToStage>(s, e, v, sz);
+            prev = zrl ? prev - 16 : b;
+            uint32_t below;   // bits below b
+            asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(below) : "r"(0), "r"(b));
+            m = zrl ? m : (m & below);
+        }
+#endif
+        prev += 32;
     }
+    if (present == 0) err = 1;   // KeyError, huffman.py:62 (the stream is void; the status word says so)
     e = tab_entry<kAuto>(ac_tab, 0u);
     s.put(tab_code<kAuto>(e), tab_len<kAuto>(e));                // EOB always, huffman.py:33
     return s.finish();
