@@ -951,6 +951,7 @@ static int make_quant_params(int quality, QuantParams& qp) {
         qp.zmul[k] = hthr > 0.0 ? (float)(m / hthr * (1.0 + 1.0e-6)) : 3.0e38f;
     }
     qp.dcinv = 1.0 / (8.0 * qp.qt[0]);
+    qp.dcinv_f = (float)qp.dcinv;
     // tensor-core path: the accumulator holds t / hthr * 2^E with ONE power of two per quality, chosen so that the
     // largest entry of B = basis / (qt * hthr) * 2^E is in [2^13, 2^14): its f16 hi + lo split then carries >= 21 bits.
     double mx = 0.0;

@@ -68,7 +68,12 @@ namespace tic {
 #define TIC_QUANT_F32X2 1  // the tensor-core quantiser rounds coefficient pairs with packed FP32 instructions
 #endif
 #ifndef TIC_PREFETCH_L2
-#define TIC_PREFETCH_L2 1  // the pixel rows of a group's next tile are pulled into L2 one tile ahead (one bulk prefetch per row)
+#define TIC_PREFETCH_L2 0  // 1 / 2: the pixel rows of a group's next tile are pulled into L2 one tile ahead (bulk prefetch per row /
+                           // one PREFETCH per line).  Measured: long-scoreboard stalls 8.5 -> 6.5 %, kernel time unchanged or worse
+                           // (4.62 vs 4.50 ms next to the FP32 predictor, 4.56 vs 4.58 ms without): off.
+#endif
+#ifndef TIC_HALO_F32
+#define TIC_HALO_F32 1     // tensor-core path: the DC predictor in front of a warp from its pixel sum in FP32 (ties: exact path)
 #endif
 #ifndef TIC_RAT_FAST
 #define TIC_RAT_FAST 1     // ties at the four rational positions: the float64 sequence with its power-of-two factors moved to the end
@@ -105,6 +110,7 @@ struct QuantParams {
     int tc_exp;
     double qt[64];    // [u*8+v]  the reference's float64 divisor (utils.py:50-53)
     double dcinv;     // 1 / (8 * qt[0]): quantised DC = (sum of pixels - 8192) * dcinv
+    float dcinv_f;    // the same in FP32 (tensor-core path: the predictor in front of a warp, transform_tile_tc)
 };
 
 struct ImageDesc {
@@ -1190,9 +1196,20 @@ __device__ __forceinline__ void transform_tile_tc(const TileInfo& ti, const Quan
         }
         halo_item = 1;
         if (have_sum) {
+#if TIC_HALO_F32
+            // FP32 is enough to tell "nowhere near a tie": |sum - 8192| <= 8192 is exact, the product is off by at
+            // most |tq| * 2^-22 <= 3200 * 2^-22 = 7.7e-4 (the rounded reciprocal and the multiplication; quality 99 has
+            // the smallest divisor, 8 * 0.32), and everything within 2e-3 of a tie goes to the exact path.  (The float64 form spent 3 % of the kernel's stall samples
+            // waiting for the FP64 pipe, profiles/r2f.)
+            const float tq = (float)(sum - 8192) * qp.dcinv_f;
+            const float rq = rintf(tq);
+            halo_dc = (int)rq;
+            halo_item = (fabsf(tq - rq) < 0.5f - 2.0e-3f) ? 0 : 1;
+#else
             const double tq = __dmul_rn((double)(sum - 8192), qp.dcinv);
             halo_dc = __double2int_rn(tq);
             halo_item = (fabs(tq - (double)halo_dc) < 0.5 - 1.0e-9) ? 0 : 1;   // on a tie the exact path decides
+#endif
         }
     }
     // ---- accumulator -> quantised coefficients ------------------------------------------------------------
