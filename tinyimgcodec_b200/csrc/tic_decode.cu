@@ -221,6 +221,44 @@ __device__ __forceinline__ void lookup(const DecTable* t, uint32_t v, int& sym, 
     len = -1;
 }
 
+// The same lookup for a DecTable that lives in SHARED memory, addressed through its 32-bit shared address: the fixed
+// tables of every CTA.  (Through a `const DecTable*` that may also point at a per-image table in global memory the
+// compiler has to emit generic loads with 64-bit address arithmetic: LD.E + IMAD.WIDE + IADD3 + IMAD.X per access,
+// two accesses per symbol in the hottest loop of the decoder.)
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t shared_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void lookup_sh(uint32_t tab, uint32_t v, int& sym, int& len) {
+    uint32_t e = lds_u16(tab + ((v >> 24) << 1));   // DecTable::lut
+    if (e & kLeaf) { sym = (int)(e & 0xffu); len = (int)((e >> 8) & 0x7fu); return; }
+    len = 8;
+    uint32_t node = e;
+    while (node != 0 && len < 16) {
+        uint32_t c = lds_u16(tab + 512u + node * 4u + (((v >> (31 - len)) & 1u) << 1));   // DecTable::child
+        len++;
+        if (c & kLeaf) { sym = (int)(c & 0xffu); return; }
+        node = c;
+    }
+    sym = 0;
+    len = -1;
+}
+static_assert(offsetof(DecTable, child) == 512 && sizeof(uint16_t[2]) == 4, "lookup_sh addresses DecTable by hand");
+// read_int (bitbuffer.py:56-66) on the window t = v << len: `size` bits, a leading 0 = negative (one's complement)
+__device__ __forceinline__ int read_value(uint32_t t, int size) {
+    uint32_t vb, ones;
+    asm("shr.b32 %0, %1, %2;" : "=r"(vb) : "r"(t), "r"(32 - size));    // size == 0: shift by 32 = 0 (PTX clamps)
+    asm("bmsk.clamp.b32 %0, %1, %2;" : "=r"(ones) : "r"(0), "r"(size));   // (1 << size) - 1
+    return (int)vb - ((int)t >= 0 ? (int)ones : 0);
+}
+
 // A subsequence's bits staged in shared memory: kSubBits/32 words plus the two words a symbol that starts in
 // the last bit can reach (16 code bits + 15 value bits), MSB-first, zeros past the end of the stream.
 constexpr int kSubWords = kSubBits / 32;
@@ -259,28 +297,37 @@ struct SubResult {
 // Decode one subsequence from `entry`, reading its bits from the staged row `sw`; nothing is stored (phases 1
 // and 2; dec_write_kernel walks the same parse once more with the stores).  `end_rel`: bits of the subsequence
 // that belong to the stream (kSubBits except at the end).
-__device__ SubResult decode_sub(const uint32_t* sw, int end_rel, const DecTable* tdc, const DecTable* tac, uint32_t entry) {
+// kSh: the tables are the CTA's fixed tables in shared memory (sh_tabs = shared address of the DecTables); the row and the
+// tables are then read with 32-bit shared addresses, and the iteration cap is not needed (every symbol of the fixed
+// tables is at least one bit long, so a subsequence has at most kSubBits + 31 symbols).
+template <bool kSh>
+__device__ SubResult decode_sub(const uint32_t* sw, int end_rel, const DecTable* tdc, const DecTable* tac, uint32_t sh_tabs,
+                                uint32_t entry) {
     int p = (int)(entry & 0xffffu);
     int z = (int)((entry >> 16) & 0xffu);
     SubResult r;
     r.n = 0; r.dsum = 0; r.err = 0;
+    const uint32_t row = shared_addr(sw);
     int it = 0;
-    for (; p < end_rel && it < kMaxSymbols; it++) {
-        const int wi = p >> 5;
-        uint32_t v = __funnelshift_l(sw[wi + 1], sw[wi], (uint32_t)(p & 31));
+    for (; p < end_rel && (kSh || it < kMaxSymbols); it++) {
+        uint32_t v;
         int sym, len;
-        lookup(z == 0 ? tdc : tac, v, sym, len);
+        if constexpr (kSh) {
+            const uint32_t a = row + ((uint32_t)(p >> 5) << 2);
+            v = __funnelshift_l(lds_u32(a + 4u), lds_u32(a), (uint32_t)(p & 31));
+            lookup_sh(sh_tabs + (z == 0 ? 0u : (uint32_t)sizeof(DecTable)), v, sym, len);
+        } else {
+            const int wi = p >> 5;
+            v = __funnelshift_l(sw[wi + 1], sw[wi], (uint32_t)(p & 31));
+            lookup(z == 0 ? tdc : tac, v, sym, len);
+        }
         if (len < 0) {   // no codeword: a deterministic rule so that decode(entry) stays a function
             r.err |= TIC_DSTATUS_CODE;
             p += 1;
             continue;
         }
-        int size = sym & 15;   // DC: the category is the size; AC: (run, size), huffman.py:89-93
-        int val = 0;
-        if (size) {            // read_int, bitbuffer.py:56-66: leading 0 = negative, one's complement
-            uint32_t vb = (v << len) >> (32 - size);
-            val = (vb >> (size - 1)) ? (int)vb : (int)vb - (1 << size) + 1;
-        }
+        const int size = sym & 15;   // DC: the category is the size; AC: (run, size), huffman.py:89-93
+        const int val = read_value(v << len, size);
         const int p0 = p;
         p += len + size;
         if (z == 0) {
@@ -502,7 +549,8 @@ __global__ void __launch_bounds__(kSyncThreads) dec_sync_kernel(const DecImage* 
             uint32_t e = Ev[g];
             if (e != used) {
                 used = e;
-                SubResult r = decode_sub(sw, end_rel, &tb->dc, &tb->ac, e);
+                SubResult r = tb == &sh_def ? decode_sub<true>(sw, end_rel, nullptr, nullptr, shared_addr(&sh_def), e)
+                                            : decode_sub<false>(sw, end_rel, &tb->dc, &tb->ac, 0u, e);
                 ND[g] = make_int2(r.n, r.dsum);
                 if (has_next && Ev[g + 1] != r.exit) { Ev[g + 1] = r.exit; wrote = true; }
             }
@@ -688,6 +736,8 @@ __global__ void __launch_bounds__(kSyncThreads) dec_write_kernel(const DecImage*
     int16_t* slot = slots[threadIdx.x];
     const DecTable* tdc = &tb->dc;
     const DecTable* tac = &tb->ac;
+    const bool fixed_tabs = tb == &sh_def;
+    const uint32_t sh_tabs = shared_addr(&sh_def), row = shared_addr(sw);
     uint32_t entry = active ? E[g] : 0u;
     int p = (int)(entry & 0xffffu), z = (int)((entry >> 16) & 0xffu);
     int blk = nb.x, dc_run = nb.y, cur = nb.x - 1, it = 0;
@@ -699,20 +749,17 @@ __global__ void __launch_bounds__(kSyncThreads) dec_write_kernel(const DecImage*
         bool ready = false;
         if (running) {
             it++;
-            const int wi = p >> 5;
-            uint32_t v = __funnelshift_l(sw[wi + 1], sw[wi], (uint32_t)(p & 31));
+            const uint32_t a = row + ((uint32_t)(p >> 5) << 2);
+            const uint32_t v = __funnelshift_l(lds_u32(a + 4u), lds_u32(a), (uint32_t)(p & 31));
             int sym, len;
-            lookup(z == 0 ? tdc : tac, v, sym, len);
+            if (fixed_tabs) lookup_sh(sh_tabs + (z == 0 ? 0u : (uint32_t)sizeof(DecTable)), v, sym, len);   // warp-uniform but at image boundaries
+            else lookup(z == 0 ? tdc : tac, v, sym, len);
             if (len < 0) {   // the same rules as decode_sub: this pass must follow the parse the entries belong to
                 err |= TIC_DSTATUS_CODE;
                 p += 1;
             } else {
-                int size = sym & 15;
-                int val = 0;
-                if (size) {
-                    uint32_t vb = (v << len) >> (32 - size);
-                    val = (vb >> (size - 1)) ? (int)vb : (int)vb - (1 << size) + 1;
-                }
+                const int size = sym & 15;
+                const int val = read_value(v << len, size);
                 const int p0 = p;
                 p += len + size;
                 if (z == 0) {

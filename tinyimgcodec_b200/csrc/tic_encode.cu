@@ -486,41 +486,65 @@ __device__ __forceinline__ uint32_t tile_bits_at(const uint32_t* __restrict__ sr
 }
 
 constexpr int kCompactThreads = 256;
+// Output word j of a tile (j = 0 is the word that holds the tile's first bit, `off` bits into it) is
+// (T[j-1] : T[j]) >> off with T = the tile's words in the arena and T[-1] = the last bits in front of the tile: every
+// lane loads ONE word per round and takes its left neighbour's from a shuffle (the first version loaded two words per
+// output word and did its index arithmetic in 64 bits: 25 instructions per word, one warp two latencies deep per
+// tile).  The next tile's record and position are fetched before the current tile's words.
 __global__ void __launch_bounds__(kCompactThreads)
 compact_kernel(const TileRec* __restrict__ recs, const long long* __restrict__ tile_pos, long long ntiles,
                const uint32_t* __restrict__ arena_words, uint32_t* __restrict__ out_words, long long out_cap) {
     const int lane = threadIdx.x & 31;
     const long long nwarps = ((long long)gridDim.x * kCompactThreads) >> 5;
-    for (long long tile = ((long long)blockIdx.x * kCompactThreads + threadIdx.x) >> 5; tile < ntiles; tile += nwarps) {
-        const TileRec r = recs[tile];
-        if (r.pad) continue;   // the arena was exhausted: TIC_E_CAPACITY is already flagged
-        const long long bits = (long long)(r.bits & kRecBitsMask);
-        const long long P = tile_pos[tile], E = P + bits;
+    long long tile = ((long long)blockIdx.x * kCompactThreads + threadIdx.x) >> 5;
+    if (tile >= ntiles) return;
+    TileRec r = recs[tile];
+    long long P = tile_pos[tile];
+    for (; tile < ntiles; tile += nwarps) {
+        const TileRec cur = r;
+        const long long Pc = P;
+        if (tile + nwarps < ntiles) { r = recs[tile + nwarps]; P = tile_pos[tile + nwarps]; }
+        if (cur.pad) continue;   // the arena was exhausted: TIC_E_CAPACITY is already flagged
+        const long long bits = (long long)(cur.bits & kRecBitsMask);
+        const long long E = Pc + bits;
         if (((((E + 7) >> 3) + 3) & ~3ll) > out_cap) continue;   // nothing past out_capacity is written
-        const uint32_t* src = arena_words + (size_t)r.off16 * 4;
+        const uint32_t* src = arena_words + (size_t)cur.off16 * 4;
         const int nw = (int)((bits + 31) >> 5);
-        const long long w_lo = P >> 5;
-        const long long w_hi = (r.bits & kRecClosing) ? ((E + 31) >> 5) : (E >> 5);
-        for (long long W = w_lo + lane; W < w_hi; W += 32) {
-            const long long rb = W * 32 - P;   // tile-relative bit of the word's first bit
-            uint32_t val;
-            if (rb >= 0) {
-                val = tile_bits_at(src, nw, rb);
-            } else {   // the word starts in earlier tiles (never in another image: streams start 128-bit aligned)
-                int need = (int)(-rb);   // 1..31 leading bits
-                val = (nw > 0 ? __ldg(src) : 0u) >> need;
-                for (long long pt = tile - 1; need > 0 && pt >= 0; pt--) {
-                    const TileRec pr = recs[pt];
-                    const long long pb = (long long)(pr.bits & kRecBitsMask);
-                    if (pb == 0) continue;
-                    const int take = pb < need ? (int)pb : need;
-                    const uint32_t* psrc = arena_words + (size_t)pr.off16 * 4;
-                    const uint32_t v = tile_bits_at(psrc, (int)((pb + 31) >> 5), pb - take) >> (32 - take);
-                    val |= v << (32 - need);
-                    need -= take;
-                }
+        const int off = (int)(Pc & 31);
+        const long long w_lo = Pc >> 5;
+        const int nout = (int)(((cur.bits & kRecClosing) ? ((E + 31) >> 5) : (E >> 5)) - w_lo);   // words this tile owns
+        if (nout <= 0) continue;   // warp-uniform
+        // T[-1]: the `off` bits in front of the tile, right-aligned (never from another image: streams start 128-bit
+        // aligned, so off > 0 means the image has earlier tiles)
+        uint32_t lead = 0;
+        if (off > 0 && lane == 0) {
+            int need = off;
+            for (long long pt = tile - 1; need > 0 && pt >= 0; pt--) {
+                const TileRec pr = recs[pt];
+                const long long pb = (long long)(pr.bits & kRecBitsMask);
+                if (pb == 0) continue;
+                const int take = pb < need ? (int)pb : need;
+                const uint32_t* psrc = arena_words + (size_t)pr.off16 * 4;
+                const uint32_t v = tile_bits_at(psrc, (int)((pb + 31) >> 5), pb - take) >> (32 - take);   // the tile's last `take` bits
+                lead |= v << (off - need);
+                need -= take;
             }
-            out_words[W] = __byte_perm(val, 0, 0x0123);
+        }
+        uint32_t* dst = out_words + w_lo;
+        uint32_t carry = lead;   // lane 0: the word in front of this round's first word
+        for (int j0 = 0; j0 < nout; j0 += 128) {   // four rounds of 32 words, their loads in flight together
+            uint32_t x[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) x[u] = j0 + 32 * u + lane < nw ? __ldg(src + j0 + 32 * u + lane) : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = j0 + 32 * u + lane;
+                uint32_t prev = __shfl_up_sync(0xffffffffu, x[u], 1);
+                if (lane == 0) prev = carry;
+                carry = __shfl_sync(0xffffffffu, x[u], 31);
+                const uint32_t val = __funnelshift_r(x[u], prev, off);   // off == 0: x itself
+                if (j < nout) dst[j] = __byte_perm(val, 0, 0x0123);
+            }
         }
     }
 }
