@@ -194,6 +194,11 @@ int64_t tic_last_guard_misses(tic_handle h);
                                        over the blocks whose pixels the FP32 pass cannot guarantee.  Same pixels
                                        either way (tests compare the two); for verification and profiling. */
 
+#define TIC_DFLAG_FUSED 4u          /* opt-in: the coefficient pass transforms a block as soon as it is complete instead of
+                                       writing its coefficients out for the inverse-transform kernels.  Same pixels either
+                                       way (tests compare the two); removes the coefficient buffer's traffic but measures
+                                       slower (csrc/tic_decode.cu, dec_write_kernel).  For verification and profiling. */
+
 /* per-stream status bits of the decode side */
 #define TIC_DSTATUS_HEADER 1     /* shorter than 16 bytes, or height / width differ from the caller's */
 #define TIC_DSTATUS_CODE 2       /* no codeword matches (ValueError, huffman.py:72-73) or a run passes

@@ -181,6 +181,11 @@ def test_config4_images_on_device_round_trip(tic):
         exact, _ = enc.decode_batch_device((res.out, offs), sizes, [1024] * n, [1024] * n, exact_only=True)
         assert enc.decode_stats()["exact_blocks"] == 0
         assert torch.equal(outs, exact), f"q{q}: {(outs != exact).sum().item()} pixels differ between the two IDCT paths"
+        # the opt-in fused coefficient pass (a complete block is transformed where it is decoded; its work list also
+        # holds the blocks that span subsequences: one in 7 at q90, one in 27 at q50)
+        fused, _ = enc.decode_batch_device((res.out, offs), sizes, [1024] * n, [1024] * n, fused=True)
+        assert 1 <= enc.decode_stats()["exact_blocks"] < 0.4 * st["blocks"], enc.decode_stats()
+        assert torch.equal(outs, fused.clone()), f"q{q}: {(outs != fused).sum().item()} pixels differ between the fused pass and the separate kernels"
         host = res.to_bytes()
         for i in (0, 17, n - 1):
             _same(outs[i].cpu().numpy(), O.decompress(host[i]), f"q{q} image {i}")

@@ -366,13 +366,14 @@ class Encoder:
             raise TicStreamError(msg, status)
         raise TicError(rc, msg)
 
-    def decompress(self, data, strict=True, accept_be_flag=False, exact_only=False):
+    def decompress(self, data, strict=True, accept_be_flag=False, exact_only=False, fused=False):
         """tinyimgcodec.codec.decompress (codec.py:167-189) for one stream in host memory."""
         height, width, _, _ = parse_header(data)
         buf = np.frombuffer(bytes(data), dtype=np.uint8)
         out = np.zeros((height, width), dtype=np.uint8)   # a stream the device does not decode at all (strict=False) reads as 0
         status = ctypes.c_int32(0)
-        flags = (_lib.TIC_DFLAG_ACCEPT_BE_FLAG if accept_be_flag else 0) | (_lib.TIC_DFLAG_EXACT_ONLY if exact_only else 0)
+        flags = (_lib.TIC_DFLAG_ACCEPT_BE_FLAG if accept_be_flag else 0) | (_lib.TIC_DFLAG_EXACT_ONLY if exact_only else 0) | \
+            (_lib.TIC_DFLAG_FUSED if fused else 0)
         with self._lock:
             rc = self.lib.tic_decompress_host(self.handle, buf.ctypes.data, buf.size, flags, out.ctypes.data,
                                               out.size, ctypes.byref(status))
@@ -381,7 +382,7 @@ class Encoder:
         return out
 
     def decode_batch_device(self, d_streams, sizes, heights, widths, pixels=None, stream=None,
-                            accept_be_flag=False, strict=True, exact_only=False):
+                            accept_be_flag=False, strict=True, exact_only=False, fused=False):
         """Decode streams resident in HBM.  `d_streams`: list of CUDA uint8 tensors (each 4-byte aligned), or
         one CUDA uint8 tensor plus `sizes` and byte offsets given as d_streams=(tensor, offsets).  Returns the
         CUDA uint8 (H, W) images (a list of views of one pixel buffer, or one (N, H, W) view when all shapes are
@@ -413,7 +414,7 @@ class Encoder:
             d_status = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
             stream = stream or torch.cuda.current_stream(dev)
             flags = (_lib.TIC_DFLAG_ACCEPT_BE_FLAG if accept_be_flag else 0) | \
-                    (_lib.TIC_DFLAG_EXACT_ONLY if exact_only else 0)
+                    (_lib.TIC_DFLAG_EXACT_ONLY if exact_only else 0) | (_lib.TIC_DFLAG_FUSED if fused else 0)
             if n == 0:
                 return [], np.zeros(0, dtype=np.int32)
             with self._lock:
@@ -438,7 +439,7 @@ class Encoder:
                       for i in range(n)]
         return images, status
 
-    def decompress_batch(self, streams, strict=True, accept_be_flag=False, exact_only=False):
+    def decompress_batch(self, streams, strict=True, accept_be_flag=False, exact_only=False, fused=False):
         """decompress() for a list of `bytes`: one pinned H2D copy of all streams, one decode, one D2H copy of all
         pixels.  Returns a list of uint8 (H, W) arrays."""
         import torch
@@ -455,7 +456,7 @@ class Encoder:
                 h_np[o: o + len(s)] = np.frombuffer(s, dtype=np.uint8)
             d_buf = h_buf.to(dev, non_blocking=True)
             imgs, _ = self.decode_batch_device((d_buf, offs[:-1]), sizes, [h[0] for h in hdrs], [h[1] for h in hdrs],
-                                               strict=strict, accept_be_flag=accept_be_flag, exact_only=exact_only)
+                                               strict=strict, accept_be_flag=accept_be_flag, exact_only=exact_only, fused=fused)
             return [im.cpu().numpy() for im in imgs]
 
     def decompress_batch_pinned(self, h_streams, index, heights, widths, chunk=64, nbuf=3, strict=True):
@@ -630,9 +631,9 @@ def encode(image, quality=50, device=None):
     return get_encoder(device).encode(image, quality)
 
 
-def decompress(data, device=None, strict=True, accept_be_flag=False, exact_only=False):
+def decompress(data, device=None, strict=True, accept_be_flag=False, exact_only=False, fused=False):
     """Drop-in for tinyimgcodec.codec.decompress (codec.py:167-189)."""
-    return get_encoder(device).decompress(data, strict=strict, accept_be_flag=accept_be_flag, exact_only=exact_only)
+    return get_encoder(device).decompress(data, strict=strict, accept_be_flag=accept_be_flag, exact_only=exact_only, fused=fused)
 
 
 def decode(data, device=None):
@@ -640,10 +641,10 @@ def decode(data, device=None):
     return get_encoder(device).decode(data)
 
 
-def decompress_batch(streams, device=None, strict=True, accept_be_flag=False, exact_only=False):
+def decompress_batch(streams, device=None, strict=True, accept_be_flag=False, exact_only=False, fused=False):
     """decompress() for a list of streams in one launch sequence."""
     return get_encoder(device).decompress_batch(streams, strict=strict, accept_be_flag=accept_be_flag,
-                                                exact_only=exact_only)
+                                                exact_only=exact_only, fused=fused)
 
 
 def compress_c(image, qfactor="med", device=None):

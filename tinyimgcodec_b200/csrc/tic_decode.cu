@@ -58,6 +58,7 @@ constexpr int kMaxSymbols = 4096;   // symbols decoded per subsequence at most (
 constexpr int kSyncThreads = 128;
 constexpr int kSyncIters = 64;      // in-CTA repair rounds per launch
 constexpr uint32_t kLeaf = 0x8000u;
+constexpr int kMulfStride = 128;    // FP32 multipliers per image: [u*8+v] then the transposed copy [v*8+u]
 
 // Decode table of one alphabet: the reference's `table.inverse` dict (huffman.py:83) as a binary trie
 // (child[n][bit]: 0 = no code, kLeaf | symbol, else node index) plus a first-level table over the next
@@ -154,8 +155,9 @@ __host__ __device__ inline void table_finish(DecTable& t, int root_leaf) {
     }
 }
 
-static void build_default_tables(DecTables& t) {
-    int nodes, root = -1;
+// Returns the larger trie node count of the two tables (the kernels keep kShNodes = 256 of them in shared memory).
+static int build_default_tables(DecTables& t) {
+    int nodes, root = -1, most = 0;
     table_clear(t.dc, nodes);
     uint32_t code = 0;
     int k = 0;
@@ -164,6 +166,7 @@ static void build_default_tables(DecTables& t) {
         code <<= 1;
     }
     table_finish(t.dc, -1);
+    most = nodes;
     table_clear(t.ac, nodes);
     code = 0;
     k = 0;
@@ -172,6 +175,7 @@ static void build_default_tables(DecTables& t) {
         code <<= 1;
     }
     table_finish(t.ac, -1);
+    return nodes > most ? nodes : most;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -251,6 +255,31 @@ __device__ __forceinline__ void lookup_sh(uint32_t tab, uint32_t v, int& sym, in
     len = -1;
 }
 static_assert(offsetof(DecTable, child) == 512 && sizeof(uint16_t[2]) == 4, "lookup_sh addresses DecTable by hand");
+// The shared-memory copy of the FIXED tables: the same layout with 256 trie nodes instead of kMaxNodes (a prefix code
+// over at most 256 symbols has at most 255 inner nodes, and table_insert numbers them in order of creation; the host
+// checks the count of the default tables).  3 KB per CTA instead of 9.2 KB.
+constexpr int kShNodes = 256;
+struct ShTable {
+    uint16_t lut[256];
+    uint16_t child[kShNodes][2];
+};
+struct ShTables {
+    ShTable dc, ac;
+};
+// all threads of the CTA; the caller synchronises before the first lookup
+__device__ __forceinline__ void load_sh_tables(ShTables& sh, const DecTables* __restrict__ deftab, int nthreads) {
+    const DecTable* src[2] = {&deftab->dc, &deftab->ac};
+    ShTable* dst[2] = {&sh.dc, &sh.ac};
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const uint32_t* sl = reinterpret_cast<const uint32_t*>(src[k]->lut);
+        const uint32_t* sc = reinterpret_cast<const uint32_t*>(src[k]->child);
+        uint32_t* dl = reinterpret_cast<uint32_t*>(dst[k]->lut);
+        uint32_t* dc = reinterpret_cast<uint32_t*>(dst[k]->child);
+        for (int i = threadIdx.x; i < 128; i += nthreads) dl[i] = __ldg(sl + i);
+        for (int i = threadIdx.x; i < kShNodes; i += nthreads) dc[i] = __ldg(sc + i);
+    }
+}
 // read_int (bitbuffer.py:56-66) on the window t = v << len: `size` bits, a leading 0 = negative (one's complement)
 __device__ __forceinline__ int read_value(uint32_t t, int size) {
     uint32_t vb, ones;
@@ -315,7 +344,7 @@ __device__ SubResult decode_sub(const uint32_t* sw, int end_rel, const DecTable*
         if constexpr (kSh) {
             const uint32_t a = row + ((uint32_t)(p >> 5) << 2);
             v = __funnelshift_l(lds_u32(a + 4u), lds_u32(a), (uint32_t)(p & 31));
-            lookup_sh(sh_tabs + (z == 0 ? 0u : (uint32_t)sizeof(DecTable)), v, sym, len);
+            lookup_sh(sh_tabs + (z == 0 ? 0u : (uint32_t)sizeof(ShTable)), v, sym, len);
         } else {
             const int wi = p >> 5;
             v = __funnelshift_l(sw[wi + 1], sw[wi], (uint32_t)(p & 31));
@@ -402,8 +431,12 @@ __device__ inline uint32_t fill_mul(DecImage& im, double* __restrict__ m, float*
         long long factor = 200 - 2 * (long long)q;
         for (int k = 0; k < 64; k++) m[k] = __ddiv_rn((double)((long long)c_qbase[k] * factor), 100.0);
     }
-    // the fast pass's single-precision multiplier: one rounding of the whole factor (dec_idct_fast_kernel)
-    for (int k = 0; k < 64; k++) mf[k] = (float)(im.mode == MODE_SCALED ? m[k] * im.two_q / d_ann[k] : m[k]);
+    // the fast pass's single-precision multiplier: one rounding of the whole factor (dec_idct_fast_kernel); a second
+    // copy with the indices transposed (v*8+u) for the fused coefficient pass, whose lanes hold COLUMNS (kMulfStride)
+    for (int k = 0; k < 64; k++) {
+        mf[k] = (float)(im.mode == MODE_SCALED ? m[k] * im.two_q / d_ann[k] : m[k]);
+        mf[64 + (k & 7) * 8 + (k >> 3)] = mf[k];
+    }
     return 0;
 }
 
@@ -444,7 +477,7 @@ __global__ void __launch_bounds__(32) dec_setup_kernel(DecImage* __restrict__ im
             if ((flags & TIC_DFLAG_ACCEPT_BE_FLAG) && f == 0x00000080u) f = 0x80000000u;
             if (f & 0x80000000u) im.mode = MODE_TABLES;
             else if (f & 0x40000000u) im.mode = MODE_SCALED;
-            st |= fill_mul(im, mul + (size_t)i * 64, mulf + (size_t)i * 64);
+            st |= fill_mul(im, mul + (size_t)i * 64, mulf + (size_t)i * kMulfStride);
         }
         if (st == 0 && im.mode == MODE_TABLES) {
             long long p = 128;
@@ -512,18 +545,14 @@ __global__ void __launch_bounds__(kSyncThreads) dec_sync_kernel(const DecImage* 
                                                                 uint32_t* __restrict__ U, int2* __restrict__ ND,
                                                                 int* __restrict__ changed) {
     __shared__ uint32_t rows[kSyncThreads][kRowWords];
-    __shared__ DecTables sh_def;   // the fixed tables; per-image tables stay in global memory
-    {
-        const uint32_t* s = reinterpret_cast<const uint32_t*>(deftab);
-        uint32_t* d = reinterpret_cast<uint32_t*>(&sh_def);
-        for (int i = threadIdx.x; i < (int)(sizeof(DecTables) / 4); i += kSyncThreads) d[i] = __ldg(s + i);
-    }
+    __shared__ ShTables sh_def;   // the fixed tables; per-image tables stay in global memory
+    load_sh_tables(sh_def, deftab, kSyncThreads);
     long long g = (long long)blockIdx.x * kSyncThreads + threadIdx.x;
     bool active = g < total_subs;
     int idx = 0, k = 0, end_rel = 0;
     bool has_next = false;
     uint32_t used = 0xffffffffu;
-    const DecTables* tb = &sh_def;
+    const DecTables* tb = nullptr;   // per-image tables (global memory); null: the fixed tables in shared memory
     BitSrc src = {};
     idx = find_owner_cta(sub_first, n_images, (long long)blockIdx.x * kSyncThreads, g, total_subs);   // barrier inside
     if (active) {
@@ -549,7 +578,7 @@ __global__ void __launch_bounds__(kSyncThreads) dec_sync_kernel(const DecImage* 
             uint32_t e = Ev[g];
             if (e != used) {
                 used = e;
-                SubResult r = tb == &sh_def ? decode_sub<true>(sw, end_rel, nullptr, nullptr, shared_addr(&sh_def), e)
+                SubResult r = tb == nullptr ? decode_sub<true>(sw, end_rel, nullptr, nullptr, shared_addr(&sh_def), e)
                                             : decode_sub<false>(sw, end_rel, &tb->dc, &tb->ac, 0u, e);
                 ND[g] = make_int2(r.n, r.dsum);
                 if (has_next && Ev[g + 1] != r.exit) { Ev[g + 1] = r.exit; wrote = true; }
@@ -569,6 +598,15 @@ __global__ void __launch_bounds__(kSyncThreads) dec_sync_kernel(const DecImage* 
 // needs several slices — a single large image — first gets its slice totals (dec_scan_totals_kernel), then
 // every slice starts from the sum of the totals in front of it.
 // ---------------------------------------------------------------------------------------------------
+// A block goes to the exact pass (dec_idct_kernel over `list`): its index, once.  Entries beyond the capacity are
+// dropped and reported (TIC_DSTATUS_CODE on the batch: only streams that are not valid .img data can get there).
+__device__ __forceinline__ void list_push(long long* __restrict__ list, int* __restrict__ list_count, int list_cap,
+                                          long long block, int* __restrict__ summary) {
+    const int slot = atomicAdd(list_count, 1);
+    if (slot < list_cap) list[slot] = block;
+    else atomicOr(summary, TIC_DSTATUS_CODE);
+}
+
 constexpr int kSliceSubs = 32768;
 struct ScanSlice {
     int img, first, count, index_in_img;
@@ -613,7 +651,9 @@ __global__ void __launch_bounds__(1024) dec_scan_kernel(const DecImage* __restri
                                                         const int2* __restrict__ slice_tot, const int2* __restrict__ ND,
                                                         int2* __restrict__ NB, int* __restrict__ status,
                                                         int* __restrict__ summary, const uint32_t* __restrict__ E,
-                                                        int16_t* __restrict__ coef, int* __restrict__ ndec) {
+                                                        int16_t* __restrict__ coef, int* __restrict__ ndec,
+                                                        long long* __restrict__ list, int* __restrict__ list_count,
+                                                        int list_cap) {
     const ScanSlice sl = slices[blockIdx.x];
     const DecImage& im = imgs[sl.img];
     if (im.skip_entropy) return;
@@ -659,6 +699,10 @@ __global__ void __launch_bounds__(1024) dec_scan_kernel(const DecImage* __restri
                 uint4* dst = reinterpret_cast<uint4*>(coef + (im.blk_first + first_blk - 1) * 64);
 #pragma unroll
                 for (int i = 0; i < 8; i++) dst[i] = make_uint4(0u, 0u, 0u, 0u);
+                // fused coefficient pass: these blocks are transformed by the exact pass.  A block entered in the middle
+                // by two subsequences (longer than one of them) would be listed twice: only the first entry counts
+                if (list != nullptr && (sl.first + k == 0 || ND[base_g + k - 1].x > 0))
+                    list_push(list, list_count, list_cap, im.blk_first + first_blk - 1, summary);
             }
         }
         __syncthreads();
@@ -674,35 +718,97 @@ __global__ void __launch_bounds__(1024) dec_scan_kernel(const DecImage* __restri
     }
 }
 
+// FP32 8-point inverse transform and the pixel store shared by the fused coefficient pass (dec_write_kernel) and
+// dec_idct_fast_kernel; the error bound that makes it usable is derived at dec_idct_fast_kernel.
+__device__ __forceinline__ void idct8_fast(float& x0, float& x1, float& x2, float& x3, float& x4, float& x5, float& x6,
+                                           float& x7) {
+    // c(u) cos((2y+1) u pi / 16), c(0) = sqrt(1/8), c(u > 0) = 1/2: even columns u = 0,2,4,6 and odd u = 1,3,5,7
+    const float A = 0.35355339059327379f, B = 0.46193976625564337f, C = 0.19134171618254489f;
+    const float P = 0.49039264020161522f, Q = 0.41573480615127262f, R = 0.27778511650980111f, T = 0.09754516100806413f;
+    const float e0 = fmaf(C, x6, fmaf(A, x4, fmaf(B, x2, A * x0)));
+    const float e1 = fmaf(-B, x6, fmaf(-A, x4, fmaf(C, x2, A * x0)));
+    const float e2 = fmaf(B, x6, fmaf(-A, x4, fmaf(-C, x2, A * x0)));
+    const float e3 = fmaf(-C, x6, fmaf(A, x4, fmaf(-B, x2, A * x0)));
+    const float o0 = fmaf(T, x7, fmaf(R, x5, fmaf(Q, x3, P * x1)));
+    const float o1 = fmaf(-R, x7, fmaf(-P, x5, fmaf(-T, x3, Q * x1)));
+    const float o2 = fmaf(Q, x7, fmaf(T, x5, fmaf(-P, x3, R * x1)));
+    const float o3 = fmaf(-P, x7, fmaf(Q, x5, fmaf(-R, x3, T * x1)));
+    x0 = e0 + o0; x7 = e0 - o0;
+    x1 = e1 + o1; x6 = e1 - o1;
+    x2 = e2 + o2; x5 = e2 - o2;
+    x3 = e3 + o3; x4 = e3 - o3;
+}
+
+__device__ __forceinline__ void store_pixel_row(const DecImage& im, int y, int x0, uint32_t lo, uint32_t hi) {
+    if (y >= im.height) return;
+    uint8_t* row = im.pixels + (size_t)y * (size_t)im.width + x0;
+    if (x0 + 8 <= im.width && (((uintptr_t)im.pixels | (uintptr_t)im.width) & 7u) == 0) {
+        *reinterpret_cast<uint2*>(row) = make_uint2(lo, hi);
+    } else {
+#pragma unroll
+        for (int v = 0; v < 8; v++)
+            if (x0 + v < im.width) row[v] = (uint8_t)((v < 4 ? lo >> (8 * v) : hi >> (8 * (v - 4))) & 0xffu);
+    }
+}
+
+// 8 x 8 transpose across the 8 lanes of a group (lane j = lane & 7): in: a[u] = element (u, j), out: a[v] = element (j, v).
+__device__ __forceinline__ void transpose8(float (&a)[8], int j) {
+#pragma unroll
+    for (int d = 4; d >= 1; d >>= 1) {
+        const bool up = (j & d) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if ((i & d) == 0) {   // element (i + d, j) of a lane with bit d clear <-> element (i, j ^ d) of its partner
+                const float got = __shfl_xor_sync(0xffffffffu, up ? a[i] : a[i + d], d);
+                if (up) a[i] = got; else a[i + d] = got;
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
-// dec_write_kernel: phase 4.  coef: int16[total_blocks][64] in RASTER order (u*8+v), zero-filled before.
+// dec_write_kernel: phase 4.  coef: int16[total_blocks][64] in RASTER order (u*8+v).
+// !kFused (the default): every block's coefficients into the buffer; the inverse transform is two kernels of its own.
+// kFused (TIC_DFLAG_FUSED, opt-in): a block whose symbols all lie in one subsequence never reaches the coefficient
+// buffer — the warp that has just completed it (four blocks per pass, 8 lanes each) dequantises it, runs the FP32
+// inverse transform with the guard band of dec_idct_fast_kernel and stores the pixels.  Only three kinds of block still
+// go through the buffer and the work list of the exact pass: blocks that span subsequences (listed by
+// dec_scan_kernel), blocks the stream ends in, and blocks with a pixel inside the guard band.  It removes 8.6 GB
+// written + 8.6 GB read for the benchmark batch (five times the pixels) and is bit-identical — and it is SLOWER:
+// 15.8 ms + 1.7 ms (exact pass) against 5.3 + 5.1 ms for the two separate kernels.  A warp completes about 4 blocks per
+// symbol step, so a pass of ~330 warp instructions serves 2.9 blocks on average (113 per block; the thread-per-block
+// kernel needs 49), inside a loop that was latency-bound, not bandwidth-bound, to begin with.  Kept for the record.
 // ---------------------------------------------------------------------------------------------------
+template <bool kFused>
 __global__ void __launch_bounds__(kSyncThreads) dec_write_kernel(const DecImage* __restrict__ imgs,
                                                                  const long long* __restrict__ sub_first, int n_images,
                                                                  long long total_subs, const DecTables* __restrict__ deftab,
                                                                  const DecTables* __restrict__ tabs,
                                                                  const uint32_t* __restrict__ E, const int2* __restrict__ NB,
                                                                  int16_t* __restrict__ coef, int* __restrict__ status,
-                                                                 int* __restrict__ summary) {
+                                                                 int* __restrict__ summary, const double* __restrict__ mul,
+                                                                 const float* __restrict__ mulf, long long* __restrict__ list,
+                                                                 int* __restrict__ list_count, int list_cap) {
     __shared__ uint32_t rows[kSyncThreads][kRowWords];
-    __shared__ DecTables sh_def;
-    __shared__ uint8_t zz[64];
+    __shared__ ShTables sh_def;
+    __shared__ uint8_t zz[64];    // zigzag index -> raster index u*8+v (direct stores into the coefficient buffer)
+    __shared__ uint8_t zzs[64];   // zigzag index -> index in a slot: raster, or (kFused) transposed v*8+u: a slot row is a COLUMN
     __shared__ __align__(16) int16_t slots[kSyncThreads][64];   // one block under construction per thread
     for (int i = threadIdx.x; i < kSyncThreads * 8; i += kSyncThreads)
         reinterpret_cast<uint4*>(&slots[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
-    {
-        const uint32_t* s = reinterpret_cast<const uint32_t*>(deftab);
-        uint32_t* d = reinterpret_cast<uint32_t*>(&sh_def);
-        for (int i = threadIdx.x; i < (int)(sizeof(DecTables) / 4); i += kSyncThreads) d[i] = __ldg(s + i);
+    load_sh_tables(sh_def, deftab, kSyncThreads);
+    if (threadIdx.x < 64) {
+        const int r = c_zigzag[threadIdx.x];
+        zz[threadIdx.x] = (uint8_t)r;
+        zzs[threadIdx.x] = (uint8_t)(kFused ? (r & 7) * 8 + (r >> 3) : r);
     }
-    if (threadIdx.x < 64) zz[threadIdx.x] = c_zigzag[threadIdx.x];
     long long g = (long long)blockIdx.x * kSyncThreads + threadIdx.x;
     int idx = find_owner_cta(sub_first, n_images, (long long)blockIdx.x * kSyncThreads, g, total_subs);   // barrier inside
     bool active = g < total_subs;
     int k = 0, end_rel = 0, nblk = 0;
     bool last_sub = false;
     int2 nb = make_int2(0, 0);
-    const DecTables* tb = &sh_def;
+    const DecTables* tb = nullptr;   // per-image tables (global memory); null: the fixed tables in shared memory
     BitSrc src = {};
     long long blk0 = 0;   // index of the image's first block in the batch
     if (active) {
@@ -734,9 +840,9 @@ __global__ void __launch_bounds__(kSyncThreads) dec_write_kernel(const DecImage*
     const int lane = threadIdx.x & 31;
     const uint32_t* sw = rows[threadIdx.x];
     int16_t* slot = slots[threadIdx.x];
-    const DecTable* tdc = &tb->dc;
-    const DecTable* tac = &tb->ac;
-    const bool fixed_tabs = tb == &sh_def;
+    const bool fixed_tabs = tb == nullptr;
+    const DecTable* tdc = fixed_tabs ? nullptr : &tb->dc;
+    const DecTable* tac = fixed_tabs ? nullptr : &tb->ac;
     const uint32_t sh_tabs = shared_addr(&sh_def), row = shared_addr(sw);
     uint32_t entry = active ? E[g] : 0u;
     int p = (int)(entry & 0xffffu), z = (int)((entry >> 16) & 0xffu);
@@ -752,7 +858,7 @@ __global__ void __launch_bounds__(kSyncThreads) dec_write_kernel(const DecImage*
             const uint32_t a = row + ((uint32_t)(p >> 5) << 2);
             const uint32_t v = __funnelshift_l(lds_u32(a + 4u), lds_u32(a), (uint32_t)(p & 31));
             int sym, len;
-            if (fixed_tabs) lookup_sh(sh_tabs + (z == 0 ? 0u : (uint32_t)sizeof(DecTable)), v, sym, len);   // warp-uniform but at image boundaries
+            if (fixed_tabs) lookup_sh(sh_tabs + (z == 0 ? 0u : (uint32_t)sizeof(ShTable)), v, sym, len);   // warp-uniform but at image boundaries
             else lookup(z == 0 ? tdc : tac, v, sym, len);
             if (len < 0) {   // the same rules as decode_sub: this pass must follow the parse the entries belong to
                 err |= TIC_DSTATUS_CODE;
@@ -788,7 +894,7 @@ __global__ void __launch_bounds__(kSyncThreads) dec_write_kernel(const DecImage*
                         }
                     } else {
                         if (val != 0) {
-                            if (staged) slot[zz[z]] = (int16_t)val;
+                            if (staged) slot[zzs[z]] = (int16_t)val;
                             else if (cur >= 0 && cur < nblk) coef[(blk0 + cur) * 64 + zz[z]] = (int16_t)val;
                         }
                         z += 1;
@@ -812,23 +918,92 @@ __global__ void __launch_bounds__(kSyncThreads) dec_write_kernel(const DecImage*
             }
             m = mm;
             const long long dst_block = __shfl_sync(0xffffffffu, my_block, src_lane & 31);
-            if (src_lane >= 0) {
-                uint4* sp = reinterpret_cast<uint4*>(slots[(threadIdx.x & ~31) + src_lane]) + (lane & 7);
-                reinterpret_cast<uint4*>(coef + dst_block * 64)[lane & 7] = *sp;
-                *sp = make_uint4(0u, 0u, 0u, 0u);
+            if constexpr (!kFused) {
+                if (src_lane >= 0) {
+                    uint4* sp = reinterpret_cast<uint4*>(slots[(threadIdx.x & ~31) + src_lane]) + (lane & 7);
+                    reinterpret_cast<uint4*>(coef + dst_block * 64)[lane & 7] = *sp;
+                    *sp = make_uint4(0u, 0u, 0u, 0u);
+                }
+            } else {
+                // ---- the group's block: column j of its coefficients -> row j of its pixels ----------------------
+                const int j = lane & 7, gshift = lane & ~7;
+                const bool valid = src_lane >= 0;
+                const int sidx = __shfl_sync(0xffffffffu, idx, valid ? src_lane : lane);   // the block's image
+                uint4 q = make_uint4(0u, 0u, 0u, 0u);
+                if (valid) {
+                    uint4* sp = reinterpret_cast<uint4*>(slots[(threadIdx.x & ~31) + src_lane]) + j;
+                    q = *sp;
+                    *sp = make_uint4(0u, 0u, 0u, 0u);
+                }
+                const DecImage& sim = imgs[sidx];
+                const float4* mT = reinterpret_cast<const float4*>(mulf + (size_t)sidx * kMulfStride + 64 + j * 8);
+                const float4 m0 = __ldg(mT), m1 = __ldg(mT + 1);
+                float a[8];
+                a[0] = (float)(int)(short)(q.x & 0xffffu) * m0.x; a[1] = (float)((int)q.x >> 16) * m0.y;
+                a[2] = (float)(int)(short)(q.y & 0xffffu) * m0.z; a[3] = (float)((int)q.y >> 16) * m0.w;
+                a[4] = (float)(int)(short)(q.z & 0xffffu) * m1.x; a[5] = (float)((int)q.z >> 16) * m1.y;
+                a[6] = (float)(int)(short)(q.w & 0xffffu) * m1.z; a[7] = (float)((int)q.w >> 16) * m1.w;
+                float S = ((fabsf(a[0]) + fabsf(a[1])) + (fabsf(a[2]) + fabsf(a[3]))) + ((fabsf(a[4]) + fabsf(a[5])) + (fabsf(a[6]) + fabsf(a[7])));
+                S += __shfl_xor_sync(0xffffffffu, S, 1);
+                S += __shfl_xor_sync(0xffffffffu, S, 2);
+                S += __shfl_xor_sync(0xffffffffu, S, 4);
+                const bool has_ac = ((j == 0 ? (q.x & 0xffff0000u) : q.x) | q.y | q.z | q.w) != 0u;
+                const unsigned acm = (__ballot_sync(0xffffffffu, has_ac) >> gshift) & 0xffu;
+                idct8_fast(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);   // down column j
+                transpose8(a, j);
+                idct8_fast(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);   // along row j
+                // the same decision as dec_idct_fast_kernel: a pixel further than delta from every integer is final
+                const float delta = fmaf(6e-7f, S, 4e-5f);
+                float rmin = 1.0f;
+                uint32_t lo = 0, hi = 0;
+#pragma unroll
+                for (int v = 0; v < 8; v++) {
+                    const float W = a[v] + 128.0f;
+                    const float d = W - ((W + 12582912.0f) - 12582912.0f);   // W - rint(W), exact below 2^22
+                    rmin = fminf(rmin, fabsf(d));
+                    const uint32_t px = (uint32_t)min(max(__float2int_rz(W), 0), 255);
+                    if (v < 4) lo |= px << (8 * v); else hi |= px << (8 * (v - 4));
+                }
+                const bool flag = !(delta < 0.25f) || rmin <= delta;
+                unsigned flm = (__ballot_sync(0xffffffffu, flag) >> gshift) & 0xffu;
+                const int dc_q = __shfl_sync(0xffffffffu, (int)(short)(q.x & 0xffffu), gshift);   // the group's lane 0 holds (0, 0)
+                if (acm == 0) {   // DC only: idct8_exact on (T, 0, ..., 0) gives 0.25 RN(T sqrt2) everywhere; twice
+                    const double SQ2 = 0x1.6a09e667f3bcdp+0;
+                    double t = (double)dc_q;
+                    if (sim.mode == MODE_SCALED) t = __dmul_rn(__ddiv_rn(t, d_ann[0]), sim.two_q);
+                    t = __dmul_rn(t, __ldg(mul + (size_t)sidx * 64));
+                    t = __dmul_rn(0.25, __dmul_rn(t, SQ2));
+                    t = __dmul_rn(0.25, __dmul_rn(t, SQ2));
+                    lo = hi = (uint32_t)min(max(__double2int_rz(__dadd_rn(t, 128.0)), 0), 255) * 0x01010101u;
+                    flm = 0;
+                }
+                if (valid && !sim.skip_pixels) {
+                    if (flm) {   // the exact pass decides: the block's coefficients (this lane: column j) and its index
+                        int16_t* dst = coef + dst_block * 64 + j;
+                        dst[0] = (int16_t)(q.x & 0xffffu); dst[8] = (int16_t)(q.x >> 16);
+                        dst[16] = (int16_t)(q.y & 0xffffu); dst[24] = (int16_t)(q.y >> 16);
+                        dst[32] = (int16_t)(q.z & 0xffffu); dst[40] = (int16_t)(q.z >> 16);
+                        dst[48] = (int16_t)(q.w & 0xffffu); dst[56] = (int16_t)(q.w >> 16);
+                        if (j == 0) list_push(list, list_count, list_cap, dst_block, summary);
+                    } else {
+                        const int b = (int)(dst_block - sim.blk_first);
+                        const int by = b / sim.bw, bx = b - by * sim.bw;
+                        store_pixel_row(sim, by * 8 + j, bx * 8, lo, hi);
+                    }
+                }
             }
         }
         __syncwarp();
     }
     if (staged) {
+        // slot index i -> raster index (kFused: the slot is transposed)
         if (last_sub) {   // the stream ends inside the block (truncated): nobody else writes it
-#pragma unroll
-            for (int i = 0; i < 8; i++)
-                reinterpret_cast<uint4*>(coef + (blk0 + cur) * 64)[i] = reinterpret_cast<uint4*>(slot)[i];
-        } else {          // the block goes on in the next subsequence
+            for (int i = 0; i < 64; i++) coef[(blk0 + cur) * 64 + (kFused ? (i & 7) * 8 + (i >> 3) : i)] = slot[i];
+            if constexpr (kFused) list_push(list, list_count, list_cap, blk0 + cur, summary);
+        } else {          // the block goes on in the next subsequence (dec_scan_kernel zeroed and, kFused, listed it)
             for (int i = 0; i < 64; i++) {
                 int16_t c = slot[i];
-                if (c != 0) coef[(blk0 + cur) * 64 + i] = c;
+                if (c != 0) coef[(blk0 + cur) * 64 + (kFused ? (i & 7) * 8 + (i >> 3) : i)] = c;
             }
         }
     }
@@ -916,6 +1091,19 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
     return r;
 }
 
+__device__ __forceinline__ float fmin3(float a, float b, float c) {   // FMNMX3
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+// np.clip(x, 0, 255).astype(np.uint8) of four already truncated values, p0 in the low byte
+__device__ __forceinline__ uint32_t pack_px4(int p0, int p1, int p2, int p3) {
+    uint32_t t, r;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(t) : "r"(p3), "r"(p2), "r"(0));
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(p1), "r"(p0), "r"(t));
+    return r;
+}
+
 // idct8_fast (below) on two independent 8-point inputs at once
 __device__ __forceinline__ void idct8_fast2(f32x2& x0, f32x2& x1, f32x2& x2, f32x2& x3, f32x2& x4, f32x2& x5, f32x2& x6,
                                             f32x2& x7) {
@@ -939,37 +1127,6 @@ __device__ __forceinline__ void idct8_fast2(f32x2& x0, f32x2& x1, f32x2& x2, f32
     x1 = add2(e1, o1); x6 = sub2(e1, o1);
     x2 = add2(e2, o2); x5 = sub2(e2, o2);
     x3 = add2(e3, o3); x4 = sub2(e3, o3);
-}
-
-__device__ __forceinline__ void idct8_fast(float& x0, float& x1, float& x2, float& x3, float& x4, float& x5, float& x6,
-                                           float& x7) {
-    // c(u) cos((2y+1) u pi / 16), c(0) = sqrt(1/8), c(u > 0) = 1/2: even columns u = 0,2,4,6 and odd u = 1,3,5,7
-    const float A = 0.35355339059327379f, B = 0.46193976625564337f, C = 0.19134171618254489f;
-    const float P = 0.49039264020161522f, Q = 0.41573480615127262f, R = 0.27778511650980111f, T = 0.09754516100806413f;
-    const float e0 = fmaf(C, x6, fmaf(A, x4, fmaf(B, x2, A * x0)));
-    const float e1 = fmaf(-B, x6, fmaf(-A, x4, fmaf(C, x2, A * x0)));
-    const float e2 = fmaf(B, x6, fmaf(-A, x4, fmaf(-C, x2, A * x0)));
-    const float e3 = fmaf(-C, x6, fmaf(A, x4, fmaf(-B, x2, A * x0)));
-    const float o0 = fmaf(T, x7, fmaf(R, x5, fmaf(Q, x3, P * x1)));
-    const float o1 = fmaf(-R, x7, fmaf(-P, x5, fmaf(-T, x3, Q * x1)));
-    const float o2 = fmaf(Q, x7, fmaf(T, x5, fmaf(-P, x3, R * x1)));
-    const float o3 = fmaf(-P, x7, fmaf(Q, x5, fmaf(-R, x3, T * x1)));
-    x0 = e0 + o0; x7 = e0 - o0;
-    x1 = e1 + o1; x6 = e1 - o1;
-    x2 = e2 + o2; x5 = e2 - o2;
-    x3 = e3 + o3; x4 = e3 - o3;
-}
-
-__device__ __forceinline__ void store_pixel_row(const DecImage& im, int y, int x0, uint32_t lo, uint32_t hi) {
-    if (y >= im.height) return;
-    uint8_t* row = im.pixels + (size_t)y * (size_t)im.width + x0;
-    if (x0 + 8 <= im.width && (((uintptr_t)im.pixels | (uintptr_t)im.width) & 7u) == 0) {
-        *reinterpret_cast<uint2*>(row) = make_uint2(lo, hi);
-    } else {
-#pragma unroll
-        for (int v = 0; v < 8; v++)
-            if (x0 + v < im.width) row[v] = (uint8_t)((v < 4 ? lo >> (8 * v) : hi >> (8 * (v - 4))) & 0xffu);
-    }
 }
 
 __global__ void __launch_bounds__(128, TICD_FAST_MIN_CTAS) dec_idct_fast_kernel(const DecImage* __restrict__ imgs,
@@ -1027,7 +1184,7 @@ __global__ void __launch_bounds__(128, TICD_FAST_MIN_CTAS) dec_idct_fast_kernel(
         return;
     }
     // pairs of horizontally adjacent coefficients — the two int16 of one coefficient word — through the column pass
-    const float2* __restrict__ fm = reinterpret_cast<const float2*>(mulf + (size_t)idx * 64);
+    const float2* __restrict__ fm = reinterpret_cast<const float2*>(mulf + (size_t)idx * kMulfStride);
     f32x2 c2[8][4];
     float S = 0.0f;
 #pragma unroll
@@ -1062,21 +1219,25 @@ __global__ void __launch_bounds__(128, TICD_FAST_MIN_CTAS) dec_idct_fast_kernel(
             r2[2 * vp + 1] = pk2(a1, b1);
         }
         idct8_fast2(r2[0], r2[1], r2[2], r2[3], r2[4], r2[5], r2[6], r2[7]);
-        uint32_t l0 = 0, h0 = 0, l1 = 0, h1 = 0;
+        // truncate (F2I), then clamp and pack four pixels with two saturating pack instructions (the first version
+        // spent 9 instructions per pixel here: a third of the kernel)
 #pragma unroll
-        for (int v = 0; v < 8; v++) {
-            const f32x2 W2 = add2(r2[v], k128);
-            const f32x2 d2 = sub2(W2, sub2(add2(W2, kmag), kmag));   // W - rint(W), exact below 2^22
-            float W0, W1, d0, d1;
-            upk2(W2, W0, W1);
-            upk2(d2, d0, d1);
-            rmin = fminf(rmin, fminf(fabsf(d0), fabsf(d1)));
-            const uint32_t p0 = (uint32_t)min(max(__float2int_rz(W0), 0), 255);
-            const uint32_t p1 = (uint32_t)min(max(__float2int_rz(W1), 0), 255);
-            if (v < 4) { l0 |= p0 << (8 * v); l1 |= p1 << (8 * v); }
-            else { h0 |= p0 << (8 * (v - 4)); h1 |= p1 << (8 * (v - 4)); }
+        for (int half = 0; half < 2; half++) {
+            int i0[4], i1[4];
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                const f32x2 W2 = add2(r2[4 * half + v], k128);
+                const f32x2 d2 = sub2(W2, sub2(add2(W2, kmag), kmag));   // W - rint(W), exact below 2^22
+                float W0, W1, d0, d1;
+                upk2(W2, W0, W1);
+                upk2(d2, d0, d1);
+                rmin = fmin3(rmin, fabsf(d0), fabsf(d1));
+                i0[v] = __float2int_rz(W0);
+                i1[v] = __float2int_rz(W1);
+            }
+            const uint32_t a = pack_px4(i0[0], i0[1], i0[2], i0[3]), b = pack_px4(i1[0], i1[1], i1[2], i1[3]);
+            if (half == 0) { lo[2 * up] = a; lo[2 * up + 1] = b; } else { hi[2 * up] = a; hi[2 * up + 1] = b; }
         }
-        lo[2 * up] = l0; hi[2 * up] = h0; lo[2 * up + 1] = l1; hi[2 * up + 1] = h1;
     }
     flag |= rmin <= delta;
     if (flag) {
@@ -1101,10 +1262,10 @@ __global__ void __launch_bounds__(kIdctBlocks * 8) dec_idct_kernel(const DecImag
                                                                    long long total_blocks, const int16_t* __restrict__ coef,
                                                                    const double* __restrict__ mul, const int* __restrict__ ndec,
                                                                    const long long* __restrict__ list,
-                                                                   const int* __restrict__ list_count) {
+                                                                   const int* __restrict__ list_count, int list_cap) {
     __shared__ double tile[kIdctBlocks][8][9];   // 9: column and row accesses both conflict-free
     const bool listed = list != nullptr;
-    const long long total = listed ? (long long)*list_count : total_blocks;
+    const long long total = listed ? (long long)min(*list_count, list_cap) : total_blocks;
     const int lb = threadIdx.x >> 3, t = threadIdx.x & 7;
     const long long cta0 = (long long)blockIdx.x * (kIdctBlocks * kIdctIters);
     if (cta0 >= total) return;
@@ -1166,6 +1327,20 @@ __global__ void __launch_bounds__(kIdctBlocks * 8) dec_idct_kernel(const DecImag
     }
 }
 
+// Fused coefficient pass: the blocks a stream never reaches (truncated streams; images whose every block is zero bits
+// long) have all-zero coefficients, i.e. pixel 128 everywhere (idct8_exact of zeros is exactly zero in both modes).
+// grid (images, chunks); returns at once for every image that was decoded completely.
+__global__ void __launch_bounds__(256) dec_fill_kernel(const DecImage* __restrict__ imgs, const int* __restrict__ ndec) {
+    const DecImage& im = imgs[blockIdx.x];
+    const int first = ndec[blockIdx.x];
+    if (im.skip_pixels || first >= im.nblk) return;
+    for (long long b = (long long)first + blockIdx.y * 256 + threadIdx.x; b < im.nblk; b += (long long)gridDim.y * 256) {
+        const int by = (int)(b / im.bw), bx = (int)(b - (long long)by * im.bw);
+#pragma unroll
+        for (int u = 0; u < 8; u++) store_pixel_row(im, by * 8 + u, bx * 8, 0x80808080u, 0x80808080u);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // decode() from coefficient arrays (codec.py:46-70): dc[nblk] differences, ac[nblk][63] in zigzag order.
 // The DC cumsum (codec.py:53) reuses dec_scan_kernel with one "subsequence" per block.
@@ -1203,6 +1378,7 @@ struct DecWs {
     DecTables* d_deftab = nullptr;
     uint32_t* d_E = nullptr; uint32_t* d_U = nullptr; int2* d_ND = nullptr; int2* d_NB = nullptr; size_t subs_cap = 0;
     int16_t* d_coef = nullptr; long long* d_list = nullptr; size_t blocks_cap = 0;   // coefficients; exact-pass work list
+    int list_cap = 0;         // entries of d_list (2 x blocks_cap: spanning + flagged blocks, see list_push)
     int* d_flags = nullptr;   // [0] changed, [1] summary, [2] blocks listed for the exact IDCT pass
     int* h_flags = nullptr;   // pinned
     int* d_status_own = nullptr; size_t status_cap = 0;
@@ -1268,7 +1444,11 @@ static int ensure_base(tic_handle h, DecWs* w) {
     TICD_CUDA(h, cudaMallocHost(&w->h_flags, 4 * sizeof(int)));
     for (auto& e : w->ev) TICD_CUDA(h, cudaEventCreate(&e));
     DecTables* def = new DecTables();
-    build_default_tables(*def);
+    if (build_default_tables(*def) > 256) {   // kShNodes, see ShTable
+        delete def;
+        tic_internal_set_error(h, "the fixed Huffman tables need more than 256 trie nodes");
+        return TIC_E_INVALID;
+    }
     cudaError_t e1 = cudaMalloc(&w->d_deftab, sizeof(DecTables));
     if (e1 == cudaSuccess) e1 = cudaMemcpy(w->d_deftab, def, sizeof(DecTables), cudaMemcpyHostToDevice);
     delete def;
@@ -1286,7 +1466,7 @@ static int grow(tic_handle h, T*& p, size_t n) {
 
 // Phase 3 on `stream`: h_slices must list the slices of the images in image order.
 static int launch_scan(tic_handle h, DecWs* w, int* status, cudaStream_t stream, long long& launches,
-                       const uint32_t* E, int16_t* coef) {
+                       const uint32_t* E, int16_t* coef, bool list_spanning = false) {
     const size_t ns = w->h_slices.size();
     if (ns == 0) return TIC_OK;
     if (ns > w->slices_cap) {
@@ -1304,7 +1484,8 @@ static int launch_scan(tic_handle h, DecWs* w, int* status, cudaStream_t stream,
         launches++;
     }
     dec_scan_kernel<<<(unsigned)ns, 1024, 0, stream>>>(w->d_imgs, w->d_slices, w->d_slice_tot, w->d_ND, w->d_NB, status,
-                                                       w->d_flags + 1, E, coef, w->d_ndec);
+                                                       w->d_flags + 1, E, coef, w->d_ndec,
+                                                       list_spanning ? w->d_list : nullptr, w->d_flags + 2, w->list_cap);
     launches++;
     TICD_CUDA(h, cudaGetLastError());
     return TIC_OK;
@@ -1318,14 +1499,14 @@ static int launch_idct(tic_handle h, DecWs* w, const long long* d_blk_first, int
     const unsigned exact_grid = (unsigned)((blocks + kIdctBlocks * kIdctIters - 1) / (kIdctBlocks * kIdctIters));
     if (flags & TIC_DFLAG_EXACT_ONLY) {
         dec_idct_kernel<<<exact_grid, kIdctBlocks * 8, 0, stream>>>(w->d_imgs, d_blk_first, n_images, blocks, w->d_coef, w->d_mul,
-                                                                    w->d_ndec, nullptr, nullptr);
+                                                                    w->d_ndec, nullptr, nullptr, 0);
         launches++;
     } else {
         dec_idct_fast_kernel<<<(unsigned)((blocks + 127) / 128), 128, 0, stream>>>(w->d_imgs, d_blk_first, n_images, blocks,
                                                                                  w->d_coef, w->d_mul, w->d_mulf, w->d_ndec,
                                                                                  w->d_list, w->d_flags + 2);
         dec_idct_kernel<<<exact_grid, kIdctBlocks * 8, 0, stream>>>(w->d_imgs, d_blk_first, n_images, blocks, w->d_coef, w->d_mul,
-                                                                    w->d_ndec, w->d_list, w->d_flags + 2);
+                                                                    w->d_ndec, w->d_list, w->d_flags + 2, w->list_cap);
         launches += 2;
     }
     TICD_CUDA(h, cudaGetLastError());
@@ -1366,7 +1547,7 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
         if (int rc = grow(h, w->d_first, 2 * (cap + 1))) return rc;
         if (int rc = grow(h, w->d_tabs, cap)) return rc;
         if (int rc = grow(h, w->d_mul, cap * 64)) return rc;
-        if (int rc = grow(h, w->d_mulf, cap * 64)) return rc;
+        if (int rc = grow(h, w->d_mulf, cap * kMulfStride)) return rc;
         if (int rc = grow(h, w->d_status_own, cap)) return rc;
         if (int rc = grow(h, w->d_ndec, cap)) return rc;
         TICD_CUDA(h, cudaMallocHost(&w->h_imgs, cap * sizeof(DecImage)));
@@ -1427,7 +1608,8 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
         size_t cap = (size_t)blocks + (size_t)blocks / 8 + 1024;
         w->blocks_cap = 0;
         if (int rc = grow(h, w->d_coef, cap * 64)) return rc;
-        if (int rc = grow(h, w->d_list, cap)) return rc;
+        if (int rc = grow(h, w->d_list, 2 * cap)) return rc;
+        w->list_cap = (int)std::min<size_t>(2 * cap, 0x7fffffffu);
         w->blocks_cap = cap;
     }
     int* status = d_status ? d_status : w->d_status_own;
@@ -1450,6 +1632,7 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
     TICD_CUDA(h, cudaGetLastError());
     TICD_CUDA(h, cudaEventRecord(w->ev[1], stream));
     long long rounds = 0;
+    const bool fused = (flags & TIC_DFLAG_FUSED) != 0 && (flags & TIC_DFLAG_EXACT_ONLY) == 0;
     if (subs) {
         unsigned grid = (unsigned)((subs + kSyncThreads - 1) / kSyncThreads);
         for (;;) {
@@ -1468,11 +1651,17 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
             }
         }
         TICD_CUDA(h, cudaEventRecord(w->ev[2], stream));
-        if (int rc = launch_scan(h, w, status, stream, launches, w->d_E, w->d_coef)) return rc;
+        if (int rc = launch_scan(h, w, status, stream, launches, w->d_E, w->d_coef, fused)) return rc;
         TICD_CUDA(h, cudaEventRecord(w->ev[3], stream));
-        dec_write_kernel<<<grid, kSyncThreads, 0, stream>>>(w->d_imgs, d_sub_first, n_images, subs, w->d_deftab,
-                                                            w->d_tabs, w->d_E, w->d_NB, w->d_coef, status,
-                                                            w->d_flags + 1);
+        if (fused)
+            dec_write_kernel<true><<<grid, kSyncThreads, 0, stream>>>(w->d_imgs, d_sub_first, n_images, subs, w->d_deftab,
+                                                                      w->d_tabs, w->d_E, w->d_NB, w->d_coef, status,
+                                                                      w->d_flags + 1, w->d_mul, w->d_mulf, w->d_list,
+                                                                      w->d_flags + 2, w->list_cap);
+        else
+            dec_write_kernel<false><<<grid, kSyncThreads, 0, stream>>>(w->d_imgs, d_sub_first, n_images, subs, w->d_deftab,
+                                                                       w->d_tabs, w->d_E, w->d_NB, w->d_coef, status,
+                                                                       w->d_flags + 1, nullptr, nullptr, nullptr, nullptr, 0);
         launches++;
         TICD_CUDA(h, cudaGetLastError());
     } else {
@@ -1480,7 +1669,19 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
         TICD_CUDA(h, cudaEventRecord(w->ev[3], stream));
     }
     TICD_CUDA(h, cudaEventRecord(w->ev[4], stream));
-    if (int rc = launch_idct(h, w, d_blk_first, n_images, blocks, flags, stream, launches)) return rc;
+    if (fused) {
+        // what the coefficient pass did not finish itself: unreached blocks (pixel 128), then the exact pass over the
+        // listed blocks (spanning subsequences, guard band, end of a truncated stream)
+        if (blocks) {
+            dec_fill_kernel<<<dim3((unsigned)n_images, 32), 256, 0, stream>>>(w->d_imgs, w->d_ndec);
+            const unsigned exact_grid = (unsigned)((blocks + kIdctBlocks * kIdctIters - 1) / (kIdctBlocks * kIdctIters));
+            dec_idct_kernel<<<exact_grid, kIdctBlocks * 8, 0, stream>>>(w->d_imgs, d_blk_first, n_images, blocks, w->d_coef,
+                                                                        w->d_mul, w->d_ndec, w->d_list, w->d_flags + 2,
+                                                                        w->list_cap);
+            launches += 2;
+            TICD_CUDA(h, cudaGetLastError());
+        }
+    } else if (int rc = launch_idct(h, w, d_blk_first, n_images, blocks, flags, stream, launches)) return rc;
     TICD_CUDA(h, cudaEventRecord(w->ev[5], stream));
     TICD_CUDA(h, cudaMemcpyAsync(w->h_flags + 1, w->d_flags + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
     w->stats[0] = launches;
@@ -1511,7 +1712,7 @@ int tic_decode_coeffs(tic_handle h, const int32_t* d_dc, const int32_t* d_ac, in
         if (int rc = grow(h, w->d_first, 2 * (cap + 1))) return rc;
         if (int rc = grow(h, w->d_tabs, cap)) return rc;
         if (int rc = grow(h, w->d_mul, cap * 64)) return rc;
-        if (int rc = grow(h, w->d_mulf, cap * 64)) return rc;
+        if (int rc = grow(h, w->d_mulf, cap * kMulfStride)) return rc;
         if (int rc = grow(h, w->d_status_own, cap)) return rc;
         if (int rc = grow(h, w->d_ndec, cap)) return rc;
         TICD_CUDA(h, cudaMallocHost(&w->h_imgs, cap * sizeof(DecImage)));
@@ -1531,7 +1732,8 @@ int tic_decode_coeffs(tic_handle h, const int32_t* d_dc, const int32_t* d_ac, in
         size_t cap = (size_t)nblk + 1024;
         w->blocks_cap = 0;
         if (int rc = grow(h, w->d_coef, cap * 64)) return rc;
-        if (int rc = grow(h, w->d_list, cap)) return rc;
+        if (int rc = grow(h, w->d_list, 2 * cap)) return rc;
+        w->list_cap = (int)std::min<size_t>(2 * cap, 0x7fffffffu);
         w->blocks_cap = cap;
     }
     DecImage& im = w->h_imgs[0];
