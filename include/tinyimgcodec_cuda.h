@@ -199,6 +199,10 @@ int64_t tic_last_guard_misses(tic_handle h);
                                        way (tests compare the two); removes the coefficient buffer's traffic but measures
                                        slower (csrc/tic_decode.cu, dec_write_kernel).  For verification and profiling. */
 
+#define TIC_DFLAG_NO_EARLY_STOP 8u  /* synchronisation rounds: decode a subsequence to its end every time, instead of
+                                       stopping where a repeat decode meets the previous one.  Same result (tests compare);
+                                       for verification and profiling. */
+
 /* per-stream status bits of the decode side */
 #define TIC_DSTATUS_HEADER 1     /* shorter than 16 bytes, or height / width differ from the caller's */
 #define TIC_DSTATUS_CODE 2       /* no codeword matches (ValueError, huffman.py:72-73) or a run passes

@@ -186,6 +186,8 @@ def test_config4_images_on_device_round_trip(tic):
         fused, _ = enc.decode_batch_device((res.out, offs), sizes, [1024] * n, [1024] * n, fused=True)
         assert 1 <= enc.decode_stats()["exact_blocks"] < 0.4 * st["blocks"], enc.decode_stats()
         assert torch.equal(outs, fused.clone()), f"q{q}: {(outs != fused).sum().item()} pixels differ between the fused pass and the separate kernels"
+        plain, _ = enc.decode_batch_device((res.out, offs), sizes, [1024] * n, [1024] * n, early_stop=False)
+        assert torch.equal(outs, plain.clone()), f"q{q}: the early stop of repeat decodes changes {(outs != plain).sum().item()} pixels"
         host = res.to_bytes()
         for i in (0, 17, n - 1):
             _same(outs[i].cpu().numpy(), O.decompress(host[i]), f"q{q} image {i}")
@@ -317,6 +319,11 @@ def test_random_sweep_vs_oracle(tic):
         outs = tic.decompress_batch(streams, exact_only=exact_only)
         for i, (px, ref_px) in enumerate(zip(outs, want)):
             _same(px, ref_px, f"case {i} exact_only={exact_only}")
+    # synchronisation rounds without the early stop of repeat decodes, and the fused coefficient pass
+    for kw in ({"early_stop": False}, {"fused": True}):
+        outs = tic.decompress_batch(streams, **kw)
+        for i, (px, ref_px) in enumerate(zip(outs, want)):
+            _same(px, ref_px, f"case {i} {kw}")
 
 
 @pytest.mark.parametrize("chunk", [1, 3, 8])

@@ -382,7 +382,7 @@ class Encoder:
         return out
 
     def decode_batch_device(self, d_streams, sizes, heights, widths, pixels=None, stream=None,
-                            accept_be_flag=False, strict=True, exact_only=False, fused=False):
+                            accept_be_flag=False, strict=True, exact_only=False, fused=False, early_stop=True):
         """Decode streams resident in HBM.  `d_streams`: list of CUDA uint8 tensors (each 4-byte aligned), or
         one CUDA uint8 tensor plus `sizes` and byte offsets given as d_streams=(tensor, offsets).  Returns the
         CUDA uint8 (H, W) images (a list of views of one pixel buffer, or one (N, H, W) view when all shapes are
@@ -414,7 +414,8 @@ class Encoder:
             d_status = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
             stream = stream or torch.cuda.current_stream(dev)
             flags = (_lib.TIC_DFLAG_ACCEPT_BE_FLAG if accept_be_flag else 0) | \
-                    (_lib.TIC_DFLAG_EXACT_ONLY if exact_only else 0) | (_lib.TIC_DFLAG_FUSED if fused else 0)
+                    (_lib.TIC_DFLAG_EXACT_ONLY if exact_only else 0) | (_lib.TIC_DFLAG_FUSED if fused else 0) | \
+                    (0 if early_stop else _lib.TIC_DFLAG_NO_EARLY_STOP)
             if n == 0:
                 return [], np.zeros(0, dtype=np.int32)
             with self._lock:
@@ -439,7 +440,7 @@ class Encoder:
                       for i in range(n)]
         return images, status
 
-    def decompress_batch(self, streams, strict=True, accept_be_flag=False, exact_only=False, fused=False):
+    def decompress_batch(self, streams, strict=True, accept_be_flag=False, exact_only=False, fused=False, early_stop=True):
         """decompress() for a list of `bytes`: one pinned H2D copy of all streams, one decode, one D2H copy of all
         pixels.  Returns a list of uint8 (H, W) arrays."""
         import torch
@@ -456,7 +457,8 @@ class Encoder:
                 h_np[o: o + len(s)] = np.frombuffer(s, dtype=np.uint8)
             d_buf = h_buf.to(dev, non_blocking=True)
             imgs, _ = self.decode_batch_device((d_buf, offs[:-1]), sizes, [h[0] for h in hdrs], [h[1] for h in hdrs],
-                                               strict=strict, accept_be_flag=accept_be_flag, exact_only=exact_only, fused=fused)
+                                               strict=strict, accept_be_flag=accept_be_flag, exact_only=exact_only, fused=fused,
+                                               early_stop=early_stop)
             return [im.cpu().numpy() for im in imgs]
 
     def decompress_batch_pinned(self, h_streams, index, heights, widths, chunk=64, nbuf=3, strict=True):
@@ -633,7 +635,8 @@ def encode(image, quality=50, device=None):
 
 def decompress(data, device=None, strict=True, accept_be_flag=False, exact_only=False, fused=False):
     """Drop-in for tinyimgcodec.codec.decompress (codec.py:167-189)."""
-    return get_encoder(device).decompress(data, strict=strict, accept_be_flag=accept_be_flag, exact_only=exact_only, fused=fused)
+    return get_encoder(device).decompress(data, strict=strict, accept_be_flag=accept_be_flag, exact_only=exact_only,
+                                          fused=fused)
 
 
 def decode(data, device=None):
@@ -641,10 +644,11 @@ def decode(data, device=None):
     return get_encoder(device).decode(data)
 
 
-def decompress_batch(streams, device=None, strict=True, accept_be_flag=False, exact_only=False, fused=False):
+def decompress_batch(streams, device=None, strict=True, accept_be_flag=False, exact_only=False, fused=False,
+                     early_stop=True):
     """decompress() for a list of streams in one launch sequence."""
     return get_encoder(device).decompress_batch(streams, strict=strict, accept_be_flag=accept_be_flag,
-                                                exact_only=exact_only, fused=fused)
+                                                exact_only=exact_only, fused=fused, early_stop=early_stop)
 
 
 def compress_c(image, qfactor="med", device=None):
