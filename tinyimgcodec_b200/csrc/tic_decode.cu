@@ -178,6 +178,9 @@ static int build_default_tables(DecTables& t) {
     return nodes > most ? nodes : most;
 }
 
+struct ShTables;
+static bool build_sh_tables(const DecTables& t, ShTables& sh);   // defined next to ShTables
+
 // ---------------------------------------------------------------------------------------------------
 // Bit access: the stream is MSB-first bytes (bitarray(endian="big"), bitbuffer.py:7); 32 bits starting at
 // bit p, zeros past the end (a slice past the end of a bitarray is empty).
@@ -240,46 +243,68 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
     return v;
 }
 __device__ __forceinline__ uint32_t shared_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void lookup_sh(uint32_t tab, uint32_t v, int& sym, int& len) {
-    uint32_t e = lds_u16(tab + ((v >> 24) << 1));   // DecTable::lut
-    if (e & kLeaf) { sym = (int)(e & 0xffu); len = (int)((e >> 8) & 0x7fu); return; }
-    len = 8;
-    uint32_t node = e;
-    while (node != 0 && len < 16) {
-        uint32_t c = lds_u16(tab + 512u + node * 4u + (((v >> (31 - len)) & 1u) << 1));   // DecTable::child
-        len++;
-        if (c & kLeaf) { sym = (int)(c & 0xffu); return; }
-        node = c;
-    }
-    sym = 0;
-    len = -1;
-}
-static_assert(offsetof(DecTable, child) == 512 && sizeof(uint16_t[2]) == 4, "lookup_sh addresses DecTable by hand");
-// The shared-memory copy of the FIXED tables: the same layout with 256 trie nodes instead of kMaxNodes (a prefix code
-// over at most 256 symbols has at most 255 inner nodes, and table_insert numbers them in order of creation; the host
-// checks the count of the default tables).  3 KB per CTA instead of 9.2 KB.
-constexpr int kShNodes = 256;
-struct ShTable {
-    uint16_t lut[256];
-    uint16_t child[kShNodes][2];
-};
+// The shared-memory form of the FIXED tables: two levels, no bit-by-bit walk.  Level 1 = DecTable::lut of each
+// alphabet over the next 8 bits (a leaf entry: kLeaf | length << 8 | symbol); for a code longer than 8 bits the entry
+// is 1 + the number of a level-2 block (no kLeaf bit), and that block resolves the following 8 bits the same way
+// (length = the whole code's).  The reference's tables need 1 block for the DC and 5 for the AC alphabet; the host
+// builds the image once per handle (build_sh_tables) and every CTA copies its 5 KB.  In the benchmark's streams one
+// symbol in eight has a code of more than 8 bits, so some lane of a warp took the bit-by-bit branch in 98 % of all symbol
+// steps — 15 instructions with ONE lane active (profiles/r2g_dec_sync_kernel).
+constexpr int kL2Blocks = 8;
 struct ShTables {
-    ShTable dc, ac;
+    uint16_t lut_dc[256], lut_ac[256];
+    uint16_t lut2[kL2Blocks][256];
 };
 // all threads of the CTA; the caller synchronises before the first lookup
-__device__ __forceinline__ void load_sh_tables(ShTables& sh, const DecTables* __restrict__ deftab, int nthreads) {
-    const DecTable* src[2] = {&deftab->dc, &deftab->ac};
-    ShTable* dst[2] = {&sh.dc, &sh.ac};
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-        const uint32_t* sl = reinterpret_cast<const uint32_t*>(src[k]->lut);
-        const uint32_t* sc = reinterpret_cast<const uint32_t*>(src[k]->child);
-        uint32_t* dl = reinterpret_cast<uint32_t*>(dst[k]->lut);
-        uint32_t* dc = reinterpret_cast<uint32_t*>(dst[k]->child);
-        for (int i = threadIdx.x; i < 128; i += nthreads) dl[i] = __ldg(sl + i);
-        for (int i = threadIdx.x; i < kShNodes; i += nthreads) dc[i] = __ldg(sc + i);
-    }
+__device__ __forceinline__ void load_sh_tables(ShTables& sh, const ShTables* __restrict__ image, int nthreads) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(image);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sh);
+    for (int i = threadIdx.x; i < (int)(sizeof(ShTables) / 4); i += nthreads) dst[i] = __ldg(src + i);
 }
+// tabs: shared address of the ShTables.  No branch: the second load is always issued (entry 0 of block 0 for a leaf).
+__device__ __forceinline__ void lookup_sh(uint32_t tabs, bool is_dc, uint32_t v, int& sym, int& len) {
+    const uint32_t e1 = lds_u16(tabs + (is_dc ? 0u : 512u) + ((v >> 24) << 1));
+    const bool leaf = (e1 & kLeaf) != 0;
+    const uint32_t e2 = lds_u16(tabs + 1024u + (leaf || e1 == 0 ? 0u : ((e1 - 1u) << 9) + ((v >> 15) & 0x1feu)));
+    const uint32_t e = leaf ? e1 : (e1 == 0 ? 0u : e2);
+    sym = (int)(e & 0xffu);
+    len = (e & kLeaf) ? (int)((e >> 8) & 0x7fu) : -1;   // no codeword of at most 16 bits matches
+}
+static_assert(offsetof(ShTables, lut_ac) == 512 && offsetof(ShTables, lut2) == 1024, "lookup_sh addresses ShTables by hand");
+// Host: the two-level image of the fixed tables from their tries.  False if they need more than kL2Blocks blocks.
+static bool build_sh_tables(const DecTables& t, ShTables& sh) {
+    memset(&sh, 0, sizeof sh);
+    int blocks = 0;
+    const DecTable* src[2] = {&t.dc, &t.ac};
+    uint16_t* lut[2] = {sh.lut_dc, sh.lut_ac};
+    for (int a = 0; a < 2; a++) {
+        int node_block[kMaxNodes];
+        for (int i = 0; i < kMaxNodes; i++) node_block[i] = -1;
+        for (int x = 0; x < 256; x++) {
+            const uint16_t e = src[a]->lut[x];
+            if ((e & kLeaf) || e == 0) { lut[a][x] = e; continue; }
+            if (node_block[e] < 0) {   // a new level-2 block: the 8 bits behind trie node e
+                if (blocks >= kL2Blocks) return false;
+                const int b = blocks++;
+                node_block[e] = b;
+                for (int y = 0; y < 256; y++) {
+                    int node = e;
+                    uint16_t out = 0;
+                    for (int d = 0; d < 8; d++) {
+                        const uint16_t c = src[a]->child[node][(y >> (7 - d)) & 1];
+                        if (c == 0) break;
+                        if (c & kLeaf) { out = (uint16_t)(kLeaf | ((uint32_t)(9 + d) << 8) | (c & 0xffu)); break; }
+                        node = c;
+                    }
+                    sh.lut2[b][y] = out;
+                }
+            }
+            lut[a][x] = (uint16_t)(node_block[e] + 1);
+        }
+    }
+    return true;
+}
+
 // read_int (bitbuffer.py:56-66) on the window t = v << len: `size` bits, a leading 0 = negative (one's complement)
 __device__ __forceinline__ int read_value(uint32_t t, int size) {
     uint32_t vb, ones;
@@ -336,7 +361,6 @@ struct SubResult {
 // (tests/test_sync_model.py): two parses of one subsequence meet after 39 bits on average at quality 50 (p90 70,
 // max 159 of 1024), 108 bits at quality 90: the repeat decode of the synchronisation rounds shrinks from ~210
 // symbols to ~15.  valid: the record describes a complete decode and has not been used yet.
-constexpr int kRecStarts = 4;
 struct SubRec {
     uint32_t pos01 = 0xffffffffu, pos23 = 0xffffffffu;   // bit positions of the first block starts, 16 bits each (0xffff: none)
     int pre1 = 0, pre2 = 0, pre3 = 0;                    // sum of the DC differences of the blocks in front of start 1, 2, 3
@@ -355,12 +379,16 @@ __device__ SubResult decode_sub(const uint32_t* sw, int end_rel, const DecTable*
     const uint32_t row = shared_addr(sw);
     const bool match = kSh && rec != nullptr && rec->valid, record = kSh && rec != nullptr && !rec->valid;
     if (record) { rec->pos01 = rec->pos23 = 0xffffffffu; rec->pre1 = rec->pre2 = rec->pre3 = 0; }
+    // the bookkeeping below only runs while it can still matter: the first four block starts of a recording
+    // decode, the stretch up to the last remembered start of a comparing one (one branch per symbol step otherwise)
+    int watch_end = record ? end_rel : (match ? (int)(rec->pos23 >> 16 != 0xffffu ? rec->pos23 >> 16 : (rec->pos23 & 0xffffu) != 0xffffu ? rec->pos23 & 0xffffu : rec->pos01 >> 16 != 0xffffu ? rec->pos01 >> 16 : rec->pos01 & 0xffffu) : -1);
+    if (match && watch_end == 0xffff) watch_end = -1;   // nothing remembered
     int it = 0;
     for (; p < end_rel && (kSh || it < kMaxSymbols); it++) {
         uint32_t v;
         int sym, len;
         if constexpr (kSh) {
-            if (z == 0 && rec != nullptr) {   // a block starts here
+            if (z == 0 && p <= watch_end) {   // a block starts here
                 if (match) {
                     const uint32_t pp = (uint32_t)p;
                     const int j = pp == (rec->pos01 & 0xffffu) ? 0 : (pp == (rec->pos01 >> 16) ? 1 : (pp == (rec->pos23 & 0xffffu) ? 2 : (pp == (rec->pos23 >> 16) ? 3 : -1)));
@@ -371,17 +399,18 @@ __device__ SubResult decode_sub(const uint32_t* sw, int end_rel, const DecTable*
                         rec->valid = false;
                         return r;
                     }
-                } else if (r.n < kRecStarts) {   // (a position that fails to decode is overwritten: n has not moved)
+                } else {   // (a position that fails to decode is overwritten: n has not moved)
                     const uint32_t pp = (uint32_t)p;
                     if (r.n == 0) rec->pos01 = (rec->pos01 & 0xffff0000u) | pp;
                     else if (r.n == 1) { rec->pos01 = (rec->pos01 & 0x0000ffffu) | (pp << 16); rec->pre1 = r.dsum; }
                     else if (r.n == 2) { rec->pos23 = (rec->pos23 & 0xffff0000u) | pp; rec->pre2 = r.dsum; }
-                    else { rec->pos23 = (rec->pos23 & 0x0000ffffu) | (pp << 16); rec->pre3 = r.dsum; }
+                    else if (r.n == 3) { rec->pos23 = (rec->pos23 & 0x0000ffffu) | (pp << 16); rec->pre3 = r.dsum; }
+                    else watch_end = -1;   // four starts are on record
                 }
             }
             const uint32_t a = row + ((uint32_t)(p >> 5) << 2);
             v = __funnelshift_l(lds_u32(a + 4u), lds_u32(a), (uint32_t)(p & 31));
-            lookup_sh(sh_tabs + (z == 0 ? 0u : (uint32_t)sizeof(ShTable)), v, sym, len);
+            lookup_sh(sh_tabs, z == 0, v, sym, len);
         } else {
             const int wi = p >> 5;
             v = __funnelshift_l(sw[wi + 1], sw[wi], (uint32_t)(p & 31));
@@ -581,7 +610,7 @@ __global__ void __launch_bounds__(32) dec_setup_kernel(DecImage* __restrict__ im
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kSyncThreads) dec_sync_kernel(const DecImage* __restrict__ imgs,
                                                                 const long long* __restrict__ sub_first, int n_images,
-                                                                long long total_subs, const DecTables* __restrict__ deftab,
+                                                                long long total_subs, const ShTables* __restrict__ deftab,
                                                                 const DecTables* __restrict__ tabs, uint32_t* E,
                                                                 uint32_t* __restrict__ U, int2* __restrict__ ND,
                                                                 int* __restrict__ changed, int early_stop) {
@@ -824,7 +853,7 @@ __device__ __forceinline__ void transpose8(float (&a)[8], int j) {
 template <bool kFused>
 __global__ void __launch_bounds__(kSyncThreads) dec_write_kernel(const DecImage* __restrict__ imgs,
                                                                  const long long* __restrict__ sub_first, int n_images,
-                                                                 long long total_subs, const DecTables* __restrict__ deftab,
+                                                                 long long total_subs, const ShTables* __restrict__ deftab,
                                                                  const DecTables* __restrict__ tabs,
                                                                  const uint32_t* __restrict__ E, const int2* __restrict__ NB,
                                                                  int16_t* __restrict__ coef, int* __restrict__ status,
@@ -900,7 +929,7 @@ __global__ void __launch_bounds__(kSyncThreads) dec_write_kernel(const DecImage*
             const uint32_t a = row + ((uint32_t)(p >> 5) << 2);
             const uint32_t v = __funnelshift_l(lds_u32(a + 4u), lds_u32(a), (uint32_t)(p & 31));
             int sym, len;
-            if (fixed_tabs) lookup_sh(sh_tabs + (z == 0 ? 0u : (uint32_t)sizeof(ShTable)), v, sym, len);   // warp-uniform but at image boundaries
+            if (fixed_tabs) lookup_sh(sh_tabs, z == 0, v, sym, len);   // warp-uniform but at image boundaries
             else lookup(z == 0 ? tdc : tac, v, sym, len);
             if (len < 0) {   // the same rules as decode_sub: this pass must follow the parse the entries belong to
                 err |= TIC_DSTATUS_CODE;
@@ -1417,7 +1446,7 @@ struct DecWs {
     DecImage* d_imgs = nullptr; DecImage* h_imgs = nullptr; size_t imgs_cap = 0;
     long long* d_first = nullptr; long long* h_first = nullptr;   // sub_first[n+1] then blk_first[n+1]
     DecTables* d_tabs = nullptr; double* d_mul = nullptr; float* d_mulf = nullptr;
-    DecTables* d_deftab = nullptr;
+    ShTables* d_deftab = nullptr;   // the fixed tables in the two-level form the kernels keep in shared memory
     uint32_t* d_E = nullptr; uint32_t* d_U = nullptr; int2* d_ND = nullptr; int2* d_NB = nullptr; size_t subs_cap = 0;
     int16_t* d_coef = nullptr; long long* d_list = nullptr; size_t blocks_cap = 0;   // coefficients; exact-pass work list
     int list_cap = 0;         // entries of d_list (2 x blocks_cap: spanning + flagged blocks, see list_push)
@@ -1486,14 +1515,20 @@ static int ensure_base(tic_handle h, DecWs* w) {
     TICD_CUDA(h, cudaMallocHost(&w->h_flags, 4 * sizeof(int)));
     for (auto& e : w->ev) TICD_CUDA(h, cudaEventCreate(&e));
     DecTables* def = new DecTables();
-    if (build_default_tables(*def) > 256) {   // kShNodes, see ShTable
-        delete def;
-        tic_internal_set_error(h, "the fixed Huffman tables need more than 256 trie nodes");
+    ShTables* sh = new ShTables();
+    build_default_tables(*def);
+    const bool fits = build_sh_tables(*def, *sh);
+    cudaError_t e1 = cudaSuccess;
+    if (fits) {
+        e1 = cudaMalloc(&w->d_deftab, sizeof(ShTables));
+        if (e1 == cudaSuccess) e1 = cudaMemcpy(w->d_deftab, sh, sizeof(ShTables), cudaMemcpyHostToDevice);
+    }
+    delete def;
+    delete sh;
+    if (!fits) {
+        tic_internal_set_error(h, "the fixed Huffman tables need more than 8 second-level blocks");
         return TIC_E_INVALID;
     }
-    cudaError_t e1 = cudaMalloc(&w->d_deftab, sizeof(DecTables));
-    if (e1 == cudaSuccess) e1 = cudaMemcpy(w->d_deftab, def, sizeof(DecTables), cudaMemcpyHostToDevice);
-    delete def;
     TICD_CUDA(h, e1);
     return TIC_OK;
 }
