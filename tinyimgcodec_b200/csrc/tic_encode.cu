@@ -615,6 +615,76 @@ symbol_stats_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
     if (t == 0 && sm.tc_timeout) atomicExch(&counters[kCtrTcTimeout], 1ull);
 }
 
+// The same statistics from the persistent multi-group structure of encode_tiles_kernel (tensor-core path only): G groups
+// per CTA share one TMEM allocation and one B operand, 24 warps per SM instead of the 16 that four single-group CTAs
+// give (TMEM: 4 x 128 columns).  Every GROUP takes a contiguous range of tiles and keeps one image's statistics in its
+// own staging window until the image changes.
+template <int G>
+__global__ void __launch_bounds__(kTile * G, 1)
+symbol_stats_groups_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __restrict__ descs, int n_images,
+                           int uniform_tpi, long long ntiles, unsigned long long* __restrict__ counters,
+                           uint32_t* __restrict__ g_hist, unsigned long long* __restrict__ g_first,
+                           int* __restrict__ status, const uint4* __restrict__ bmat) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int t = tid(), g = (int)threadIdx.x / kTile, lane = t & 31, warp = t >> 5;
+    TcGroup tg{};
+    uint32_t tmem_base = 0;
+    unsigned char* gbase = tc_cta_setup<G>(smem_raw, bmat, g, tg, tmem_base);
+    TileShared& sm = *reinterpret_cast<TileShared*>(gbase + (size_t)g * kGroupStride);
+    uint32_t* hist = sm.stage;                                                       // 272 counters
+    unsigned long long* first = reinterpret_cast<unsigned long long*>(sm.stage + 512); // 272 keys
+    const ExactStats st{&sm};
+    if (t == 0) { sm.stat_items = sm.stat_changed = sm.stat_unflagged = sm.tc_timeout = 0u; sm.warp_err[0] = 0; }
+    for (int i = t; i < 272; i += kTile) { hist[i] = 0; first[i] = ~0ull; }
+    const long long ngroups = (long long)gridDim.x * G, gi = (long long)blockIdx.x * G + g;
+    const long long per = (ntiles + ngroups - 1) / ngroups;
+    const long long t_lo = gi * per, t_hi = t_lo + per < ntiles ? t_lo + per : ntiles;
+    group_sync<G>(g);
+    int cur_img = -1;
+    auto flush = [&]() {   // all threads of the group; barriers inside
+        group_sync<G>(g);
+        if (cur_img >= 0) {
+            for (int i = t; i < 272; i += kTile) {
+                const uint32_t c = hist[i];
+                if (c) {
+                    atomicAdd(&g_hist[(size_t)cur_img * 272 + i], c);
+                    atomicMin(&g_first[(size_t)cur_img * 272 + i], first[i]);
+                }
+            }
+            if (t == 0 && sm.warp_err[0]) atomicOr(&status[cur_img], TIC_STATUS_TABLE);
+        }
+        group_sync<G>(g);
+        for (int i = t; i < 272; i += kTile) { hist[i] = 0; first[i] = ~0ull; }
+        if (t == 0) sm.warp_err[0] = 0;
+        group_sync<G>(g);
+    };
+    for (long long tile = t_lo; tile < t_hi; tile++) {
+        if (warp == 0) {
+            const TileInfo r = locate_tile(descs, n_images, tile, uniform_tpi);
+            if (lane == 0) sm.tinfo[0] = r;
+        }
+        group_sync<G>(g);
+        const TileInfo& ti = sm.tinfo[0];
+        if (ti.img != cur_img) {   // group-uniform
+            flush();
+            cur_img = ti.img;
+        }
+        if (ti.nb > 0) {
+            uint2 rows[8];
+            load_block_rows(ti, t, rows);
+            transform_tile_tc<G>(ti, qp, sm, tg, g, false, st, rows, load_tile_halo(ti, t), [] {});
+        }
+        int err = 0;
+        if ((t & ~31) < ti.nb) warp_block_stats(sm, t, t < ti.nb, (unsigned long long)ti.blk0, hist, first, err);   // warp-uniform
+        if (err) sm.warp_err[0] = 1;
+        group_sync<G>(g);   // the next tile's description and staging overwrite what this tile's statistics read
+    }
+    flush();
+    tc_cta_teardown<G>(tmem_base);
+    group_sync<G>(g);
+    if (t == 0 && sm.tc_timeout) atomicExch(&counters[kCtrTcTimeout], 1ull);
+}
+
 // One warp per image, everything in shared memory: HuffmanTree (huffman.py:112-194) on CPython's heapq, which
 // queue.PriorityQueue uses — leaves pushed in first-occurrence order, nodes compared by frequency
 // only, DFS with left = "0" — then write_huffman_table (codec.py:73-84) into the header words.  The heap and the
@@ -1041,6 +1111,7 @@ static int ensure_tables(tic_handle h) {
     TIC_CUDA(h, cudaMemcpyToSymbol(c_cvar_scaled_quant, sq, sizeof sq));
     TIC_CUDA(h, cudaFuncSetAttribute(coeffs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSingle));
     TIC_CUDA(h, cudaFuncSetAttribute(symbol_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemSingle));
+    if (kFdctTc) TIC_CUDA(h, cudaFuncSetAttribute(symbol_stats_groups_kernel<kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemEncode));
     int per_sm = 0, per_sm_c = 0, per_sm_single = 0;
     TIC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, encode_tiles_kernel<0, kGroups>, kTile * kGroups, kSmemEncode));
     TIC_CUDA(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, encode_tiles_kernel<2, 1>, kTile, kSmemEncodeC));
@@ -1311,8 +1382,12 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
         }
         TIC_CUDA(h, cudaMemsetAsync(h->d_hist, 0, (size_t)n_images * 272 * sizeof(uint32_t), stream));
         TIC_CUDA(h, cudaMemsetAsync(h->d_first, 0xff, (size_t)n_images * 272 * sizeof(unsigned long long), stream));
-        symbol_stats_kernel<<<(unsigned)grid_single, kTile, kSmemSingle, stream>>>(
-            qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_counters, h->d_hist, h->d_first, d_status, d_bmat);
+        if (kFdctTc && TIC_STATS_GROUPS)
+            symbol_stats_groups_kernel<kGroups><<<(unsigned)grid, kTile * kGroups, kSmemEncode, stream>>>(
+                qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_counters, h->d_hist, h->d_first, d_status, d_bmat);
+        else
+            symbol_stats_kernel<<<(unsigned)grid_single, kTile, kSmemSingle, stream>>>(
+                qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_counters, h->d_hist, h->d_first, d_status, d_bmat);
         TIC_CUDA(h, cudaGetLastError());
         build_tables_kernel<<<n_images, 32, 0, stream>>>(h->d_descs, n_images, quality, (flags & TIC_FLAG_AUTO_LE_FLAG) ? 1 : 0,
                                                          h->d_hist, h->d_first, h->d_tabs, d_status);

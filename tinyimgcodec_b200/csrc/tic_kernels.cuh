@@ -72,6 +72,9 @@ namespace tic {
                            // one PREFETCH per line).  Measured: long-scoreboard stalls 8.5 -> 6.5 %, kernel time unchanged or worse
                            // (4.62 vs 4.50 ms next to the FP32 predictor, 4.56 vs 4.58 ms without): off.
 #endif
+#ifndef TIC_STATS_GROUPS
+#define TIC_STATS_GROUPS 1 // per-image tables: symbol statistics by the persistent multi-group kernel (0: single-group CTAs)
+#endif
 #ifndef TIC_HALO_F32
 #define TIC_HALO_F32 1     // tensor-core path: the DC predictor in front of a warp from its pixel sum in FP32 (ties: exact path)
 #endif
