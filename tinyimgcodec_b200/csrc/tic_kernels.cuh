@@ -42,8 +42,11 @@ namespace tic {
 // 128-thread GROUPS per CTA of the persistent encode kernel: one CTA per SM, every group works on its own tile
 // with its own named barrier, TMEM columns and mbarrier; the B operand and the TMEM allocation are shared.
 #ifndef TIC_GROUPS
-#define TIC_GROUPS 6
+#define TIC_GROUPS 7
 #endif
+// 7 groups (28 warps per SM) need 64 TMEM columns per group (7 x 80 > 512: the 16 column-sum outputs of TIC_RATIONAL go),
+// 72 registers per thread and a group state of at most 30.1 KB (TIC_PRIV 8, TIC_WIN 1056).  Measured: 4.29 ms against
+// 4.50 ms for 6 groups with the column sums (6 groups without them: 4.60 ms).
 // (Prefetching a group's next tile was measured and dropped: held in registers it spills — with 227 KB of shared
 // memory there is no L1 to catch a spill — and through cp.async + LDS it costs more than the latency it hides:
 // 5.52 ms against 5.01 ms for plain loads at the top of the tile, profiles/r2_variants.md.)
@@ -55,14 +58,14 @@ namespace tic {
 #define TIC_CTAS 6
 #endif
 #ifndef TIC_PRIV
-#define TIC_PRIV 16
+#define TIC_PRIV 8
 #endif
 // 1: only warp 0 of a group polls the MMA's mbarrier, the other warps sleep at the group barrier
 #ifndef TIC_POLL_WARP0
 #define TIC_POLL_WARP0 0
 #endif
 #ifndef TIC_WIN
-#define TIC_WIN 1152
+#define TIC_WIN 1056
 #endif
 #ifndef TIC_QUANT_F32X2
 #define TIC_QUANT_F32X2 1  // the tensor-core quantiser rounds coefficient pairs with packed FP32 instructions

@@ -26,7 +26,8 @@ constexpr int kABytes = 128 * 64 * 2;   // A operand of one tile: 128 blocks x 6
 // operation before the last multiply acts on integers), i.e. for the four coefficients whose quotients can sit on
 // exact .5 ties: (0,0), (4,0), (0,4), (4,4).  A lane with such a tie reads them from tensor memory.
 #ifndef TIC_RATIONAL
-#define TIC_RATIONAL 1   // 1: the 16 column-sum outputs exist and ties at the four rational positions are settled from them
+#define TIC_RATIONAL 0   // 1: the 16 column-sum outputs exist and ties at the four rational positions are settled from them
+                         // (N = 80: at most 6 groups per CTA share the 512 TMEM columns; 0: N = 64, 7 groups — faster, tic_kernels.cuh)
 #endif
 constexpr int kN = TIC_RATIONAL ? 80 : 64;
 constexpr int kBBytes = kN * 128 * 2;   // B operand: 80 columns x (64 hi + 64 lo) f16
