@@ -20,7 +20,7 @@ done
 ncu -i $G/prof_${T}_encode.ncu-rep --page source --csv --print-source sass > $G/${T}_encode_sass.csv 2>/dev/null
 { python tools/ncu_src_summary.py $G/${T}_encode_sass.csv 25
   echo; echo "=== by source line / function (sources as built: gpurun_out/src_$T) ==="
-  python tools/ncu_by_line.py $G/${T}_encode_sass.csv $G/lib_$T.so encode_tiles_kernelILi0ELi6 40; } > $P/${T}_encode_tiles_source_summary.txt
+  python tools/ncu_by_line.py $G/${T}_encode_sass.csv $G/lib_$T.so encode_tiles_kernelILi0ELi7 40; } > $P/${T}_encode_tiles_source_summary.txt
 python tools/ncu_kernel_table.py $P/${T}_*_ncu_raw.csv > $P/${T}_kernel_table.md
 python tools/sass_histogram.py $G/lib_$T.so > $P/${T}_sass_histogram.txt
 ls -la $P | grep ${T}_
