@@ -593,8 +593,8 @@ def run_gpu_arm(args):
                   "phases_ms": {k: dst[k] for k in ("sync_ms", "scan_ms", "scatter_ms", "idct_ms")},
                   "sync_rounds": int(dst["sync_rounds"]), "subsequences": int(dst["subsequences"]),
                   "launches": int(dst["launches"]), "mean_abs_error_image0": mae,
-                  "what": "tic_decode_batch on the batch's own q50 streams, device-resident, CUDA events around the "
-                          "call (the host reads one flag per synchronisation round inside it)"}
+                  "what": "tic_decode_batch + tic_decode_finish on the batch's own q50 streams, device-resident, CUDA "
+                          "events around the two calls (no host synchronisation inside tic_decode_batch)"}
         if rank == 0:
             from oracle import oracle_lib as O
             host = res.to_bytes()

@@ -203,6 +203,12 @@ int64_t tic_last_guard_misses(tic_handle h);
                                        stopping where a repeat decode meets the previous one.  Same result (tests compare);
                                        for verification and profiling. */
 
+#define TIC_DFLAG_SYNC_ROUNDS 16u    /* read the "anything repaired?" flag on the host after every synchronisation round
+                                       (tic_decode_batch then blocks until the rounds have settled: the first version's
+                                       behaviour).  By default two rounds (more once a handle has needed more) are
+                                       enqueued blindly, the call returns at once, and tic_decode_finish repeats the
+                                       batch with this flag in the rare case that the last of them still repaired. */
+
 /* per-stream status bits of the decode side */
 #define TIC_DSTATUS_HEADER 1     /* shorter than 16 bytes, or height / width differ from the caller's */
 #define TIC_DSTATUS_CODE 2       /* no codeword matches (ValueError, huffman.py:72-73) or a run passes
@@ -229,15 +235,18 @@ int tic_parse_header(const uint8_t *data, int64_t nbytes, int32_t *height, int32
  *                 row-major, contiguous.
  *   d_status      device int32[n] of TIC_DSTATUS_* bits, or NULL.
  *
- * Enqueued on `stream`, but NOT fully asynchronous: the self-synchronising Huffman decode relaunches
- * until no subsequence changes its entry state, and the host reads that flag once per round (typically
- * 2-4 rounds).  Pixels are valid after tic_decode_finish().
+ * Enqueued on `stream`; asynchronous (no host synchronisation) unless TIC_DFLAG_SYNC_ROUNDS is given: the
+ * self-synchronising Huffman decode is launched a fixed number of times (two on a fresh handle) and whether the
+ * last launch still changed an entry state is reported with the batch.  Streams, pixel buffers and d_status must
+ * stay valid until tic_decode_finish(), which may decode the batch once more (then checking every round) before
+ * it returns; pixels and status are valid after it.
  */
 int tic_decode_batch(tic_handle h, const void *const *d_streams, const int64_t *sizes,
                      const int32_t *heights, const int32_t *widths, int32_t n_images, uint32_t flags,
                      void *const *d_pixels, int32_t *d_status, void *stream);
 
-/* Synchronise `stream` and report the last tic_decode_batch: TIC_OK or TIC_E_STREAM. */
+/* Synchronise `stream`, repeat the last tic_decode_batch if its blind synchronisation rounds had not settled, and
+ * report it: TIC_OK or TIC_E_STREAM. */
 int tic_decode_finish(tic_handle h, void *stream);
 
 /* Host-buffer convenience: what a ctypes binding of decompress() for one `bytes` object calls.

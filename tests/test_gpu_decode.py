@@ -259,6 +259,27 @@ def test_flat_and_periodic_streams_synchronise(tic):
     _same(tic.decompress(s), O.decompress(s), "blockalt")
 
 
+def test_blind_rounds_fall_back_when_they_do_not_settle(tic):
+    """tic_decode_batch enqueues its synchronisation rounds without looking at their outcome (asynchronous call);
+    tic_decode_finish must notice a batch whose last blind round still repaired entry states and decode it again.
+    Uniform noise needs more rounds than a fresh handle enqueues; the flag-per-round path is the reference point."""
+    import tinyimgcodec_b200 as T
+    enc = T.Encoder(0)   # a handle of its own: what the shared one has learned must not hide the fallback
+    img = make_case({"kind": "noise", "shape": (2048, 2048), "seed": 5})
+    streams = [O.compress(img, q) for q in (50, 90)] + [O.compress(synthetic_image(512, 768, 3), 50)]
+    want = [O.decompress(s) for s in streams]
+    first = enc.decompress_batch(streams)
+    rounds_first = enc.decode_stats()["sync_rounds"]
+    again = enc.decompress_batch(streams)
+    rounds_again = enc.decode_stats()["sync_rounds"]
+    plain = enc.decompress_batch(streams, sync_rounds=True)
+    for i in range(len(streams)):
+        _same(first[i], want[i], f"stream {i}, first call ({rounds_first} rounds)")
+        _same(again[i], want[i], f"stream {i}, second call ({rounds_again} rounds)")
+        _same(plain[i], want[i], f"stream {i}, flag per round")
+    assert rounds_again <= rounds_first, (rounds_first, rounds_again)   # a handle remembers what it needed
+
+
 def test_damaged_and_random_streams_never_crash(tic):
     """Bit flips, truncations and random bytes behind a valid header (with and without the per-image-table flag):
     the decoder must come back with a status, a correctly shaped image and an intact GPU — whatever the bits say."""

@@ -29,6 +29,7 @@ TIC_DFLAG_ACCEPT_BE_FLAG = 1
 TIC_DFLAG_EXACT_ONLY = 2
 TIC_DFLAG_FUSED = 4
 TIC_DFLAG_NO_EARLY_STOP = 8
+TIC_DFLAG_SYNC_ROUNDS = 16
 TIC_DSTATUS_HEADER = 1
 TIC_DSTATUS_CODE = 2
 TIC_DSTATUS_TRUNCATED = 4

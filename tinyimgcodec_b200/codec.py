@@ -382,7 +382,7 @@ class Encoder:
         return out
 
     def decode_batch_device(self, d_streams, sizes, heights, widths, pixels=None, stream=None,
-                            accept_be_flag=False, strict=True, exact_only=False, fused=False, early_stop=True):
+                            accept_be_flag=False, strict=True, exact_only=False, fused=False, early_stop=True, sync_rounds=False):
         """Decode streams resident in HBM.  `d_streams`: list of CUDA uint8 tensors (each 4-byte aligned), or
         one CUDA uint8 tensor plus `sizes` and byte offsets given as d_streams=(tensor, offsets).  Returns the
         CUDA uint8 (H, W) images (a list of views of one pixel buffer, or one (N, H, W) view when all shapes are
@@ -415,7 +415,7 @@ class Encoder:
             stream = stream or torch.cuda.current_stream(dev)
             flags = (_lib.TIC_DFLAG_ACCEPT_BE_FLAG if accept_be_flag else 0) | \
                     (_lib.TIC_DFLAG_EXACT_ONLY if exact_only else 0) | (_lib.TIC_DFLAG_FUSED if fused else 0) | \
-                    (0 if early_stop else _lib.TIC_DFLAG_NO_EARLY_STOP)
+                    (0 if early_stop else _lib.TIC_DFLAG_NO_EARLY_STOP) | (_lib.TIC_DFLAG_SYNC_ROUNDS if sync_rounds else 0)
             if n == 0:
                 return [], np.zeros(0, dtype=np.int32)
             with self._lock:
@@ -440,7 +440,8 @@ class Encoder:
                       for i in range(n)]
         return images, status
 
-    def decompress_batch(self, streams, strict=True, accept_be_flag=False, exact_only=False, fused=False, early_stop=True):
+    def decompress_batch(self, streams, strict=True, accept_be_flag=False, exact_only=False, fused=False, early_stop=True,
+                         sync_rounds=False):
         """decompress() for a list of `bytes`: one pinned H2D copy of all streams, one decode, one D2H copy of all
         pixels.  Returns a list of uint8 (H, W) arrays."""
         import torch
@@ -458,7 +459,7 @@ class Encoder:
             d_buf = h_buf.to(dev, non_blocking=True)
             imgs, _ = self.decode_batch_device((d_buf, offs[:-1]), sizes, [h[0] for h in hdrs], [h[1] for h in hdrs],
                                                strict=strict, accept_be_flag=accept_be_flag, exact_only=exact_only, fused=fused,
-                                               early_stop=early_stop)
+                                               early_stop=early_stop, sync_rounds=sync_rounds)
             return [im.cpu().numpy() for im in imgs]
 
     def decompress_batch_pinned(self, h_streams, index, heights, widths, chunk=64, nbuf=3, strict=True):
@@ -522,7 +523,7 @@ class Encoder:
                 P["s_comp"].wait_event(ev_in[c])
                 if c >= nbuf:
                     P["s_comp"].wait_event(ev_out[c - nbuf])
-                # tic_decode_batch reads one flag per synchronisation round on the host: the call returns when chunk c is
+                # decode_batch_device ends with tic_decode_finish (a stream synchronisation): the call returns when chunk c is
                 # decoded; the copies of its neighbours run meanwhile on their own streams
                 self.decode_batch_device((P["d_in"][c % nbuf], offs[lo:hi] - brange[c][0]), sizes[lo:hi], hs[lo:hi], ws[lo:hi],
                                          pixels=P["d_px"][c % nbuf], stream=P["s_comp"], strict=strict)
@@ -645,10 +646,11 @@ def decode(data, device=None):
 
 
 def decompress_batch(streams, device=None, strict=True, accept_be_flag=False, exact_only=False, fused=False,
-                     early_stop=True):
+                     early_stop=True, sync_rounds=False):
     """decompress() for a list of streams in one launch sequence."""
     return get_encoder(device).decompress_batch(streams, strict=strict, accept_be_flag=accept_be_flag,
-                                                exact_only=exact_only, fused=fused, early_stop=early_stop)
+                                                exact_only=exact_only, fused=fused, early_stop=early_stop,
+                                                sync_rounds=sync_rounds)
 
 
 def compress_c(image, qfactor="med", device=None):

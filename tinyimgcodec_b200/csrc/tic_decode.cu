@@ -1462,6 +1462,15 @@ struct DecWs {
     cudaEvent_t ev[6] = {};
     long long stats[12] = {};
     bool pending_times = false;
+    // the batch tic_decode_batch enqueued last (tic_decode_finish may have to run its rounds again, see run_batch)
+    struct {
+        bool active = false, speculative = false;
+        int n_images = 0;
+        long long subs = 0, blocks = 0;
+        uint32_t flags = 0;
+        int* status = nullptr;
+    } run;
+    int spec_rounds = 2;   // synchronisation launches enqueued without looking at their outcome; raised when a batch needed more
 };
 
 }  // namespace ticd
@@ -1598,6 +1607,96 @@ static void push_slices(std::vector<ScanSlice>& v, int img, long long nsubs) {
     }
 }
 
+// Everything of a batch that runs on the device once descriptors, E / U / ND and the status words are in place:
+// header + tables, synchronisation rounds, scan, coefficient pass, inverse transform.
+// speculative: `spec_rounds` synchronisation launches are enqueued without reading their outcome, so the call is
+// asynchronous (no host synchronisation; it could be captured in a graph); the flag of the LAST of them — did it still
+// repair an entry state? — travels to the host with the batch's summary, and tic_decode_finish runs the batch again
+// from the state it reached, this time reading the flag after every round (speculative = false), if it did.  Two
+// launches settle everything measured except uniform noise at q >= 50 (three); a handle remembers what it needed.
+static int run_batch(tic_handle h, DecWs* w, cudaStream_t stream, bool speculative) {
+    const int n_images = w->run.n_images;
+    const size_t n = (size_t)n_images;
+    const long long subs = w->run.subs, blocks = w->run.blocks;
+    const uint32_t flags = w->run.flags;
+    int* status = w->run.status;
+    const long long* d_sub_first = w->d_first;
+    const long long* d_blk_first = w->d_first + (n + 1);
+    TICD_CUDA(h, cudaEventRecord(w->ev[0], stream));
+    TICD_CUDA(h, cudaMemsetAsync(w->d_ndec, 0, n * sizeof(int), stream));   // the coefficient buffer itself needs no fill
+    long long launches = 0;
+    dec_setup_kernel<<<n_images, 32, 0, stream>>>(w->d_imgs, n_images, flags, w->d_tabs, w->d_mul, w->d_mulf, w->d_E, status,
+                                                  w->d_flags + 1);
+    launches++;
+    TICD_CUDA(h, cudaGetLastError());
+    TICD_CUDA(h, cudaEventRecord(w->ev[1], stream));
+    long long rounds = 0;
+    const bool fused = (flags & TIC_DFLAG_FUSED) != 0 && (flags & TIC_DFLAG_EXACT_ONLY) == 0;
+    if (subs) {
+        unsigned grid = (unsigned)((subs + kSyncThreads - 1) / kSyncThreads);
+        for (;;) {
+            if (speculative && rounds == w->spec_rounds - 1) TICD_CUDA(h, cudaMemsetAsync(w->d_flags, 0, sizeof(int), stream));
+            dec_sync_kernel<<<grid, kSyncThreads, 0, stream>>>(w->d_imgs, d_sub_first, n_images, subs, w->d_deftab,
+                                                               w->d_tabs, w->d_E, w->d_U, w->d_ND, w->d_flags,
+                                                               (flags & TIC_DFLAG_NO_EARLY_STOP) ? 0 : 1);
+            launches++;
+            rounds++;
+            TICD_CUDA(h, cudaGetLastError());
+            if (speculative) {
+                if (rounds >= w->spec_rounds) break;
+                continue;
+            }
+            TICD_CUDA(h, cudaMemcpyAsync(w->h_flags, w->d_flags, sizeof(int), cudaMemcpyDeviceToHost, stream));
+            TICD_CUDA(h, cudaMemsetAsync(w->d_flags, 0, sizeof(int), stream));
+            TICD_CUDA(h, cudaStreamSynchronize(stream));
+            if (!w->h_flags[0]) break;
+            if (rounds > subs + 2) {
+                tic_internal_set_error(h, "tic_decode_batch: synchronisation did not converge");
+                return TIC_E_CUDA;
+            }
+        }
+        TICD_CUDA(h, cudaEventRecord(w->ev[2], stream));
+        if (int rc = launch_scan(h, w, status, stream, launches, w->d_E, w->d_coef, fused)) return rc;
+        TICD_CUDA(h, cudaEventRecord(w->ev[3], stream));
+        if (fused)
+            dec_write_kernel<true><<<grid, kSyncThreads, 0, stream>>>(w->d_imgs, d_sub_first, n_images, subs, w->d_deftab,
+                                                                      w->d_tabs, w->d_E, w->d_NB, w->d_coef, status,
+                                                                      w->d_flags + 1, w->d_mul, w->d_mulf, w->d_list,
+                                                                      w->d_flags + 2, w->list_cap);
+        else
+            dec_write_kernel<false><<<grid, kSyncThreads, 0, stream>>>(w->d_imgs, d_sub_first, n_images, subs, w->d_deftab,
+                                                                       w->d_tabs, w->d_E, w->d_NB, w->d_coef, status,
+                                                                       w->d_flags + 1, nullptr, nullptr, nullptr, nullptr, 0);
+        launches++;
+        TICD_CUDA(h, cudaGetLastError());
+    } else {
+        TICD_CUDA(h, cudaEventRecord(w->ev[2], stream));
+        TICD_CUDA(h, cudaEventRecord(w->ev[3], stream));
+    }
+    TICD_CUDA(h, cudaEventRecord(w->ev[4], stream));
+    if (fused) {
+        // what the coefficient pass did not finish itself: unreached blocks (pixel 128), then the exact pass over the
+        // listed blocks (spanning subsequences, guard band, end of a truncated stream)
+        if (blocks) {
+            dec_fill_kernel<<<dim3((unsigned)n_images, 32), 256, 0, stream>>>(w->d_imgs, w->d_ndec);
+            const unsigned exact_grid = (unsigned)((blocks + kIdctBlocks * kIdctIters - 1) / (kIdctBlocks * kIdctIters));
+            dec_idct_kernel<<<exact_grid, kIdctBlocks * 8, 0, stream>>>(w->d_imgs, d_blk_first, n_images, blocks, w->d_coef,
+                                                                        w->d_mul, w->d_ndec, w->d_list, w->d_flags + 2,
+                                                                        w->list_cap);
+            launches += 2;
+            TICD_CUDA(h, cudaGetLastError());
+        }
+    } else if (int rc = launch_idct(h, w, d_blk_first, n_images, blocks, flags, stream, launches)) return rc;
+    TICD_CUDA(h, cudaEventRecord(w->ev[5], stream));
+    // [0] the last synchronisation launch still repaired something (speculative runs), [1] summary, [2] exact-pass blocks
+    TICD_CUDA(h, cudaMemcpyAsync(w->h_flags + (speculative && subs ? 0 : 1), w->d_flags + (speculative && subs ? 0 : 1),
+                                 (speculative && subs ? 3 : 2) * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    w->stats[0] += launches;
+    w->stats[2] += rounds;
+    w->pending_times = true;
+    return TIC_OK;
+}
+
 int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* sizes, const int32_t* heights,
                      const int32_t* widths, int32_t n_images, uint32_t flags, void* const* d_pixels,
                      int32_t* d_status, void* stream_v) {
@@ -1611,8 +1710,9 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
     DecWs* w = get_ws(h);
     memset(w->stats, 0, sizeof w->stats);
     w->pending_times = false;
+    w->run.active = false;
     if (int rc = ensure_base(h, w)) return rc;
-    w->h_flags[1] = 0; w->h_flags[2] = 0;
+    w->h_flags[0] = 0; w->h_flags[1] = 0; w->h_flags[2] = 0;
     TICD_CUDA(h, cudaMemsetAsync(w->d_flags, 0, 4 * sizeof(int), stream));
     if (n_images == 0) return TIC_OK;
     const size_t n = (size_t)n_images;
@@ -1692,82 +1792,22 @@ int tic_decode_batch(tic_handle h, const void* const* d_streams, const int64_t* 
     int* status = d_status ? d_status : w->d_status_own;
     TICD_CUDA(h, cudaMemcpyAsync(w->d_imgs, w->h_imgs, n * sizeof(DecImage), cudaMemcpyHostToDevice, stream));
     TICD_CUDA(h, cudaMemcpyAsync(w->d_first, w->h_first, 2 * (n + 1) * sizeof(long long), cudaMemcpyHostToDevice, stream));
-    const long long* d_sub_first = w->d_first;
-    const long long* d_blk_first = w->d_first + (n + 1);
     TICD_CUDA(h, cudaMemsetAsync(status, 0, n * sizeof(int), stream));
     if (subs) {
         TICD_CUDA(h, cudaMemsetAsync(w->d_E, 0, (size_t)subs * 4, stream));
         TICD_CUDA(h, cudaMemsetAsync(w->d_U, 0xff, (size_t)subs * 4, stream));
         TICD_CUDA(h, cudaMemsetAsync(w->d_ND, 0, (size_t)subs * sizeof(int2), stream));
     }
-    TICD_CUDA(h, cudaEventRecord(w->ev[0], stream));
-    TICD_CUDA(h, cudaMemsetAsync(w->d_ndec, 0, n * sizeof(int), stream));   // the coefficient buffer itself needs no fill
-    long long launches = 0;
-    dec_setup_kernel<<<n_images, 32, 0, stream>>>(w->d_imgs, n_images, flags, w->d_tabs, w->d_mul, w->d_mulf, w->d_E, status,
-                                                  w->d_flags + 1);
-    launches++;
-    TICD_CUDA(h, cudaGetLastError());
-    TICD_CUDA(h, cudaEventRecord(w->ev[1], stream));
-    long long rounds = 0;
-    const bool fused = (flags & TIC_DFLAG_FUSED) != 0 && (flags & TIC_DFLAG_EXACT_ONLY) == 0;
-    if (subs) {
-        unsigned grid = (unsigned)((subs + kSyncThreads - 1) / kSyncThreads);
-        for (;;) {
-            dec_sync_kernel<<<grid, kSyncThreads, 0, stream>>>(w->d_imgs, d_sub_first, n_images, subs, w->d_deftab,
-                                                               w->d_tabs, w->d_E, w->d_U, w->d_ND, w->d_flags,
-                                                               (flags & TIC_DFLAG_NO_EARLY_STOP) ? 0 : 1);
-            launches++;
-            rounds++;
-            TICD_CUDA(h, cudaGetLastError());
-            TICD_CUDA(h, cudaMemcpyAsync(w->h_flags, w->d_flags, sizeof(int), cudaMemcpyDeviceToHost, stream));
-            TICD_CUDA(h, cudaMemsetAsync(w->d_flags, 0, sizeof(int), stream));
-            TICD_CUDA(h, cudaStreamSynchronize(stream));
-            if (!w->h_flags[0]) break;
-            if (rounds > subs + 2) {
-                tic_internal_set_error(h, "tic_decode_batch: synchronisation did not converge");
-                return TIC_E_CUDA;
-            }
-        }
-        TICD_CUDA(h, cudaEventRecord(w->ev[2], stream));
-        if (int rc = launch_scan(h, w, status, stream, launches, w->d_E, w->d_coef, fused)) return rc;
-        TICD_CUDA(h, cudaEventRecord(w->ev[3], stream));
-        if (fused)
-            dec_write_kernel<true><<<grid, kSyncThreads, 0, stream>>>(w->d_imgs, d_sub_first, n_images, subs, w->d_deftab,
-                                                                      w->d_tabs, w->d_E, w->d_NB, w->d_coef, status,
-                                                                      w->d_flags + 1, w->d_mul, w->d_mulf, w->d_list,
-                                                                      w->d_flags + 2, w->list_cap);
-        else
-            dec_write_kernel<false><<<grid, kSyncThreads, 0, stream>>>(w->d_imgs, d_sub_first, n_images, subs, w->d_deftab,
-                                                                       w->d_tabs, w->d_E, w->d_NB, w->d_coef, status,
-                                                                       w->d_flags + 1, nullptr, nullptr, nullptr, nullptr, 0);
-        launches++;
-        TICD_CUDA(h, cudaGetLastError());
-    } else {
-        TICD_CUDA(h, cudaEventRecord(w->ev[2], stream));
-        TICD_CUDA(h, cudaEventRecord(w->ev[3], stream));
-    }
-    TICD_CUDA(h, cudaEventRecord(w->ev[4], stream));
-    if (fused) {
-        // what the coefficient pass did not finish itself: unreached blocks (pixel 128), then the exact pass over the
-        // listed blocks (spanning subsequences, guard band, end of a truncated stream)
-        if (blocks) {
-            dec_fill_kernel<<<dim3((unsigned)n_images, 32), 256, 0, stream>>>(w->d_imgs, w->d_ndec);
-            const unsigned exact_grid = (unsigned)((blocks + kIdctBlocks * kIdctIters - 1) / (kIdctBlocks * kIdctIters));
-            dec_idct_kernel<<<exact_grid, kIdctBlocks * 8, 0, stream>>>(w->d_imgs, d_blk_first, n_images, blocks, w->d_coef,
-                                                                        w->d_mul, w->d_ndec, w->d_list, w->d_flags + 2,
-                                                                        w->list_cap);
-            launches += 2;
-            TICD_CUDA(h, cudaGetLastError());
-        }
-    } else if (int rc = launch_idct(h, w, d_blk_first, n_images, blocks, flags, stream, launches)) return rc;
-    TICD_CUDA(h, cudaEventRecord(w->ev[5], stream));
-    TICD_CUDA(h, cudaMemcpyAsync(w->h_flags + 1, w->d_flags + 1, 2 * sizeof(int), cudaMemcpyDeviceToHost, stream));
-    w->stats[0] = launches;
+    w->run.active = true;
+    w->run.speculative = (flags & TIC_DFLAG_SYNC_ROUNDS) == 0;
+    w->run.n_images = n_images;
+    w->run.subs = subs;
+    w->run.blocks = blocks;
+    w->run.flags = flags;
+    w->run.status = status;
     w->stats[1] = subs;
-    w->stats[2] = rounds;
     w->stats[3] = blocks;
-    w->pending_times = true;
-    return TIC_OK;
+    return run_batch(h, w, stream, w->run.speculative);
 }
 
 int tic_decode_coeffs(tic_handle h, const int32_t* d_dc, const int32_t* d_ac, int32_t height, int32_t width,
@@ -1779,7 +1819,8 @@ int tic_decode_coeffs(tic_handle h, const int32_t* d_dc, const int32_t* d_ac, in
     if (int rc = ensure_base(h, w)) return rc;
     memset(w->stats, 0, sizeof w->stats);
     w->pending_times = false;
-    w->h_flags[1] = 0; w->h_flags[2] = 0;
+    w->run.active = false;
+    w->h_flags[0] = 0; w->h_flags[1] = 0; w->h_flags[2] = 0;
     TICD_CUDA(h, cudaMemsetAsync(w->d_flags, 0, 4 * sizeof(int), stream));
     long long nblk = (height == 0 || width == 0) ? 0 : (long long)((height + 7) / 8) * ((width + 7) / 8);
     if (nblk == 0) return TIC_OK;
@@ -1845,7 +1886,21 @@ int tic_decode_finish(tic_handle h, void* stream_v) {
     if (!h) return TIC_E_INVALID;
     DecWs* w = get_ws(h);
     TICD_CUDA(h, cudaSetDevice(tic_internal_device(h)));
-    TICD_CUDA(h, cudaStreamSynchronize(static_cast<cudaStream_t>(stream_v)));
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_v);
+    TICD_CUDA(h, cudaStreamSynchronize(stream));
+    if (w->run.active && w->run.speculative && w->run.subs && w->h_flags[0]) {
+        // The last of the synchronisation launches enqueued blindly still repaired an entry state: what followed worked on
+        // an unsettled parse.  Again from the state reached (E / U / ND are intact), this time looking at every round;
+        // status words, summary and work-list count start over (dec_setup_kernel reports the header errors again).
+        TICD_CUDA(h, cudaMemsetAsync(w->run.status, 0, (size_t)w->run.n_images * sizeof(int), stream));
+        TICD_CUDA(h, cudaMemsetAsync(w->d_flags, 0, 4 * sizeof(int), stream));
+        w->h_flags[0] = w->h_flags[1] = w->h_flags[2] = 0;
+        if (int rc = run_batch(h, w, stream, false)) { w->run.active = false; return rc; }
+        TICD_CUDA(h, cudaStreamSynchronize(stream));
+        const long long needed = w->stats[2];   // launches in all, the last one without a repair
+        if (needed > w->spec_rounds) w->spec_rounds = (int)(needed < 6 ? needed : 6);
+    }
+    w->run.active = false;
     if (w->pending_times) {
         float ms = 0.f;
         // [4] synchronisation rounds, [5] scan, [6] coefficient scatter (+ its zero fill), [7] IDCT: device ns
@@ -1903,10 +1958,14 @@ int tic_decompress_host(tic_handle h, const uint8_t* data, int64_t nbytes, uint3
     int64_t sz = nbytes;
     int rc = tic_decode_batch(h, &sp, &sz, &H, &W, 1, flags, &pp, nullptr, s);
     if (rc) return rc;
+    // finish first: it repeats the batch when its blindly enqueued synchronisation rounds did not settle, and only then
+    // are status and pixels final
+    rc = tic_decode_finish(h, s);
+    if (rc != TIC_OK && rc != TIC_E_STREAM) return rc;
     int st = 0;
     TICD_CUDA(h, cudaMemcpyAsync(&st, w->d_status_own, sizeof(int), cudaMemcpyDeviceToHost, s));
     if (npx) TICD_CUDA(h, cudaMemcpyAsync(out, w->d_px, (size_t)npx, cudaMemcpyDeviceToHost, s));
-    rc = tic_decode_finish(h, s);
+    TICD_CUDA(h, cudaStreamSynchronize(s));
     // A stream the device refuses as a whole (header mismatch, quality 0) writes no pixel: the reused workspace
     // still holds the previous decode.  The caller gets zeros, not somebody else's image.
     if (npx && (st & (TIC_DSTATUS_HEADER | TIC_DSTATUS_QUALITY))) memset(out, 0, (size_t)npx);
