@@ -564,8 +564,8 @@ symbol_stats_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
     if constexpr (kFdctTc) gbase = tc_cta_setup<1>(smem_raw, bmat, 0, tg, tmem_base);
     TileShared& sm = *reinterpret_cast<TileShared*>(gbase);
     const int t = threadIdx.x;
-    uint32_t* hist = sm.stage;                                                       // 272 counters
-    unsigned long long* first = reinterpret_cast<unsigned long long*>(sm.stage + 512); // 272 keys
+    uint32_t* hist = stats_hist(sm);                     // 272 counters
+    unsigned long long* first = stats_first(sm);         // 272 keys
     const ExactStats st{&sm};
     if (t == 0) sm.stat_items = sm.stat_changed = sm.stat_unflagged = sm.tc_timeout = 0u;
     // Every CTA takes a CONTIGUOUS range of tiles and keeps one image's statistics in shared memory until the image
@@ -631,8 +631,8 @@ symbol_stats_groups_kernel(const __grid_constant__ QuantParams qp, const ImageDe
     uint32_t tmem_base = 0;
     unsigned char* gbase = tc_cta_setup<G>(smem_raw, bmat, g, tg, tmem_base);
     TileShared& sm = *reinterpret_cast<TileShared*>(gbase + (size_t)g * kGroupStride);
-    uint32_t* hist = sm.stage;                                                       // 272 counters
-    unsigned long long* first = reinterpret_cast<unsigned long long*>(sm.stage + 512); // 272 keys
+    uint32_t* hist = stats_hist(sm);                     // 272 counters
+    unsigned long long* first = stats_first(sm);         // 272 keys
     const ExactStats st{&sm};
     if (t == 0) { sm.stat_items = sm.stat_changed = sm.stat_unflagged = sm.tc_timeout = 0u; sm.warp_err[0] = 0; }
     for (int i = t; i < 272; i += kTile) { hist[i] = 0; first[i] = ~0ull; }

@@ -58,7 +58,7 @@ namespace tic {
 #define TIC_CTAS 7   // CTAs per SM of the single-group kernels (the C-variant encoder: 72 registers, 28 warps per SM; 6: 1.49 vs 1.45 ms per 1024 images)
 #endif
 #ifndef TIC_PRIV
-#define TIC_PRIV 8
+#define TIC_PRIV 10
 #endif
 // 1: only warp 0 of a group polls the MMA's mbarrier, the other warps sleep at the group barrier
 #ifndef TIC_POLL_WARP0
@@ -99,7 +99,7 @@ constexpr int kPrivWords = TIC_PRIV;                           // private words 
 // whose stream is longer (worst case 128 x 1662 bits + a table header) is emitted in several rounds.
 constexpr int kWinWords = TIC_WIN;
 static_assert(kTile % 32 == 0 && kTile >= 64 && kTile <= 512, "a tile is 2..16 warps of blocks");
-static_assert(kWinWords % 4 == 0 && kWinWords >= 1056, "window: 16-byte copies; symbol_stats_kernel keeps 272 counters + 272 keys in it");
+static_assert(kWinWords % 4 == 0 && kWinWords >= 256, "window: 16-byte copies");
 static_assert(kPrivWords >= 2 && kPrivWords <= 52, "a block has at most 1662 bits");
 constexpr int kWarpWork = 32;                               // exact-path worklist entries per warp and round
 
@@ -383,7 +383,6 @@ struct TileShared {
     int dc_halo[kWarps];             // quantised DC of the block in front of the warp's first block
     int blocksum[kWarps];            // tensor-core path: pixel sum of the warp's last block (the next warp's predictor)
     uint32_t work[kWarps][kWarpWork];// exact-path worklist: lane << 6 | zigzag index; bit 31: halo DC
-    double colres[kWarps][4][8];
     int work_count[kWarps];
     int pending[kWarps];             // flagged coefficients that did not fit the worklist this round
     // per (run << 4 | size).  Fixed tables: ONE 32-bit word per entry, (len + size) << 27 | code << size (0: not in
@@ -401,6 +400,24 @@ struct TileShared {
     unsigned int stat_items, stat_changed, stat_unflagged, tc_timeout;   // flushed to the batch counters at the end
     alignas(16) uint32_t stage[kWinWords];   // window of the tile-relative MSB-first bit buffer (kept zeroed)
 };
+
+// Two tenants of the private-word area while no walk is using it:
+//   rows 0-1, the WARP'S OWN 32 columns   exact path: the column pass results of the warp's 4 entries in flight
+//                                         (4 x 8 doubles = 2 x 128 bytes).  A warp's exact path runs in front of its own
+//                                         walk, and no other warp touches its columns — the warps of a group are not
+//                                         synchronised between the two, so a group-wide array here would be overwritten
+//                                         by a faster warp's private words.
+//   bytes [1024, 5248)                    per-image tables: 272 symbol counters (room for 512) + 272 first-occurrence
+//                                         keys (the statistics kernels never walk)
+__device__ __forceinline__ double* exact_colres(TileShared& sm, int warp, int grp) {
+    return reinterpret_cast<double*>(&sm.priv[grp >> 1][32 * warp + (grp & 1) * 16]);
+}
+__device__ __forceinline__ uint32_t* stats_hist(TileShared& sm) { return &sm.priv[0][0] + 256; }
+__device__ __forceinline__ unsigned long long* stats_first(TileShared& sm) {
+    return reinterpret_cast<unsigned long long*>(&sm.priv[0][0] + 256 + 512);
+}
+static_assert((kPrivWords + 1) * kTile * 4 >= 1024 + (512 + 2 * 272) * 4 && kTile * 4 * 2 == 1024,
+              "the private-word area also holds the exact path's column results and the statistics bins");
 
 // Tile number lt of image `img`.
 __device__ __forceinline__ TileInfo tile_info(const ImageDesc& d, int img, long long lt) {
@@ -764,11 +781,11 @@ __device__ __forceinline__ void exact_round(const TileInfo& ti, const QuantParam
                 x4 = load_px_exact(ti, y0 + 4, x); x5 = load_px_exact(ti, y0 + 5, x);
                 x6 = load_px_exact(ti, y0 + 6, x); x7 = load_px_exact(ti, y0 + 7, x);
             }
-            sm.colres[warp][grp][c] = dct8_exact(x0, x1, x2, x3, x4, x5, x6, x7, u);
+            exact_colres(sm, warp, grp)[c] = dct8_exact(x0, x1, x2, x3, x4, x5, x6, x7, u);
         }
         __syncwarp();
         if (act && c == 0) {
-            const double* cr = sm.colres[warp][grp];
+            const double* cr = exact_colres(sm, warp, grp);
             double y = dct8_exact(cr[0], cr[1], cr[2], cr[3], cr[4], cr[5], cr[6], cr[7], v);
             int q = __double2int_rn(__ddiv_rn(y, qp.qt[r]));   // np.round(coeffs / qt), utils.py:53
             if (halo) {
