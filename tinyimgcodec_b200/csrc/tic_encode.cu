@@ -14,6 +14,16 @@
 
 namespace tic {
 
+// The second walk of a block longer than the private words, out of line (TIC_SLOW_WALK_CALL): the loop is a tenth of the
+// kernel's code and runs for one block in thousands on ordinary content.
+template <bool kAuto>
+__device__ __noinline__ void walk_block_to_stage(TileShared* sm, uint32_t sbase, int t, int diff, int w0, int sh) {
+    BitSink<true> s;
+    s.stage = sm->stage; s.w0 = w0; s.sh = sh;
+    int e2 = 0;
+    walk_block<kAuto, true>(*sm, sbase, t, diff, s, e2);
+}
+
 // Huffman tables -> shared memory in the form the walk wants (see TileShared::ac_tab).  All threads of a group call.
 template <bool kAuto>
 __device__ __forceinline__ void load_tables(TileShared& sm, const HuffTables& g) {
@@ -254,10 +264,14 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
                         }
                     }
                 } else {   // long block: walk again, straight into the window
+#if TIC_SLOW_WALK_CALL
+                    walk_block_to_stage<kAuto>(&sm, sbase, t, diff, w0, sh);
+#else
                     BitSink<true> s;
                     s.stage = sm.stage; s.w0 = w0; s.sh = sh;
                     int e2 = 0;
                     walk_block<kAuto, true>(sm, sbase, t, diff, s, e2);
+#endif
                 }
             }
             group_sync<G>(g);   // B2: window complete, arena offset visible

@@ -71,7 +71,11 @@ __device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity)
 #ifndef TIC_POLL_SLEEP_NS
 #define TIC_POLL_SLEEP_NS 0   // > 0: sleep between two polls of the MMA's mbarrier (fewer issue slots spent polling)
 #endif
+#ifndef TIC_POLL_FIRST_SLEEP_NS
+#define TIC_POLL_FIRST_SLEEP_NS 0   // > 0: one sleep in front of the first poll (the MMAs of a tile take that long anyway)
+#endif
 __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
+    if (TIC_POLL_FIRST_SLEEP_NS > 0) __nanosleep(TIC_POLL_FIRST_SLEEP_NS);
 #pragma unroll 1
     for (int i = 0; i < (1 << 16); i++) {
         if (mbar_try_wait(bar, parity)) return true;
