@@ -462,11 +462,20 @@ def run_gpu_arm(args):
     if rank == 0:
         try:
             from oracle import oracle_lib as O
+            # every 16th image of the rank's batch (all of them with --parity-all) against the C restatement of the
+            # reference path, on all host threads (the library call releases the GIL)
+            import torch
+            from concurrent.futures import ThreadPoolExecutor
             streams = res.to_bytes()
-            for i in sorted({0, 1, n_local // 2, n_local - 1}):
-                px = d_images[i].cpu().numpy()
-                parity["checked"] += 1
-                parity["identical"] += int(streams[i] == O.compress(px, QUALITY))
+            step = 1 if args.parity_all else max(1, n_local // 256)
+            picks = sorted(set(range(0, n_local, step)) | {0, 1, n_local // 2, n_local - 1})
+            with ThreadPoolExecutor(max(1, len(os.sched_getaffinity(0)))) as ex:
+                for lo in range(0, len(picks), 256):   # 256 MB of pixels at a time
+                    part = picks[lo:lo + 256]
+                    px = d_images[torch.tensor(part, device=d_images.device)].cpu().numpy()
+                    same = list(ex.map(lambda j: streams[part[j]] == O.compress(px[j], QUALITY), range(len(part))))
+                    parity["checked"] += len(part)
+                    parity["identical"] += int(sum(same))
             del streams
         except Exception as ex:
             parity["error"] = f"{type(ex).__name__}: {ex}"
@@ -657,6 +666,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--images", type=int, default=TOTAL_IMAGES, help="total images in the batch (default 4096)")
+    ap.add_argument("--parity-all", action="store_true", help="compare EVERY stream of the batch with the oracle (default: every 16th)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host end-to-end leg (profiling runs)")
     ap.add_argument("--no-decode", action="store_true", help="skip the decode-side leg")
