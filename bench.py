@@ -467,8 +467,8 @@ def run_gpu_arm(args):
             import torch
             from concurrent.futures import ThreadPoolExecutor
             streams = res.to_bytes()
-            step = 1 if args.parity_all else max(1, n_local // 256)
-            picks = sorted(set(range(0, n_local, step)) | {0, 1, n_local // 2, n_local - 1})
+            stride = 1 if args.parity_all else max(1, n_local // 256)
+            picks = sorted(set(range(0, n_local, stride)) | {0, 1, n_local // 2, n_local - 1})
             with ThreadPoolExecutor(max(1, len(os.sched_getaffinity(0)))) as ex:
                 for lo in range(0, len(picks), 256):   # 256 MB of pixels at a time
                     part = picks[lo:lo + 256]

@@ -55,7 +55,10 @@ namespace ticd {
 constexpr int kSubBits = TICD_SUB_BITS;   // bits per subsequence (one thread each)
 constexpr int kMaxNodes = 1024;     // trie nodes per table (a Huffman tree over <= 256 symbols has <= 255)
 constexpr int kMaxSymbols = 4096;   // symbols decoded per subsequence at most (zero-length codes)
-constexpr int kSyncThreads = 128;
+#ifndef TICD_SYNC_THREADS
+#define TICD_SYNC_THREADS 128
+#endif
+constexpr int kSyncThreads = TICD_SYNC_THREADS;   // subsequences (= threads) per CTA of the symbol passes
 constexpr int kSyncIters = 64;      // in-CTA repair rounds per launch
 constexpr uint32_t kLeaf = 0x8000u;
 constexpr int kMulfStride = 128;    // FP32 multipliers per image: [u*8+v] then the transposed copy [v*8+u]
