@@ -43,31 +43,113 @@ TOTAL_IMAGES = 4096
 
 
 # ---------------------------------------------------------------------------------------------------
-# synthetic data: the BASELINE.md §4 generator (coarse random grid, integer bilinear x32, +-10 noise),
-# evaluated on the GPU with torch's generator (seed = global image index // chunk) so that 4 GiB of
-# distinct pixels never cross PCIe.  Integer-only, deterministic for a given torch build.
+# synthetic data: the BASELINE.md §4 generator, seed = global image index, bit for bit what
+# tests/cases.py::synthetic_image(1024, 1024, seed) returns.  The two `rng.integers` draws of an image (coarse
+# grid, +-10 noise) are made with numpy on the host — worker processes forked before CUDA is touched, results in
+# shared memory — and the integer bilinear x32 upsample, the sum and the clip run on the GPU
+# (tests/test_host_bench.py::test_bench_generator_is_the_numpy_generator compares the two on the CPU).
+# `--generator torch` keeps round 1's variant: same construction, torch's RNG on the device, no host work.
 # ---------------------------------------------------------------------------------------------------
-def synth_images_device(first, count, device, h=IMG_H, w=IMG_W, chunk=128):
+def synth_draws(seed, h=IMG_H, w=IMG_W):
+    """The random draws of BASELINE.md §4 for one image: (grid uint8 [h/32+2, w/32+2], noise int8 [h, w])."""
+    rng = np.random.default_rng(seed)
+    g = rng.integers(0, 256, (h // 32 + 2, w // 32 + 2))
+    noise = rng.integers(-10, 11, (h, w))
+    return g.astype(np.uint8), noise.astype(np.int8)
+
+
+def synth_assemble(g, noise, device):
+    """Images [n, h, w] uint8 from the draws of n images (torch tensors or arrays: g [n, gh, gw], noise [n, h, w])."""
     import torch
-    out = torch.empty((count, h, w), dtype=torch.uint8, device=device)
+    g = torch.as_tensor(g).to(device=device, dtype=torch.int32)
+    noise = torch.as_tensor(noise).to(device=device, dtype=torch.int32)
+    n, h, w = noise.shape
     ys = torch.arange(h, device=device)
     xs = torch.arange(w, device=device)
     gy, fy = ys // 32, (ys % 32).view(1, h, 1).to(torch.int32)
     gx, fx = xs // 32, (xs % 32).view(1, 1, w).to(torch.int32)
+    a = g[:, gy][:, :, gx]
+    b = g[:, gy][:, :, gx + 1]
+    c = g[:, gy + 1][:, :, gx]
+    d = g[:, gy + 1][:, :, gx + 1]
+    base = ((a * (32 - fx) + b * fx) * (32 - fy) + (c * (32 - fx) + d * fx) * fy) // 1024
+    return (base + noise).clamp_(0, 255).to(torch.uint8)
+
+
+def _draw_worker(G, N, first, lo, hi):
+    for i in range(lo, hi):
+        G[i], N[i] = synth_draws(first + i, N.shape[1], N.shape[2])
+
+
+class HostDraws:
+    """The draws of images first .. first+count-1 in an anonymous shared mapping (not /dev/shm: a container's mount
+    may be 64 MB), filled by forked workers.  Create it BEFORE the process initialises CUDA; .arrays(), .close()."""
+
+    def __init__(self, first, count, h=IMG_H, w=IMG_W, workers=None):
+        import mmap
+        import multiprocessing as mp
+        self.count = count
+        gh, gw = h // 32 + 2, w // 32 + 2
+        self.shape_g, self.shape_n = (count, gh, gw), (count, h, w)
+        self.mg = mmap.mmap(-1, max(1, count * gh * gw))
+        self.mn = mmap.mmap(-1, max(1, count * h * w))
+        G, N = self.arrays()
+        workers = max(1, min(workers or len(os.sched_getaffinity(0)), 64, count))
+        t0 = time.perf_counter()
+        try:
+            ctx = mp.get_context("fork")
+            procs = []
+            for k in range(workers):
+                p = ctx.Process(target=_draw_worker, args=(G, N, first, k * count // workers, (k + 1) * count // workers))
+                p.start()
+                procs.append(p)
+            for p in procs:
+                p.join()
+            if any(p.exitcode != 0 for p in procs):
+                raise RuntimeError("a generator worker failed")
+            self.how = f"{workers} forked workers"
+        except Exception as ex:   # no fork here: the same draws in this process (about 7 ms per image)
+            _draw_worker(G, N, first, 0, count)
+            self.how = f"in-process ({type(ex).__name__})"
+        del G, N
+        self.seconds = time.perf_counter() - t0
+
+    def arrays(self):
+        return (np.ndarray(self.shape_g, dtype=np.uint8, buffer=self.mg),
+                np.ndarray(self.shape_n, dtype=np.int8, buffer=self.mn))
+
+    def close(self):
+        for m in (self.mg, self.mn):
+            try:
+                m.close()
+            except Exception:
+                pass
+
+
+def synth_images_numpy(draws, device, chunk=128):
+    """draws: HostDraws -> [count, h, w] uint8 on `device`, identical to tests/cases.py::synthetic_image per seed."""
+    import torch
+    G, N = draws.arrays()
+    out = torch.empty(draws.shape_n, dtype=torch.uint8, device=device)
+    for lo in range(0, draws.count, chunk):
+        hi = min(draws.count, lo + chunk)
+        out[lo:hi] = synth_assemble(torch.from_numpy(G[lo:hi]), torch.from_numpy(N[lo:hi]), device)
+    del G, N
+    return out
+
+
+def synth_images_device(first, count, device, h=IMG_H, w=IMG_W, chunk=128):
+    """`--generator torch`: the same construction with torch's generator on the device (seed per chunk of 128)."""
+    import torch
+    out = torch.empty((count, h, w), dtype=torch.uint8, device=device)
     for lo in range(0, count, chunk):
         n = min(chunk, count - lo)
         gen = torch.Generator(device=device)
         gen.manual_seed(1_000_003 * (first + lo) + 17)
         g = torch.randint(0, 256, (n, h // 32 + 2, w // 32 + 2), generator=gen, device=device, dtype=torch.int32)
-        a = g[:, gy][:, :, gx]
-        b = g[:, gy][:, :, gx + 1]
-        c = g[:, gy + 1][:, :, gx]
-        d = g[:, gy + 1][:, :, gx + 1]
-        base = ((a * (32 - fx) + b * fx) * (32 - fy) + (c * (32 - fx) + d * fx) * fy) // 1024
-        del a, b, c, d
         noise = torch.randint(-10, 11, (n, h, w), generator=gen, device=device, dtype=torch.int32)
-        out[lo:lo + n] = (base + noise).clamp_(0, 255).to(torch.uint8)
-        del base, noise
+        out[lo:lo + n] = synth_assemble(g, noise, device)
+        del g, noise
     return out
 
 
@@ -293,6 +375,12 @@ def ncu_traffic(workload_key):
 
 
 def run_gpu_arm(args):
+    # the numpy draws of this rank's images first: the workers are forked, so before anything initialises CUDA
+    draws = None
+    if args.generator == "numpy":
+        _w, _r = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+        _lo, _hi = _r * args.images // _w, (_r + 1) * args.images // _w
+        draws = HostDraws(_lo, _hi - _lo, workers=max(1, len(os.sched_getaffinity(0)) // _w))
     import torch
     import torch.distributed as dist
     import tinyimgcodec_b200 as tic
@@ -326,7 +414,14 @@ def run_gpu_arm(args):
     n_local = hi - lo
 
     enc = tic.get_encoder(local_rank)
-    d_images = synth_images_device(lo, n_local, dev)
+    if draws is not None:
+        d_images = synth_images_numpy(draws, dev)
+        generator = (f"BASELINE.md §4 numpy generator, seed = image index (draws by numpy on the host, {draws.how}, "
+                     f"{draws.seconds:.1f} s; integer upsample + clip on the device)")
+        draws.close()
+    else:
+        d_images = synth_images_device(lo, n_local, dev)
+        generator = "BASELINE.md §4 synthetic generator evaluated on-device (torch RNG)"
     torch.cuda.synchronize()
     out_cap = int(n_local * IMG_H * IMG_W * 0.5) + (1 << 20)
     d_out = torch.empty(out_cap, dtype=torch.uint8, device=dev)
@@ -645,7 +740,7 @@ def run_gpu_arm(args):
             "config": {"workload": f"{total} synthetic {IMG_H}x{IMG_W} grayscale images, quality {QUALITY}, "
                                    f"default Huffman tables, sharded by image over {n_gpus} GPU(s)",
                        "images_per_gpu": n_local, "l2": "inputs larger than L2 (per-GPU pixel bytes >> 126 MB)",
-                       "generator": "BASELINE.md §4 synthetic generator evaluated on-device (torch RNG)",
+                       "generator": generator,
                        "stream_bytes": stream_bytes_total, "bits_per_pixel": 8.0 * stream_bytes_total / total_px,
                        "exact_path": {k: stats[k] for k in ("exact_items", "exact_changed", "blocks", "tiles")}},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(stats["launches"]) * args.steps * n_gpus, "roofline": roofline,
@@ -667,6 +762,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--images", type=int, default=TOTAL_IMAGES, help="total images in the batch (default 4096)")
     ap.add_argument("--parity-all", action="store_true", help="compare EVERY stream of the batch with the oracle (default: every 16th)")
+    ap.add_argument("--generator", default="numpy", choices=["numpy", "torch"],
+                    help="numpy: BASELINE.md §4 generator with seed = image index (default); torch: the same construction with the device RNG")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host end-to-end leg (profiling runs)")
     ap.add_argument("--no-decode", action="store_true", help="skip the decode-side leg")
@@ -680,7 +777,8 @@ def main():
                "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__),
                "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup),
                "--images", str(args.images)] + (["--no-cpu"] if args.no_cpu else []) + (["--no-e2e"] if args.no_e2e else []) + \
-              (["--no-decode"] if args.no_decode else [])
+              (["--no-decode"] if args.no_decode else []) + ["--generator", args.generator] + \
+              (["--parity-all"] if args.parity_all else [])
         return subprocess.call(cmd)
     return run_gpu_arm(args)
 

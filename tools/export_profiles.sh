@@ -11,7 +11,7 @@ cp $G/configs_$T.jsonl $P/${T}_other_configs.jsonl
 cp $G/dec_plain_$T.json $P/${T}_decode_1024_images.json
 cp $G/auto_plain_$T.json $P/${T}_auto_cvariant_1024_images.json
 declare -A NAME=( [encode]=encode [compact]=compact [encode_auto]=encode_auto [encode_cvar]=encode_cvar
-  [symbol_stats_kernel]=symbol_stats_kernel [build_tables_kernel]=build_tables_kernel [coeffs_kernel]=coeffs_kernel
+  [symbol_stats]=symbol_stats_kernel [build_tables_kernel]=build_tables_kernel [coeffs_kernel]=coeffs_kernel
   [scan_chunks_kernel]=scan_chunks_kernel [scan_apply_kernel]=scan_apply_kernel )
 for k in "${!NAME[@]}"; do
   f=$G/prof_${T}_$k.ncu-rep

@@ -26,7 +26,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:comp
 echo "full capture (compact) rc=$?"
 APROF="python tools/auto_bench.py --images 1024 --steps 1"
 $APROF > gpurun_out/auto_plain_${TAG}.json 2> gpurun_out/auto_plain_${TAG}.err; echo "auto plain rc=$?"; cut -c1-600 gpurun_out/auto_plain_${TAG}.json
-for K in symbol_stats_kernel build_tables_kernel coeffs_kernel scan_chunks_kernel scan_apply_kernel; do
+for K in symbol_stats build_tables_kernel coeffs_kernel scan_chunks_kernel scan_apply_kernel; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -s 0 -c 1 \
       -o gpurun_out/prof_${TAG}_$K -f $APROF > gpurun_out/auto_ncu_${TAG}_$K.log 2>&1
   echo "full capture $K rc=$?"
