@@ -17,17 +17,17 @@ namespace tic {
 // The second walk of a block longer than the private words, out of line (TIC_SLOW_WALK_CALL): the loop is a tenth of the
 // kernel's code and runs for one block in thousands on ordinary content.
 template <bool kAuto>
-__device__ __noinline__ void walk_block_to_stage(TileShared* sm, uint32_t sbase, int t, int diff, int w0, int sh) {
+__device__ __noinline__ void walk_block_to_stage(TileShared* sm, uint32_t sbase, uint32_t tabbase, int t, int diff, int w0, int sh) {
     BitSink<true> s;
     s.stage = sm->stage; s.w0 = w0; s.sh = sh;
     int e2 = 0;
-    walk_block<kAuto, true>(*sm, sbase, t, diff, s, e2);
+    walk_block<kAuto, true>(*sm, sbase, tabbase, t, diff, s, e2);
 }
 
-// Huffman tables -> shared memory in the form the walk wants (see TileShared::ac_tab).  All threads of a group call.
+// Huffman tables -> shared memory in the form the walk wants (see TabShared).  All threads of ONE group call.
 template <bool kAuto>
-__device__ __forceinline__ void load_tables(TileShared& sm, const HuffTables& g) {
-    uint32_t* ac32 = reinterpret_cast<uint32_t*>(sm.ac_tab);   // fixed tables: 32-bit entries (TileShared::ac_tab)
+__device__ __forceinline__ void load_tables(TabShared& sm, const HuffTables& g) {
+    uint32_t* ac32 = reinterpret_cast<uint32_t*>(sm.ac_tab);   // fixed tables: 32-bit entries (TabShared)
     uint32_t* dc32 = reinterpret_cast<uint32_t*>(sm.dc_tab);
     for (int i = tid(); i < 256; i += kTile) {
         const uint32_t len = g.ac[i].len, code = g.ac[i].code;
@@ -43,18 +43,25 @@ __device__ __forceinline__ void load_tables(TileShared& sm, const HuffTables& g)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Shared memory of a CTA: [B operand | mbarriers + TMEM base] (tensor-core kernels only), then one TileShared
-// per group.  tc_cta_setup: B -> shared memory, one mbarrier per group, one TMEM allocation per CTA.
+// Shared memory of a CTA: [B operand | mbarriers + TMEM base] (tensor-core kernels only), then either one TileShared
+// per group, each with its own tables behind it (per-image tables, C variant, single-group kernels), or — kShareTab —
+// ONE TabShared for the CTA and the groups packed without theirs (fixed tables; the statistics kernel, which needs
+// none, keeps the same layout).  tc_cta_setup: B -> shared memory, one mbarrier per group, one TMEM allocation per CTA.
 // ---------------------------------------------------------------------------------------------
 constexpr size_t kTcCtlBytes = 128;   // G mbarriers (8 bytes each, G <= 8) + the TMEM base address at byte 64
 constexpr size_t kGroupStride = (sizeof(TileShared) + 127) & ~(size_t)127;
-template <int G, bool kTc>
-constexpr size_t cta_smem_bytes() { return (kTc ? (size_t)tc::kBBytes + kTcCtlBytes : 0) + (size_t)G * kGroupStride; }
+constexpr size_t kGroupStrideNoTab = (offsetof(TileShared, tab) + 127) & ~(size_t)127;
+constexpr size_t kTabBytes = (sizeof(TabShared) + 127) & ~(size_t)127;
+template <int G, bool kTc, bool kShareTab = false>
+constexpr size_t cta_smem_bytes() {
+    return (kTc ? (size_t)tc::kBBytes + kTcCtlBytes : 0) + (kShareTab ? kTabBytes + (size_t)G * kGroupStrideNoTab : (size_t)G * kGroupStride);
+}
 template <int G>
 struct TmemCols {   // TMEM allocations are powers of two >= 32 columns
     static constexpr uint32_t value = G * tc::kColsPerGroup <= 64 ? 64u : (G * tc::kColsPerGroup <= 128 ? 128u : (G * tc::kColsPerGroup <= 256 ? 256u : 512u));
 };
 static_assert(kGroups >= 1 && kGroups <= 8 && kGroups * tc::kColsPerGroup <= 512, "TMEM has 512 columns");
+static_assert(kGroupsAuto >= 1 && kGroupsAuto <= 8 && kGroupsAuto * tc::kColsPerGroup <= 512, "TMEM has 512 columns");
 
 template <int G>
 __device__ __forceinline__ unsigned char* tc_cta_setup(unsigned char* smem_raw, const uint4* __restrict__ bmat, int g,
@@ -100,18 +107,24 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
                     const uint4* __restrict__ bmat, uint32_t flags) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr bool kAuto = kMode == 1, kCVar = kMode == 2, kTc = kFdctTc && !kCVar;
+    constexpr bool kShareTab = kTc && !kAuto;   // fixed tables: one copy per CTA in front of the groups
     const int t = tid(), g = (int)threadIdx.x / kTile;
     const int lane = t & 31, warp = t >> 5;
     unsigned char* gbase = smem_raw;
     TcGroup tg{};
     uint32_t tmem_base = 0;
     if constexpr (kTc) gbase = tc_cta_setup<G>(smem_raw, bmat, g, tg, tmem_base);
-    TileShared& sm = *reinterpret_cast<TileShared*>(gbase + (size_t)g * kGroupStride);
+    TileShared& sm = *reinterpret_cast<TileShared*>(gbase + (kShareTab ? kTabBytes + (size_t)g * kGroupStrideNoTab : (size_t)g * kGroupStride));
+    TabShared& tabs = kShareTab ? *reinterpret_cast<TabShared*>(gbase) : sm.tab;
     uint32_t sbase = smem_u32(&sm);   // kept in a register: the walk addresses shared memory directly
     asm volatile("mov.u32 %0, %0;" : "+r"(sbase));
+    const uint32_t tabbase = kShareTab ? smem_u32(gbase) : sbase + (uint32_t)offsetof(TileShared, tab);
     const bool debug_all = (flags & TIC_FLAG_DEBUG_ALL_EXACT) != 0;
 
-    if constexpr (!kAuto) load_tables<false>(sm, c_default_tables);   // constants.py:53-242
+    if constexpr (!kAuto) {   // constants.py:53-242
+        if (!kShareTab || g == 0) load_tables<false>(tabs, c_default_tables);
+        if constexpr (kShareTab && G > 1) __syncthreads();   // group 0's copy serves every group
+    }
     for (int i = t; i < kWinWords; i += kTile) sm.stage[i] = 0;
     group_sync<G>(g);
 
@@ -161,7 +174,7 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
         if constexpr (kAuto) {
             if (tab_img != ti.img) {   // per-image tables (codec.py:146-148); group-uniform branch
                 group_sync<G>(g);      // everyone is done with the previous image's tables
-                load_tables<true>(sm, auto_tabs[ti.img].tab);
+                load_tables<true>(tabs, auto_tabs[ti.img].tab);
                 tab_img = ti.img;
                 group_sync<G>(g);
             }
@@ -186,7 +199,7 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
             BitSink<false> s;
             s.ptr = sbase + (uint32_t)offsetof(TileShared, priv) + (uint32_t)tw * 4u;
             s.ptr_end = s.ptr + (uint32_t)kPrivWords * kTile * 4u;
-            bits = walk_block<kAuto, false>(sm, sbase, tw, diff, s, err);
+            bits = walk_block<kAuto, false>(sm, sbase, tabbase, tw, diff, s, err);
             nwords = (bits + 31) >> 5;
         }
         int incl = bits;
@@ -265,12 +278,12 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
                     }
                 } else {   // long block: walk again, straight into the window
 #if TIC_SLOW_WALK_CALL
-                    walk_block_to_stage<kAuto>(&sm, sbase, t, diff, w0, sh);
+                    walk_block_to_stage<kAuto>(&sm, sbase, tabbase, t, diff, w0, sh);
 #else
                     BitSink<true> s;
                     s.stage = sm.stage; s.w0 = w0; s.sh = sh;
                     int e2 = 0;
-                    walk_block<kAuto, true>(sm, sbase, t, diff, s, e2);
+                    walk_block<kAuto, true>(sm, sbase, tabbase, t, diff, s, e2);
 #endif
                 }
             }
@@ -644,7 +657,7 @@ symbol_stats_groups_kernel(const __grid_constant__ QuantParams qp, const ImageDe
     TcGroup tg{};
     uint32_t tmem_base = 0;
     unsigned char* gbase = tc_cta_setup<G>(smem_raw, bmat, g, tg, tmem_base);
-    TileShared& sm = *reinterpret_cast<TileShared*>(gbase + (size_t)g * kGroupStride);
+    TileShared& sm = *reinterpret_cast<TileShared*>(gbase + kTabBytes + (size_t)g * kGroupStrideNoTab);   // encode_tiles_kernel<0>'s layout
     uint32_t* hist = stats_hist(sm);                     // 272 counters
     unsigned long long* first = stats_first(sm);         // 272 keys
     const ExactStats st{&sm};
@@ -1106,11 +1119,13 @@ static void build_bmat(const QuantParams& qp, __half* blob /* tc::kN x 128, zero
         }
 }
 
-constexpr size_t kSmemEncode = cta_smem_bytes<kGroups, kFdctTc>();       // persistent encode kernel, modes 0 and 1
+constexpr size_t kSmemEncode = cta_smem_bytes<kGroups, kFdctTc, kFdctTc>();   // persistent encode kernel, fixed tables; statistics
+constexpr size_t kSmemEncodeAuto = cta_smem_bytes<kGroupsAuto, kFdctTc>();    // persistent encode kernel, per-image tables
 constexpr size_t kSmemEncodeC = cta_smem_bytes<1, false>();               // C variant: CUDA-core integer transform
 constexpr size_t kSmemSingle = cta_smem_bytes<1, kFdctTc>();              // symbol_stats_kernel, coeffs_kernel
 #ifndef TIC_SKIP_SMEM_ASSERT
 static_assert(kSmemEncode <= 232448, "shared memory of the persistent encode kernel exceeds 227 KB: lower TIC_GROUPS");
+static_assert(kSmemEncodeAuto <= 232448, "shared memory of the persistent encode kernel exceeds 227 KB: lower TIC_GROUPS_AUTO");
 #endif
 
 static int ensure_tables(tic_handle h) {
@@ -1119,7 +1134,7 @@ static int ensure_tables(tic_handle h) {
     build_default_tables(t);
     TIC_CUDA(h, cudaMemcpyToSymbol(c_default_tables, &t, sizeof t));
     TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel<0, kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemEncode));
-    TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel<1, kGroups>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemEncode));
+    TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel<1, kGroupsAuto>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemEncodeAuto));
     TIC_CUDA(h, cudaFuncSetAttribute(encode_tiles_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemEncodeC));
     uint16_t sq[4][64];   // c/img.c:157-181
     for (int f = 0; f < 4; f++)
@@ -1378,7 +1393,9 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
     }
     // persistent kernel: one CTA of kGroups groups per SM; every group takes tiles round-robin
     long long grid = (long long)h->sm_count * h->ctas_per_sm;
+    long long grid_auto = grid;
     if (grid > (ntiles + kGroups - 1) / kGroups) grid = (ntiles + kGroups - 1) / kGroups;
+    if (grid_auto > (ntiles + kGroupsAuto - 1) / kGroupsAuto) grid_auto = (ntiles + kGroupsAuto - 1) / kGroupsAuto;
     long long grid_c = (long long)h->sm_count * h->ctas_per_sm_c;
     if (grid_c > ntiles) grid_c = ntiles;
     long long grid_single = (long long)h->sm_count * h->ctas_per_sm_single;
@@ -1411,7 +1428,7 @@ int tic_encode_batch(tic_handle h, const void* const* d_pixels, const int32_t* h
         d_tabs = h->d_tabs;
         h->last_launches = 8;
         TIC_CUDA(h, cudaEventRecord(evq[0], stream));
-        encode_tiles_kernel<1, kGroups><<<(unsigned)grid, kTile * kGroups, kSmemEncode, stream>>>(
+        encode_tiles_kernel<1, kGroupsAuto><<<(unsigned)grid_auto, kTile * kGroupsAuto, kSmemEncodeAuto, stream>>>(
             qp, h->d_descs, n_images, uniform_tpi, ntiles, h->d_recs, h->d_arena, (unsigned long long)h->arena_cap16,
             h->d_counters, d_status, quality, d_tabs, d_bmat, kflags);
     } else if (c_variant) {

@@ -42,7 +42,10 @@ namespace tic {
 // 128-thread GROUPS per CTA of the persistent encode kernel: one CTA per SM, every group works on its own tile
 // with its own named barrier, TMEM columns and mbarrier; the B operand and the TMEM allocation are shared.
 #ifndef TIC_GROUPS
-#define TIC_GROUPS 7
+#define TIC_GROUPS 8
+#endif
+#ifndef TIC_GROUPS_AUTO
+#define TIC_GROUPS_AUTO 7   // per-image tables: every group keeps its own image's tables (TabShared) in shared memory
 #endif
 // 7 groups (28 warps per SM) need 64 TMEM columns per group (7 x 80 > 512: the 16 column-sum outputs of TIC_RATIONAL go),
 // 72 registers per thread and a group state of at most 30.1 KB (TIC_PRIV 8, TIC_WIN 1056).  Measured: 4.29 ms against
@@ -58,14 +61,14 @@ namespace tic {
 #define TIC_CTAS 7   // CTAs per SM of the single-group kernels (the C-variant encoder: 72 registers, 28 warps per SM; 6: 1.49 vs 1.45 ms per 1024 images)
 #endif
 #ifndef TIC_PRIV
-#define TIC_PRIV 10
+#define TIC_PRIV 8
 #endif
 // 1: only warp 0 of a group polls the MMA's mbarrier, the other warps sleep at the group barrier
 #ifndef TIC_POLL_WARP0
 #define TIC_POLL_WARP0 0
 #endif
 #ifndef TIC_WIN
-#define TIC_WIN 1056
+#define TIC_WIN 832
 #endif
 #ifndef TIC_QUANT_F32X2
 #define TIC_QUANT_F32X2 1  // the tensor-core quantiser rounds coefficient pairs with packed FP32 instructions
@@ -93,7 +96,8 @@ namespace tic {
 constexpr int kTile = TIC_TILE;                             // blocks (= threads) per tile
 constexpr int kWarps = kTile / 32;
 constexpr int kCtasPerSm = TIC_CTAS;                        // CTAs per SM of the single-group kernels
-constexpr int kGroups = TIC_GROUPS;
+constexpr int kGroups = TIC_GROUPS;             // groups per CTA: fixed tables (one table copy per CTA), statistics
+constexpr int kGroupsAuto = TIC_GROUPS_AUTO;    // groups per CTA: per-image tables
 constexpr bool kFdctTc = TIC_FDCT_TC != 0;
 static_assert(!kFdctTc || kTile == 128, "the tensor-core transform is M = 128: one tile = 128 blocks");
 static_assert((kTile & (kTile - 1)) == 0, "thread-in-group = threadIdx.x & (kTile - 1)");
@@ -379,6 +383,16 @@ struct TileInfo {
 // ---------------------------------------------------------------------------------------------
 // shared memory of one CTA
 // ---------------------------------------------------------------------------------------------
+// Huffman tables in the form the walk wants, per (run << 4 | size).  Fixed tables: ONE 32-bit word per entry,
+// (len + size) << 27 | code << size (0: not in the table), in the first half of the array — a random-index 64-bit
+// lookup cost 6.6 shared-memory wavefronts, a third of the kernel's LSU traffic (profiles/r2d) — and one copy per CTA
+// (they are the same for every group: 2 KB per group back, which is what lets 8 groups fit 227 KB).  Per-image
+// tables: {code, kHuffPresent | len}, .y == 0: absent; one copy per group, behind its TileShared.
+struct TabShared {
+    uint2 ac_tab[256];
+    uint2 dc_tab[16];
+};
+
 struct TileShared {
     uint32_t coef[32][kTile];        // zigzag pairs (2i, 2i+1) packed lo/hi int16, one column per thread
     uint32_t priv[kPrivWords + 1][kTile];   // the block's bits, MSB-first from block bit 0, one column per
@@ -391,11 +405,6 @@ struct TileShared {
     uint32_t work[kWarps][kWarpWork];// exact-path worklist: lane << 6 | zigzag index; bit 31: halo DC
     int work_count[kWarps];
     int pending[kWarps];             // flagged coefficients that did not fit the worklist this round
-    // per (run << 4 | size).  Fixed tables: ONE 32-bit word per entry, (len + size) << 27 | code << size (0: not in
-    // the table), in the first half of the array — a random-index 64-bit lookup cost 6.6 shared-memory wavefronts,
-    // a third of the kernel's LSU traffic (profiles/r2d).  Per-image tables: {code, kHuffPresent | len}, .y == 0: absent.
-    uint2 ac_tab[256];
-    uint2 dc_tab[16];
     int warp_bits[kWarps];
     int warp_err[kWarps];
     unsigned int arena_off;          // 16-byte units; 0xffffffff: arena exhausted
@@ -405,6 +414,9 @@ struct TileShared {
     int u_img, u_lt;                 // uniform batches: (image, tile in image) of the tile after tinfo's newest (lane 0 of warp 0)
     unsigned int stat_items, stat_changed, stat_unflagged, tc_timeout;   // flushed to the batch counters at the end
     alignas(16) uint32_t stage[kWinWords];   // window of the tile-relative MSB-first bit buffer (kept zeroed)
+    // LAST member: the kernels that keep ONE table copy per CTA (fixed tables) or none (statistics) pack their groups
+    // at kGroupStrideNoTab and never touch this member — it overlaps the next group there.
+    TabShared tab;
 };
 
 // Two tenants of the private-word area while no walk is using it:
@@ -413,16 +425,16 @@ struct TileShared {
 //                                         walk, and no other warp touches its columns — the warps of a group are not
 //                                         synchronised between the two, so a group-wide array here would be overwritten
 //                                         by a faster warp's private words.
-//   bytes [1024, 5248)                    per-image tables: 272 symbol counters (room for 512) + 272 first-occurrence
+//   bytes [1024, 4352)                    per-image tables: 272 symbol counters (room for 288) + 272 first-occurrence
 //                                         keys (the statistics kernels never walk)
 __device__ __forceinline__ double* exact_colres(TileShared& sm, int warp, int grp) {
     return reinterpret_cast<double*>(&sm.priv[grp >> 1][32 * warp + (grp & 1) * 16]);
 }
 __device__ __forceinline__ uint32_t* stats_hist(TileShared& sm) { return &sm.priv[0][0] + 256; }
 __device__ __forceinline__ unsigned long long* stats_first(TileShared& sm) {
-    return reinterpret_cast<unsigned long long*>(&sm.priv[0][0] + 256 + 512);
+    return reinterpret_cast<unsigned long long*>(&sm.priv[0][0] + 256 + 288);
 }
-static_assert((kPrivWords + 1) * kTile * 4 >= 1024 + (512 + 2 * 272) * 4 && kTile * 4 * 2 == 1024,
+static_assert((kPrivWords + 1) * kTile * 4 >= 1024 + (288 + 2 * 272) * 4 && kTile * 4 * 2 == 1024,
               "the private-word area also holds the exact path's column results and the statistics bins");
 
 // Tile number lt of image `img`.
@@ -1477,12 +1489,12 @@ __device__ __forceinline__ uint32_t tab_present(uint2 e) { return e.y; }   // 0:
 // Emits the bits of thread t's block (DC difference `diff`, AC from sm.coef / nz masks) and returns
 // their number.  |quantised value| <= 1024 / 0.2 (quality 99), so a size never exceeds 14 and the
 // table index stays inside the 16 x 16 table; sizes missing from the table have length word 0.
-// sbase: shared address of `sm`.
+// sbase: shared address of `sm`; tabbase: shared address of the TabShared in force.
 template <bool kAuto, bool kToStage>
-__device__ __forceinline__ int walk_block(const TileShared& sm, uint32_t sbase, int t, int diff,
+__device__ __forceinline__ int walk_block(const TileShared& sm, uint32_t sbase, uint32_t tabbase, int t, int diff,
                                           BitSink<kToStage>& s, int& err) {
-    const uint32_t dc_tab = sbase + (uint32_t)offsetof(TileShared, dc_tab);
-    const uint32_t ac_tab = sbase + (uint32_t)offsetof(TileShared, ac_tab);
+    const uint32_t dc_tab = tabbase + (uint32_t)offsetof(TabShared, dc_tab);
+    const uint32_t ac_tab = tabbase + (uint32_t)offsetof(TabShared, ac_tab);
     const uint32_t col = sbase + (uint32_t)offsetof(TileShared, coef) + (uint32_t)t * 4u;
     int sz = msb_index((uint32_t)(diff < 0 ? -diff : diff)) + 1;  // bits_required, utils.py:9-10
     uint2 e = tab_entry<kAuto>(dc_tab, (uint32_t)sz);
