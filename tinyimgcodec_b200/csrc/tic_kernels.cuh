@@ -84,6 +84,12 @@ namespace tic {
 #ifndef TIC_STATS_GROUPS
 #define TIC_STATS_GROUPS 1 // per-image tables: symbol statistics by the persistent multi-group kernel (0: single-group CTAs)
 #endif
+#ifndef TIC_LOAD_EARLY
+#define TIC_LOAD_EARLY 0   // 1: the next tile's pixel rows are requested behind barrier B1 and held across placement + copy-out
+#endif
+#ifndef TIC_STATS_DIRECT
+#define TIC_STATS_DIRECT 1 // per-image tables: AC symbol counts by one shared-memory atomic per lane (1) or combined per warp and step with match.any (0)
+#endif
 #ifndef TIC_HALO_F32
 #define TIC_HALO_F32 1     // tensor-core path: the DC predictor in front of a warp from its pixel sum in FP32 (ties: exact path)
 #endif
@@ -1578,6 +1584,14 @@ __device__ __forceinline__ void stats_step(int sym, unsigned rel, unsigned long 
         if (k < first[sym]) atomicMin(&first[sym], k);                   // only until the symbol's first occurrence is settled
     }
 }
+// TIC_STATS_DIRECT: the AC symbols without the vote — every lane adds 1 to its symbol's counter (shared-memory
+// atomic, no return value) and offers its key only while it is smaller than the one on record.
+__device__ __forceinline__ void stats_step_direct(int sym, unsigned rel, unsigned long long key0, uint32_t* hist, unsigned long long* first) {
+    if (sym < 0) return;
+    atomicAdd(&hist[sym], 1u);
+    const unsigned long long k = key0 + rel;
+    if (k < *reinterpret_cast<volatile unsigned long long*>(&first[sym])) atomicMin(&first[sym], k);
+}
 __device__ __forceinline__ void warp_block_stats(const TileShared& sm, int t, bool active, unsigned long long blk0,
                                                  uint32_t* hist, unsigned long long* first, int& err) {
     const unsigned long long key0 = blk0 << 8;
@@ -1615,7 +1629,11 @@ __device__ __forceinline__ void warp_block_stats(const TileShared& sm, int t, bo
             pend_sym = -1;
             ord += 1;
         }
+#if TIC_STATS_DIRECT
+        stats_step_direct(sym, rel, key0, hist, first);
+#else
         stats_step(sym, rel, key0, hist, first);
+#endif
     }
     stats_step(active ? 0 : -1, rel0 | (unsigned)ord, key0, hist, first);   // EOB (huffman.py:33)
 }
