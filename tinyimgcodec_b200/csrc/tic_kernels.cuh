@@ -84,6 +84,9 @@ namespace tic {
 #ifndef TIC_STATS_GROUPS
 #define TIC_STATS_GROUPS 1 // per-image tables: symbol statistics by the persistent multi-group kernel (0: single-group CTAs)
 #endif
+#ifndef TIC_EXACT_INT_COLS
+#define TIC_EXACT_INT_COLS 1 // exact path: the column pass for u = 0 / 4 from one integer sum per column (exact by the same argument as settle_rational)
+#endif
 #ifndef TIC_LOAD_EARLY
 #define TIC_LOAD_EARLY 0   // 1: the next tile's pixel rows are requested behind barrier B1 and held across placement + copy-out
 #endif
@@ -317,16 +320,14 @@ __device__ __noinline__ double dct8_exact(const double x0, const double x1, cons
                  TW3 = 0x1.6a09e667f3bccp-1, TW4 = 0x1.1c73b39ae68c8p-1, TW5 = 0x1.87de2a6aea963p-2,
                  TW6 = 0x1.8f8b83c69a60ap-3;
     const double WR = 0x1.6a09e667f3bccp-1, WI = 0x1.6a09e667f3bcdp-1, HSQ = 0x1.6a09e667f3bcdp-1;
+    // (every value keeps its own operation sequence; what outputs 0 and 4 do not need is computed behind their return)
     double c0 = __dmul_rn(2.0, x0), c7 = __dmul_rn(2.0, x7);
-    double c1 = __dadd_rn(x1, x2), c2 = __dsub_rn(x2, x1);
-    double c3 = __dadd_rn(x3, x4), c4 = __dsub_rn(x4, x3);
-    double c5 = __dadd_rn(x5, x6), c6 = __dsub_rn(x6, x5);
-    double h0 = __dadd_rn(c0, c7), h4 = __dsub_rn(c0, c7);
-    double h3 = __dmul_rn(2.0, c3), h7 = __dmul_rn(-2.0, c4);
-    double h1 = __dadd_rn(c1, c5), tr = __dsub_rn(c1, c5);
-    double ti = __dadd_rn(c2, c6), h2 = __dsub_rn(c2, c6);
-    double h6 = __dadd_rn(__dmul_rn(WR, ti), __dmul_rn(WI, tr));
-    double h5 = __dsub_rn(__dmul_rn(WR, tr), __dmul_rn(WI, ti));
+    double c1 = __dadd_rn(x1, x2);
+    double c3 = __dadd_rn(x3, x4);
+    double c5 = __dadd_rn(x5, x6);
+    double h0 = __dadd_rn(c0, c7);
+    double h3 = __dmul_rn(2.0, c3);
+    double h1 = __dadd_rn(c1, c5);
     double s;  // 0.25 * r_k for the FFT output(s) this selection needs
     if (sel == 0 || sel == 4) {
         double a = __dadd_rn(h0, h3);
@@ -338,6 +339,12 @@ __device__ __noinline__ double dct8_exact(const double x0, const double x1, cons
         s = __dmul_rn(0.25, __dsub_rn(a, e1));
         return __dmul_rn(s, TW3);
     }
+    double c2 = __dsub_rn(x2, x1), c4 = __dsub_rn(x4, x3), c6 = __dsub_rn(x6, x5);
+    double h4 = __dsub_rn(c0, c7), h7 = __dmul_rn(-2.0, c4);
+    double tr = __dsub_rn(c1, c5);
+    double ti = __dadd_rn(c2, c6), h2 = __dsub_rn(c2, c6);
+    double h6 = __dadd_rn(__dmul_rn(WR, ti), __dmul_rn(WI, tr));
+    double h5 = __dsub_rn(__dmul_rn(WR, tr), __dmul_rn(WI, ti));
     double b = __dsub_rn(h0, h3);
     double e2 = __dmul_rn(2.0, h2);
     double a2 = __dadd_rn(h4, h7), b2 = __dsub_rn(h4, h7);
@@ -789,23 +796,43 @@ __device__ __forceinline__ void exact_round(const TileInfo& ti, const QuantParam
         const int u = r >> 3, v = r & 7;
         const int b = halo ? ti.blk0 + wt0 - 1 : ti.blk0 + owner;
         if (act) {
-            const int br = b / ti.bw, bc = b - br * ti.bw;
+            int br, bc;
+            if (ti.bw_shift >= 0) { br = b >> ti.bw_shift; bc = b & (ti.bw - 1); }   // uniform branch: no division routine
+            else { br = b / ti.bw; bc = b - br * ti.bw; }
             const int y0 = br * 8, x = bc * 8 + c;
             double x0, x1, x2, x3, x4, x5, x6, x7;
-            if (y0 + 8 <= ti.h && bc * 8 + 8 <= ti.w) {   // interior block: no reflection (uniform per group)
+            const bool interior = y0 + 8 <= ti.h && bc * 8 + 8 <= ti.w;   // no reflection (uniform per group)
+#if TIC_EXACT_INT_COLS
+            if (interior && (u & 3) == 0) {
+                // u = 0 or 4 (9 in 10 of all items: the true .5 ties sit at (0,0), (4,0), (0,4), (4,4)): every operation
+                // of dct8_exact's column pass in front of its last multiplication acts on small integers and is exact —
+                // s = 0.5 * (x0 + x7 + x3 + x4 +- (x1 + x2 + x5 + x6)) — so the result is RN(s * HSQ) resp. RN(s * TW3),
+                // from one integer sum (the same identity as dc_exact_from_colsums / settle_rational)
+                const uint8_t* p = ti.px + (size_t)y0 * ti.w + x;
+                const size_t w = (size_t)ti.w;
+                const int p0 = __ldg(p), p1 = __ldg(p + w), p2 = __ldg(p + 2 * w), p3 = __ldg(p + 3 * w);
+                const int p4 = __ldg(p + 4 * w), p5 = __ldg(p + 5 * w), p6 = __ldg(p + 6 * w), p7 = __ldg(p + 7 * w);
+                const int outer = p0 + p7 + p3 + p4, inner = p1 + p2 + p5 + p6;
+                const int sum = u == 0 ? outer + inner - 1024 : outer - inner;   // level shift: 8 x 128 resp. 0
+                const double m = u == 0 ? 0x1.6a09e667f3bcdp-1 : 0x1.6a09e667f3bccp-1;   // HSQ : TW3
+                exact_colres(sm, warp, grp)[c] = __dmul_rn(__dmul_rn(0.5, (double)sum), m);
+            } else
+#endif
+            if (interior) {
                 const uint8_t* p = ti.px + (size_t)y0 * ti.w + x;
                 const size_t w = (size_t)ti.w;
                 x0 = (double)((int)__ldg(p) - 128);         x1 = (double)((int)__ldg(p + w) - 128);
                 x2 = (double)((int)__ldg(p + 2 * w) - 128); x3 = (double)((int)__ldg(p + 3 * w) - 128);
                 x4 = (double)((int)__ldg(p + 4 * w) - 128); x5 = (double)((int)__ldg(p + 5 * w) - 128);
                 x6 = (double)((int)__ldg(p + 6 * w) - 128); x7 = (double)((int)__ldg(p + 7 * w) - 128);
+                exact_colres(sm, warp, grp)[c] = dct8_exact(x0, x1, x2, x3, x4, x5, x6, x7, u);
             } else {
                 x0 = load_px_exact(ti, y0 + 0, x); x1 = load_px_exact(ti, y0 + 1, x);
                 x2 = load_px_exact(ti, y0 + 2, x); x3 = load_px_exact(ti, y0 + 3, x);
                 x4 = load_px_exact(ti, y0 + 4, x); x5 = load_px_exact(ti, y0 + 5, x);
                 x6 = load_px_exact(ti, y0 + 6, x); x7 = load_px_exact(ti, y0 + 7, x);
+                exact_colres(sm, warp, grp)[c] = dct8_exact(x0, x1, x2, x3, x4, x5, x6, x7, u);
             }
-            exact_colres(sm, warp, grp)[c] = dct8_exact(x0, x1, x2, x3, x4, x5, x6, x7, u);
         }
         __syncwarp();
         if (act && c == 0) {
@@ -817,17 +844,8 @@ __device__ __forceinline__ void exact_round(const TileInfo& ti, const QuantParam
             } else {
                 int old = k == 0 ? sm.dcq[owner] : coef_get(sm, owner, k);
                 if (old != q) {
-                    // two flagged coefficients of one block may share a packed word: serialise
-                    // through a 32-bit CAS on that word
-                    uint32_t* wp = &sm.coef[k >> 1][owner];
-                    uint32_t seen = *wp, want;
-                    do {
-                        const uint32_t qb = (uint32_t)q & 0xffffu;
-                        want = (k & 1) ? ((seen & 0x0000ffffu) | (qb << 16)) : ((seen & 0xffff0000u) | qb);
-                        uint32_t prev = atomicCAS(wp, seen, want);
-                        if (prev == seen) break;
-                        seen = prev;
-                    } while (true);
+                    // two flagged coefficients of one block may share a packed word: a 16-bit store touches its own half only
+                    reinterpret_cast<short*>(&sm.coef[k >> 1][owner])[k & 1] = (short)q;
                     if (k == 0) {
                         sm.dcq[owner] = q;
                     } else {
@@ -1139,7 +1157,9 @@ __device__ __noinline__ unsigned settle_rational(uint32_t taddr /* the lane's ac
 __device__ __forceinline__ bool tile_halo_is_fast(const TileInfo& ti, int& y0, int& x0) {
     const int hb = ti.blk0 - 1;
     if (hb < 0) return false;
-    const int br = hb / ti.bw, bc = hb - br * ti.bw;
+    int br, bc;
+    if (ti.bw_shift >= 0) { br = hb >> ti.bw_shift; bc = hb & (ti.bw - 1); }
+    else { br = hb / ti.bw; bc = hb - br * ti.bw; }
     y0 = br * 8; x0 = bc * 8;
     return ((ti.w & 7) == 0) && ((reinterpret_cast<uintptr_t>(ti.px) & 7) == 0) && (y0 + 8 <= ti.h);
 }
