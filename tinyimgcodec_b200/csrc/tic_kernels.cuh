@@ -90,6 +90,12 @@ namespace tic {
 #ifndef TIC_EXACT_PREFETCH
 #define TIC_EXACT_PREFETCH 0 // 1: lanes flagged in zigzag groups 0-1 prefetch their block's pixel rows into L1 for the exact path (CCTL.PF1; measured: 4.24 against 3.87 ms)
 #endif
+#ifndef TIC_EXACT_RANK
+#define TIC_EXACT_RANK 0     // 1: the exact path's worklist filled by vote + rank (count in registers) instead of a shared-memory atomic counter (measured: 3.91 against 3.87 ms)
+#endif
+#ifndef TIC_EXACT_ROW_INLINE
+#define TIC_EXACT_ROW_INLINE 1   // 1: the exact path's row pass for v = 0 / 4 inline, no call (3.84 against 3.87 ms)
+#endif
 #ifndef TIC_EXACT_BALLOT
 #define TIC_EXACT_BALLOT 0   // 1: the exact path's items of a round by vote + shuffle instead of the worklist in shared memory (measured: 3.95 against 3.88 ms)
 #endif
@@ -839,7 +845,18 @@ __device__ __forceinline__ void exact_item(const TileInfo& ti, const QuantParams
         __syncwarp();
         if (act && c == 0) {
             const double* cr = exact_colres(sm, warp, grp);
-            double y = dct8_exact(cr[0], cr[1], cr[2], cr[3], cr[4], cr[5], cr[6], cr[7], v);
+            double y;
+#if TIC_EXACT_ROW_INLINE
+            if ((v & 3) == 0) {   // outputs 0 and 4: dct8_exact's sequence for them, without the call
+                const double c0 = __dmul_rn(2.0, cr[0]), c7 = __dmul_rn(2.0, cr[7]);
+                const double c1 = __dadd_rn(cr[1], cr[2]), c3 = __dadd_rn(cr[3], cr[4]), c5 = __dadd_rn(cr[5], cr[6]);
+                const double h0 = __dadd_rn(c0, c7), h3 = __dmul_rn(2.0, c3), h1 = __dadd_rn(c1, c5);
+                const double a = __dadd_rn(h0, h3), e1 = __dmul_rn(2.0, h1);
+                y = v == 0 ? __dmul_rn(__dmul_rn(0.25, __dadd_rn(a, e1)), 0x1.6a09e667f3bcdp-1)
+                           : __dmul_rn(__dmul_rn(0.25, __dsub_rn(a, e1)), 0x1.6a09e667f3bccp-1);
+            } else
+#endif
+            y = dct8_exact(cr[0], cr[1], cr[2], cr[3], cr[4], cr[5], cr[6], cr[7], v);
             int q = __double2int_rn(__ddiv_rn(y, qp.qt[r]));   // np.round(coeffs / qt), utils.py:53
             if (halo) {
                 sm.dc_halo[warp] = q;
@@ -1416,6 +1433,46 @@ __device__ __forceinline__ void transform_tile_tc(const TileInfo& ti, const Quan
                 else { if (k < 32) dbg_lo ^= bit; else dbg_hi ^= bit; }
             }
             halo_left = 0;
+        }
+        __syncwarp();
+        return;
+    }
+#endif
+#if TIC_EXACT_RANK
+    // The worklist is filled by rank, not by an atomic counter: in every pass each lane with a flag left takes slot
+    // count + (flagged lanes below it) for its first flagged coefficient; `count` stays in registers (warp-uniform).  The
+    // shared-memory counter cost an atomic with a return value, a warp barrier and two loads — on the critical path of
+    // the group's slowest warp, for which the other three wait at barrier B1.
+    {
+        uint32_t dbg_lo = 0, dbg_hi = 0;   // coefficients that go to the exact path although the guard did not flag them
+        if (debug_all && t < ti.nb) { dbg_lo = ~fl_lo; dbg_hi = ~fl_hi; }
+        int count = 0;
+        if (halo_item) { if (lane == 0) sm.work[warp][0] = kWorkHalo | kWorkGuard; count = 1; }
+        else if (lane == 0) sm.dc_halo[warp] = halo_dc;
+        const uint32_t below = (1u << lane) - 1u;
+        while (true) {
+            while (count < kWarpWork) {
+                const bool guard = (fl_lo | fl_hi) != 0;
+                uint32_t& lo = guard ? fl_lo : dbg_lo;
+                uint32_t& hi = guard ? fl_hi : dbg_hi;
+                const uint32_t m = __ballot_sync(0xffffffffu, (lo | hi) != 0u);
+                if (m == 0u) break;
+                const int slot = count + __popc(m & below);
+                if ((lo | hi) != 0u && slot < kWarpWork) {
+                    const int k = lo ? __clz(lo) : 32 + __clz(hi);
+                    sm.work[warp][slot] = (guard ? kWorkGuard : 0u) | ((uint32_t)lane << 6) | (uint32_t)k;
+                    if (k < 32) lo ^= 0x80000000u >> k; else hi ^= 0x80000000u >> (k - 32);
+                }
+                count += __popc(m);
+                if (count > kWarpWork) count = kWarpWork;
+            }
+            __syncwarp();
+            if (count) {   // warp-uniform
+                if (lane == 0) st.items((unsigned)count);
+                exact_round(ti, qp, sm, warp, count, st);
+            }
+            if (__ballot_sync(0xffffffffu, (fl_lo | fl_hi | dbg_lo | dbg_hi) != 0u) == 0u) break;
+            count = 0;
         }
         __syncwarp();
         return;
