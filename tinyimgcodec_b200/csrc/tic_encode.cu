@@ -665,7 +665,7 @@ symbol_stats_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
 }
 
 // The same statistics from the persistent multi-group structure of encode_tiles_kernel (tensor-core path only): G groups
-// per CTA share one TMEM allocation and one B operand, 24 warps per SM instead of the 16 that four single-group CTAs
+// per CTA share one TMEM allocation and one B operand, 32 warps per SM instead of the 16 that four single-group CTAs
 // give (TMEM: 4 x 128 columns).  Every GROUP takes a contiguous range of tiles and keeps one image's statistics in its
 // own staging window until the image changes.
 template <int G>

@@ -47,9 +47,10 @@ namespace tic {
 #ifndef TIC_GROUPS_AUTO
 #define TIC_GROUPS_AUTO 7   // per-image tables: every group keeps its own image's tables (TabShared) in shared memory
 #endif
-// 7 groups (28 warps per SM) need 64 TMEM columns per group (7 x 80 > 512: the 16 column-sum outputs of TIC_RATIONAL go),
-// 72 registers per thread and a group state of at most 30.1 KB (TIC_PRIV 8, TIC_WIN 1056).  Measured: 4.29 ms against
-// 4.50 ms for 6 groups with the column sums (6 groups without them: 4.60 ms).
+// 8 groups (32 warps per SM: everything an SM holds) need 64 TMEM columns per group (the 16 column-sum outputs of
+// TIC_RATIONAL go: 7 x 80 > 512), 64 registers per thread and a group state of at most 26 KB: the fixed Huffman tables
+// live once per CTA (TabShared), TIC_PRIV 8, TIC_WIN 832.  Measured: 4.10 ms against 4.29 ms for 7 groups at 72
+// registers and 4.50 ms for 6 groups with the column sums (6 groups without them: 4.60 ms).
 // (Prefetching a group's next tile was measured and dropped: held in registers it spills — with 227 KB of shared
 // memory there is no L1 to catch a spill — and through cp.async + LDS it costs more than the latency it hides:
 // 5.52 ms against 5.01 ms for plain loads at the top of the tile, profiles/r2_variants.md.)
@@ -122,7 +123,7 @@ constexpr int kGroupsAuto = TIC_GROUPS_AUTO;    // groups per CTA: per-image tab
 constexpr bool kFdctTc = TIC_FDCT_TC != 0;
 static_assert(!kFdctTc || kTile == 128, "the tensor-core transform is M = 128: one tile = 128 blocks");
 static_assert((kTile & (kTile - 1)) == 0, "thread-in-group = threadIdx.x & (kTile - 1)");
-constexpr int kPrivWords = TIC_PRIV;                           // private words per block on the fast path (512 bits)
+constexpr int kPrivWords = TIC_PRIV;                           // private words per block on the fast path (256 bits)
 // The bits of a tile are assembled in a WINDOW of kWinWords 32-bit words of shared memory: a tile
 // whose stream is longer (worst case 128 x 1662 bits + a table header) is emitted in several rounds.
 constexpr int kWinWords = TIC_WIN;

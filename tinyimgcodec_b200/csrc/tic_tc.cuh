@@ -27,7 +27,7 @@ constexpr int kABytes = 128 * 64 * 2;   // A operand of one tile: 128 blocks x 6
 // exact .5 ties: (0,0), (4,0), (0,4), (4,4).  A lane with such a tie reads them from tensor memory.
 #ifndef TIC_RATIONAL
 #define TIC_RATIONAL 0   // 1: the 16 column-sum outputs exist and ties at the four rational positions are settled from them
-                         // (N = 80: at most 6 groups per CTA share the 512 TMEM columns; 0: N = 64, 7 groups — faster, tic_kernels.cuh)
+                         // (N = 80: at most 6 groups per CTA share the 512 TMEM columns; 0: N = 64, 8 groups — faster, tic_kernels.cuh)
 #endif
 constexpr int kN = TIC_RATIONAL ? 80 : 64;
 constexpr int kBBytes = kN * 128 * 2;   // B operand: 80 columns x (64 hi + 64 lo) f16
