@@ -3,6 +3,7 @@ import os
 import sys
 
 import numpy as np
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -11,6 +12,7 @@ import bench  # noqa: E402
 from tests.cases import synthetic_image  # noqa: E402
 
 
+@pytest.mark.timeout(120)
 def test_bench_generator_is_the_numpy_generator():
     """Host draws (forked workers, shared memory) + the integer upsample in torch == tests/cases.py::synthetic_image
     (the BASELINE.md §4 generator the golden fixtures were made with), seed = global image index."""
