@@ -157,15 +157,9 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
     group_sync<G>(g);
 
     constexpr int kDescWarp = (kTc && kWarps > 1) ? 1 : 0;   // warp 0 already issues the MMA and owns the tile's halo
-    // TIC_LOAD_EARLY: a tile's pixel rows are requested behind barrier B1 of the tile BEFORE it — its description is
-    // in shared memory by then — and held in registers across the placement and the copy-out only (few other values
-    // are live there), so that the DRAM round trip is over when the next iteration stages them.
-    constexpr bool kLoadEarly = kTc && TIC_LOAD_EARLY != 0;
-    uint2 rows[8];   // tensor-core path only (never touched, so no registers, elsewhere)
-    uint2 halo_v;
-    if constexpr (kLoadEarly) {
-        if (first < ntiles_u && sm.tinfo[0].nb > 0) load_block_rows(sm.tinfo[0], t, rows);
-    }
+    // (Requesting a tile's pixel rows one step earlier — behind barrier B1 of the tile before it, or in front of B2 — and
+    // holding them in registers across the placement and the copy-out was measured: 4.47 / 4.63 ms against 4.10, and
+    // 4.50 against 4.29 at 7 groups without a spill; commit 5d47ac4)
     // one loop register for two values: bits 0-30 the tile, bit 31 the slot of its description in sm.tinfo (the tile
     // loop is where the kernel's register pressure peaks; ntiles < 2^31)
     for (unsigned tcur = first; (tcur & 0x7fffffffu) < ntiles_u; tcur = (tcur + stride) ^ 0x80000000u) {
@@ -196,10 +190,9 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
         if constexpr (kCVar) { describe_next(); transform_warp_c(ti, quality, sm); }
         else if constexpr (kTc) {
             if (ti.nb > 0) {
-                // the block in front of the tile: with the tile's own rows — one DRAM latency, not two; with early rows
-                // it is only needed in the tensor core's shadow and mostly an L2 hit (another group has just read it)
-                if constexpr (!kLoadEarly) load_block_rows(ti, t, rows);
-                halo_v = load_tile_halo(ti, t);
+                uint2 rows[8];
+                load_block_rows(ti, t, rows);
+                const uint2 halo_v = load_tile_halo(ti, t);   // with the tile's own rows: one DRAM latency, not two
                 transform_tile_tc<G>(ti, qp, sm, tg, g, debug_all, st, rows, halo_v, describe_next);
             } else {
                 describe_next();
@@ -255,14 +248,6 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
             *reinterpret_cast<uint4*>(&recs[tile]) = *reinterpret_cast<uint4*>(&r);
             if (tile_err) atomicOr(&status[ti.img], TIC_STATUS_CATEGORY);
         }
-        // the next tile's rows (described one tile ahead; B1 made the description visible)
-        auto load_next = [&]() {
-            if (tile + stride < ntiles_u) {
-                const TileInfo& nx = sm.tinfo[slot ^ 1];
-                if (nx.nb > 0) load_block_rows(nx, t, rows);
-            }
-        };
-        if constexpr (kLoadEarly && TIC_LOAD_EARLY == 1) load_next();
 
         const int hdr_words = (hdr_bits + 31) >> 5;
         for (int wbase = 0;;) {   // one round per window; a second one only for tiles longer than the window
@@ -308,7 +293,6 @@ encode_tiles_kernel(const __grid_constant__ QuantParams qp, const ImageDesc* __r
 #endif
                 }
             }
-            if constexpr (kLoadEarly && TIC_LOAD_EARLY == 2) { if (wbase == 0) load_next(); }   // held across B2 and the copy-out only
             group_sync<G>(g);   // B2: window complete, arena offset visible
 
             // ---- window -> arena (16-byte stores), and the window is zero again -----------------

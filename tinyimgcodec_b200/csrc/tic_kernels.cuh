@@ -88,20 +88,8 @@ namespace tic {
 #ifndef TIC_EXACT_INT_COLS
 #define TIC_EXACT_INT_COLS 1 // exact path: the column pass for u = 0 / 4 from one integer sum per column (exact by the same argument as settle_rational)
 #endif
-#ifndef TIC_EXACT_PREFETCH
-#define TIC_EXACT_PREFETCH 0 // 1: lanes flagged in zigzag groups 0-1 prefetch their block's pixel rows into L1 for the exact path (CCTL.PF1; measured: 4.24 against 3.87 ms)
-#endif
-#ifndef TIC_EXACT_RANK
-#define TIC_EXACT_RANK 0     // 1: the exact path's worklist filled by vote + rank (count in registers) instead of a shared-memory atomic counter (measured: 3.91 against 3.87 ms)
-#endif
 #ifndef TIC_EXACT_ROW_INLINE
 #define TIC_EXACT_ROW_INLINE 1   // 1: the exact path's row pass for v = 0 / 4 inline, no call (3.84 against 3.87 ms)
-#endif
-#ifndef TIC_EXACT_BALLOT
-#define TIC_EXACT_BALLOT 0   // 1: the exact path's items of a round by vote + shuffle instead of the worklist in shared memory (measured: 3.95 against 3.88 ms)
-#endif
-#ifndef TIC_LOAD_EARLY
-#define TIC_LOAD_EARLY 0   // 1: the next tile's pixel rows are requested behind barrier B1 and held across placement + copy-out
 #endif
 #ifndef TIC_STATS_DIRECT
 #define TIC_STATS_DIRECT 1 // per-image tables: AC symbol counts by one shared-memory atomic per lane (1) or combined per warp and step with match.any (0)
@@ -1337,20 +1325,6 @@ __device__ __forceinline__ void transform_tile_tc(const TileInfo& ti, const Quan
         tc::tmem_wait_ld8(rb);
         tc::tmem_ld8(tmem + 16, ra);
         quantise_group_tc<1>(rb, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
-#if TIC_EXACT_PREFETCH
-        // Three of the four tie positions (zigzag 0, 10, 14) are known now: a lane with a flag asks for its block's pixel
-        // rows in L1, so that the exact path — on the critical path of the group's slowest warp — finds them there
-        // instead of in L2 once the other six groups are quantised.
-        if (__any_sync(0xffffffffu, fl_lo != 0u)) {   // warp-uniform
-            int y0, x0;
-            block_origin(ti, t, y0, x0);
-            if (fl_lo != 0u && t < ti.nb && block_is_fast(ti, y0)) {
-                const uint8_t* p = ti.px + (size_t)y0 * ti.w + x0;
-#pragma unroll
-                for (int i = 0; i < 8; i++) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (size_t)i * ti.w) : "memory");
-            }
-        }
-#endif
         tc::tmem_wait_ld8(ra);
         tc::tmem_ld8(tmem + 24, rb);
         quantise_group_tc<2>(ra, qp, sm, t, debug_all, nz_lo, nz_hi, fl_lo, fl_hi, dc);
@@ -1395,90 +1369,6 @@ __device__ __forceinline__ void transform_tile_tc(const TileInfo& ti, const Quan
             }
         }
     }
-#if TIC_EXACT_BALLOT
-    // No worklist in shared memory: the items of a round are the DC in front of the warp (if it needs the exact path)
-    // and the first flagged coefficient of the lowest flagged lanes, four in all, named by a vote and a shuffle (the
-    // worklist cost an atomic with a return value, two warp barriers and two loads on the critical path of the group's
-    // slowest warp: the other three wait at barrier B1 for this).  Under TIC_FLAG_DEBUG_ALL_EXACT a lane whose guard flags
-    // are served goes on with all its other coefficients (guard = false: a change there is a guard miss).
-    {
-        uint32_t dbg_lo = 0, dbg_hi = 0;   // coefficients that go to the exact path although the guard did not flag them
-        if (debug_all && t < ti.nb) { dbg_lo = ~fl_lo; dbg_hi = ~fl_hi; }
-        if (lane == 0 && !halo_item) sm.dc_halo[warp] = halo_dc;
-        const int grp = lane >> 3, c = lane & 7;
-        int halo_left = halo_item;   // warp-uniform
-        while (true) {
-            const bool guard = (fl_lo | fl_hi) != 0u;
-            const uint32_t lo = guard ? fl_lo : dbg_lo, hi = guard ? fl_hi : dbg_hi;
-            const uint32_t m = __ballot_sync(0xffffffffu, (lo | hi) != 0u);
-            if (m == 0u && !halo_left) break;
-            const int myk = (lo ? __clz(lo) : 32 + __clz(hi)) | (guard ? 64 : 0);
-            const int j = grp - halo_left;                 // this group's item among the flagged lanes; -1: the halo DC
-            uint32_t mm = m, rest = m;
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                if (i < j) mm &= mm - 1u;                  // drop the j lowest flagged lanes
-                if (i < 4 - halo_left) rest &= rest - 1u;  // flagged lanes NOT served this round
-            }
-            const bool is_halo = j < 0;
-            const bool act = is_halo || mm != 0u;
-            const int src = (!is_halo && mm != 0u) ? __ffs((int)mm) - 1 : 0;
-            const int ksrc = __shfl_sync(0xffffffffu, myk, src);
-            if (lane == 0) st.items((unsigned)(__popc(m ^ rest) + halo_left));
-            exact_item(ti, qp, sm, warp, grp, c, act, is_halo, is_halo || (ksrc & 64) != 0, warp * 32 + src,
-                       is_halo ? 0 : (ksrc & 63), st);
-            if (((m ^ rest) >> lane) & 1u) {               // served: this lane's first flag is settled
-                const int k = myk & 63;
-                const uint32_t bit = 0x80000000u >> (k & 31);
-                if (guard) { if (k < 32) fl_lo ^= bit; else fl_hi ^= bit; }
-                else { if (k < 32) dbg_lo ^= bit; else dbg_hi ^= bit; }
-            }
-            halo_left = 0;
-        }
-        __syncwarp();
-        return;
-    }
-#endif
-#if TIC_EXACT_RANK
-    // The worklist is filled by rank, not by an atomic counter: in every pass each lane with a flag left takes slot
-    // count + (flagged lanes below it) for its first flagged coefficient; `count` stays in registers (warp-uniform).  The
-    // shared-memory counter cost an atomic with a return value, a warp barrier and two loads — on the critical path of
-    // the group's slowest warp, for which the other three wait at barrier B1.
-    {
-        uint32_t dbg_lo = 0, dbg_hi = 0;   // coefficients that go to the exact path although the guard did not flag them
-        if (debug_all && t < ti.nb) { dbg_lo = ~fl_lo; dbg_hi = ~fl_hi; }
-        int count = 0;
-        if (halo_item) { if (lane == 0) sm.work[warp][0] = kWorkHalo | kWorkGuard; count = 1; }
-        else if (lane == 0) sm.dc_halo[warp] = halo_dc;
-        const uint32_t below = (1u << lane) - 1u;
-        while (true) {
-            while (count < kWarpWork) {
-                const bool guard = (fl_lo | fl_hi) != 0;
-                uint32_t& lo = guard ? fl_lo : dbg_lo;
-                uint32_t& hi = guard ? fl_hi : dbg_hi;
-                const uint32_t m = __ballot_sync(0xffffffffu, (lo | hi) != 0u);
-                if (m == 0u) break;
-                const int slot = count + __popc(m & below);
-                if ((lo | hi) != 0u && slot < kWarpWork) {
-                    const int k = lo ? __clz(lo) : 32 + __clz(hi);
-                    sm.work[warp][slot] = (guard ? kWorkGuard : 0u) | ((uint32_t)lane << 6) | (uint32_t)k;
-                    if (k < 32) lo ^= 0x80000000u >> k; else hi ^= 0x80000000u >> (k - 32);
-                }
-                count += __popc(m);
-                if (count > kWarpWork) count = kWarpWork;
-            }
-            __syncwarp();
-            if (count) {   // warp-uniform
-                if (lane == 0) st.items((unsigned)count);
-                exact_round(ti, qp, sm, warp, count, st);
-            }
-            if (__ballot_sync(0xffffffffu, (fl_lo | fl_hi | dbg_lo | dbg_hi) != 0u) == 0u) break;
-            count = 0;
-        }
-        __syncwarp();
-        return;
-    }
-#endif
     if (lane == 0) {
         if (halo_item) sm.work[warp][atomicAdd(&sm.work_count[warp], 1)] = kWorkHalo | kWorkGuard;   // slot 0: nothing pushed yet
         else sm.dc_halo[warp] = halo_dc;
