@@ -31,3 +31,24 @@ def test_bench_generator_full_size_image():
     g, n = bench.synth_draws(4095)
     img = bench.synth_assemble(g[None], n[None], "cpu")[0].numpy()
     assert np.array_equal(img, synthetic_image(1024, 1024, 4095))
+
+
+def test_bench_helpers_are_not_shadowed():
+    """run_gpu_arm's nested helpers (step, barrier) are called by every later leg of the bench: a loop variable of the
+    same name silently turns the leg into an error entry of the JSON line (it happened to the decode leg once)."""
+    import ast
+    tree = ast.parse(open(os.path.join(ROOT, "bench.py")).read())
+    fn = next(n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name == "run_gpu_arm")
+    defs = {n.name for n in ast.walk(fn) if isinstance(n, ast.FunctionDef) and n is not fn}
+    assigned = set()
+    for n in ast.walk(fn):
+        targets = []
+        if isinstance(n, ast.Assign):
+            targets = n.targets
+        elif isinstance(n, (ast.For, ast.comprehension, ast.AugAssign, ast.AnnAssign, ast.NamedExpr)):
+            targets = [n.target]
+        elif isinstance(n, ast.With):
+            targets = [i.optional_vars for i in n.items if i.optional_vars is not None]
+        for t in targets:
+            assigned |= {x.id for x in ast.walk(t) if isinstance(x, ast.Name)}
+    assert defs and not (defs & assigned), sorted(defs & assigned)
